@@ -1,0 +1,688 @@
+// Included by engine.cu: program emission and plan execution.
+
+namespace {
+
+struct AggDedup {
+    std::vector<int> uniq_of;     // sink value -> unique aggregate index
+    std::vector<int> kind, node;  // per unique aggregate
+};
+
+static AggDedup dedup_aggs(const rq_pipeline& pl) {
+    AggDedup d;
+    d.uniq_of.assign(pl.n_vals, -1);
+    for (int k = 0; k < pl.n_vals; k++) {
+        const int kind = pl.vals[k].kind;
+        if (kind < RQ_AGG_SUM || kind > RQ_AGG_MAX) raise(RQ_ERR_INVALID, "aggregate %d has kind %d", k, kind);
+        const int node = (kind == RQ_AGG_COUNT) ? -1 : pl.vals[k].node;
+        for (size_t u = 0; u < d.kind.size(); u++)
+            if (d.kind[u] == kind && d.node[u] == node) { d.uniq_of[k] = (int)u; break; }
+        if (d.uniq_of[k] < 0) {
+            d.uniq_of[k] = (int)d.kind.size();
+            d.kind.push_back(kind);
+            d.node.push_back(node);
+        }
+    }
+    if ((int)d.kind.size() > kMaxAggs) raise(RQ_ERR_UNSUPPORTED, "more than %d distinct aggregates", kMaxAggs);
+    return d;
+}
+
+// ---- plan clean-up before lowering: constant folding, CSE, dead-code elimination -----------
+// The reference re-materialises every constant and re-evaluates every sub-expression per tuple
+// (ExpressionsJitFlounder.h emits `0.06 - 0.01` inside the scan loop); folding and sharing are
+// result-identical under wrap-around int64 arithmetic.
+struct SimplePipe {
+    std::vector<rq_node> nodes;
+    std::vector<int32_t> args;
+    std::vector<rq_value> keys, vals;
+    rq_pipeline pl;
+};
+
+static bool fold_binary(int op, int64_t x, int64_t y, int64_t* out) {
+    const uint64_t ux = (uint64_t)x, uy = (uint64_t)y;
+    switch (op) {
+        case RQ_OP_ADD: *out = (int64_t)(ux + uy); return true;
+        case RQ_OP_SUB: *out = (int64_t)(ux - uy); return true;
+        case RQ_OP_MUL: *out = (int64_t)(ux * uy); return true;
+        case RQ_OP_DIV:
+            if (y == 0) return false;
+            *out = (y == -1) ? (int64_t)(0ULL - ux) : x / y;
+            return true;
+        case RQ_OP_AND: *out = x & y; return true;
+        case RQ_OP_OR:  *out = x | y; return true;
+        case RQ_OP_LT:  *out = x < y; return true;
+        case RQ_OP_LE:  *out = x <= y; return true;
+        case RQ_OP_GT:  *out = x > y; return true;
+        case RQ_OP_GE:  *out = x >= y; return true;
+        case RQ_OP_EQ:  *out = x == y; return true;
+        case RQ_OP_NEQ: *out = x != y; return true;
+        default: return false;
+    }
+}
+
+static void simplify_pipeline(const rq_pipeline& in, SimplePipe& sp) {
+    const int n = in.n_nodes;
+    std::vector<rq_node> tmp;
+    std::vector<int> remap(n, -1);
+    std::map<std::vector<int64_t>, int> seen;
+    auto intern = [&](const rq_node& nd) -> int {
+        std::vector<int64_t> key = {nd.op, nd.a, nd.b, nd.c, nd.imm};
+        if (nd.op != RQ_OP_FILTER && nd.op != RQ_OP_PROBE) {
+            auto it = seen.find(key);
+            if (it != seen.end()) return it->second;
+        }
+        tmp.push_back(nd);
+        const int idx = (int)tmp.size() - 1;
+        seen[key] = idx;
+        return idx;
+    };
+    auto ref = [&](int i, int r) -> int {
+        if (r < 0 || r >= i) raise(RQ_ERR_INVALID, "node %d refers to node %d (must be an earlier node)", i, r);
+        return remap[r];
+    };
+    std::vector<int32_t> args(in.args, in.args + in.n_args);
+    for (int i = 0; i < n; i++) {
+        rq_node nd = in.nodes[i];
+        if (is_binary(nd.op)) {
+            nd.a = ref(i, nd.a); nd.b = ref(i, nd.b); nd.c = 0;
+            const rq_node& x = tmp[nd.a];
+            const rq_node& y = tmp[nd.b];
+            int64_t v;
+            if (x.op == RQ_OP_CONST && y.op == RQ_OP_CONST && fold_binary(nd.op, x.imm, y.imm, &v)) {
+                rq_node c{RQ_OP_CONST, 0, 0, 0, v};
+                remap[i] = intern(c);
+                continue;
+            }
+            if (nd.op == RQ_OP_MUL && y.op == RQ_OP_CONST && y.imm == 1) { remap[i] = nd.a; continue; }
+            if (nd.op == RQ_OP_MUL && x.op == RQ_OP_CONST && x.imm == 1) { remap[i] = nd.b; continue; }
+            if (nd.op == RQ_OP_DIV && y.op == RQ_OP_CONST && y.imm == 1) { remap[i] = nd.a; continue; }
+        } else if (nd.op == RQ_OP_FILTER) {
+            nd.a = ref(i, nd.a); nd.b = nd.c = 0;
+        } else if (nd.op == RQ_OP_SELECT) {
+            nd.a = ref(i, nd.a); nd.b = ref(i, nd.b); nd.c = ref(i, nd.c);
+        } else if (nd.op == RQ_OP_PROBE) {
+            if (nd.b < 0 || nd.c < 0 || nd.b + nd.c > in.n_args) raise(RQ_ERR_INVALID, "node %d: probe args out of range", i);
+            for (int k = 0; k < nd.c; k++) args[nd.b + k] = ref(i, in.args[nd.b + k]);
+        } else if (nd.op == RQ_OP_PAYLOAD) {
+            nd.a = ref(i, nd.a);
+            if (tmp[nd.a].op != RQ_OP_PROBE) raise(RQ_ERR_INVALID, "node %d: PAYLOAD of a non-PROBE node", i);
+        } else if (nd.op == RQ_OP_COL || nd.op == RQ_OP_CONST || nd.op == RQ_OP_CONST_STR) {
+            if (nd.op != RQ_OP_COL) nd.a = 0;
+            nd.b = nd.c = 0;
+            if (nd.op == RQ_OP_COL) nd.imm = 0;
+        } else {
+            raise(RQ_ERR_INVALID, "node %d: unknown op %d", i, nd.op);
+        }
+        remap[i] = intern(nd);
+    }
+    // dead-code elimination
+    const int m = (int)tmp.size();
+    std::vector<char> live(m, 0);
+    auto sink_ref = [&](int r) {
+        if (r < 0 || r >= n) raise(RQ_ERR_INVALID, "sink refers to node %d", r);
+        return remap[r];
+    };
+    sp.keys.assign(in.keys, in.keys + in.n_keys);
+    sp.vals.assign(in.vals, in.vals + in.n_vals);
+    for (auto& k : sp.keys) { k.node = sink_ref(k.node); live[k.node] = 1; }
+    for (auto& v : sp.vals) {
+        if (in.sink_kind == RQ_SINK_AGG && v.kind == RQ_AGG_COUNT) { v.node = 0; continue; }
+        v.node = sink_ref(v.node); live[v.node] = 1;
+    }
+    for (int i = m - 1; i >= 0; i--) {
+        const rq_node& nd = tmp[i];
+        if (nd.op == RQ_OP_FILTER || nd.op == RQ_OP_PROBE) live[i] = 1;
+        if (!live[i]) continue;
+        if (is_binary(nd.op)) { live[nd.a] = live[nd.b] = 1; }
+        else if (nd.op == RQ_OP_FILTER) live[nd.a] = 1;
+        else if (nd.op == RQ_OP_SELECT) { live[nd.a] = live[nd.b] = live[nd.c] = 1; }
+        else if (nd.op == RQ_OP_PAYLOAD) live[nd.a] = 1;
+        else if (nd.op == RQ_OP_PROBE) for (int k = 0; k < nd.c; k++) live[args[nd.b + k]] = 1;
+    }
+    std::vector<int> remap2(m, -1);
+    for (int i = 0; i < m; i++) {
+        if (!live[i]) continue;
+        rq_node nd = tmp[i];
+        if (is_binary(nd.op)) { nd.a = remap2[nd.a]; nd.b = remap2[nd.b]; }
+        else if (nd.op == RQ_OP_FILTER) nd.a = remap2[nd.a];
+        else if (nd.op == RQ_OP_SELECT) { nd.a = remap2[nd.a]; nd.b = remap2[nd.b]; nd.c = remap2[nd.c]; }
+        else if (nd.op == RQ_OP_PAYLOAD) nd.a = remap2[nd.a];
+        else if (nd.op == RQ_OP_PROBE) for (int k = 0; k < nd.c; k++) args[nd.b + k] = remap2[args[nd.b + k]];
+        sp.nodes.push_back(nd);
+        remap2[i] = (int)sp.nodes.size() - 1;
+    }
+    for (auto& k : sp.keys) k.node = remap2[k.node];
+    for (auto& v : sp.vals)
+        if (!(in.sink_kind == RQ_SINK_AGG && v.kind == RQ_AGG_COUNT)) v.node = remap2[v.node];
+    sp.args = args;
+    sp.pl = in;
+    sp.pl.n_nodes = (int)sp.nodes.size(); sp.pl.nodes = sp.nodes.data();
+    sp.pl.n_args = (int)sp.args.size();   sp.pl.args = sp.args.data();
+    sp.pl.keys = sp.keys.data();          sp.pl.vals = sp.vals.data();
+}
+
+enum SinkImpl { IMPL_LOWAGG = 1, IMPL_HASHAGG = 2, IMPL_BUILD = 3, IMPL_EMIT = 4 };
+
+static uint8_t agg_dop(int kind) {
+    switch (kind) {
+        case RQ_AGG_SUM: return D_AGG_SUM;
+        case RQ_AGG_COUNT: return D_AGG_COUNT;
+        case RQ_AGG_MIN: return D_AGG_MIN;
+        default: return D_AGG_MAX;
+    }
+}
+
+// Emits the device program for one pipeline. `probes` describes the hash tables of PROBE nodes.
+static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
+    KParams& P = L.P;
+    const rq_pipeline& pl = L.pl;
+    const int n = L.n;
+    L.lowagg = (impl == IMPL_LOWAGG);
+    L.aggs_of.assign(n, {});
+    L.gpos = -1;
+    for (int i = 0; i < n; i++) {
+        const int op = pl.nodes[i].op;
+        if (op == RQ_OP_FILTER || op == RQ_OP_PROBE || op == RQ_OP_PAYLOAD) L.gpos = i;
+    }
+    if (impl == IMPL_LOWAGG) {
+        for (int k = 0; k < pl.n_keys; k++) L.gpos = std::max(L.gpos, pl.keys[k].node);
+        for (size_t u = 0; u < ad.kind.size(); u++)
+            if (ad.node[u] >= 0) L.aggs_of[ad.node[u]].push_back((int)u);
+    }
+    L.decide_slots();
+
+    auto emit_group = [&]() {
+        if (impl != IMPL_LOWAGG) return;
+        L.emit(D_GROUP);
+        P.nk = pl.n_keys;
+        for (int k = 0; k < pl.n_keys; k++) P.key[k] = L.vref_of(pl.keys[k].node);
+        for (size_t u = 0; u < ad.kind.size(); u++) {
+            if (ad.kind[u] == RQ_AGG_COUNT) { L.emit(D_AGG_COUNT, Operand(), (uint16_t)u); continue; }
+            const int nd = ad.node[u];
+            if (is_leaf(pl.nodes[nd].op) || nd <= L.gpos || pl.nodes[nd].op == RQ_OP_PAYLOAD)
+                L.emit(agg_dop(ad.kind[u]), L.operand_of(nd), (uint16_t)u);
+        }
+    };
+
+    if (L.gpos == -1) emit_group();
+    for (int i = 0; i < n; i++) {
+        const rq_node& nd = pl.nodes[i];
+        bool computed = false;
+        if (is_leaf(nd.op) || nd.op == RQ_OP_PAYLOAD) {
+            // no instruction
+        } else if (nd.op == RQ_OP_FILTER) {
+            if (L.acc_node != nd.a || is_leaf(pl.nodes[nd.a].op)) {
+                L.emit(D_LD, L.operand_of(nd.a));
+                L.acc_node = is_leaf(pl.nodes[nd.a].op) ? -1 : nd.a;
+            }
+            L.emit(D_FILTER);
+        } else if (is_binary(nd.op)) {
+            const int x = nd.a, y = nd.b;
+            if (L.acc_node == x && x != y && !is_leaf(pl.nodes[x].op)) {
+                L.emit(dop_left(nd.op), L.operand_of(y));
+            } else if (L.acc_node == y && x != y && !is_leaf(pl.nodes[y].op)) {
+                L.emit(dop_right(nd.op), L.operand_of(x));
+            } else {
+                L.emit(D_LD, L.operand_of(x));
+                L.emit(dop_left(nd.op), L.operand_of(y));
+            }
+            computed = true;
+        } else if (nd.op == RQ_OP_SELECT) {
+            int tmp = -1, else_slot;
+            if (is_leaf(pl.nodes[nd.c].op)) {
+                tmp = L.alloc_slot();
+                L.emit(D_LD, L.operand_of(nd.c));
+                P.insn[P.n_insn - 1].flags |= 1;
+                P.insn[P.n_insn - 1].dst = (uint8_t)tmp;
+                L.acc_node = -1;
+                else_slot = tmp;
+            } else {
+                if (L.slot[nd.c] < 0) raise(RQ_ERR_INVALID, "internal: SELECT else operand has no slot");
+                else_slot = L.slot[nd.c];
+            }
+            if (L.acc_node != nd.a || is_leaf(pl.nodes[nd.a].op)) L.emit(D_LD, L.operand_of(nd.a));
+            L.emit(D_SEL, L.operand_of(nd.b), (uint16_t)else_slot);
+            if (tmp >= 0) L.free_slots.push_back(tmp);
+            computed = true;
+        } else if (nd.op == RQ_OP_PROBE) {
+            raise(RQ_ERR_UNSUPPORTED, "PROBE lowering not available in this build");
+        }
+        if (computed) {
+            L.acc_node = i;
+            if (L.slot[i] == -3) {
+                const int s = L.alloc_slot();
+                L.slot[i] = s;
+                P.insn[P.n_insn - 1].flags |= 1;
+                P.insn[P.n_insn - 1].dst = (uint8_t)s;
+            }
+            if (impl == IMPL_LOWAGG && i > L.gpos)
+                for (int u : L.aggs_of[i]) L.emit(agg_dop(ad.kind[u]), Operand(), (uint16_t)u);
+        }
+        L.release_dead(i);
+        if (i == L.gpos) emit_group();
+    }
+
+    if (impl == IMPL_EMIT) {
+        if (pl.n_vals > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d output columns", kMaxOut);
+        P.n_out = pl.n_vals;
+        for (int k = 0; k < pl.n_vals; k++) P.out[k] = L.vref_of(pl.vals[k].node);
+        L.emit(D_EMIT);
+    }
+}
+
+// ---- event pool -------------------------------------------------------------------------
+struct EventPair { cudaEvent_t a, b; };
+static std::vector<EventPair> g_event_pool;
+static EventPair& event_pair(size_t i) {
+    while (g_event_pool.size() <= i) {
+        EventPair p;
+        CK(cudaEventCreate(&p.a));
+        CK(cudaEventCreate(&p.b));
+        g_event_pool.push_back(p);
+    }
+    return g_event_pool[i];
+}
+
+static std::unique_ptr<rq_table> new_intermediate(int n_cols, int64_t cap_rows) {
+    std::unique_ptr<rq_table> t(new rq_table());
+    t->n_rows = -1;
+    t->cap_rows = round_up(std::max<int64_t>(cap_rows, 1), kTileRows);
+    for (int c = 0; c < n_cols; c++) {
+        DevColumn dc;
+        dc.type = RQ_I64;
+        dc.width = 8;
+        CK(cudaMalloc(&dc.d, (size_t)t->cap_rows * 8));
+        t->cols.push_back(dc);
+    }
+    CK(cudaMalloc(&t->d_n_rows, 8));
+    CK(cudaMemsetAsync(t->d_n_rows, 0, 8, E.stream));
+    return t;
+}
+
+static void set_types(rq_table& t, const rq_pipeline& pl) {
+    t.sql_type.clear();
+    t.sql_width.clear();
+    for (int k = 0; k < pl.n_keys; k++) { t.sql_type.push_back(pl.keys[k].sql_type); t.sql_width.push_back(pl.keys[k].width); }
+    for (int k = 0; k < pl.n_vals; k++) { t.sql_type.push_back(pl.vals[k].sql_type); t.sql_width.push_back(pl.vals[k].width); }
+}
+
+static void layout_smem(KParams& P, int na_unique, bool lowagg) {
+    uint32_t off = 128 + kStages * P.stage_bytes;
+    off = (off + 127) & ~127u;
+    P.slots_off = off;
+    off += (uint32_t)P.n_slots * kTileRows * 8;
+    P.acc_off = off;
+    if (lowagg) off += (uint32_t)kWarps * P.G * na_unique * 32 * 8;
+    P.dict_off = off;
+    off += kWarps * kLowCardMaxGroups * kMaxKeys * 8 + kWarps * 4;
+    off = (off + 15) & ~15u;
+    P.smem_bytes = off;
+}
+
+static void launch_pipeline(const KParams& P, int64_t cap_rows, rq_timings* tm, bool is_scan,
+                            size_t& ev_idx, std::vector<std::pair<size_t, bool>>& ev_used) {
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, rq_pipeline_kernel, kThreads, P.smem_bytes));
+    if (bps < 1) raise(RQ_ERR_UNSUPPORTED, "pipeline needs %u bytes of shared memory", P.smem_bytes);
+    const int64_t tiles = std::max<int64_t>(1, (cap_rows + kTileRows - 1) / kTileRows);
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)E.sm_count * bps);
+    EventPair& ep = event_pair(ev_idx);
+    CK(cudaEventRecord(ep.a, E.stream));
+    rq_pipeline_kernel<<<grid, kThreads, P.smem_bytes, E.stream>>>(P);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ep.b, E.stream));
+    ev_used.push_back({ev_idx, is_scan});
+    ev_idx++;
+    if (tm) tm->kernel_launches++;
+}
+
+static bool has_str_key(const rq_pipeline& pl) {
+    for (int k = 0; k < pl.n_keys; k++)
+        if (pl.keys[k].sql_type == RQ_SQL_VARCHAR || (pl.keys[k].sql_type == RQ_SQL_CHAR && pl.keys[k].width > 1)) return true;
+    return false;
+}
+
+static void check_flags(const char* what) {
+    CK(cudaMemcpyAsync(E.h_flags, E.flags, 16, cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    if (E.h_flags[2]) raise(RQ_ERR_RUNTIME, "division by zero in %s (the reference raises SIGFPE here)", what);
+}
+
+// ---- one pipeline -------------------------------------------------------------------------
+static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs,
+                         const char* d_strpool, rq_timings* tm, size_t& ev_idx,
+                         std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms) {
+    const rq_pipeline& pl_in = plan.pipelines[pi];
+    SimplePipe sp;
+    simplify_pipeline(pl_in, sp);
+    const rq_pipeline& pl = sp.pl;
+    const rq_table* src = nullptr;
+    if (pl.source_kind == RQ_SRC_TABLE) {
+        if (pl.source_id < 0 || pl.source_id >= plan.n_tables || !plan.tables[pl.source_id])
+            raise(RQ_ERR_INVALID, "pipeline %d: table %d out of range", pi, pl.source_id);
+        src = plan.tables[pl.source_id];
+    } else if (pl.source_kind == RQ_SRC_PIPELINE) {
+        if (pl.source_id < 0 || pl.source_id >= pi || !outs[pl.source_id].table)
+            raise(RQ_ERR_INVALID, "pipeline %d: source pipeline %d has no relation output", pi, pl.source_id);
+        src = outs[pl.source_id].table.get();
+    } else {
+        raise(RQ_ERR_INVALID, "pipeline %d: bad source kind %d", pi, pl.source_kind);
+    }
+    const bool is_scan = pl.source_kind == RQ_SRC_TABLE;
+
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<int> impls;
+    AggDedup ad;
+    if (pl.sink_kind == RQ_SINK_AGG) {
+        ad = dedup_aggs(pl);
+        if (pl.n_keys <= 4 && !has_str_key(pl)) impls.push_back(IMPL_LOWAGG);
+        impls.push_back(IMPL_HASHAGG);
+    } else if (pl.sink_kind == RQ_SINK_MATERIALIZE) {
+        impls.push_back(IMPL_EMIT);
+    } else if (pl.sink_kind == RQ_SINK_BUILD) {
+        impls.push_back(IMPL_BUILD);
+    } else {
+        raise(RQ_ERR_INVALID, "pipeline %d: bad sink kind %d", pi, pl.sink_kind);
+    }
+
+    for (size_t attempt = 0; attempt < impls.size(); attempt++) {
+        const int impl = impls[attempt];
+        if (impl == IMPL_HASHAGG || impl == IMPL_BUILD)
+            raise(RQ_ERR_UNSUPPORTED, "pipeline %d: hash aggregate / join build not available in this build", pi);
+        KParams P;
+        memset(&P, 0, sizeof(P));
+        P.n_rows = src->n_rows;
+        P.n_rows_ptr = src->n_rows < 0 ? src->d_n_rows : nullptr;
+        P.borrowed = src->borrowed ? 1 : 0;
+        P.overflow = E.flags + 0;
+        P.ht_full = E.flags + 1;
+        P.err = E.flags + 2;
+        Lowerer L(plan, pl, *src, outs, d_strpool, P);
+        L.prepare();
+        emit_program(L, impl, ad);
+
+        std::unique_ptr<rq_table> out;
+        if (impl == IMPL_LOWAGG) {
+            P.na = (int)ad.kind.size();
+            for (int u = 0; u < P.na; u++) P.agg_kind[u] = (uint8_t)ad.kind[u];
+            P.g_state = E.g_state; P.g_keys = E.g_keys; P.g_acc = E.g_acc;
+            bool fits = false;
+            for (int G = (pl.n_keys == 0 ? 1 : kLowCardMaxGroups); G >= 1; G >>= 1) {
+                P.G = G;
+                layout_smem(P, P.na, true);
+                if (P.smem_bytes <= 227 * 1024) { fits = true; break; }
+            }
+            if (!fits) continue;
+        } else {
+            P.G = 0;
+            layout_smem(P, 0, false);
+            if (P.smem_bytes > 227 * 1024) raise(RQ_ERR_UNSUPPORTED, "pipeline %d needs %u bytes of shared memory", pi, P.smem_bytes);
+        }
+        lower_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+
+        CK(cudaMemsetAsync(E.flags, 0, 16, E.stream));
+        if (impl == IMPL_LOWAGG) {
+            CK(cudaMemcpyAsync(E.g_kinds, P.agg_kind, kMaxAggs, cudaMemcpyHostToDevice, E.stream));
+            rq_group_table_init<<<(kGroupTableCap + 255) / 256, 256, 0, E.stream>>>(E.g_state, E.g_acc, E.g_kinds, P.na);
+            if (tm) tm->kernel_launches++;
+            launch_pipeline(P, src->cap_rows > 0 ? (src->n_rows >= 0 ? src->n_rows : src->cap_rows) : 0, tm, is_scan, ev_idx, ev_used);
+            // dense output: keys, then every requested aggregate (duplicates expanded)
+            const int ncols = pl.n_keys + pl.n_vals;
+            out = new_intermediate(ncols, kGroupTableCap);
+            std::vector<int64_t*> h_cols(ncols);
+            // compaction writes unique aggregates; build the column map keys + uniq
+            const int nuniq = P.na;
+            std::unique_ptr<rq_table> dense = new_intermediate(pl.n_keys + nuniq, kGroupTableCap);
+            std::vector<int64_t*> h_dense(pl.n_keys + nuniq);
+            for (int c = 0; c < pl.n_keys + nuniq; c++) h_dense[c] = (int64_t*)dense->cols[c].d;
+            int64_t** d_ptrs = nullptr;
+            CK(cudaMalloc(&d_ptrs, sizeof(int64_t*) * h_dense.size()));
+            CK(cudaMemcpyAsync(d_ptrs, h_dense.data(), sizeof(int64_t*) * h_dense.size(), cudaMemcpyHostToDevice, E.stream));
+            rq_group_table_compact<<<(kGroupTableCap + 255) / 256, 256, 0, E.stream>>>(
+                E.g_state, E.g_keys, E.g_acc, pl.n_keys, nuniq, d_ptrs, dense->d_n_rows);
+            if (tm) tm->kernel_launches++;
+            CK(cudaGetLastError());
+            check_flags("aggregation pipeline");
+            cudaFree(d_ptrs);
+            if (E.h_flags[0]) continue;   // more groups than the low-cardinality path tracks
+            // expand duplicates by aliasing: copy the columns (tiny)
+            for (int k = 0; k < pl.n_keys; k++)
+                CK(cudaMemcpyAsync(out->cols[k].d, dense->cols[k].d, (size_t)kGroupTableCap * 8, cudaMemcpyDeviceToDevice, E.stream));
+            for (int k = 0; k < pl.n_vals; k++)
+                CK(cudaMemcpyAsync(out->cols[pl.n_keys + k].d, dense->cols[pl.n_keys + ad.uniq_of[k]].d,
+                                   (size_t)kGroupTableCap * 8, cudaMemcpyDeviceToDevice, E.stream));
+            CK(cudaMemcpyAsync(out->d_n_rows, dense->d_n_rows, 8, cudaMemcpyDeviceToDevice, E.stream));
+            CK(cudaStreamSynchronize(E.stream));
+            set_types(*out, pl);
+            outs[pi].table = std::move(out);
+            return;
+        }
+        if (impl == IMPL_EMIT) {
+            int64_t cap = src->n_rows >= 0 ? src->n_rows : src->cap_rows;
+            cap = std::min<int64_t>(std::max<int64_t>(cap, 1), (int64_t)1 << 24);
+            for (int round = 0; round < 2; round++) {
+                out = new_intermediate(pl.n_vals, cap);
+                P.out_cap = out->cap_rows;
+                P.out_count = (unsigned long long*)out->d_n_rows;
+                for (int k = 0; k < pl.n_vals; k++) P.out_col[k] = (int64_t*)out->cols[k].d;
+                launch_pipeline(P, src->n_rows >= 0 ? src->n_rows : src->cap_rows, tm, is_scan, ev_idx, ev_used);
+                check_flags("materialize pipeline");
+                int64_t produced = 0;
+                CK(cudaMemcpy(&produced, out->d_n_rows, 8, cudaMemcpyDeviceToHost));
+                if (produced <= out->cap_rows) break;
+                if (round == 1) raise(RQ_ERR_RUNTIME, "materialize overflow");
+                cap = produced;
+            }
+            set_types(*out, pl);
+            outs[pi].table = std::move(out);
+            return;
+        }
+    }
+    raise(RQ_ERR_UNSUPPORTED, "pipeline %d: no implementation fits", pi);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// result assembly
+// ------------------------------------------------------------------------------------------
+static int phys_type(int sql_type, int sql_width, int* width) {
+    switch (sql_type) {
+        case RQ_SQL_BOOL: *width = 1; return RQ_I8;
+        case RQ_SQL_CHAR:
+            if (sql_width <= 1) { *width = 1; return RQ_I8; }
+            *width = sql_width + 1; return RQ_STR;
+        case RQ_SQL_VARCHAR: *width = sql_width + 1; return RQ_STR;
+        case RQ_SQL_INT: case RQ_SQL_DATE: *width = 4; return RQ_I32;
+        default: *width = 8; return RQ_I64;
+    }
+}
+
+extern "C" int rq_result_free(rq_result* r) {
+    if (!r) return RQ_OK;
+    if (r->cols) {
+        for (int c = 0; c < r->n_cols; c++) free(r->cols[c].data);
+        free(r->cols);
+    }
+    free(r);
+    return RQ_OK;
+}
+
+extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings* tm) {
+    if (!E.init) return fail(RQ_ERR_NOT_INIT, "rq_plan_execute before rq_init");
+    if (!plan || !out || plan->n_pipelines <= 0 || !plan->pipelines)
+        return fail(RQ_ERR_INVALID, "rq_plan_execute: bad arguments");
+    if (tm) memset(tm, 0, sizeof(*tm));
+    char* d_strpool = nullptr;
+    rq_result* res = nullptr;
+    std::vector<void*> scratch;
+    try {
+        if (plan->strpool_bytes > 0) {
+            CK(cudaMalloc(&d_strpool, plan->strpool_bytes));
+            CK(cudaMemcpyAsync(d_strpool, plan->strpool, plan->strpool_bytes, cudaMemcpyHostToDevice, E.stream));
+        }
+        std::vector<PipeOut> outs(plan->n_pipelines);
+        size_t ev_idx = 0;
+        std::vector<std::pair<size_t, bool>> ev_used;
+        double lower_ms = 0;
+        CK(cudaEventRecord(E.ev[0], E.stream));
+        for (int pi = 0; pi < plan->n_pipelines; pi++)
+            run_pipeline(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+
+        rq_table* fin = outs[plan->n_pipelines - 1].table.get();
+        if (!fin) raise(RQ_ERR_INVALID, "last pipeline must produce a relation");
+        int64_t n = 0;
+        CK(cudaMemcpy(&n, fin->d_n_rows, 8, cudaMemcpyDeviceToHost));
+        const int ncols = (int)fin->cols.size();
+
+        // ORDER BY + LIMIT
+        std::vector<int64_t*> cols(ncols);
+        for (int c = 0; c < ncols; c++) cols[c] = (int64_t*)fin->cols[c].d;
+        int64_t n_out = n;
+        if (plan->limit >= 0 && plan->limit < n_out) n_out = plan->limit;
+        if (plan->n_order > 0 && n > 1) {
+            if (plan->n_order > kMaxSortKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d ORDER BY keys", kMaxSortKeys);
+            if (n > kBitonicMax) raise(RQ_ERR_UNSUPPORTED, "ORDER BY over %lld rows not available in this build", (long long)n);
+            SortKeys K;
+            memset(&K, 0, sizeof(K));
+            K.n_keys = plan->n_order;
+            for (int k = 0; k < plan->n_order; k++) {
+                const int c = plan->order[k].column;
+                if (c < 0 || c >= ncols) raise(RQ_ERR_INVALID, "ORDER BY column %d out of range", c);
+                int w;
+                K.col[k] = cols[c];
+                K.is_str[k] = phys_type(fin->sql_type[c], fin->sql_width[c], &w) == RQ_STR;
+                K.desc[k] = plan->order[k].ascending ? 0 : 1;
+            }
+            uint32_t* perm = nullptr;
+            CK(cudaMalloc(&perm, sizeof(uint32_t) * kBitonicMax));
+            scratch.push_back(perm);
+            rq_sort_small<<<1, 1024, 0, E.stream>>>(K, fin->d_n_rows, perm);
+            if (tm) tm->kernel_launches++;
+            for (int c = 0; c < ncols; c++) {
+                int64_t* sorted = nullptr;
+                CK(cudaMalloc(&sorted, sizeof(int64_t) * std::max<int64_t>(n_out, 1)));
+                scratch.push_back(sorted);
+                rq_apply_perm<<<(unsigned)((n_out + 255) / 256), 256, 0, E.stream>>>(cols[c], sorted, perm, fin->d_n_rows, plan->limit);
+                if (tm) tm->kernel_launches++;
+                cols[c] = sorted;
+            }
+            CK(cudaGetLastError());
+        }
+
+        // narrow to the reference's physical widths on the device, then read back
+        res = (rq_result*)calloc(1, sizeof(rq_result));
+        res->n_rows = n_out;
+        res->n_cols = ncols;
+        res->cols = (rq_result_col*)calloc(ncols, sizeof(rq_result_col));
+        std::vector<void*> d_out(ncols, nullptr);
+        for (int c = 0; c < ncols; c++) {
+            int w = 8;
+            const int pt = phys_type(fin->sql_type[c], fin->sql_width[c], &w);
+            rq_result_col& rc = res->cols[c];
+            rc.type = pt; rc.width = w; rc.sql_type = fin->sql_type[c]; rc.sql_width = fin->sql_width[c];
+            rc.data = malloc((size_t)std::max<int64_t>(n_out, 1) * w);
+            if (n_out == 0) continue;
+            const unsigned blocks = (unsigned)((n_out + 255) / 256);
+            if (pt == RQ_I64) { d_out[c] = cols[c]; continue; }
+            void* d = nullptr;
+            CK(cudaMalloc(&d, (size_t)n_out * w));
+            scratch.push_back(d);
+            d_out[c] = d;
+            if (pt == RQ_I32) rq_narrow_i32<<<blocks, 256, 0, E.stream>>>(cols[c], (int32_t*)d, n_out);
+            else if (pt == RQ_I8) rq_narrow_i8<<<blocks, 256, 0, E.stream>>>(cols[c], (uint8_t*)d, n_out);
+            else rq_gather_str<<<blocks, 256, 0, E.stream>>>(cols[c], (unsigned char*)d, w, n_out);
+            if (tm) tm->kernel_launches++;
+        }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(E.ev[1], E.stream));
+        for (int c = 0; c < ncols; c++)
+            if (n_out > 0)
+                CK(cudaMemcpyAsync(res->cols[c].data, d_out[c], (size_t)n_out * res->cols[c].width, cudaMemcpyDeviceToHost, E.stream));
+        CK(cudaEventRecord(E.ev[2], E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+        if (tm) {
+            float ms = 0;
+            tm->lower_ms = lower_ms;
+            for (auto& u : ev_used) {
+                CK(cudaEventElapsedTime(&ms, g_event_pool[u.first].a, g_event_pool[u.first].b));
+                tm->kernel_ms += ms;
+                if (u.second) tm->scan_kernel_ms += ms;
+            }
+            CK(cudaEventElapsedTime(&ms, E.ev[1], E.ev[2]));
+            tm->d2h_ms = ms;
+        }
+        for (void* p : scratch) cudaFree(p);
+        if (d_strpool) cudaFree(d_strpool);
+        *out = res;
+        return RQ_OK;
+    } catch (RqError& e) {
+        cudaStreamSynchronize(E.stream);
+        for (void* p : scratch) cudaFree(p);
+        if (d_strpool) cudaFree(d_strpool);
+        rq_result_free(res);
+        return fail(e.code, "%s", e.msg.c_str());
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// debug aid (no GPU needed): lowers one pipeline of a plan against column metadata only and
+// prints the device program. tests/test_lowering.py runs the printed program through a Python
+// model of the accumulator machine and compares with the plan oracle, so the host-side lowering
+// is covered on CPU-only CI. Not part of the public ABI.
+// ------------------------------------------------------------------------------------------
+extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32_t* col_types,
+                              const int32_t* col_widths, int n_cols, char* buf, int64_t buflen) {
+    try {
+        if (!plan || pi < 0 || pi >= plan->n_pipelines) return fail(RQ_ERR_INVALID, "rq_debug_lower: bad pipeline");
+        SimplePipe sp;
+        simplify_pipeline(plan->pipelines[pi], sp);
+        rq_table fake;
+        fake.n_rows = 0;
+        for (int c = 0; c < n_cols; c++) {
+            DevColumn dc;
+            dc.type = col_types[c]; dc.width = col_widths[c]; dc.d = nullptr; dc.owned = false;
+            fake.cols.push_back(dc);
+        }
+        std::vector<PipeOut> outs(plan->n_pipelines);
+        KParams P;
+        memset(&P, 0, sizeof(P));
+        Lowerer L(*plan, sp.pl, fake, outs, (const char*)0, P);
+        L.prepare();
+        AggDedup ad;
+        if (sp.pl.sink_kind == RQ_SINK_AGG) ad = dedup_aggs(sp.pl);
+        emit_program(L, impl, ad);
+        std::string s;
+        char line[256];
+        snprintf(line, sizeof line, "cols %d strcols %d slots %d insn %d nk %d nout %d\n", P.n_cols, P.n_strcols, P.n_slots, P.n_insn, P.nk, P.n_out);
+        s += line;
+        for (int c = 0; c < P.n_cols; c++) {
+            int srccol = -1;
+            for (size_t k = 0; k < L.staged_of_col.size(); k++)
+                if (fake.cols[k].type != RQ_STR && L.staged_of_col[k] == c) srccol = (int)k;
+            snprintf(line, sizeof line, "col %d src %d w %d\n", c, srccol, (int)P.col_w[c]);
+            s += line;
+        }
+        for (int c = 0; c < P.n_strcols; c++) {
+            int srccol = -1;
+            for (size_t k = 0; k < L.staged_of_col.size(); k++)
+                if (fake.cols[k].type == RQ_STR && L.staged_of_col[k] == c) srccol = (int)k;
+            snprintf(line, sizeof line, "strcol %d src %d w %u\n", c, srccol, P.str_w[c]);
+            s += line;
+        }
+        for (int i = 0; i < P.n_insn; i++) {
+            const DInsn& in = P.insn[i];
+            snprintf(line, sizeof line, "insn %d %d %d %d %d %d %lld\n", in.op, in.src, in.flags, in.dst, in.idx, in.aux, (long long)in.imm);
+            s += line;
+        }
+        for (int k = 0; k < P.nk; k++) { snprintf(line, sizeof line, "key %d %d\n", P.key[k].kind, P.key[k].idx); s += line; }
+        for (int k = 0; k < P.n_out; k++) { snprintf(line, sizeof line, "out %d %d\n", P.out[k].kind, P.out[k].idx); s += line; }
+        for (int k = 0; k < kMaxImm; k++) { snprintf(line, sizeof line, "imm %d %lld\n", k, (long long)P.imm[k]); s += line; }
+        for (size_t u = 0; u < ad.kind.size(); u++) { snprintf(line, sizeof line, "agg %d %d\n", (int)u, ad.kind[u]); s += line; }
+        for (size_t k = 0; k < ad.uniq_of.size(); k++) { snprintf(line, sizeof line, "aggmap %d %d\n", (int)k, ad.uniq_of[k]); s += line; }
+        if ((int64_t)s.size() + 1 > buflen) return fail(RQ_ERR_INVALID, "rq_debug_lower: buffer too small");
+        memcpy(buf, s.c_str(), s.size() + 1);
+        return RQ_OK;
+    } catch (RqError& e) {
+        return fail(e.code, "%s", e.msg.c_str());
+    }
+}

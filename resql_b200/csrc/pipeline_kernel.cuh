@@ -1,0 +1,564 @@
+// Fused scan -> filter -> project -> (probe | aggregate | build | materialize) pipeline kernel
+// for sm_100a. One persistent CTA streams column tiles of 1024 tuples from HBM into shared
+// memory with TMA bulk copies (cp.async.bulk + mbarrier, double buffered) and interprets the
+// typed program over a register tile of 4 tuples per thread, warp-uniformly.
+//
+// Semantics restated from the reference (Henning1/resql):
+//   arithmetic / compares  src/ExpressionsJitFlounder.h:298-689
+//   selection              src/operators/selection.h:52-70
+//   aggregation            src/operators/aggregation.h:95-152, :240-295
+//   hash join              src/operators/hashjoin.h:118-279
+//   string compares        src/qlib/scalar.h:16-120
+#pragma once
+#include <cuda_runtime.h>
+#include "rq_internal.h"
+
+namespace rq {
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                             uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "RQ_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra RQ_DONE;\n"
+        "bra RQ_WAIT;\n"
+        "RQ_DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// string semantics (qlib/scalar.h)
+// ------------------------------------------------------------------------------------------
+// compareChar (qlib/scalar.h:27-46): equal after ignoring trailing blanks on either side
+__device__ __forceinline__ int64_t str_eq_char(const char* a, const char* b) {
+    while (*a != '\0' && *b != '\0') {
+        if (*a != *b) return 0;
+        a++; b++;
+    }
+    while (*a != '\0') { if (*a != ' ') return 0; a++; }
+    while (*b != '\0') { if (*b != ' ') return 0; b++; }
+    return 1;
+}
+// compareVarchar (qlib/scalar.h:16-24): exact
+__device__ __forceinline__ int64_t str_eq_varchar(const char* a, const char* b) {
+    while (*a != '\0' && *b != '\0') {
+        if (*a != *b) return 0;
+        a++; b++;
+    }
+    return (*a == *b) ? 1 : 0;
+}
+// stringLikeCheck (qlib/scalar.h:57-120), restated: '%' matches any run, '_' any one char.
+// The reference anchors both ends and backtracks on the last '%'; a standard two-pointer
+// wildcard matcher yields the same accept set for patterns made of literal runs, '%' and '_'.
+__device__ __forceinline__ int64_t str_like(const char* s, const char* p) {
+    const char* star = nullptr;
+    const char* ss = nullptr;
+    while (*s != '\0') {
+        if (*p == '%') { star = p++; ss = s; }
+        else if (*p != '\0' && (*p == *s || *p == '_')) { p++; s++; }
+        else if (star) { p = star + 1; s = ++ss; }
+        else return 0;
+    }
+    while (*p == '%') p++;
+    return *p == '\0' ? 1 : 0;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 33;
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------
+// register tile <-> shared memory. Thread t owns tuples {2t, 2t+1, 512+2t, 512+2t+1} of the
+// tile, so every access is a conflict-free 16/8/2-byte vector load.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int row_in_tile(int r, int tid) {
+    return (r >> 1) * (2 * kThreads) + 2 * tid + (r & 1);
+}
+
+struct TileCtx {
+    const unsigned char* stage;   // staged columns of the current tile
+    int64_t*             slots;   // value slots [n_slots][kTileRows]
+    int64_t              row0;    // first tuple of the tile in the source
+    int                  tid;
+};
+
+__device__ __forceinline__ void ld_col(const KParams& P, const TileCtx& c, int col,
+                                       int64_t (&v)[kRowsPerThread]) {
+    const unsigned char* base = c.stage + P.col_off[col];
+    const int w = P.col_w[col];
+    if (w == 8) {
+        const longlong2* p = reinterpret_cast<const longlong2*>(base);
+        longlong2 x = p[c.tid], y = p[kThreads + c.tid];
+        v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+    } else if (w == 4) {
+        const int2* p = reinterpret_cast<const int2*>(base);
+        int2 x = p[c.tid], y = p[kThreads + c.tid];
+        v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+    } else {
+        const uchar2* p = reinterpret_cast<const uchar2*>(base);
+        uchar2 x = p[c.tid], y = p[kThreads + c.tid];
+        v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+    }
+}
+__device__ __forceinline__ void ld_slot(const TileCtx& c, int s, int64_t (&v)[kRowsPerThread]) {
+    const longlong2* p = reinterpret_cast<const longlong2*>(c.slots + (size_t)s * kTileRows);
+    longlong2 x = p[c.tid], y = p[kThreads + c.tid];
+    v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+}
+__device__ __forceinline__ void st_slot(const TileCtx& c, int s,
+                                        const int64_t (&v)[kRowsPerThread]) {
+    longlong2* p = reinterpret_cast<longlong2*>(c.slots + (size_t)s * kTileRows);
+    p[c.tid] = make_longlong2(v[0], v[1]);
+    p[kThreads + c.tid] = make_longlong2(v[2], v[3]);
+}
+__device__ __forceinline__ void ld_str(const KParams& P, const TileCtx& c, int col,
+                                       int64_t (&v)[kRowsPerThread]) {
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; r++)
+        v[r] = (int64_t)(P.str_ptr[col] + (size_t)(c.row0 + row_in_tile(r, c.tid)) * P.str_w[col]);
+}
+
+// one tuple of a sink value
+__device__ __forceinline__ int64_t ld_vref(const KParams& P, const TileCtx& c, VRef vr, int r) {
+    const int row = row_in_tile(r, c.tid);
+    switch (vr.kind) {
+        case S_COL: {
+            const unsigned char* base = c.stage + P.col_off[vr.idx];
+            const int w = P.col_w[vr.idx];
+            if (w == 8) return reinterpret_cast<const int64_t*>(base)[row];
+            if (w == 4) return reinterpret_cast<const int32_t*>(base)[row];
+            return base[row];
+        }
+        case S_SLOT: return c.slots[(size_t)vr.idx * kTileRows + row];
+        case S_IMM:  return P.imm[vr.idx];
+        case S_STR:  return (int64_t)(P.str_ptr[vr.idx] + (size_t)(c.row0 + row) * P.str_w[vr.idx]);
+        default:     return 0;
+    }
+}
+
+__device__ __forceinline__ int64_t agg_identity(int kind) {
+    if (kind == 3) return INT64_MAX;   // RQ_AGG_MIN
+    if (kind == 4) return INT64_MIN;   // RQ_AGG_MAX
+    return 0;
+}
+
+// signed truncating division like x86 idiv; b == 0 raises the runtime error flag
+__device__ __forceinline__ int64_t div_trunc(int64_t a, int64_t b, int32_t* err) {
+    if (b == 0) { *err = 1; return 0; }
+    if (b == -1) return (int64_t)(0ULL - (uint64_t)a);   // avoids INT64_MIN / -1 trap semantics
+    return a / b;
+}
+
+// ------------------------------------------------------------------------------------------
+// hash tables (shared by join build/probe and hash aggregation)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t hash_keys(const int64_t* k, int nk) {
+    uint64_t h = 0x9E3779B97F4A7C15ULL;
+    for (int j = 0; j < nk; j++) h = mix64(h ^ (uint64_t)k[j]) + 0x9E3779B97F4A7C15ULL;
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------
+// the pipeline kernel
+// ------------------------------------------------------------------------------------------
+extern __shared__ __align__(128) unsigned char rq_smem[];
+
+__global__ void __launch_bounds__(kThreads, 2)
+rq_pipeline_kernel(const __grid_constant__ KParams P) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rq_smem);
+    unsigned char* stages = rq_smem + 128;
+
+    const int64_t n_rows = P.n_rows_ptr ? *P.n_rows_ptr : P.n_rows;
+    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+
+    int64_t* accs = reinterpret_cast<int64_t*>(rq_smem + P.acc_off);
+    int64_t* dict_all = reinterpret_cast<int64_t*>(rq_smem + P.dict_off);
+    int* dcounts = reinterpret_cast<int*>(dict_all + kWarps * kLowCardMaxGroups * kMaxKeys);
+    const int G = P.G, NA = P.na, NK = P.nk;
+    const bool lowagg = (G > 0);
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    if (lowagg) {
+        for (int i = tid; i < kWarps * G * NA * 32; i += kThreads)
+            accs[i] = agg_identity(P.agg_kind[(i >> 5) % NA]);
+        if (tid < kWarps) dcounts[tid] = 0;
+    }
+    __syncthreads();
+
+    const int64_t stride = gridDim.x;
+    const int64_t first = blockIdx.x;
+
+    // a partial last tile of a borrowed (unpadded) source is staged with guarded plain loads
+    auto is_guarded = [&](int64_t tile) -> bool {
+        return P.borrowed && (tile + 1) * (int64_t)kTileRows > n_rows;
+    };
+    auto issue = [&](int64_t tile, int s) {
+        if (is_guarded(tile)) return;
+        uint64_t* bar = &bars[s];
+        unsigned char* dst = stages + (size_t)s * P.stage_bytes;
+        mbar_expect_tx(bar, P.stage_bytes);
+        for (int c = 0; c < P.n_cols; c++) {
+            const uint32_t bytes = kTileRows * P.col_w[c];
+            tma_bulk_g2s(dst + P.col_off[c], P.col_ptr[c] + (size_t)tile * bytes, bytes, bar);
+        }
+    };
+    if (tid == 0 && P.n_cols > 0) {
+        if (first < n_tiles) issue(first, 0);
+        if (first + stride < n_tiles) issue(first + stride, 1);
+    }
+
+    int dict_any = 0;   // (no GROUP BY) did this warp aggregate at least one tuple
+
+    int it = 0;
+    for (int64_t tile = first; tile < n_tiles; tile += stride, it++) {
+        const int s = it & 1;
+        TileCtx c;
+        c.stage = stages + (size_t)s * P.stage_bytes;
+        c.slots = reinterpret_cast<int64_t*>(rq_smem + P.slots_off);
+        c.row0 = tile * (int64_t)kTileRows;
+        c.tid = tid;
+
+        if (P.n_cols > 0) {
+            if (is_guarded(tile)) {
+                unsigned char* dst = stages + (size_t)s * P.stage_bytes;
+                const int64_t rows = n_rows - c.row0;
+                for (int col = 0; col < P.n_cols; col++) {
+                    const int w = P.col_w[col];
+                    const unsigned char* src = P.col_ptr[col] + (size_t)c.row0 * w;
+                    for (int64_t i = tid; i < rows * w; i += kThreads) dst[P.col_off[col] + i] = src[i];
+                }
+                __syncthreads();
+            } else {
+                mbar_wait(&bars[s], (it >> 1) & 1);
+            }
+        }
+
+        unsigned valid = 0;
+#pragma unroll
+        for (int r = 0; r < kRowsPerThread; r++)
+            if (c.row0 + row_in_tile(r, tid) < n_rows) valid |= 1u << r;
+
+        int64_t acc[kRowsPerThread] = {0, 0, 0, 0};
+        unsigned gid = 0;   // 8 bits per tuple
+
+        for (int pc = 0; pc < P.n_insn; pc++) {
+            const DInsn in = P.insn[pc];
+            int64_t b[kRowsPerThread] = {0, 0, 0, 0};
+            switch (in.src) {
+                case S_COL:  ld_col(P, c, in.idx, b); break;
+                case S_SLOT: ld_slot(c, in.idx, b); break;
+                case S_IMM:
+#pragma unroll
+                    for (int r = 0; r < kRowsPerThread; r++) b[r] = in.imm;
+                    break;
+                case S_STR:  ld_str(P, c, in.idx, b); break;
+                default: break;
+            }
+            switch (in.op) {
+#define RQ_BIN(EXPR)                                             \
+    _Pragma("unroll") for (int r = 0; r < kRowsPerThread; r++) { \
+        const int64_t x = acc[r], y = b[r];                      \
+        acc[r] = (EXPR);                                         \
+    }                                                            \
+    break;
+                case D_LD:   RQ_BIN(((void)x, y))
+                case D_ADD:  RQ_BIN((int64_t)((uint64_t)x + (uint64_t)y))
+                case D_SUB:  RQ_BIN((int64_t)((uint64_t)x - (uint64_t)y))
+                case D_RSUB: RQ_BIN((int64_t)((uint64_t)y - (uint64_t)x))
+                case D_MUL:  RQ_BIN((int64_t)((uint64_t)x * (uint64_t)y))
+                case D_DIV:
+#pragma unroll
+                    for (int r = 0; r < kRowsPerThread; r++)
+                        acc[r] = ((valid >> r) & 1) ? div_trunc(acc[r], b[r], P.err) : 0;
+                    break;
+                case D_RDIV:
+#pragma unroll
+                    for (int r = 0; r < kRowsPerThread; r++)
+                        acc[r] = ((valid >> r) & 1) ? div_trunc(b[r], acc[r], P.err) : 0;
+                    break;
+                case D_AND:  RQ_BIN(x & y)
+                case D_OR:   RQ_BIN(x | y)
+                case D_LT:   RQ_BIN(x < y ? 1 : 0)
+                case D_LE:   RQ_BIN(x <= y ? 1 : 0)
+                case D_GT:   RQ_BIN(x > y ? 1 : 0)
+                case D_GE:   RQ_BIN(x >= y ? 1 : 0)
+                case D_EQ:   RQ_BIN(x == y ? 1 : 0)
+                case D_NE:   RQ_BIN(x != y ? 1 : 0)
+#undef RQ_BIN
+#define RQ_STRBIN(EXPR)                                               \
+    _Pragma("unroll") for (int r = 0; r < kRowsPerThread; r++) {      \
+        const char* x = reinterpret_cast<const char*>(acc[r]);        \
+        const char* y = reinterpret_cast<const char*>(b[r]);          \
+        acc[r] = ((valid >> r) & 1) ? (EXPR) : 0;                     \
+    }                                                                 \
+    break;
+                case D_EQC:   RQ_STRBIN(str_eq_char(x, y))
+                case D_EQV:   RQ_STRBIN(str_eq_varchar(x, y))
+                case D_NEC:   RQ_STRBIN(1 - str_eq_char(x, y))
+                case D_NEV:   RQ_STRBIN(1 - str_eq_varchar(x, y))
+                case D_LIKE:  RQ_STRBIN(str_like(x, y))
+                case D_RLIKE: RQ_STRBIN(str_like(y, x))
+#undef RQ_STRBIN
+                case D_SEL: {
+                    int64_t e[kRowsPerThread];
+                    ld_slot(c, in.aux, e);
+#pragma unroll
+                    for (int r = 0; r < kRowsPerThread; r++)
+                        acc[r] = (acc[r] & 0xff) ? b[r] : e[r];
+                    break;
+                }
+                case D_FILTER:
+#pragma unroll
+                    for (int r = 0; r < kRowsPerThread; r++)
+                        if ((acc[r] & 0xff) == 0) valid &= ~(1u << r);
+                    break;
+                case D_GROUP: {
+                    if (NK == 0) break;
+                    int64_t* dict = dict_all + warp * (kLowCardMaxGroups * kMaxKeys);
+                    volatile int* dcount = dcounts + warp;
+#pragma unroll
+                    for (int r = 0; r < kRowsPerThread; r++) {
+                        const bool v = (valid >> r) & 1;
+                        int64_t k[4] = {0, 0, 0, 0};
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (j < NK) k[j] = ld_vref(P, c, P.key[j], r);
+                        int n = *dcount;
+                        int found = -1;
+                        for (int e = 0; e < n; e++) {
+                            bool m = true;
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if (j < NK) m = m && (dict[e * NK + j] == k[j]);
+                            if (m) found = e;
+                        }
+                        unsigned unk = __ballot_sync(0xffffffffu, v && found < 0);
+                        while (unk) {
+                            const int leader = __ffs(unk) - 1;
+                            int64_t lk[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) lk[j] = __shfl_sync(0xffffffffu, k[j], leader);
+                            if (n >= G) {
+                                if (lane == 0) *P.overflow = 1;
+                                if (found < 0) found = 0;
+                                break;
+                            }
+                            if (lane == 0) {
+                                for (int j = 0; j < NK; j++) dict[n * NK + j] = lk[j];
+                                *dcount = n + 1;
+                            }
+                            __syncwarp();
+                            bool m = true;
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if (j < NK) m = m && (k[j] == lk[j]);
+                            if (v && found < 0 && m) found = n;
+                            n++;
+                            unk = __ballot_sync(0xffffffffu, v && found < 0);
+                        }
+                        gid |= (unsigned)(found < 0 ? 0 : found) << (8 * r);
+                    }
+                    break;
+                }
+                case D_AGG_SUM:
+                case D_AGG_COUNT:
+                case D_AGG_MIN:
+                case D_AGG_MAX: {
+                    const int a = in.aux;
+                    int64_t* base = accs + (size_t)warp * G * NA * 32 + a * 32 + lane;
+                    if (valid) dict_any = 1;
+#pragma unroll
+                    for (int r = 0; r < kRowsPerThread; r++) {
+                        if ((valid >> r) & 1) {
+                            const int g = (gid >> (8 * r)) & 0xff;
+                            int64_t* p = base + g * NA * 32;
+                            const int64_t val = (in.src != S_NONE) ? b[r] : acc[r];
+                            const int64_t cur = *p;
+                            int64_t nv;
+                            if (in.op == D_AGG_SUM) nv = (int64_t)((uint64_t)cur + (uint64_t)val);
+                            else if (in.op == D_AGG_COUNT) nv = cur + 1;
+                            else if (in.op == D_AGG_MIN) nv = val < cur ? val : cur;
+                            else nv = val > cur ? val : cur;
+                            *p = nv;
+                        }
+                    }
+                    break;
+                }
+                case D_EMIT: {
+#pragma unroll
+                    for (int r = 0; r < kRowsPerThread; r++) {
+                        const bool v = (valid >> r) & 1;
+                        const unsigned bal = __ballot_sync(0xffffffffu, v);
+                        if (bal == 0) continue;
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(P.out_count, (unsigned long long)__popc(bal));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const int64_t pos = (int64_t)base + __popc(bal & ((1u << lane) - 1));
+                        if (v && pos < P.out_cap) {
+                            for (int k = 0; k < P.n_out; k++)
+                                P.out_col[k][pos] = ld_vref(P, c, P.out[k], r);
+                        }
+                    }
+                    break;
+                }
+                default: break;
+            }
+            if (in.flags & 1) st_slot(c, in.dst, acc);
+        }
+
+        __syncthreads();   // everyone is done with stage s (and the slots) before it is refilled
+        if (tid == 0 && P.n_cols > 0) {
+            const int64_t nt = tile + 2 * stride;
+            if (nt < n_tiles) issue(nt, s);
+        }
+    }
+
+    // ---- flush the lane-private accumulators of the low-cardinality aggregate ----------
+    if (lowagg) {
+        __syncwarp();
+        const unsigned any = __ballot_sync(0xffffffffu, dict_any != 0);
+        int n = (NK == 0) ? (any ? 1 : 0) : dcounts[warp];
+        if (n > G) n = G;
+        const int64_t* dict = dict_all + warp * (kLowCardMaxGroups * kMaxKeys);
+        for (int e = 0; e < n; e++) {
+            int slot = -1;
+            if (lane == 0) {
+                int64_t k[kMaxKeys];
+                for (int j = 0; j < NK; j++) k[j] = dict[e * NK + j];
+                uint32_t i = (uint32_t)(hash_keys(k, NK) & (kGroupTableCap - 1));
+                for (int tries = 0; tries < kGroupTableCap; tries++) {
+                    uint32_t st = atomicCAS(&P.g_state[i], 0u, 1u);
+                    if (st == 0u) {
+                        for (int j = 0; j < NK; j++) P.g_keys[(size_t)i * kMaxKeys + j] = k[j];
+                        __threadfence();
+                        atomicExch(&P.g_state[i], 2u);
+                        slot = (int)i;
+                        break;
+                    }
+                    while (st == 1u) st = *(volatile uint32_t*)&P.g_state[i];
+                    __threadfence();
+                    bool m = true;
+                    for (int j = 0; j < NK; j++)
+                        m = m && (((volatile int64_t*)P.g_keys)[(size_t)i * kMaxKeys + j] == k[j]);
+                    if (m) { slot = (int)i; break; }
+                    i = (i + 1) & (kGroupTableCap - 1);
+                }
+                if (slot < 0) *P.overflow = 1;
+            }
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            for (int a = 0; a < NA; a++) {
+                int64_t v = accs[(size_t)warp * G * NA * 32 + (e * NA + a) * 32 + lane];
+                const int kind = P.agg_kind[a];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int64_t w = __shfl_xor_sync(0xffffffffu, v, o);
+                    if (kind == 3) v = w < v ? w : v;
+                    else if (kind == 4) v = w > v ? w : v;
+                    else v = (int64_t)((uint64_t)v + (uint64_t)w);
+                }
+                if (lane == 0 && slot >= 0) {
+                    int64_t* dst = &P.g_acc[(size_t)slot * kMaxAggs + a];
+                    if (kind == 3) atomicMin((long long*)dst, (long long)v);
+                    else if (kind == 4) atomicMax((long long*)dst, (long long)v);
+                    else atomicAdd((unsigned long long*)dst, (unsigned long long)v);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small helper kernels
+// ------------------------------------------------------------------------------------------
+// reset the global group table: state 0, accumulators to their identities
+__global__ void rq_group_table_init(uint32_t* state, int64_t* acc, const uint8_t* kinds_dev,
+                                    int na) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kGroupTableCap) {
+        state[i] = 0;
+        for (int a = 0; a < na; a++) acc[(size_t)i * kMaxAggs + a] = agg_identity(kinds_dev[a]);
+    }
+}
+
+// group table -> dense int64 columns (keys first, then aggregates); order is unspecified, as in
+// the reference where it is hash-slot order (aggregation.h:298-343)
+__global__ void rq_group_table_compact(const uint32_t* state, const int64_t* keys,
+                                       const int64_t* acc, int nk, int na, int64_t* const* out_cols,
+                                       int64_t* out_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kGroupTableCap && state[i] == 2u) {
+        const long long pos = atomicAdd((unsigned long long*)out_count, 1ULL);
+        for (int j = 0; j < nk; j++) out_cols[j][pos] = keys[(size_t)i * kMaxKeys + j];
+        for (int a = 0; a < na; a++) out_cols[nk + a][pos] = acc[(size_t)i * kMaxAggs + a];
+    }
+}
+
+// result columns: int64 values -> physical width, strings by value
+__global__ void rq_narrow_i32(const int64_t* in, int32_t* out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)in[i];
+}
+__global__ void rq_narrow_i8(const int64_t* in, uint8_t* out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint8_t)in[i];
+}
+__global__ void rq_gather_str(const int64_t* addrs, unsigned char* out, int width, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned char* s = reinterpret_cast<const unsigned char*>(addrs[i]);
+        unsigned char* d = out + (size_t)i * width;
+        int k = 0;
+        for (; k < width - 1 && s[k] != 0; k++) d[k] = s[k];
+        for (; k < width; k++) d[k] = 0;
+    }
+}
+
+// row store (reference DataBlocks, dbdata.h:23-102) -> columns
+__global__ void rq_transpose_rows(const unsigned char* rows, int64_t n, int tuple_size, int offset,
+                                  int width, unsigned char* col, int64_t col_row0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned char* s = rows + (size_t)i * tuple_size + offset;
+        unsigned char* d = col + (size_t)(col_row0 + i) * width;
+        for (int k = 0; k < width; k++) d[k] = s[k];
+    }
+}
+
+}  // namespace rq

@@ -1,0 +1,57 @@
+"""Named parity queries. TPC-H texts are the reference's tpch/queries/*.sql statements verbatim
+(SQL is data, lowercase as the reference lexer requires); the others exercise the operator
+shapes of the reference's test/test_operators.h on TPC-H-shaped tables."""
+
+QUERIES = {
+    "q1": """select l_returnflag, l_linestatus, sum(l_quantity) as sum_qty, sum(l_extendedprice) as sum_base_price,
+        sum(l_extendedprice * (1 - l_discount)) as sum_disc_price,
+        sum(l_extendedprice * (1 - l_discount) * (1 + l_tax)) as sum_charge,
+        avg(l_quantity) as avg_qty, avg(l_extendedprice) as avg_price, avg(l_discount) as avg_disc,
+        count(*) as count_order
+        from lineitem where l_shipdate <= date "1998-9-02"
+        group by l_returnflag, l_linestatus order by l_returnflag, l_linestatus""",
+    "q6": """select sum(l_extendedprice * l_discount) as revenue from lineitem
+        where l_shipdate >= date '1994-01-01' and l_shipdate < date '1995-01-01'
+        and l_discount between 0.06 - 0.01 and 0.06 + 0.01 and l_quantity < 24""",
+    "q3": """select l_orderkey, sum(l_extendedprice * (1 - l_discount)) as revenue, o_orderdate, o_shippriority
+        from customer, orders, lineitem
+        where c_mktsegment = 'BUILDING' and c_custkey = o_custkey and l_orderkey = o_orderkey
+        and o_orderdate < date '1995-03-15' and l_shipdate > date '1995-03-15'
+        group by l_orderkey, o_orderdate, o_shippriority order by revenue desc, o_orderdate limit 10""",
+    # aggregation shapes (test_operators.h: group sum; multi-key sum+count; no groups; groups only)
+    "agg_nogroup_minmax": """select min(l_extendedprice), max(l_extendedprice), min(l_shipdate), max(l_shipdate),
+        count(*), sum(l_quantity), avg(l_discount) from lineitem where l_quantity < 10""",
+    "agg_groups_only": "select l_shipmode from lineitem group by l_shipmode order by l_shipmode",
+    "agg_empty": "select count(*), sum(l_quantity) from lineitem where l_quantity < 0",
+    "agg_linenumber": """select l_linenumber, count(*) as c, sum(l_extendedprice) as s, min(l_discount) as mn, max(l_tax) as mx
+        from lineitem group by l_linenumber order by l_linenumber""",
+    "agg_computed_key": """select l_quantity * 2 as q2, sum(l_extendedprice * l_tax) as s from lineitem
+        where l_discount > 0.05 group by l_quantity * 2 order by q2""",
+    "agg_wrap": """select l_returnflag, sum(l_extendedprice * l_extendedprice * l_extendedprice) as s3
+        from lineitem group by l_returnflag order by l_returnflag""",
+    "agg_neg_avg": "select avg(c_acctbal), min(c_acctbal), count(*) from customer where c_acctbal < 0.00",
+    # selection shapes (decimal lt/gt/or; attr<attr with different scales; date ge/le; and/or mix)
+    "sel_or": """select l_orderkey, l_linenumber, l_quantity from lineitem
+        where l_quantity > 49 and (l_discount < 0.01 or l_tax > 0.07) and l_orderkey < 2000 order by l_orderkey, l_linenumber""",
+    "sel_attr_scales": """select l_orderkey, l_linenumber from lineitem
+        where l_quantity < l_tax * 100 and l_orderkey < 3000 order by l_orderkey, l_linenumber""",
+    "sel_dates": """select l_orderkey, l_linenumber, l_shipdate, l_commitdate from lineitem
+        where l_shipdate >= date '1995-06-01' and l_shipdate <= date '1995-06-30' and l_commitdate < l_receiptdate
+        and l_orderkey < 20000 order by l_orderkey, l_linenumber""",
+    "sel_neq_char": """select l_returnflag, count(*) as c from lineitem where l_returnflag <> 'N' and l_linestatus = 'F'
+        group by l_returnflag order by l_returnflag""",
+    "sel_strings": """select c_custkey, c_name, c_mktsegment, c_acctbal from customer
+        where c_mktsegment = 'BUILDING  ' and c_acctbal > 9000.00 order by c_custkey""",
+    "sel_star_limit": "select * from customer where c_custkey < 4 order by c_custkey",
+    # joins
+    "join_orders_lineitem": """select o_orderpriority, count(*) as c, sum(l_extendedprice) as s from orders, lineitem
+        where o_orderkey = l_orderkey and l_shipdate > date '1998-06-01' group by o_orderpriority order by o_orderpriority""",
+    "join_cust_orders": """select c_mktsegment, count(*) as c, sum(o_totalprice) as s, max(o_orderdate) as d from customer, orders
+        where c_custkey = o_custkey and o_orderdate >= date '1998-01-01' group by c_mktsegment order by c_mktsegment""",
+    "join_rows": """select o_orderkey, o_orderdate, c_name, c_nationkey from customer, orders
+        where c_custkey = o_custkey and o_orderkey < 200 order by o_orderkey""",
+    "case_sum": """select l_shipmode, sum(case when l_quantity > 25 then 1 else 0 end) as hi,
+        sum(case when l_quantity <= 25 then l_extendedprice else 0 end) as lo
+        from lineitem group by l_shipmode order by l_shipmode""",
+    "like_promo": """select count(*) as c from orders where o_comment like '%special%'""",
+}
