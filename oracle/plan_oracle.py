@@ -86,6 +86,11 @@ def run_plan(plan, tables):
     finally:
         np.seterr(**old)
     cols, st, sw = outs[-1][:3]
+    return finish(plan, cols, st, sw)
+
+
+def finish(plan, cols, st, sw):
+    """ORDER BY + LIMIT + conversion to the reference's physical result types"""
     n = len(cols[0]) if cols else 0
     order = plan.get("order", [])
     idx = np.arange(n)
@@ -211,21 +216,25 @@ def _run_pipeline(plan, p, tables, outs, pool):
                 norm.append(np.array([x.rstrip(b" ") for x in kv], dtype=object))   # compareChar equality
             else:
                 norm.append(kv)
-        tup = list(zip(*[list(x) for x in norm]))
-        first = {}
-        gid = np.empty(m, dtype=np.int64)
-        for r, k in enumerate(tup):
-            g = first.get(k)
-            if g is None:
-                g = len(first)
-                first[k] = g
-            gid[r] = g
-        ng = len(first)
-        rep = np.zeros(ng, dtype=np.int64)
-        seen = np.zeros(ng, dtype=bool)
-        for r in range(m - 1, -1, -1):
-            rep[gid[r]] = r
-        del seen
+        if all(x.dtype != object for x in norm):
+            mat = np.stack([x.astype(np.int64) for x in norm], axis=1)
+            _, rep, gid = np.unique(mat, axis=0, return_index=True, return_inverse=True)
+            gid = gid.reshape(-1)
+            ng = len(rep)
+        else:
+            tup = list(zip(*[list(x) for x in norm]))
+            first = {}
+            gid = np.empty(m, dtype=np.int64)
+            for r, k in enumerate(tup):
+                g = first.get(k)
+                if g is None:
+                    g = len(first)
+                    first[k] = g
+                gid[r] = g
+            ng = len(first)
+            rep = np.zeros(ng, dtype=np.int64)
+            for r in range(m - 1, -1, -1):
+                rep[gid[r]] = r
     else:
         gid = np.zeros(m, dtype=np.int64)
         ng = 1

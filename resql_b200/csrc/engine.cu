@@ -16,6 +16,7 @@
 #include <memory>
 #include <algorithm>
 #include <chrono>
+#include <functional>
 
 #include "../../include/resql_b200.h"
 #include "rq_internal.h"

@@ -59,6 +59,16 @@ static bool fold_binary(int op, int64_t x, int64_t y, int64_t* out) {
     }
 }
 
+static bool is01(int op) {
+    switch (op) {
+        case RQ_OP_LT: case RQ_OP_LE: case RQ_OP_GT: case RQ_OP_GE: case RQ_OP_EQ: case RQ_OP_NEQ:
+        case RQ_OP_EQ_CHAR: case RQ_OP_EQ_VARCHAR: case RQ_OP_NEQ_CHAR: case RQ_OP_NEQ_VARCHAR:
+        case RQ_OP_LIKE:
+            return true;
+        default: return false;
+    }
+}
+
 static void simplify_pipeline(const rq_pipeline& in, SimplePipe& sp) {
     const int n = in.n_nodes;
     std::vector<rq_node> tmp;
@@ -80,6 +90,12 @@ static void simplify_pipeline(const rq_pipeline& in, SimplePipe& sp) {
         return remap[r];
     };
     std::vector<int32_t> args(in.args, in.args + in.n_args);
+    std::function<bool(int)> is01node = [&](int t) -> bool {
+        const rq_node& x = tmp[t];
+        if (x.op == RQ_OP_AND || x.op == RQ_OP_OR) return is01node(x.a) && is01node(x.b);
+        if (x.op == RQ_OP_CONST) return x.imm == 0 || x.imm == 1;
+        return is01(x.op);
+    };
     for (int i = 0; i < n; i++) {
         rq_node nd = in.nodes[i];
         if (is_binary(nd.op)) {
@@ -97,6 +113,17 @@ static void simplify_pipeline(const rq_pipeline& in, SimplePipe& sp) {
             if (nd.op == RQ_OP_DIV && y.op == RQ_OP_CONST && y.imm == 1) { remap[i] = nd.a; continue; }
         } else if (nd.op == RQ_OP_FILTER) {
             nd.a = ref(i, nd.a); nd.b = nd.c = 0;
+            // FILTER(x AND y) == FILTER x; FILTER y when both sides are 0/1 values (compare
+            // results): no slot traffic, and whole warps can leave the program early
+            std::vector<int> stack{nd.a}, parts;
+            while (!stack.empty()) {
+                const int t = stack.back(); stack.pop_back();
+                if (tmp[t].op == RQ_OP_AND && is01node(tmp[t].a) && is01node(tmp[t].b)) {
+                    stack.push_back(tmp[t].b); stack.push_back(tmp[t].a);
+                } else parts.push_back(t);
+            }
+            for (size_t k = 0; k + 1 < parts.size(); k++) { rq_node f{RQ_OP_FILTER, parts[k], 0, 0, 0}; intern(f); }
+            nd.a = parts.back();
         } else if (nd.op == RQ_OP_SELECT) {
             nd.a = ref(i, nd.a); nd.b = ref(i, nd.b); nd.c = ref(i, nd.c);
         } else if (nd.op == RQ_OP_PROBE) {
@@ -153,6 +180,33 @@ static void simplify_pipeline(const rq_pipeline& in, SimplePipe& sp) {
     for (auto& k : sp.keys) k.node = remap2[k.node];
     for (auto& v : sp.vals)
         if (!(in.sink_kind == RQ_SINK_AGG && v.kind == RQ_AGG_COUNT)) v.node = remap2[v.node];
+    // hoist every FILTER to right behind the value it tests: the value is still in the
+    // accumulator and later work is skipped for dropped tuples (expressions are side-effect free)
+    {
+        const int k = (int)sp.nodes.size();
+        std::vector<int> order_, pos(k, -1);
+        for (int i = 0; i < k; i++) {
+            if (sp.nodes[i].op == RQ_OP_FILTER) continue;
+            order_.push_back(i);
+            for (int f = 0; f < k; f++)
+                if (sp.nodes[f].op == RQ_OP_FILTER && sp.nodes[f].a == i) order_.push_back(f);
+        }
+        for (int i = 0; i < k; i++) pos[order_[i]] = i;
+        std::vector<rq_node> re(k);
+        for (int i = 0; i < k; i++) {
+            rq_node nd = sp.nodes[order_[i]];
+            if (is_binary(nd.op)) { nd.a = pos[nd.a]; nd.b = pos[nd.b]; }
+            else if (nd.op == RQ_OP_FILTER) nd.a = pos[nd.a];
+            else if (nd.op == RQ_OP_SELECT) { nd.a = pos[nd.a]; nd.b = pos[nd.b]; nd.c = pos[nd.c]; }
+            else if (nd.op == RQ_OP_PAYLOAD) nd.a = pos[nd.a];
+            else if (nd.op == RQ_OP_PROBE) for (int q = 0; q < nd.c; q++) args[nd.b + q] = pos[args[nd.b + q]];
+            re[i] = nd;
+        }
+        sp.nodes = re;
+        for (auto& kk : sp.keys) kk.node = pos[kk.node];
+        for (auto& v : sp.vals)
+            if (!(in.sink_kind == RQ_SINK_AGG && v.kind == RQ_AGG_COUNT)) v.node = pos[v.node];
+    }
     sp.args = args;
     sp.pl = in;
     sp.pl.n_nodes = (int)sp.nodes.size(); sp.pl.nodes = sp.nodes.data();
@@ -210,11 +264,9 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
         if (is_leaf(nd.op) || nd.op == RQ_OP_PAYLOAD) {
             // no instruction
         } else if (nd.op == RQ_OP_FILTER) {
-            if (L.acc_node != nd.a || is_leaf(pl.nodes[nd.a].op)) {
-                L.emit(D_LD, L.operand_of(nd.a));
-                L.acc_node = is_leaf(pl.nodes[nd.a].op) ? -1 : nd.a;
-            }
-            L.emit(D_FILTER);
+            // tests the accumulator, or an operand without disturbing the accumulator
+            if (L.acc_node != nd.a || is_leaf(pl.nodes[nd.a].op)) L.emit(D_FILTER, L.operand_of(nd.a));
+            else L.emit(D_FILTER);
         } else if (is_binary(nd.op)) {
             const int x = nd.a, y = nd.b;
             if (L.acc_node == x && x != y && !is_leaf(pl.nodes[x].op)) {

@@ -347,7 +347,9 @@ rq_pipeline_kernel(const __grid_constant__ KParams P) {
                 case D_FILTER:
 #pragma unroll
                     for (int r = 0; r < kRowsPerThread; r++)
-                        if ((acc[r] & 0xff) == 0) valid &= ~(1u << r);
+                        if ((((in.src != S_NONE) ? b[r] : acc[r]) & 0xff) == 0) valid &= ~(1u << r);
+                    // every later instruction is warp-local: a warp without survivors is done
+                    if (!__any_sync(0xffffffffu, valid != 0)) pc = P.n_insn;
                     break;
                 case D_GROUP: {
                     if (NK == 0) break;

@@ -122,8 +122,29 @@ def load():
     lib.rq_result_free.argtypes = [C.POINTER(rq_result)]
     lib.rq_dist_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     lib.rq_dist_init.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    lib.rq_debug_lower.argtypes = [C.POINTER(rq_plan), C.c_int, C.c_int, C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32), C.c_int, C.c_char_p, C.c_int64]
     _lib = lib
     return lib
+
+
+def debug_lower(plan, pipeline, impl, col_types, col_widths):
+    """Host-side lowering of one pipeline to the device program, as text (no GPU needed)."""
+    lib = load()
+
+    class _T:
+        def __init__(self, names):
+            self.names, self.handle = names, None
+    tables = {t["name"]: _T(t["columns"]) for t in plan.tables}
+    cplan, keep = plan.to_c(tables, 0)
+    n = len(col_types)
+    ty = (C.c_int32 * n)(*col_types)
+    wi = (C.c_int32 * n)(*col_widths)
+    buf = C.create_string_buffer(1 << 16)
+    rc = lib.rq_debug_lower(C.byref(cplan), pipeline, impl, ty, wi, n, buf, len(buf))
+    if rc != 0:
+        raise EngineError(rc, lib.rq_last_error().decode())
+    return buf.value.decode()
 
 
 ABI_SYMBOLS = ["rq_init", "rq_shutdown", "rq_last_error", "rq_stream", "rq_dist_unique_id",
