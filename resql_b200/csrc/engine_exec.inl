@@ -358,7 +358,7 @@ static void set_types(rq_table& t, const rq_pipeline& pl) {
 }
 
 static void layout_smem(KParams& P, int na_unique, bool lowagg) {
-    uint32_t off = 128 + kStages * P.stage_bytes;
+    uint32_t off = 128 + P.stages * P.stage_bytes;
     off = (off + 127) & ~127u;
     P.slots_off = off;
     off += (uint32_t)P.n_slots * kTileRows * 8;
@@ -458,15 +458,21 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
             for (int u = 0; u < P.na; u++) P.agg_kind[u] = (uint8_t)ad.kind[u];
             P.g_state = E.g_state; P.g_keys = E.g_keys; P.g_acc = E.g_acc;
             bool fits = false;
-            for (int G = (pl.n_keys == 0 ? 1 : kLowCardMaxGroups); G >= 1; G >>= 1) {
-                P.G = G;
-                layout_smem(P, P.na, true);
-                if (P.smem_bytes <= 227 * 1024) { fits = true; break; }
+            for (int st = kStages; st >= 1 && !fits; st--) {
+                P.stages = st;
+                for (int G = (pl.n_keys == 0 ? 1 : kLowCardMaxGroups); G >= (st > 1 ? 4 : 1); G >>= 1) {
+                    P.G = G;
+                    layout_smem(P, P.na, true);
+                    if (P.smem_bytes <= 227 * 1024) { fits = true; break; }
+                    if (pl.n_keys == 0) break;
+                }
             }
             if (!fits) continue;
         } else {
             P.G = 0;
+            P.stages = kStages;
             layout_smem(P, 0, false);
+            if (P.smem_bytes > 227 * 1024) { P.stages = 1; layout_smem(P, 0, false); }
             if (P.smem_bytes > 227 * 1024) raise(RQ_ERR_UNSUPPORTED, "pipeline %d needs %u bytes of shared memory", pi, P.smem_bytes);
         }
         lower_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

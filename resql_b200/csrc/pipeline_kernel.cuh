@@ -239,16 +239,17 @@ rq_pipeline_kernel(const __grid_constant__ KParams P) {
             tma_bulk_g2s(dst + P.col_off[c], P.col_ptr[c] + (size_t)tile * bytes, bytes, bar);
         }
     };
+    const int n_stages = P.stages;
     if (tid == 0 && P.n_cols > 0) {
         if (first < n_tiles) issue(first, 0);
-        if (first + stride < n_tiles) issue(first + stride, 1);
+        if (n_stages > 1 && first + stride < n_tiles) issue(first + stride, 1);
     }
 
     int dict_any = 0;   // (no GROUP BY) did this warp aggregate at least one tuple
 
     int it = 0;
     for (int64_t tile = first; tile < n_tiles; tile += stride, it++) {
-        const int s = it & 1;
+        const int s = (n_stages > 1) ? (it & 1) : 0;
         TileCtx c;
         c.stage = stages + (size_t)s * P.stage_bytes;
         c.slots = reinterpret_cast<int64_t*>(rq_smem + P.slots_off);
@@ -266,7 +267,7 @@ rq_pipeline_kernel(const __grid_constant__ KParams P) {
                 }
                 __syncthreads();
             } else {
-                mbar_wait(&bars[s], (it >> 1) & 1);
+                mbar_wait(&bars[s], (n_stages > 1) ? ((it >> 1) & 1) : (it & 1));
             }
         }
 
@@ -447,7 +448,7 @@ rq_pipeline_kernel(const __grid_constant__ KParams P) {
 
         __syncthreads();   // everyone is done with stage s (and the slots) before it is refilled
         if (tid == 0 && P.n_cols > 0) {
-            const int64_t nt = tile + 2 * stride;
+            const int64_t nt = tile + n_stages * stride;
             if (nt < n_tiles) issue(nt, s);
         }
     }

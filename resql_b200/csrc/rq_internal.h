@@ -93,6 +93,7 @@ struct KParams {
     const unsigned char* str_ptr[kMaxStrCols];
     uint32_t       str_w[kMaxStrCols];
     uint32_t       stage_bytes;
+    int32_t        stages;              // 2 = double buffered, 1 when shared memory is short
     // shared memory carve-up (byte offsets)
     uint32_t       slots_off, acc_off, dict_off, smem_bytes;
     int32_t        n_slots;
