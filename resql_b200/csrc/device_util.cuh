@@ -1,0 +1,105 @@
+// Device helpers shared by the kernels: mbarrier / TMA PTX, string semantics, hashing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rq_internal.h"
+
+namespace rq {
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                             uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "RQ_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra RQ_DONE;\n"
+        "bra RQ_WAIT;\n"
+        "RQ_DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// string semantics (qlib/scalar.h)
+// ------------------------------------------------------------------------------------------
+// compareChar (qlib/scalar.h:27-46): equal after ignoring trailing blanks on either side
+__device__ __forceinline__ int64_t str_eq_char(const char* a, const char* b) {
+    while (*a != '\0' && *b != '\0') {
+        if (*a != *b) return 0;
+        a++; b++;
+    }
+    while (*a != '\0') { if (*a != ' ') return 0; a++; }
+    while (*b != '\0') { if (*b != ' ') return 0; b++; }
+    return 1;
+}
+// compareVarchar (qlib/scalar.h:16-24): exact
+__device__ __forceinline__ int64_t str_eq_varchar(const char* a, const char* b) {
+    while (*a != '\0' && *b != '\0') {
+        if (*a != *b) return 0;
+        a++; b++;
+    }
+    return (*a == *b) ? 1 : 0;
+}
+// stringLikeCheck (qlib/scalar.h:57-120), restated: '%' matches any run, '_' any one char.
+// The reference anchors both ends and backtracks on the last '%'; a standard two-pointer
+// wildcard matcher yields the same accept set for patterns made of literal runs, '%' and '_'.
+__device__ __forceinline__ int64_t str_like(const char* s, const char* p) {
+    const char* star = nullptr;
+    const char* ss = nullptr;
+    while (*s != '\0') {
+        if (*p == '%') { star = p++; ss = s; }
+        else if (*p != '\0' && (*p == *s || *p == '_')) { p++; s++; }
+        else if (star) { p = star + 1; s = ++ss; }
+        else return 0;
+    }
+    while (*p == '%') p++;
+    return *p == '\0' ? 1 : 0;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 33;
+    return h;
+}
+
+__device__ __forceinline__ int64_t agg_identity(int kind) {
+    if (kind == 3) return INT64_MAX;   // RQ_AGG_MIN
+    if (kind == 4) return INT64_MIN;   // RQ_AGG_MAX
+    return 0;
+}
+
+// signed truncating division like x86 idiv; b == 0 raises the runtime error flag
+__device__ __forceinline__ int64_t div_trunc(int64_t a, int64_t b, int32_t* err) {
+    if (b == 0) { *err = 1; return 0; }
+    if (b == -1) return (int64_t)(0ULL - (uint64_t)a);   // avoids INT64_MIN / -1 trap semantics
+    return a / b;
+}
+
+
+}  // namespace rq

@@ -522,7 +522,13 @@ struct Lowerer {
                     const rq_node& nd = pl.nodes[j];
                     int cnt = 0;
                     if (is_binary(nd.op)) cnt = (nd.a == i) + (nd.b == i);
-                    else if (nd.op == RQ_OP_SELECT) { cnt = (nd.a == i) ? 1 : 2; if (nd.b == i || nd.c == i) cnt = 2; }
+                    else if (nd.op == RQ_OP_SELECT) {
+                        cnt = (nd.a == i) ? 1 : 2;
+                        if (nd.b == i || nd.c == i) cnt = 2;
+                        // a non-constant leaf else is staged through the accumulator first
+                        const int co = pl.nodes[nd.c].op;
+                        if (is_leaf(co) && co != RQ_OP_CONST && co != RQ_OP_CONST_STR) cnt = 2;
+                    }
                     else cnt = 2;
                     if (cnt != 1) need = true;
                 }

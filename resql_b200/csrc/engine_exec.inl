@@ -279,24 +279,53 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
             }
             computed = true;
         } else if (nd.op == RQ_OP_SELECT) {
-            int tmp = -1, else_slot;
-            if (is_leaf(pl.nodes[nd.c].op)) {
+            // acc = cond ? then : else. A constant else travels in the immediate table
+            // (flags bit1), anything else in a slot.
+            int tmp = -1, else_ref;
+            bool else_imm = false;
+            if (pl.nodes[nd.c].op == RQ_OP_CONST || pl.nodes[nd.c].op == RQ_OP_CONST_STR) {
+                if (L.n_imm >= kMaxImm) raise(RQ_ERR_UNSUPPORTED, "too many constants");
+                P.imm[L.n_imm] = L.leaf_op[nd.c].imm;
+                else_ref = L.n_imm++;
+                else_imm = true;
+            } else if (is_leaf(pl.nodes[nd.c].op)) {
                 tmp = L.alloc_slot();
                 L.emit(D_LD, L.operand_of(nd.c));
                 P.insn[P.n_insn - 1].flags |= 1;
                 P.insn[P.n_insn - 1].dst = (uint8_t)tmp;
                 L.acc_node = -1;
-                else_slot = tmp;
+                else_ref = tmp;
             } else {
                 if (L.slot[nd.c] < 0) raise(RQ_ERR_INVALID, "internal: SELECT else operand has no slot");
-                else_slot = L.slot[nd.c];
+                else_ref = L.slot[nd.c];
             }
             if (L.acc_node != nd.a || is_leaf(pl.nodes[nd.a].op)) L.emit(D_LD, L.operand_of(nd.a));
-            L.emit(D_SEL, L.operand_of(nd.b), (uint16_t)else_slot);
+            L.emit(D_SEL, L.operand_of(nd.b), (uint16_t)else_ref);
+            if (else_imm) P.insn[P.n_insn - 1].flags |= 2;
             if (tmp >= 0) L.free_slots.push_back(tmp);
             computed = true;
         } else if (nd.op == RQ_OP_PROBE) {
-            raise(RQ_ERR_UNSUPPORTED, "PROBE lowering not available in this build");
+            if (P.n_probes >= kMaxProbes) raise(RQ_ERR_UNSUPPORTED, "more than %d joins in one pipeline", kMaxProbes);
+            if (nd.a < 0 || nd.a >= (int)L.outs.size() || !L.outs[nd.a].ht)
+                raise(RQ_ERR_INVALID, "PROBE refers to pipeline %d which built no hash table", nd.a);
+            DProbe& pr = P.probe[P.n_probes];
+            pr.ht = L.outs[nd.a].ht->d;
+            if (nd.c != pr.ht.nk) raise(RQ_ERR_INVALID, "PROBE has %d keys, the build side %d", nd.c, pr.ht.nk);
+            for (int k = 0; k < nd.c; k++) pr.key[k] = L.vref_of(pl.args[nd.b + k]);
+            pr.single = (int32_t)(nd.imm & 1);
+            pr.n_out = pr.ht.nv;
+            memset(pr.out_slot, 0xff, sizeof(pr.out_slot));
+            pr.dup_counter = (unsigned long long*)(E.flags + 4);
+            for (int j = i + 1; j < n; j++) {
+                if (pl.nodes[j].op != RQ_OP_PAYLOAD || pl.nodes[j].a != i) continue;
+                const int b = pl.nodes[j].b;
+                if (b < 0 || b >= pr.ht.nv || b >= kMaxOut) raise(RQ_ERR_INVALID, "PAYLOAD %d out of range", b);
+                const int sl = L.alloc_slot();
+                L.slot[j] = sl;
+                pr.out_slot[b] = (uint8_t)sl;
+            }
+            L.emit(D_PROBE, Operand(), (uint16_t)P.n_probes);
+            P.n_probes++;
         }
         if (computed) {
             L.acc_node = i;
@@ -313,6 +342,24 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
         if (i == L.gpos) emit_group();
     }
 
+    if (impl == IMPL_BUILD || impl == IMPL_HASHAGG) {
+        if (pl.n_keys > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
+        P.nk = pl.n_keys;
+        for (int k = 0; k < pl.n_keys; k++) P.key[k] = L.vref_of(pl.keys[k].node);
+        if (impl == IMPL_BUILD) {
+            if (pl.n_vals > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d payload columns", kMaxOut);
+            P.n_out = pl.n_vals;
+            for (int k = 0; k < pl.n_vals; k++) P.out[k] = L.vref_of(pl.vals[k].node);
+            L.emit(D_BUILD);
+        } else {
+            P.na = (int)ad.kind.size();
+            for (int u = 0; u < P.na; u++) {
+                P.agg_kind[u] = (uint8_t)ad.kind[u];
+                if (ad.kind[u] != RQ_AGG_COUNT) P.agg_src[u] = L.vref_of(ad.node[u]);
+            }
+            L.emit(D_HAGG);
+        }
+    }
     if (impl == IMPL_EMIT) {
         if (pl.n_vals > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d output columns", kMaxOut);
         P.n_out = pl.n_vals;
@@ -394,9 +441,12 @@ static bool has_str_key(const rq_pipeline& pl) {
 }
 
 static void check_flags(const char* what) {
-    CK(cudaMemcpyAsync(E.h_flags, E.flags, 16, cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaMemcpyAsync(E.h_flags, E.flags, 24, cudaMemcpyDeviceToHost, E.stream));
     CK(cudaStreamSynchronize(E.stream));
     if (E.h_flags[2]) raise(RQ_ERR_RUNTIME, "division by zero in %s (the reference raises SIGFPE here)", what);
+    if (*(unsigned long long*)(E.h_flags + 4) != 0)
+        raise(RQ_ERR_UNSUPPORTED, "%s: a probe tuple matches several build tuples; multi-match expansion "
+              "(hashjoin.h:118-165) is not available in this build", what);
 }
 
 // ---- one pipeline -------------------------------------------------------------------------
@@ -438,8 +488,6 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
 
     for (size_t attempt = 0; attempt < impls.size(); attempt++) {
         const int impl = impls[attempt];
-        if (impl == IMPL_HASHAGG || impl == IMPL_BUILD)
-            raise(RQ_ERR_UNSUPPORTED, "pipeline %d: hash aggregate / join build not available in this build", pi);
         KParams P;
         memset(&P, 0, sizeof(P));
         P.n_rows = src->n_rows;
@@ -477,7 +525,7 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
         }
         lower_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
-        CK(cudaMemsetAsync(E.flags, 0, 16, E.stream));
+        CK(cudaMemsetAsync(E.flags, 0, 24, E.stream));
         if (impl == IMPL_LOWAGG) {
             CK(cudaMemcpyAsync(E.g_kinds, P.agg_kind, kMaxAggs, cudaMemcpyHostToDevice, E.stream));
             rq_group_table_init<<<(kGroupTableCap + 255) / 256, 256, 0, E.stream>>>(E.g_state, E.g_acc, E.g_kinds, P.na);
@@ -510,6 +558,85 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
                                    (size_t)kGroupTableCap * 8, cudaMemcpyDeviceToDevice, E.stream));
             CK(cudaMemcpyAsync(out->d_n_rows, dense->d_n_rows, 8, cudaMemcpyDeviceToDevice, E.stream));
             CK(cudaStreamSynchronize(E.stream));
+            set_types(*out, pl);
+            outs[pi].table = std::move(out);
+            return;
+        }
+        if (impl == IMPL_BUILD || impl == IMPL_HASHAGG) {
+            const int64_t rows_bound = std::max<int64_t>(1, src->n_rows >= 0 ? src->n_rows : src->cap_rows);
+            int64_t want = rows_bound;
+            if (pl.size_hint > 0) want = std::min<int64_t>(rows_bound, std::max<int64_t>(pl.size_hint, 2048));
+            uint64_t cap = 4096;
+            while (cap < (uint64_t)(2 * want)) cap <<= 1;
+            uint64_t cap_max = 4096;
+            while (cap_max < (uint64_t)(2 * rows_bound)) cap_max <<= 1;
+            const int nk = pl.n_keys;
+            if (nk > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
+            const int nv = impl == IMPL_BUILD ? pl.n_vals : (int)ad.kind.size();
+            std::unique_ptr<HashTableDev> ht;
+            for (;;) {
+                ht.reset(new HashTableDev());
+                ht->capacity = cap;
+                ht->d.cap_mask = cap - 1;
+                ht->d.nk = nk; ht->d.nv = nv;
+                for (int k = 0; k < nk && k < kMaxKeys; k++) {
+                    const int st = pl.keys[k].sql_type;
+                    ht->d.key_kind[k] = st == RQ_SQL_VARCHAR ? 2 : (st == RQ_SQL_CHAR && pl.keys[k].width > 1) ? 1 : 0;
+                }
+                CK(cudaMalloc(&ht->d.tags, cap * 8));
+                CK(cudaMalloc(&ht->d.keys, (size_t)std::max(nk, 1) * cap * 8));
+                CK(cudaMalloc(&ht->d.vals, (size_t)std::max(nv, 1) * cap * 8));
+                CK(cudaMemsetAsync(ht->d.tags, 0, cap * 8, E.stream));
+                if (impl == IMPL_HASHAGG) {
+                    CK(cudaMemcpyAsync(E.g_kinds, P.agg_kind, kMaxAggs, cudaMemcpyHostToDevice, E.stream));
+                    rq_ht_init_vals<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d.vals, cap, nv, E.g_kinds);
+                    if (tm) tm->kernel_launches++;
+                }
+                P.ht = ht->d;
+                CK(cudaMemsetAsync(E.flags, 0, 24, E.stream));
+                launch_pipeline(P, rows_bound, tm, is_scan, ev_idx, ev_used);
+                check_flags(impl == IMPL_BUILD ? "join build pipeline" : "hash aggregation pipeline");
+                if (!E.h_flags[1]) break;
+                if (cap >= cap_max) raise(RQ_ERR_RUNTIME, "pipeline %d: hash table overflow at capacity %llu", pi, (unsigned long long)cap);
+                cap = std::min<uint64_t>(cap * 8, cap_max);
+            }
+            if (impl == IMPL_BUILD) {
+                for (int k = 0; k < pl.n_vals; k++) {
+                    outs[pi].payload_sql_type.push_back(pl.vals[k].sql_type);
+                    outs[pi].payload_sql_width.push_back(pl.vals[k].width);
+                }
+                outs[pi].ht = std::move(ht);
+                return;
+            }
+            // dense relation out of the aggregation table
+            unsigned long long* d_count = nullptr;
+            CK(cudaMalloc(&d_count, 8));
+            CK(cudaMemsetAsync(d_count, 0, 8, E.stream));
+            rq_ht_count<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d.tags, cap, d_count);
+            if (tm) tm->kernel_launches++;
+            unsigned long long n_groups = 0;
+            CK(cudaMemcpyAsync(&n_groups, d_count, 8, cudaMemcpyDeviceToHost, E.stream));
+            CK(cudaStreamSynchronize(E.stream));
+            cudaFree(d_count);
+            const int ncols = pl.n_keys + pl.n_vals;
+            out = new_intermediate(ncols, (int64_t)n_groups);
+            std::vector<int> colmap(ncols);
+            std::vector<int64_t*> h_cols(ncols);
+            for (int k = 0; k < pl.n_keys; k++) colmap[k] = k;
+            for (int k = 0; k < pl.n_vals; k++) colmap[pl.n_keys + k] = pl.n_keys + ad.uniq_of[k];
+            for (int c = 0; c < ncols; c++) h_cols[c] = (int64_t*)out->cols[c].d;
+            int* d_map = nullptr;
+            int64_t** d_ptrs = nullptr;
+            CK(cudaMalloc(&d_map, sizeof(int) * ncols));
+            CK(cudaMalloc(&d_ptrs, sizeof(int64_t*) * ncols));
+            CK(cudaMemcpyAsync(d_map, colmap.data(), sizeof(int) * ncols, cudaMemcpyHostToDevice, E.stream));
+            CK(cudaMemcpyAsync(d_ptrs, h_cols.data(), sizeof(int64_t*) * ncols, cudaMemcpyHostToDevice, E.stream));
+            rq_ht_compact<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, d_map, ncols, d_ptrs, (unsigned long long*)out->d_n_rows);
+            if (tm) tm->kernel_launches++;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(E.stream));
+            cudaFree(d_map);
+            cudaFree(d_ptrs);
             set_types(*out, pl);
             outs[pi].table = std::move(out);
             return;
@@ -599,7 +726,6 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         if (plan->limit >= 0 && plan->limit < n_out) n_out = plan->limit;
         if (plan->n_order > 0 && n > 1) {
             if (plan->n_order > kMaxSortKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d ORDER BY keys", kMaxSortKeys);
-            if (n > kBitonicMax) raise(RQ_ERR_UNSUPPORTED, "ORDER BY over %lld rows not available in this build", (long long)n);
             SortKeys K;
             memset(&K, 0, sizeof(K));
             K.n_keys = plan->n_order;
@@ -612,10 +738,51 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
                 K.desc[k] = plan->order[k].ascending ? 0 : 1;
             }
             uint32_t* perm = nullptr;
-            CK(cudaMalloc(&perm, sizeof(uint32_t) * kBitonicMax));
+            CK(cudaMalloc(&perm, sizeof(uint32_t) * std::max<int64_t>(n, kBitonicMax)));
             scratch.push_back(perm);
-            rq_sort_small<<<1, 1024, 0, E.stream>>>(K, fin->d_n_rows, perm);
-            if (tm) tm->kernel_launches++;
+            if (n <= kBitonicMax) {
+                rq_sort_small<<<1, 1024, 0, E.stream>>>(K, fin->d_n_rows, perm);
+                if (tm) tm->kernel_launches++;
+            } else {
+                // LSD radix sort, least significant ORDER BY key first; every pass is stable
+                if (n > 0xffffffffLL) raise(RQ_ERR_UNSUPPORTED, "ORDER BY over more than 2^32 rows");
+                uint32_t* perm2 = nullptr; uint64_t *k1 = nullptr, *k2 = nullptr; uint32_t* hist = nullptr;
+                unsigned long long* bits = nullptr;
+                const unsigned nb = (unsigned)((n + kRadixChunk - 1) / kRadixChunk);
+                const unsigned eb = (unsigned)((n + 255) / 256);
+                CK(cudaMalloc(&perm2, sizeof(uint32_t) * n)); scratch.push_back(perm2);
+                CK(cudaMalloc(&k1, sizeof(uint64_t) * n)); scratch.push_back(k1);
+                CK(cudaMalloc(&k2, sizeof(uint64_t) * n)); scratch.push_back(k2);
+                CK(cudaMalloc(&hist, sizeof(uint32_t) * 16 * nb)); scratch.push_back(hist);
+                CK(cudaMalloc(&bits, 16)); scratch.push_back(bits);
+                rq_sort_iota<<<eb, 256, 0, E.stream>>>(perm, n);
+                if (tm) tm->kernel_launches++;
+                for (int k = plan->n_order - 1; k >= 0; k--) {
+                    const int c = plan->order[k].column;
+                    const int words = K.is_str[k] ? (fin->sql_width[c] + 7) / 8 : 1;
+                    for (int w = words - 1; w >= 0; w--) {
+                        rq_sort_make_keys<<<eb, 256, 0, E.stream>>>(K.col[k], perm, k1, n, K.is_str[k], w, K.desc[k]);
+                        const unsigned long long init[2] = {0ULL, ~0ULL};
+                        CK(cudaMemcpyAsync(bits, init, 16, cudaMemcpyHostToDevice, E.stream));
+                        rq_sort_key_bits<<<std::min(eb, 1024u), 256, 0, E.stream>>>(k1, n, bits);
+                        unsigned long long h_bits[2];
+                        CK(cudaMemcpyAsync(h_bits, bits, 16, cudaMemcpyDeviceToHost, E.stream));
+                        CK(cudaStreamSynchronize(E.stream));
+                        if (tm) tm->kernel_launches += 2;
+                        const uint64_t varying = h_bits[0] ^ h_bits[1];
+                        for (int shift = 0; shift < 64; shift += 4) {
+                            if (((varying >> shift) & 15) == 0) continue;
+                            rq_radix_hist<<<nb, kRadixThreads, 0, E.stream>>>(k1, n, shift, hist);
+                            rq_radix_scan<<<1, 1024, 0, E.stream>>>(hist, (int64_t)16 * nb);
+                            rq_radix_scatter<<<nb, kRadixThreads, 0, E.stream>>>(k1, perm, k2, perm2, n, shift, hist);
+                            if (tm) tm->kernel_launches += 3;
+                            std::swap(k1, k2);
+                            std::swap(perm, perm2);
+                        }
+                    }
+                }
+                CK(cudaGetLastError());
+            }
             for (int c = 0; c < ncols; c++) {
                 int64_t* sorted = nullptr;
                 CK(cudaMalloc(&sorted, sizeof(int64_t) * std::max<int64_t>(n_out, 1)));

@@ -12,90 +12,10 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "rq_internal.h"
+#include "device_util.cuh"
+#include "hash_kernels.cuh"
 
 namespace rq {
-
-// ------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + TMA bulk copy
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes,
-                                             uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "RQ_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra RQ_DONE;\n"
-        "bra RQ_WAIT;\n"
-        "RQ_DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
-// ------------------------------------------------------------------------------------------
-// string semantics (qlib/scalar.h)
-// ------------------------------------------------------------------------------------------
-// compareChar (qlib/scalar.h:27-46): equal after ignoring trailing blanks on either side
-__device__ __forceinline__ int64_t str_eq_char(const char* a, const char* b) {
-    while (*a != '\0' && *b != '\0') {
-        if (*a != *b) return 0;
-        a++; b++;
-    }
-    while (*a != '\0') { if (*a != ' ') return 0; a++; }
-    while (*b != '\0') { if (*b != ' ') return 0; b++; }
-    return 1;
-}
-// compareVarchar (qlib/scalar.h:16-24): exact
-__device__ __forceinline__ int64_t str_eq_varchar(const char* a, const char* b) {
-    while (*a != '\0' && *b != '\0') {
-        if (*a != *b) return 0;
-        a++; b++;
-    }
-    return (*a == *b) ? 1 : 0;
-}
-// stringLikeCheck (qlib/scalar.h:57-120), restated: '%' matches any run, '_' any one char.
-// The reference anchors both ends and backtracks on the last '%'; a standard two-pointer
-// wildcard matcher yields the same accept set for patterns made of literal runs, '%' and '_'.
-__device__ __forceinline__ int64_t str_like(const char* s, const char* p) {
-    const char* star = nullptr;
-    const char* ss = nullptr;
-    while (*s != '\0') {
-        if (*p == '%') { star = p++; ss = s; }
-        else if (*p != '\0' && (*p == *s || *p == '_')) { p++; s++; }
-        else if (star) { p = star + 1; s = ++ss; }
-        else return 0;
-    }
-    while (*p == '%') p++;
-    return *p == '\0' ? 1 : 0;
-}
-
-__device__ __forceinline__ uint64_t mix64(uint64_t h) {
-    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL;
-    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL;
-    h ^= h >> 33;
-    return h;
-}
 
 // ------------------------------------------------------------------------------------------
 // register tile <-> shared memory. Thread t owns tuples {2t, 2t+1, 512+2t, 512+2t+1} of the
@@ -164,28 +84,6 @@ __device__ __forceinline__ int64_t ld_vref(const KParams& P, const TileCtx& c, V
         case S_STR:  return (int64_t)(P.str_ptr[vr.idx] + (size_t)(c.row0 + row) * P.str_w[vr.idx]);
         default:     return 0;
     }
-}
-
-__device__ __forceinline__ int64_t agg_identity(int kind) {
-    if (kind == 3) return INT64_MAX;   // RQ_AGG_MIN
-    if (kind == 4) return INT64_MIN;   // RQ_AGG_MAX
-    return 0;
-}
-
-// signed truncating division like x86 idiv; b == 0 raises the runtime error flag
-__device__ __forceinline__ int64_t div_trunc(int64_t a, int64_t b, int32_t* err) {
-    if (b == 0) { *err = 1; return 0; }
-    if (b == -1) return (int64_t)(0ULL - (uint64_t)a);   // avoids INT64_MIN / -1 trap semantics
-    return a / b;
-}
-
-// ------------------------------------------------------------------------------------------
-// hash tables (shared by join build/probe and hash aggregation)
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t hash_keys(const int64_t* k, int nk) {
-    uint64_t h = 0x9E3779B97F4A7C15ULL;
-    for (int j = 0; j < nk; j++) h = mix64(h ^ (uint64_t)k[j]) + 0x9E3779B97F4A7C15ULL;
-    return h;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -339,7 +237,12 @@ rq_pipeline_kernel(const __grid_constant__ KParams P) {
 #undef RQ_STRBIN
                 case D_SEL: {
                     int64_t e[kRowsPerThread];
-                    ld_slot(c, in.aux, e);
+                    if (in.flags & 2) {
+#pragma unroll
+                        for (int r = 0; r < kRowsPerThread; r++) e[r] = P.imm[in.aux];
+                    } else {
+                        ld_slot(c, in.aux, e);
+                    }
 #pragma unroll
                     for (int r = 0; r < kRowsPerThread; r++)
                         acc[r] = (acc[r] & 0xff) ? b[r] : e[r];
@@ -424,6 +327,78 @@ rq_pipeline_kernel(const __grid_constant__ KParams P) {
                     }
                     break;
                 }
+                case D_PROBE: {
+                    // hash-join probe (hashjoin.h:118-214): tuples without a match are dropped;
+                    // the matching entry's payload words land in value slots
+                    const DProbe& pr = P.probe[in.aux];
+                    const uint64_t cap = pr.ht.cap_mask + 1;
+#pragma unroll 1
+                    for (int r = 0; r < kRowsPerThread; r++) {
+                        if (!((valid >> r) & 1)) continue;
+                        int64_t k[kMaxKeys];
+                        for (int j = 0; j < pr.ht.nk; j++) k[j] = ld_vref(P, c, pr.key[j], r);
+                        const uint64_t h = hash_typed(k, pr.ht.key_kind, pr.ht.nk);
+                        const uint64_t tag = h | 2ULL;
+                        uint64_t i = h & pr.ht.cap_mask;
+                        int64_t found = -1;
+                        unsigned matches = 0;
+                        for (uint64_t tries = 0; tries < cap; tries++) {
+                            const uint64_t t = pr.ht.tags[i];
+                            if (t == 0ULL) break;
+                            if (t == tag && slot_keys_equal(pr.ht, i, k)) {
+                                if (found < 0) found = (int64_t)i;
+                                matches++;
+                                if (pr.single) break;
+                            }
+                            i = (i + 1) & pr.ht.cap_mask;
+                        }
+                        if (found < 0) { valid &= ~(1u << r); continue; }
+                        if (matches > 1) atomicAdd(pr.dup_counter, (unsigned long long)(matches - 1));
+                        const int row = row_in_tile(r, tid);
+                        for (int q = 0; q < pr.n_out; q++)
+                            if (pr.out_slot[q] != 0xff)
+                                c.slots[(size_t)pr.out_slot[q] * kTileRows + row] = pr.ht.vals[(size_t)q * cap + found];
+                    }
+                    if (!__any_sync(0xffffffffu, valid != 0)) pc = P.n_insn;
+                    break;
+                }
+                case D_BUILD: {
+                    const uint64_t cap = P.ht.cap_mask + 1;
+#pragma unroll 1
+                    for (int r = 0; r < kRowsPerThread; r++) {
+                        if (!((valid >> r) & 1)) continue;
+                        int64_t k[kMaxKeys];
+                        for (int j = 0; j < P.ht.nk; j++) k[j] = ld_vref(P, c, P.key[j], r);
+                        const uint64_t h = hash_typed(k, P.ht.key_kind, P.ht.nk);
+                        uint64_t slot;
+                        if (!ht_insert_dup(P.ht, k, h, &slot)) { *P.ht_full = 1; continue; }
+                        for (int q = 0; q < P.n_out; q++)
+                            P.ht.vals[(size_t)q * cap + slot] = ld_vref(P, c, P.out[q], r);
+                    }
+                    break;
+                }
+                case D_HAGG: {
+                    const uint64_t cap = P.ht.cap_mask + 1;
+#pragma unroll 1
+                    for (int r = 0; r < kRowsPerThread; r++) {
+                        if (!((valid >> r) & 1)) continue;
+                        int64_t k[kMaxKeys];
+                        for (int j = 0; j < P.ht.nk; j++) k[j] = ld_vref(P, c, P.key[j], r);
+                        const uint64_t h = hash_typed(k, P.ht.key_kind, P.ht.nk);
+                        uint64_t slot;
+                        if (!ht_find_or_insert(P.ht, k, h, &slot)) { *P.ht_full = 1; continue; }
+                        for (int a = 0; a < P.na; a++) {
+                            int64_t* dst = &P.ht.vals[(size_t)a * cap + slot];
+                            const int kind = P.agg_kind[a];
+                            if (kind == 2) { atomicAdd((unsigned long long*)dst, 1ULL); continue; }
+                            const int64_t v = ld_vref(P, c, P.agg_src[a], r);
+                            if (kind == 1) atomicAdd((unsigned long long*)dst, (unsigned long long)v);
+                            else if (kind == 3) atomicMin((long long*)dst, (long long)v);
+                            else atomicMax((long long*)dst, (long long)v);
+                        }
+                    }
+                    break;
+                }
                 case D_EMIT: {
 #pragma unroll
                     for (int r = 0; r < kRowsPerThread; r++) {
@@ -465,7 +440,9 @@ rq_pipeline_kernel(const __grid_constant__ KParams P) {
             if (lane == 0) {
                 int64_t k[kMaxKeys];
                 for (int j = 0; j < NK; j++) k[j] = dict[e * NK + j];
-                uint32_t i = (uint32_t)(hash_keys(k, NK) & (kGroupTableCap - 1));
+                uint64_t hh = 0x9E3779B97F4A7C15ULL;
+                for (int j = 0; j < NK; j++) hh = mix64(hh ^ (uint64_t)k[j]) + 0x9E3779B97F4A7C15ULL;
+                uint32_t i = (uint32_t)(hh & (kGroupTableCap - 1));
                 for (int tries = 0; tries < kGroupTableCap; tries++) {
                     uint32_t st = atomicCAS(&P.g_state[i], 0u, 1u);
                     if (st == 0u) {

@@ -69,6 +69,7 @@ struct DHashTable {
     int64_t*  keys;         // [nk][capacity]
     int64_t*  vals;         // [nv][capacity]  payload / accumulators
     int32_t   nk, nv;
+    uint8_t   key_kind[kMaxKeys];   // 0 integer, 1 CHAR, 2 VARCHAR
 };
 
 struct DProbe {

@@ -75,4 +75,134 @@ __global__ void rq_apply_perm(const int64_t* in, int64_t* out, const uint32_t* p
     if (i < n) out[i] = in[perm[i]];
 }
 
+// ---- LSD radix sort (n > kBitonicMax): 4-bit digits over order-preserving 64-bit keys -------
+constexpr int kRadixThreads = 256;
+constexpr int kRadixItems = 8;
+constexpr int kRadixChunk = kRadixThreads * kRadixItems;
+
+// order-preserving key of one ORDER BY column (word w of a string = 8 bytes, big endian)
+__global__ void rq_sort_make_keys(const int64_t* col, const uint32_t* perm, uint64_t* keys, int64_t n,
+                                  int is_str, int word, int desc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t v = col[perm[i]];
+    uint64_t k;
+    if (is_str) {
+        const unsigned char* s = reinterpret_cast<const unsigned char*>(v);
+        int len = 0;
+        while (s[len] != 0) len++;
+        k = 0;
+        for (int b = 0; b < 8; b++) {
+            const int p = word * 8 + b;
+            k = (k << 8) | (uint64_t)(p < len ? s[p] : 0);
+        }
+    } else {
+        k = (uint64_t)v ^ 0x8000000000000000ULL;
+    }
+    keys[i] = desc ? ~k : k;
+}
+
+__global__ void rq_sort_iota(uint32_t* perm, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[i] = (uint32_t)i;
+}
+
+// OR / AND of all keys: digits where both agree are constant and their pass is skipped
+__global__ void rq_sort_key_bits(const uint64_t* keys, int64_t n, unsigned long long* or_and) {
+    uint64_t o = 0, a = ~0ULL;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        o |= keys[i]; a &= keys[i];
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        o |= __shfl_xor_sync(0xffffffffu, o, s);
+        a &= __shfl_xor_sync(0xffffffffu, a, s);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicOr(&or_and[0], o); atomicAnd(&or_and[1], a); }
+}
+
+// per-thread digit counts of its kRadixItems consecutive items -> exclusive offsets inside the
+// block (stable: items keep their order) and the block total per digit
+__device__ __forceinline__ void radix_block_offsets(const uint64_t* keys, int64_t n, int shift,
+                                                    uint32_t (&mine)[16], uint32_t* s_cnt /*[16][kRadixThreads]*/,
+                                                    uint32_t* s_tot /*[16]*/) {
+    const int t = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * kRadixChunk + (int64_t)t * kRadixItems;
+#pragma unroll
+    for (int d = 0; d < 16; d++) mine[d] = 0;
+    for (int q = 0; q < kRadixItems; q++)
+        if (base + q < n) mine[(keys[base + q] >> shift) & 15]++;
+#pragma unroll
+    for (int d = 0; d < 16; d++) s_cnt[d * kRadixThreads + t] = mine[d];
+    __syncthreads();
+    // one warp per two digits: exclusive scan over the 256 thread counts
+    const int warp = t >> 5, lane = t & 31;
+    for (int d = warp; d < 16; d += kRadixThreads / 32) {
+        uint32_t run = 0;
+        for (int c0 = 0; c0 < kRadixThreads; c0 += 32) {
+            const uint32_t v = s_cnt[d * kRadixThreads + c0 + lane];
+            uint32_t x = v;
+            for (int s = 1; s < 32; s <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, s);
+                if (lane >= s) x += y;
+            }
+            s_cnt[d * kRadixThreads + c0 + lane] = run + x - v;
+            run += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (lane == 0) s_tot[d] = run;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kRadixThreads)
+rq_radix_hist(const uint64_t* keys, int64_t n, int shift, uint32_t* hist /*[16][n_blocks]*/) {
+    __shared__ uint32_t s_cnt[16 * kRadixThreads];
+    __shared__ uint32_t s_tot[16];
+    uint32_t mine[16];
+    radix_block_offsets(keys, n, shift, mine, s_cnt, s_tot);
+    if (threadIdx.x < 16) hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s_tot[threadIdx.x];
+}
+
+// exclusive scan over hist in digit-major order (single CTA)
+__global__ void __launch_bounds__(1024) rq_radix_scan(uint32_t* hist, int64_t m) {
+    __shared__ uint32_t s_part[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (m + 1023) / 1024;
+    const int64_t lo = t * per, hi = (lo + per < m) ? lo + per : m;
+    uint32_t sum = 0;
+    for (int64_t i = lo; i < hi; i++) sum += hist[i];
+    s_part[t] = sum;
+    __syncthreads();
+    if (t == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 1024; i++) { const uint32_t v = s_part[i]; s_part[i] = run; run += v; }
+    }
+    __syncthreads();
+    uint32_t run = s_part[t];
+    for (int64_t i = lo; i < hi; i++) { const uint32_t v = hist[i]; hist[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(kRadixThreads)
+rq_radix_scatter(const uint64_t* keys_in, const uint32_t* perm_in, uint64_t* keys_out, uint32_t* perm_out,
+                 int64_t n, int shift, const uint32_t* hist) {
+    __shared__ uint32_t s_cnt[16 * kRadixThreads];
+    __shared__ uint32_t s_tot[16];
+    uint32_t mine[16];
+    radix_block_offsets(keys_in, n, shift, mine, s_cnt, s_tot);
+    const int t = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * kRadixChunk + (int64_t)t * kRadixItems;
+    uint32_t run[16];
+#pragma unroll
+    for (int d = 0; d < 16; d++) run[d] = hist[(size_t)d * gridDim.x + blockIdx.x] + s_cnt[d * kRadixThreads + t];
+    for (int q = 0; q < kRadixItems; q++) {
+        if (base + q >= n) break;
+        const uint64_t k = keys_in[base + q];
+        const int d = (int)((k >> shift) & 15);
+        uint32_t pos = 0;
+#pragma unroll
+        for (int e = 0; e < 16; e++) if (e == d) pos = run[e]++;
+        keys_out[pos] = k;
+        perm_out[pos] = perm_in[base + q];
+    }
+}
+
 }  // namespace rq

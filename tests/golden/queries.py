@@ -53,5 +53,15 @@ QUERIES = {
     "case_sum": """select l_shipmode, sum(case when l_quantity > 25 then 1 else 0 end) as hi,
         sum(case when l_quantity <= 25 then l_extendedprice else 0 end) as lo
         from lineitem group by l_shipmode order by l_shipmode""",
+    # ORDER BY beyond one CTA (radix path), multi-key, strings, descending
+    "sort_large": """select l_orderkey, l_linenumber, l_extendedprice from lineitem where l_quantity > 40
+        order by l_extendedprice desc, l_orderkey, l_linenumber""",
+    "sort_strings_small": "select c_name, c_mktsegment, c_acctbal from customer order by c_mktsegment desc, c_name",
+    "sort_strings_large": """select o_orderkey, o_orderpriority, o_clerk from orders
+        order by o_orderpriority, o_clerk desc, o_orderkey""",
+    "agg_string_keys": """select o_orderpriority, o_orderstatus, count(*) as c, sum(o_totalprice) as s from orders
+        group by o_orderpriority, o_orderstatus order by o_orderpriority, o_orderstatus""",
+    "agg_many_groups": """select l_orderkey, count(*) as c, sum(l_quantity) as q, max(l_shipdate) as d from lineitem
+        group by l_orderkey order by l_orderkey""",
     "like_promo": """select count(*) as c from orders where o_comment like '%special%'""",
 }

@@ -107,7 +107,7 @@ def run_pipeline_vm(plan, pi, src_cols, pool_strings):
             acc = r if op == D_EQV else 1 - r
         elif op == D_LIKE: acc = np.array([PO._like(u, v) for u, v in zip(acc, b)], dtype=np.int64)
         elif op == D_RLIKE: acc = np.array([PO._like(v, u) for u, v in zip(acc, b)], dtype=np.int64)
-        elif op == D_SEL: acc = np.where((acc & 0xFF) != 0, b, slots[aux])
+        elif op == D_SEL: acc = np.where((acc & 0xFF) != 0, b, (np.full(n, prog['imm'][aux], dtype=np.int64) if flags & 2 else slots[aux]))
         elif op == D_FILTER: valid = valid & (((b if src != S_NONE else acc) & 0xFF) != 0)
         elif op == D_GROUP:
             keys = [vref(k, i) for k, i in prog["key"]]
