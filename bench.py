@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: TPC-H Q1/Q6/Q3 pipelines on TPC-H-shaped synthetic data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--sf SF] [--impl ours|reference]
+
+Metric (BASELINE.json): lineitem tuples/s over Q1+Q6+Q3 at SF100 (+ fraction of the HBM roofline).
+A step = one pass of the three queries over the resident tables (3 scans of lineitem plus the
+orders/customer build pipelines of Q3). `value` is timed with the tables resident in HBM;
+`e2e` re-uploads the tables from pinned host memory through the C ABI every step.
+N > 1: one process per GPU (torchrun), lineitem row-range sharded, SF fixed (strong scaling),
+partial aggregates merged inside the library with NCCL.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BYTES_PER_TUPLE = {"q1": 38, "q6": 28, "q3": 24}     # widths of the touched lineitem columns
+QUERIES = ("q1", "q6", "q3")
+
+
+def load_plan(name):
+    with open(os.path.join(ROOT, "tests/golden/plans", name + ".json")) as f:
+        return json.load(f)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference engine itself (oracle/_ref/resql-oracle)
+# ---------------------------------------------------------------------------------------------
+def run_reference(sample_sf, reps, threads):
+    """Times the UNMODIFIED reference (its own JIT, `threads=<all cores>`) on a bounded sample of
+    the same workload. Returns dict with tuples/s and per-query execute ms."""
+    from resql_b200 import tpch
+    from golden.queries import QUERIES as SQL
+    exe = os.path.join(ROOT, "oracle/_ref/resql-oracle")
+    kind = "reference"
+    if not os.path.exists(exe):
+        return None
+    data = tpch.generate(sample_sf, seed=42)
+    n = len(data["lineitem"]["l_orderkey"])
+    with tempfile.TemporaryDirectory() as tmp:
+        create = os.path.join(tmp, "create.sql")
+        stm = []
+        for name in ("lineitem", "orders", "customer"):
+            fields = []
+            for c, k, a in tpch.SCHEMAS[name]:
+                ty = {"int": "int", "date": "date"}.get(k) or (f"decimal(12,{a})" if k == "dec" else f"{k}({a})")
+                fields.append(f"{c} {ty}")
+            stm.append(f"create table {name} ( " + ", ".join(fields) + " )")
+        with open(create, "w") as f:
+            f.write(";\n".join(stm) + ";\n")
+        args = [exe, "--quiet", f"exec {create}"]
+        for name in ("lineitem", "orders", "customer"):
+            p = os.path.join(tmp, name + ".bin")
+            tpch.to_rows(name, data[name]).tofile(p)
+            args.append(f"binload {name} {p}")
+        args += [f"threads={threads}", f"repeat {reps}"]
+        for q in QUERIES:
+            args.append(" ".join(SQL[q].split()))
+        t0 = time.perf_counter()
+        r = subprocess.run(args, capture_output=True, text=True, timeout=1500)
+        wall = time.perf_counter() - t0
+    ms = [float(l.split("execute_ms=")[1]) for l in r.stdout.split("\n") if l.startswith("#select")]
+    if len(ms) != reps * len(QUERIES):
+        raise RuntimeError("reference run failed: " + r.stdout[-400:] + r.stderr[-400:])
+    per_q = {q: ms[i * reps:(i + 1) * reps] for i, q in enumerate(QUERIES)}
+    return {"kind": kind, "rows": n, "per_query_ms": per_q, "wall_s": wall, "threads": threads}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--sf", type=float, default=float(os.environ.get("RESQL_BENCH_SF", "100")))
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--sample-sf", type=float, default=0.5, help="scale factor of the CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    cores = os.cpu_count() or 1
+
+    # ---------------- reference arm: CPU only, rank 0 only ------------------------------------
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        res = run_reference(a.sample_sf, a.steps + a.warmup, cores)
+        if res is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/resql-oracle not built"}))
+            return 0
+        step_ms = [sum(res["per_query_ms"][q][i] for q in QUERIES) for i in range(a.warmup, a.warmup + a.steps)]
+        t = sum(step_ms) / 1e3
+        value = 3.0 * res["rows"] * a.steps / t
+        sample = f"TPC-H-shaped SF{a.sample_sf} ({res['rows']} lineitem rows), Q1+Q6+Q3, reference JIT, threads={cores}"
+        print(json.dumps({
+            "impl": "reference", "metric": "tpch_q1_q6_q3_lineitem_tuples_per_s", "value": value, "unit": "tuples/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": f"TPC-H SF{a.sf:g} Q1+Q6+Q3 (bounded CPU sample: SF{a.sample_sf})", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "tuples/s", "cores": cores, "kind": res["kind"], "sample": sample},
+            "e2e": {"value": value, "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "queries": {q: {"ms": statistics.median(res["per_query_ms"][q][a.warmup:]),
+                            "tuples_per_s": res["rows"] / (statistics.median(res["per_query_ms"][q][a.warmup:]) / 1e3)} for q in QUERIES},
+        }))
+        return 0
+
+    # ---------------- our arm --------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    from resql_b200 import Engine, Plan
+    from resql_b200 import native as N
+    from resql_b200 import tpch_device as TD
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(local_rank)
+    if world > 1:
+        uid = [eng.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.dist_init(rank, world, uid[0])
+    flags = N.RQ_PLAN_SHARDED if world > 1 else 0
+
+    orders, li, cust = TD.gen_orders_lineitem(a.sf, 42, dev, rank=rank, world=world)
+    torch.cuda.synchronize()
+    n_local = li["l_orderkey"].numel()
+    n_total = n_local
+    if world > 1:
+        t = torch.tensor([n_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        n_total = int(t.item())
+
+    plans = {q: load_plan(q) for q in QUERIES}
+    src = {"lineitem": li, "orders": orders, "customer": cust}
+
+    def make_tables(d, cols_of):
+        tabs = {}
+        for t in d["tables"]:
+            tabs[t["name"]] = cols_of(t["name"], t["columns"])
+        return tabs
+
+    def dev_table(name, cols):
+        n = src[name][cols[0]].shape[0]
+        return eng.upload_device(name, TD.as_device_columns(src[name], cols), n, borrow=True)
+
+    resident = {q: make_tables(plans[q], dev_table) for q in QUERIES}
+    cplans = {q: Plan(plans[q]) for q in QUERIES}
+
+    def step_resident():
+        out = {}
+        for q in QUERIES:
+            out[q] = eng.execute(cplans[q], resident[q], flags)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step_resident()
+    launches = 0
+    per_q = {q: {"kernel_ms": [], "scan_ms": [], "nccl_ms": []} for q in QUERIES}
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            r = step_resident()
+            for q in QUERIES:
+                tm = r[q][1]
+                launches += tm.kernel_launches
+                per_q[q]["kernel_ms"].append(tm.kernel_ms)
+                per_q[q]["scan_ms"].append(tm.scan_kernel_ms)
+                per_q[q]["nccl_ms"].append(tm.nccl_ms)
+        barrier()
+        dt = time.perf_counter() - t0
+    last = r
+    clocks = clk.summary()
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    value = 3.0 * n_total * a.steps / dt
+
+    # ---- independent check at full size: the same queries evaluated with torch int64 ops -------
+    checks = {}
+    if world == 1:
+        m = (li["l_shipdate"] >= 19940101) & (li["l_shipdate"] < 19950101) & (li["l_discount"] >= 5) & \
+            (li["l_discount"] <= 7) & (li["l_quantity"] < 24)
+        want = int((li["l_extendedprice"] * li["l_discount"])[m].sum().item())
+        got = int(last["q6"][0].columns[0][0]) if last["q6"][0].n_rows else None
+        checks["q6_vs_torch"] = (got == want)
+        m1 = li["l_shipdate"] <= 19980902
+        key = li["l_returnflag"].to(torch.int64) * 256 + li["l_linestatus"].to(torch.int64)
+        charge = li["l_extendedprice"] * (100 - li["l_discount"]) * (100 + li["l_tax"])
+        ok = True
+        res1 = last["q1"][0]
+        for i in range(res1.n_rows):
+            kk = int(res1.columns[0][i]) * 256 + int(res1.columns[1][i])
+            sel = m1 & (key == kk)
+            ok &= int(res1.columns[9][i]) == int(sel.sum().item())
+            ok &= int(res1.columns[5][i]) == int(charge[sel].sum().item())
+            ok &= int(res1.columns[2][i]) == int(li["l_quantity"][sel].sum().item())
+        checks["q1_vs_torch"] = bool(ok) and res1.n_rows > 0
+        del m, m1, key, charge
+
+    # ---- e2e: host buffers through the C ABI, H2D inside the timed region -------------------------
+    e2e = None
+    if not a.no_e2e:
+        host = {}
+        h2d = 0
+        for name in ("lineitem", "orders", "customer"):
+            used = []
+            for q in QUERIES:
+                for t in plans[q]["tables"]:
+                    if t["name"] == name:
+                        used += [c for c in t["columns"] if c not in used]
+            host[name] = {}
+            for c in used:
+                x = src[name][c]
+                hp = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+                hp.copy_(x)
+                host[name][c] = hp
+                h2d += hp.numel() * hp.element_size()
+        torch.cuda.synchronize()
+
+        def host_table(name, cols):
+            import numpy as np
+            d = {}
+            for c in cols:
+                arr = host[name][c].numpy()
+                if arr.ndim == 2:
+                    arr = arr.view(f"S{arr.shape[1]}").reshape(-1)
+                d[c] = arr
+            return eng.upload(name, d)
+
+        def step_e2e():
+            d2h = 0
+            up = {}
+            for q in QUERIES:
+                tabs = {}
+                for t in plans[q]["tables"]:
+                    key = (t["name"], tuple(t["columns"]))
+                    if key not in up:
+                        up[key] = host_table(t["name"], t["columns"])
+                    tabs[t["name"]] = up[key]
+                res, _ = eng.execute(cplans[q], tabs, flags)
+                d2h += sum(c.nbytes for c in res.columns)
+            for h in up.values():
+                h.free()
+            return d2h
+
+        for _ in range(2):
+            step_e2e()
+        e_steps = max(2, min(a.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            d2h = step_e2e()
+        barrier()
+        et = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([et], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            et = float(t.item())
+        # each query uploads the columns it scans (shared uploads counted once per step)
+        h2d_step = 0
+        seen = set()
+        for q in QUERIES:
+            for t in plans[q]["tables"]:
+                key = (t["name"], tuple(t["columns"]))
+                if key in seen:
+                    continue
+                seen.add(key)
+                for c in t["columns"]:
+                    h2d_step += host[t["name"]][c].numel() * host[t["name"]][c].element_size()
+        e2e = {"value": 3.0 * n_total * e_steps / et, "unit": "tuples/s", "h2d_bytes_per_step": int(h2d_step),
+               "d2h_bytes_per_step": int(d2h), "steps": e_steps, "ms_per_step": 1e3 * et / e_steps}
+        del host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    qinfo = {}
+    for q in QUERIES:
+        scan = statistics.median(per_q[q]["scan_ms"])
+        kern = statistics.median(per_q[q]["kernel_ms"])
+        qinfo[q] = {"kernel_ms": kern, "lineitem_scan_kernel_ms": scan,
+                    "nccl_ms": statistics.median(per_q[q]["nccl_ms"]),
+                    "tuples_per_s": n_total / (kern / 1e3) if kern > 0 else None}
+    # dominant kernel: the Q1 lineitem scan (38 algorithmic bytes per tuple)
+    q1_scan_ms = qinfo["q1"]["lineitem_scan_kernel_ms"]
+    achieved = (n_local * BYTES_PER_TUPLE["q1"]) / (q1_scan_ms / 1e3) / 1e9 if q1_scan_ms > 0 else 0.0
+    for q in ("q1", "q6"):
+        ms = qinfo[q]["lineitem_scan_kernel_ms"]
+        qinfo[q]["hbm_frac_of_measured"] = (n_local * BYTES_PER_TUPLE[q]) / (ms / 1e3) / 1e9 / peak if ms > 0 else None
+    out = {
+        "metric": "tpch_q1_q6_q3_lineitem_tuples_per_s", "value": value, "unit": "tuples/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"TPC-H SF{a.sf:g} Q1+Q6+Q3, lineitem {n_total} rows (row-range sharded over {world} GPU), "
+                               "dbgen-shaped synthetic generated in HBM, seed 42",
+                   "l2": "inputs (>=14 GB per query) larger than the 126 MB L2", "timing": "wall clock between device syncs, max over ranks"},
+        "clocks": clocks, "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "rq_pipeline_kernel (Q1 lineitem scan->filter->aggregate)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_tuple": BYTES_PER_TUPLE["q1"],
+                     "tuples_per_launch": n_local, "launch_ms": q1_scan_ms},
+        "queries": qinfo, "checks": checks,
+    }
+    if e2e is not None:
+        out["e2e"] = e2e
+    if not a.no_cpu:
+        try:
+            ref = run_reference(a.sample_sf, 3, cores)
+            if ref is not None:
+                t = sum(statistics.median(ref["per_query_ms"][q]) for q in QUERIES) / 1e3
+                out["cpu_baseline"] = {
+                    "value": 3.0 * ref["rows"] / t, "unit": "tuples/s", "cores": cores, "kind": ref["kind"],
+                    "sample": f"TPC-H-shaped SF{a.sample_sf} ({ref['rows']} lineitem rows), Q1+Q6+Q3, reference JIT threads={cores}, median of 3",
+                    "per_query_ms": {q: statistics.median(ref["per_query_ms"][q]) for q in QUERIES}}
+        except Exception as e:  # the baseline is reported, never required for the GPU number
+            out["cpu_baseline"] = {"value": None, "unit": "tuples/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
