@@ -7,7 +7,7 @@ LIB = resql_b200/libresql_b200.so
 
 all: $(LIB)
 
-$(LIB): $(CSRC)/engine.cu $(CSRC)/engine_exec.inl $(CSRC)/pipeline_kernel.cuh $(CSRC)/hash_kernels.cuh \
+$(LIB): $(CSRC)/engine.cu $(CSRC)/engine_exec.inl $(CSRC)/scan_kernel.cuh $(CSRC)/device_util.cuh $(CSRC)/hash_kernels.cuh \
         $(CSRC)/sort_kernels.cuh $(CSRC)/rq_internal.h $(CSRC)/dist.h include/resql_b200.h
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/engine.cu -ldl
 

@@ -20,7 +20,7 @@
 
 #include "../../include/resql_b200.h"
 #include "rq_internal.h"
-#include "pipeline_kernel.cuh"
+#include "scan_kernel.cuh"
 #include "sort_kernels.cuh"
 #include "hash_kernels.cuh"
 #include "dist.h"
@@ -103,6 +103,7 @@ struct Engine {
 static Engine E;
 
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static constexpr int kSmemMax = 227 * 1024;
 
 // ------------------------------------------------------------------------------------------
 // lifecycle
@@ -125,13 +126,14 @@ extern "C" int rq_init(int device) {
         CK(cudaStreamCreateWithFlags(&E.copy_stream, cudaStreamNonBlocking));
         for (auto& e : E.ev) CK(cudaEventCreate(&e));
         CK(cudaMalloc(&E.g_state, sizeof(uint32_t) * kGroupTableCap));
-        CK(cudaMalloc(&E.g_keys, sizeof(int64_t) * kGroupTableCap * kMaxKeys));
+        CK(cudaMalloc(&E.g_keys, sizeof(int64_t) * kGroupTableCap));
         CK(cudaMalloc(&E.g_acc, sizeof(int64_t) * kGroupTableCap * kMaxAggs));
         CK(cudaMalloc(&E.g_kinds, kMaxAggs));
         CK(cudaMalloc(&E.flags, 64));
         CK(cudaMallocHost(&E.h_flags, 64));
-        CK(cudaFuncSetAttribute(rq_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                227 * 1024));
+        CK(cudaFuncSetAttribute(rq_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        CK(cudaFuncSetAttribute(rq_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        CK(cudaFuncSetAttribute(rq_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         E.init = true;
         return RQ_OK;
     } catch (RqError& e) {
@@ -189,7 +191,7 @@ extern "C" int rq_table_upload(const char* name, int32_t n_cols, const rq_column
         const bool dev = flags & RQ_DEVICE_PTR;
         const bool borrow = dev && (flags & RQ_BORROW);
         t->borrowed = borrow;
-        t->cap_rows = borrow ? n_rows : round_up(std::max<int64_t>(n_rows, 1), kTileRows);
+        t->cap_rows = borrow ? n_rows : round_up(std::max<int64_t>(n_rows, 1), kPadRows);
         for (int c = 0; c < n_cols; c++) {
             if (!valid_col(cols[c].type, cols[c].width))
                 raise(RQ_ERR_INVALID, "rq_table_upload: column %d has bad type/width %d/%d", c, cols[c].type, cols[c].width);
@@ -239,7 +241,7 @@ extern "C" int rq_table_upload_rows(const char* name, int32_t n_cols, const int3
         }
         t->name = name ? name : "";
         t->n_rows = n_rows;
-        t->cap_rows = round_up(std::max<int64_t>(n_rows, 1), kTileRows);
+        t->cap_rows = round_up(std::max<int64_t>(n_rows, 1), kPadRows);
         for (int c = 0; c < n_cols; c++) {
             if (!valid_col(types[c], widths[c]) || offsets[c] < 0 || offsets[c] + widths[c] > tuple_size)
                 raise(RQ_ERR_INVALID, "rq_table_upload_rows: column %d bad type/width/offset", c);
@@ -304,11 +306,6 @@ struct PipeOut {                    // what a finished pipeline left on the devi
     std::vector<int> payload_sql_type, payload_sql_width;
 };
 
-struct Lowered {
-    KParams P;
-    int sink_impl = 0;   // 1 low-card agg, 2 hash agg, 3 build, 4 materialize
-};
-
 bool is_leaf(int op) { return op == RQ_OP_COL || op == RQ_OP_CONST || op == RQ_OP_CONST_STR; }
 bool is_binary(int op) {
     switch (op) {
@@ -346,6 +343,21 @@ uint8_t dop_right(int op) {
     }
     return D_NOP;
 }
+// selection-fused compare: column CMP constant (constant on the right / on the left)
+uint8_t fcmp_left(int op) {
+    switch (op) {
+        case RQ_OP_LT: return D_FLT; case RQ_OP_LE: return D_FLE; case RQ_OP_GT: return D_FGT;
+        case RQ_OP_GE: return D_FGE; case RQ_OP_EQ: return D_FEQ; case RQ_OP_NEQ: return D_FNE;
+    }
+    return 0;
+}
+uint8_t fcmp_right(int op) {
+    switch (op) {
+        case RQ_OP_LT: return D_FGT; case RQ_OP_LE: return D_FGE; case RQ_OP_GT: return D_FLT;
+        case RQ_OP_GE: return D_FLE; case RQ_OP_EQ: return D_FEQ; case RQ_OP_NEQ: return D_FNE;
+    }
+    return 0;
+}
 
 struct Operand {
     uint8_t src = S_NONE;
@@ -353,6 +365,13 @@ struct Operand {
     int64_t imm = 0;
 };
 
+struct HRef {            // host-level value reference of a sink (resolved to VRef by encode)
+    uint8_t kind = S_NONE;   // DSrc
+    uint16_t idx = 0;        // staged column / slot / imm-table index / string column
+};
+
+// Host-level program of one pipeline (what tests/vm_model.py executes) plus the pieces of
+// KParams that do not depend on the shared-memory layout.
 struct Lowerer {
     const rq_plan& plan;
     const rq_pipeline& pl;
@@ -362,6 +381,12 @@ struct Lowerer {
     KParams& P;
 
     int n;
+    std::vector<DInsn> prog;
+    std::vector<HRef> hkey, hout;
+    HRef hagg_src[kMaxAggs];
+    HRef hprobe_key[kMaxProbes][kMaxKeys];
+    int n_slots = 0;
+
     std::vector<int> uses;            // consumers per node
     std::vector<int> last_use;        // last consuming node index (n = sink)
     std::vector<char> sink_ref;       // referenced by the sink (needs a slot unless leaf)
@@ -369,6 +394,7 @@ struct Lowerer {
     std::vector<Operand> leaf_op;     // operand descriptor of leaves
     std::vector<int> staged_of_col;   // source column -> staged index / str index
     std::vector<int> free_slots;
+    std::vector<char> fused;          // FILTER nodes folded into a selection-fused compare
     int acc_node = -1;
     int n_imm = 0;
 
@@ -381,9 +407,10 @@ struct Lowerer {
     }
 
     void emit(uint8_t op, Operand o = Operand(), uint16_t aux = 0) {
-        if (P.n_insn >= kMaxInsn) raise(RQ_ERR_UNSUPPORTED, "program longer than %d instructions", kMaxInsn);
-        DInsn& in = P.insn[P.n_insn++];
+        if ((int)prog.size() >= kMaxInsn - 1) raise(RQ_ERR_UNSUPPORTED, "program longer than %d instructions", kMaxInsn - 1);
+        DInsn in;
         in.op = op; in.src = o.src; in.flags = 0; in.dst = 0; in.idx = o.idx; in.aux = aux; in.imm = o.imm;
+        prog.push_back(in);
     }
 
     Operand operand_of(int node) {
@@ -392,8 +419,8 @@ struct Lowerer {
         Operand o; o.src = S_SLOT; o.idx = (uint16_t)slot[node];
         return o;
     }
-    VRef vref_of(int node) {
-        VRef v; v.pad = 0;
+    HRef href_of(int node) {
+        HRef v;
         if (is_leaf(pl.nodes[node].op)) {
             Operand o = leaf_op[node];
             if (o.src == S_IMM) {
@@ -410,8 +437,8 @@ struct Lowerer {
 
     int alloc_slot() {
         if (!free_slots.empty()) { int s = free_slots.back(); free_slots.pop_back(); return s; }
-        if (P.n_slots >= kMaxSlots) raise(RQ_ERR_UNSUPPORTED, "expression needs more than %d live temporaries", kMaxSlots);
-        return P.n_slots++;
+        if (n_slots >= kMaxSlots) raise(RQ_ERR_UNSUPPORTED, "expression needs more than %d live temporaries", kMaxSlots);
+        return n_slots++;
     }
     void release_dead(int at) {   // free slots of nodes whose last use is `at`
         for (int i = 0; i < n; i++)
@@ -420,7 +447,7 @@ struct Lowerer {
 
     void prepare() {
         uses.assign(n, 0); last_use.assign(n, -1); sink_ref.assign(n, 0); slot.assign(n, -1);
-        leaf_op.assign(n, Operand());
+        leaf_op.assign(n, Operand()); fused.assign(n, 0);
         staged_of_col.assign(src.cols.size(), -1);
         auto use = [&](int i, int ref) { check_ref(i, ref); uses[ref]++; last_use[ref] = std::max(last_use[ref], i); };
         for (int i = 0; i < n; i++) {
@@ -474,10 +501,39 @@ struct Lowerer {
         for (int k = 0; k < pl.n_keys; k++) sink_use(pl.keys[k].node);
         for (int k = 0; k < pl.n_vals; k++)
             if (!(pl.sink_kind == RQ_SINK_AGG && pl.vals[k].kind == RQ_AGG_COUNT)) sink_use(pl.vals[k].node);
-        // stage layout
+        // stage layout: one warp tile of every staged column
         uint32_t off = 0;
-        for (int c = 0; c < P.n_cols; c++) { P.col_off[c] = off; off += kTileRows * P.col_w[c]; }
+        for (int c = 0; c < P.n_cols; c++) { P.col_off[c] = off; off += kTile * P.col_w[c]; }
         P.stage_bytes = off;
+        mark_fused_filters();
+    }
+
+    // FILTER(COL cmp CONST) where the compare has no other consumer becomes one instruction that
+    // leaves the accumulator alone. 4- and 1-byte columns compare in 32 bits, so the constant
+    // must fit (it always does for dates / flags; otherwise the generic form is used).
+    int fcmp_of(int f, Operand* col, int64_t* imm) const {
+        const rq_node& fl = pl.nodes[f];
+        if (fl.op != RQ_OP_FILTER) return 0;
+        const rq_node& cm = pl.nodes[fl.a];
+        if (uses[fl.a] != 1 || sink_ref[fl.a]) return 0;
+        if (!fcmp_left(cm.op)) return 0;
+        const int xo = pl.nodes[cm.a].op, yo = pl.nodes[cm.b].op;
+        int code = 0, cn = -1, kn = -1;
+        if (xo == RQ_OP_COL && yo == RQ_OP_CONST) { code = fcmp_left(cm.op); cn = cm.a; kn = cm.b; }
+        else if (xo == RQ_OP_CONST && yo == RQ_OP_COL) { code = fcmp_right(cm.op); cn = cm.b; kn = cm.a; }
+        else return 0;
+        const Operand o = leaf_op[cn];
+        if (o.src != S_COL) return 0;
+        const int64_t k = leaf_op[kn].imm;
+        if (P.col_w[o.idx] != 8 && (k < INT32_MIN || k > INT32_MAX)) return 0;
+        *col = o; *imm = k;
+        return code;
+    }
+    void mark_fused_filters() {
+        for (int f = 0; f < n; f++) {
+            Operand o; int64_t k;
+            if (fcmp_of(f, &o, &k)) { fused[f] = 1; fused[pl.nodes[f].a] = 1; }
+        }
     }
 
     // ---- slot decision -------------------------------------------------------------------
@@ -486,7 +542,7 @@ struct Lowerer {
     // (using it as exactly one operand), or an aggregate fused right behind its input.
     bool clobbers(int j) const {
         const int op = pl.nodes[j].op;
-        return !is_leaf(op) && op != RQ_OP_FILTER && op != RQ_OP_PAYLOAD;
+        return !is_leaf(op) && op != RQ_OP_FILTER && op != RQ_OP_PAYLOAD && !fused[j];
     }
     int gpos = -1;                 // GROUP is emitted right after node gpos
     std::vector<std::vector<int>> aggs_of;   // node -> aggregate indices fed by it
@@ -502,7 +558,7 @@ struct Lowerer {
         }
         for (int i = 0; i < n; i++) {
             const int op = pl.nodes[i].op;
-            if (is_leaf(op) || op == RQ_OP_FILTER || op == RQ_OP_PROBE) continue;
+            if (is_leaf(op) || op == RQ_OP_FILTER || op == RQ_OP_PROBE || fused[i]) continue;
             if (op == RQ_OP_PAYLOAD) continue;   // slot handed out when the PROBE is emitted
             bool need = false;
             if (sink_ref[i]) {
@@ -533,8 +589,6 @@ struct Lowerer {
                     if (cnt != 1) need = true;
                 }
             }
-            // an aggregate fused behind node i clobbers nothing, but GROUP (emitted after gpos)
-            // reads keys through slots and keeps the accumulator intact as well
             if (need) slot[i] = -3;   // marker: allocate at emission
         }
     }

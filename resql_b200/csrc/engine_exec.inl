@@ -214,7 +214,7 @@ static void simplify_pipeline(const rq_pipeline& in, SimplePipe& sp) {
     sp.pl.keys = sp.keys.data();          sp.pl.vals = sp.vals.data();
 }
 
-enum SinkImpl { IMPL_LOWAGG = 1, IMPL_HASHAGG = 2, IMPL_BUILD = 3, IMPL_EMIT = 4 };
+enum SinkImpl { IMPL_LOWAGG = 1, IMPL_HASHAGG = 2, IMPL_BUILD = 3, IMPL_EMIT = 4, IMPL_REGAGG = 5 };
 
 static uint8_t agg_dop(int kind) {
     switch (kind) {
@@ -225,19 +225,19 @@ static uint8_t agg_dop(int kind) {
     }
 }
 
-// Emits the device program for one pipeline. `probes` describes the hash tables of PROBE nodes.
+// Emits the host-level program for one pipeline.
 static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
     KParams& P = L.P;
     const rq_pipeline& pl = L.pl;
     const int n = L.n;
-    L.lowagg = (impl == IMPL_LOWAGG);
+    L.lowagg = (impl == IMPL_LOWAGG || impl == IMPL_REGAGG);
     L.aggs_of.assign(n, {});
     L.gpos = -1;
     for (int i = 0; i < n; i++) {
         const int op = pl.nodes[i].op;
         if (op == RQ_OP_FILTER || op == RQ_OP_PROBE || op == RQ_OP_PAYLOAD) L.gpos = i;
     }
-    if (impl == IMPL_LOWAGG) {
+    if (L.lowagg) {
         for (int k = 0; k < pl.n_keys; k++) L.gpos = std::max(L.gpos, pl.keys[k].node);
         for (size_t u = 0; u < ad.kind.size(); u++)
             if (ad.node[u] >= 0) L.aggs_of[ad.node[u]].push_back((int)u);
@@ -245,10 +245,9 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
     L.decide_slots();
 
     auto emit_group = [&]() {
-        if (impl != IMPL_LOWAGG) return;
+        if (!L.lowagg) return;
         L.emit(D_GROUP);
-        P.nk = pl.n_keys;
-        for (int k = 0; k < pl.n_keys; k++) P.key[k] = L.vref_of(pl.keys[k].node);
+        for (int k = 0; k < pl.n_keys; k++) L.hkey.push_back(L.href_of(pl.keys[k].node));
         for (size_t u = 0; u < ad.kind.size(); u++) {
             if (ad.kind[u] == RQ_AGG_COUNT) { L.emit(D_AGG_COUNT, Operand(), (uint16_t)u); continue; }
             const int nd = ad.node[u];
@@ -263,10 +262,20 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
         bool computed = false;
         if (is_leaf(nd.op) || nd.op == RQ_OP_PAYLOAD) {
             // no instruction
+        } else if (L.fused[i] && nd.op != RQ_OP_FILTER) {
+            // compare folded into the selection that follows
         } else if (nd.op == RQ_OP_FILTER) {
-            // tests the accumulator, or an operand without disturbing the accumulator
-            if (L.acc_node != nd.a || is_leaf(pl.nodes[nd.a].op)) L.emit(D_FILTER, L.operand_of(nd.a));
-            else L.emit(D_FILTER);
+            Operand col; int64_t k;
+            const int fc = L.fused[i] ? L.fcmp_of(i, &col, &k) : 0;
+            if (fc) {
+                col.imm = k;
+                L.emit((uint8_t)fc, col);
+            } else if (L.acc_node != nd.a || is_leaf(pl.nodes[nd.a].op)) {
+                // tests an operand without disturbing the accumulator
+                L.emit(D_FILTER, L.operand_of(nd.a));
+            } else {
+                L.emit(D_FILTER);
+            }
         } else if (is_binary(nd.op)) {
             const int x = nd.a, y = nd.b;
             if (L.acc_node == x && x != y && !is_leaf(pl.nodes[x].op)) {
@@ -291,8 +300,8 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
             } else if (is_leaf(pl.nodes[nd.c].op)) {
                 tmp = L.alloc_slot();
                 L.emit(D_LD, L.operand_of(nd.c));
-                P.insn[P.n_insn - 1].flags |= 1;
-                P.insn[P.n_insn - 1].dst = (uint8_t)tmp;
+                L.prog.back().flags |= 1;
+                L.prog.back().dst = (uint8_t)tmp;
                 L.acc_node = -1;
                 else_ref = tmp;
             } else {
@@ -301,7 +310,7 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
             }
             if (L.acc_node != nd.a || is_leaf(pl.nodes[nd.a].op)) L.emit(D_LD, L.operand_of(nd.a));
             L.emit(D_SEL, L.operand_of(nd.b), (uint16_t)else_ref);
-            if (else_imm) P.insn[P.n_insn - 1].flags |= 2;
+            if (else_imm) L.prog.back().flags |= 2;
             if (tmp >= 0) L.free_slots.push_back(tmp);
             computed = true;
         } else if (nd.op == RQ_OP_PROBE) {
@@ -311,7 +320,7 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
             DProbe& pr = P.probe[P.n_probes];
             pr.ht = L.outs[nd.a].ht->d;
             if (nd.c != pr.ht.nk) raise(RQ_ERR_INVALID, "PROBE has %d keys, the build side %d", nd.c, pr.ht.nk);
-            for (int k = 0; k < nd.c; k++) pr.key[k] = L.vref_of(pl.args[nd.b + k]);
+            for (int k = 0; k < nd.c; k++) L.hprobe_key[P.n_probes][k] = L.href_of(pl.args[nd.b + k]);
             pr.single = (int32_t)(nd.imm & 1);
             pr.n_out = pr.ht.nv;
             memset(pr.out_slot, 0xff, sizeof(pr.out_slot));
@@ -332,10 +341,10 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
             if (L.slot[i] == -3) {
                 const int s = L.alloc_slot();
                 L.slot[i] = s;
-                P.insn[P.n_insn - 1].flags |= 1;
-                P.insn[P.n_insn - 1].dst = (uint8_t)s;
+                L.prog.back().flags |= 1;
+                L.prog.back().dst = (uint8_t)s;
             }
-            if (impl == IMPL_LOWAGG && i > L.gpos)
+            if (L.lowagg && i > L.gpos)
                 for (int u : L.aggs_of[i]) L.emit(agg_dop(ad.kind[u]), Operand(), (uint16_t)u);
         }
         L.release_dead(i);
@@ -344,28 +353,213 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
 
     if (impl == IMPL_BUILD || impl == IMPL_HASHAGG) {
         if (pl.n_keys > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
-        P.nk = pl.n_keys;
-        for (int k = 0; k < pl.n_keys; k++) P.key[k] = L.vref_of(pl.keys[k].node);
+        for (int k = 0; k < pl.n_keys; k++) L.hkey.push_back(L.href_of(pl.keys[k].node));
         if (impl == IMPL_BUILD) {
             if (pl.n_vals > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d payload columns", kMaxOut);
-            P.n_out = pl.n_vals;
-            for (int k = 0; k < pl.n_vals; k++) P.out[k] = L.vref_of(pl.vals[k].node);
+            for (int k = 0; k < pl.n_vals; k++) L.hout.push_back(L.href_of(pl.vals[k].node));
             L.emit(D_BUILD);
         } else {
             P.na = (int)ad.kind.size();
             for (int u = 0; u < P.na; u++) {
                 P.agg_kind[u] = (uint8_t)ad.kind[u];
-                if (ad.kind[u] != RQ_AGG_COUNT) P.agg_src[u] = L.vref_of(ad.node[u]);
+                if (ad.kind[u] != RQ_AGG_COUNT) L.hagg_src[u] = L.href_of(ad.node[u]);
             }
             L.emit(D_HAGG);
         }
     }
     if (impl == IMPL_EMIT) {
         if (pl.n_vals > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d output columns", kMaxOut);
-        P.n_out = pl.n_vals;
-        for (int k = 0; k < pl.n_vals; k++) P.out[k] = L.vref_of(pl.vals[k].node);
+        for (int k = 0; k < pl.n_vals; k++) L.hout.push_back(L.href_of(pl.vals[k].node));
         L.emit(D_EMIT);
     }
+}
+
+// ---- shared-memory layout and launch geometry --------------------------------------------
+// [mbarriers: kMaxWarps x kMaxStages][warp region 0][warp region 1]...; a warp region is
+// [stages][slots][lane-private accumulators]. As many warps as fit (latency hiding comes from
+// warps, bytes in flight from warps x stages), at least two stages when possible.
+static bool layout_smem(KParams& P, int n_slots, int acc_bytes, int max_warps) {
+    const uint32_t bars = kMaxWarps * kMaxStages * 8;
+    int bestW = 0, bestS = 0;
+    for (int S = 2; S <= kMaxStages; S++) {
+        uint32_t wb = (uint32_t)S * P.stage_bytes + (uint32_t)n_slots * kTile * 8 + (uint32_t)acc_bytes;
+        wb = (wb + 127) & ~127u;
+        if (wb == 0) wb = 128;
+        const int W = (int)std::min<int64_t>(max_warps, ((int64_t)kSmemMax - bars) / wb);
+        if (W > bestW) { bestW = W; bestS = S; }
+        else if (W == bestW && W > 0 && S <= 3) bestS = S;   // a third stage when it is free
+    }
+    if (bestW == 0) {   // single buffered as the last resort
+        uint32_t wb = P.stage_bytes + (uint32_t)n_slots * kTile * 8 + (uint32_t)acc_bytes;
+        wb = (wb + 127) & ~127u;
+        if (bars + wb > (uint32_t)kSmemMax) return false;
+        bestW = 1; bestS = 1;
+    }
+    P.stages = bestS;
+    P.warps = bestW;
+    P.n_slots = n_slots;
+    uint32_t wb = (uint32_t)bestS * P.stage_bytes + (uint32_t)n_slots * kTile * 8 + (uint32_t)acc_bytes;
+    wb = (wb + 127) & ~127u;
+    if (wb == 0) wb = 128;
+    P.warp_off = bars;
+    P.warp_bytes = wb;
+    P.slots_rel = (uint32_t)bestS * P.stage_bytes;
+    P.acc_rel = P.slots_rel + (uint32_t)n_slots * kTile * 8;
+    P.smem_bytes = bars + (uint32_t)bestW * wb;
+    return true;
+}
+
+// ---- encode: host-level program -> fused device instructions (needs the layout) -------------
+struct UOperand { uint8_t kind; uint8_t slot; uint32_t off; };
+
+static UOperand resolve(const KParams& P, uint8_t src, uint16_t idx) {
+    UOperand u{K_NONE, 0, 0};
+    switch (src) {
+        case S_COL:
+            u.kind = P.col_w[idx] == 8 ? K_M64 : (P.col_w[idx] == 4 ? K_M32 : K_M8);
+            u.off = P.col_off[idx];
+            break;
+        case S_SLOT: u.kind = K_M64; u.slot = 1; u.off = P.slots_rel + (uint32_t)idx * kTile * 8; break;
+        case S_IMM: u.kind = K_IMM; break;
+        case S_STR: u.kind = K_STR; u.off = (uint32_t)idx << 4; break;
+        default: break;
+    }
+    return u;
+}
+static VRef to_vref(const KParams& P, const HRef& h) {
+    VRef v; v.kind = K_NONE; v.slot = 0; v.off16 = 0;
+    if (h.kind == S_IMM) { v.kind = K_IMM; v.off16 = h.idx; return v; }
+    const UOperand u = resolve(P, h.kind, h.idx);
+    v.kind = u.kind; v.slot = u.slot; v.off16 = (uint16_t)(u.off >> 4);
+    return v;
+}
+
+static int bin_index(uint8_t op) {   // position in RQ_BINOPS, -1 if not a fusable binary op
+    switch (op) {
+        case D_ADD: return 0; case D_SUB: return 1; case D_RSUB: return 2; case D_MUL: return 3;
+        case D_AND: return 4; case D_OR: return 5; case D_LT: return 6; case D_LE: return 7;
+        case D_GT: return 8; case D_GE: return 9; case D_EQ: return 10; case D_NE: return 11;
+    }
+    return -1;
+}
+
+static void encode_program(const Lowerer& L, KParams& P) {
+    P.n_insn = 0;
+    auto push = [&](const UInsn& u) -> UInsn& {
+        if (P.n_insn >= kMaxInsn) raise(RQ_ERR_UNSUPPORTED, "program longer than %d instructions", kMaxInsn);
+        P.insn[P.n_insn] = u;
+        return P.insn[P.n_insn++];
+    };
+    for (size_t i = 0; i < L.prog.size(); i++) {
+        const DInsn& d = L.prog[i];
+        const UOperand o = resolve(P, d.src, d.idx);
+        UInsn u;
+        memset(&u, 0, sizeof(u));
+        u.flags = (d.flags & 1) ? UF_STORE : 0;
+        if (d.flags & 2) u.flags |= UF_ELSE_IMM;
+        if (o.slot) u.flags |= UF_SLOT;
+        u.dst = d.dst;
+        u.aux = (uint8_t)d.aux;
+        u.off16 = (uint16_t)(o.off >> 4);
+        u.imm = d.imm;
+        u.gop = d.op;
+        u.gsrc = o.kind;
+        const int bi = bin_index(d.op);
+        if (d.op == D_LD) {
+            u.code = o.kind == K_M64 ? U_LD_M64 : o.kind == K_M32 ? U_LD_M32 : o.kind == K_M8 ? U_LD_M8
+                   : o.kind == K_STR ? U_LD_STR : U_LD_IMM;
+        } else if (bi >= 0 && (o.kind == K_M64 || o.kind == K_IMM)) {
+            const int form = (o.kind == K_M64) ? 0 : 1;      // AM / AI
+            u.code = (uint8_t)(U_ADD_AM + 4 * bi + form);
+            // fuse a preceding plain 64-bit load: acc = m64 OP imm | m64 OP m64'
+            if (P.n_insn > 0) {
+                UInsn& pv = P.insn[P.n_insn - 1];
+                if (pv.code == U_LD_IMM && !(pv.flags & UF_STORE) && form == 0) {
+                    // acc = imm OP m64  ==  m64 OP' imm with the operands swapped
+                    static const int swapped[12] = {0, 2, 1, 3, 4, 5, 8, 9, 6, 7, 10, 11};
+                    UInsn f = u;
+                    f.code = (uint8_t)(U_ADD_AM + 4 * swapped[bi] + 2);   // MI
+                    f.imm = pv.imm;
+                    pv = f;
+                    continue;
+                }
+                if (pv.code == U_LD_M64 && !(pv.flags & UF_STORE)) {
+                    UInsn f = u;
+                    f.code = (uint8_t)(U_ADD_AM + 4 * bi + (form == 0 ? 3 : 2));   // MM / MI
+                    f.flags = (uint8_t)((u.flags & (UF_STORE | UF_ELSE_IMM)) | (pv.flags & UF_SLOT));
+                    f.off16 = pv.off16;
+                    if (form == 0) {
+                        f.imm = (int64_t)o.off;
+                        if (o.slot) f.flags |= UF_SLOT2;
+                    }
+                    pv = f;
+                    continue;
+                }
+            }
+        } else if (d.op == D_FILTER) {
+            u.code = (d.src == S_NONE) ? U_FILTER_A : U_FILTER_O;
+        } else if (d.op >= D_FLT && d.op <= D_FNE) {
+            const int ci = d.op - D_FLT;
+            if (o.kind == K_M64) u.code = (uint8_t)(U_FLT_M64 + ci);
+            else if (o.kind == K_M32) u.code = (uint8_t)(U_FLT_M32 + ci);
+            else if (o.kind == K_M8) u.code = (uint8_t)(U_FLT_M8 + ci);
+            else raise(RQ_ERR_INVALID, "internal: fused compare on a non-column operand");
+        } else if (d.op == D_GROUP) {
+            u.code = U_GROUP;
+        } else if (d.op == D_AGG_SUM && d.src == S_NONE) {
+            u.code = U_AGG_SUM_A;
+        } else if (d.op == D_AGG_SUM && o.kind == K_M64) {
+            u.code = U_AGG_SUM_M;
+        } else if (d.op == D_AGG_COUNT) {
+            u.code = U_AGG_COUNT;
+        } else if (d.op == D_AGG_SUM || d.op == D_AGG_MIN || d.op == D_AGG_MAX) {
+            u.code = U_AGG_GEN;
+        } else if (d.op == D_PROBE) {
+            u.code = U_PROBE;
+        } else if (d.op == D_HAGG) {
+            u.code = U_HAGG;
+        } else if (d.op == D_BUILD) {
+            u.code = U_BUILD;
+        } else if (d.op == D_EMIT) {
+            u.code = U_EMIT;
+        } else {
+            u.code = U_GEN;   // DIV, string compares, SEL, binary ops on narrow / string operands
+        }
+        push(u);
+    }
+    // sinks
+    P.nk = (int)L.hkey.size();
+    for (int k = 0; k < P.nk; k++) P.key[k] = to_vref(P, L.hkey[k]);
+    P.n_out = (int)L.hout.size();
+    for (int k = 0; k < P.n_out; k++) P.out[k] = to_vref(P, L.hout[k]);
+    for (int u = 0; u < kMaxAggs; u++) P.agg_src[u] = to_vref(P, L.hagg_src[u]);
+    for (int p = 0; p < P.n_probes; p++)
+        for (int k = 0; k < P.probe[p].ht.nk; k++) P.probe[p].key[k] = to_vref(P, L.hprobe_key[p][k]);
+}
+
+// packed group key of the low-cardinality paths: every key is a bit field of one 64-bit word
+static bool pack_group_key(const Lowerer& L, KParams& P, KeyUnpack& ku) {
+    memset(&ku, 0, sizeof(ku));
+    int total = 0;
+    ku.nk = (int)L.hkey.size();
+    if (ku.nk > kMaxKeys) return false;
+    for (int k = 0; k < ku.nk; k++) {
+        const HRef& h = L.hkey[k];
+        int bits = 64, sign = 1;
+        if (h.kind == S_COL) {
+            const int w = P.col_w[h.idx];
+            bits = 8 * w;
+            sign = (w == 1) ? 0 : 1;
+        } else if (h.kind == S_STR) {
+            return false;
+        }
+        if (total + bits > 64) return false;
+        P.key_shift[k] = (uint8_t)total; P.key_bits[k] = (uint8_t)bits;
+        ku.shift[k] = (uint8_t)total; ku.bits[k] = (uint8_t)bits; ku.sign[k] = (uint8_t)sign;
+        total += bits;
+    }
+    P.key32 = total <= 32 ? 1 : 0;
+    return true;
 }
 
 // ---- event pool -------------------------------------------------------------------------
@@ -384,7 +578,7 @@ static EventPair& event_pair(size_t i) {
 static std::unique_ptr<rq_table> new_intermediate(int n_cols, int64_t cap_rows) {
     std::unique_ptr<rq_table> t(new rq_table());
     t->n_rows = -1;
-    t->cap_rows = round_up(std::max<int64_t>(cap_rows, 1), kTileRows);
+    t->cap_rows = round_up(std::max<int64_t>(cap_rows, 1), kPadRows);
     for (int c = 0; c < n_cols; c++) {
         DevColumn dc;
         dc.type = RQ_I64;
@@ -404,29 +598,18 @@ static void set_types(rq_table& t, const rq_pipeline& pl) {
     for (int k = 0; k < pl.n_vals; k++) { t.sql_type.push_back(pl.vals[k].sql_type); t.sql_width.push_back(pl.vals[k].width); }
 }
 
-static void layout_smem(KParams& P, int na_unique, bool lowagg) {
-    uint32_t off = 128 + P.stages * P.stage_bytes;
-    off = (off + 127) & ~127u;
-    P.slots_off = off;
-    off += (uint32_t)P.n_slots * kTileRows * 8;
-    P.acc_off = off;
-    if (lowagg) off += (uint32_t)kWarps * P.G * na_unique * 32 * 8;
-    P.dict_off = off;
-    off += kWarps * kLowCardMaxGroups * kMaxKeys * 8 + kWarps * 4;
-    off = (off + 15) & ~15u;
-    P.smem_bytes = off;
-}
+static int max_warps_of(int gr) { return (gr == 4 ? ScanCfg<4>::kThreads : gr == 1 ? ScanCfg<1>::kThreads : ScanCfg<0>::kThreads) / 32; }
 
-static void launch_pipeline(const KParams& P, int64_t cap_rows, rq_timings* tm, bool is_scan,
+static void launch_pipeline(const KParams& P, int gr, int64_t rows, rq_timings* tm, bool is_scan,
                             size_t& ev_idx, std::vector<std::pair<size_t, bool>>& ev_used) {
-    int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, rq_pipeline_kernel, kThreads, P.smem_bytes));
-    if (bps < 1) raise(RQ_ERR_UNSUPPORTED, "pipeline needs %u bytes of shared memory", P.smem_bytes);
-    const int64_t tiles = std::max<int64_t>(1, (cap_rows + kTileRows - 1) / kTileRows);
-    const int grid = (int)std::min<int64_t>(tiles, (int64_t)E.sm_count * bps);
+    const int64_t tiles = std::max<int64_t>(1, (rows + kTile - 1) / kTile);
+    const int W = P.warps;
+    const int grid = (int)std::min<int64_t>((tiles + W - 1) / W, (int64_t)E.sm_count);
     EventPair& ep = event_pair(ev_idx);
     CK(cudaEventRecord(ep.a, E.stream));
-    rq_pipeline_kernel<<<grid, kThreads, P.smem_bytes, E.stream>>>(P);
+    if (gr == 4) rq_scan_kernel<4><<<grid, 32 * W, P.smem_bytes, E.stream>>>(P);
+    else if (gr == 1) rq_scan_kernel<1><<<grid, 32 * W, P.smem_bytes, E.stream>>>(P);
+    else rq_scan_kernel<0><<<grid, 32 * W, P.smem_bytes, E.stream>>>(P);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ep.b, E.stream));
     ev_used.push_back({ev_idx, is_scan});
@@ -476,7 +659,10 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
     AggDedup ad;
     if (pl.sink_kind == RQ_SINK_AGG) {
         ad = dedup_aggs(pl);
-        if (pl.n_keys <= 4 && !has_str_key(pl)) impls.push_back(IMPL_LOWAGG);
+        if (!has_str_key(pl)) {
+            if ((int)ad.kind.size() <= kNAR) impls.push_back(IMPL_REGAGG);
+            impls.push_back(IMPL_LOWAGG);
+        }
         impls.push_back(IMPL_HASHAGG);
     } else if (pl.sink_kind == RQ_SINK_MATERIALIZE) {
         impls.push_back(IMPL_EMIT);
@@ -485,6 +671,7 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
     } else {
         raise(RQ_ERR_INVALID, "pipeline %d: bad sink kind %d", pi, pl.sink_kind);
     }
+    const int64_t src_rows = src->n_rows >= 0 ? src->n_rows : src->cap_rows;
 
     for (size_t attempt = 0; attempt < impls.size(); attempt++) {
         const int impl = impls[attempt];
@@ -501,41 +688,44 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
         emit_program(L, impl, ad);
 
         std::unique_ptr<rq_table> out;
-        if (impl == IMPL_LOWAGG) {
+        int gr = 0;
+        KeyUnpack ku;
+        memset(&ku, 0, sizeof(ku));
+        if (impl == IMPL_REGAGG || impl == IMPL_LOWAGG) {
             P.na = (int)ad.kind.size();
             for (int u = 0; u < P.na; u++) P.agg_kind[u] = (uint8_t)ad.kind[u];
             P.g_state = E.g_state; P.g_keys = E.g_keys; P.g_acc = E.g_acc;
-            bool fits = false;
-            for (int st = kStages; st >= 1 && !fits; st--) {
-                P.stages = st;
-                for (int G = (pl.n_keys == 0 ? 1 : kLowCardMaxGroups); G >= (st > 1 ? 4 : 1); G >>= 1) {
+            if (!pack_group_key(L, P, ku)) continue;     // keys wider than 64 bits: hash aggregation
+            if (impl == IMPL_REGAGG) {
+                gr = pl.n_keys == 0 ? 1 : kRegGroups;
+                P.G = 0;
+                if (!layout_smem(P, L.n_slots, 0, max_warps_of(gr))) continue;
+            } else {
+                bool fits = false;
+                for (int G = (pl.n_keys == 0 ? 1 : kLowCardMaxGroups); G >= 1 && !fits; G >>= 1) {
                     P.G = G;
-                    layout_smem(P, P.na, true);
-                    if (P.smem_bytes <= 227 * 1024) { fits = true; break; }
+                    fits = layout_smem(P, L.n_slots, G * P.na * 32 * 8, max_warps_of(0)) && (P.stages > 1 || G == 1);
                     if (pl.n_keys == 0) break;
                 }
+                if (!fits) continue;
             }
-            if (!fits) continue;
         } else {
             P.G = 0;
-            P.stages = kStages;
-            layout_smem(P, 0, false);
-            if (P.smem_bytes > 227 * 1024) { P.stages = 1; layout_smem(P, 0, false); }
-            if (P.smem_bytes > 227 * 1024) raise(RQ_ERR_UNSUPPORTED, "pipeline %d needs %u bytes of shared memory", pi, P.smem_bytes);
+            if (!layout_smem(P, L.n_slots, 0, max_warps_of(0)))
+                raise(RQ_ERR_UNSUPPORTED, "pipeline %d does not fit in shared memory", pi);
         }
+        encode_program(L, P);
         lower_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
         CK(cudaMemsetAsync(E.flags, 0, 24, E.stream));
-        if (impl == IMPL_LOWAGG) {
+        if (impl == IMPL_REGAGG || impl == IMPL_LOWAGG) {
             CK(cudaMemcpyAsync(E.g_kinds, P.agg_kind, kMaxAggs, cudaMemcpyHostToDevice, E.stream));
             rq_group_table_init<<<(kGroupTableCap + 255) / 256, 256, 0, E.stream>>>(E.g_state, E.g_acc, E.g_kinds, P.na);
             if (tm) tm->kernel_launches++;
-            launch_pipeline(P, src->cap_rows > 0 ? (src->n_rows >= 0 ? src->n_rows : src->cap_rows) : 0, tm, is_scan, ev_idx, ev_used);
+            launch_pipeline(P, gr, src_rows, tm, is_scan, ev_idx, ev_used);
             // dense output: keys, then every requested aggregate (duplicates expanded)
             const int ncols = pl.n_keys + pl.n_vals;
             out = new_intermediate(ncols, kGroupTableCap);
-            std::vector<int64_t*> h_cols(ncols);
-            // compaction writes unique aggregates; build the column map keys + uniq
             const int nuniq = P.na;
             std::unique_ptr<rq_table> dense = new_intermediate(pl.n_keys + nuniq, kGroupTableCap);
             std::vector<int64_t*> h_dense(pl.n_keys + nuniq);
@@ -544,12 +734,12 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
             CK(cudaMalloc(&d_ptrs, sizeof(int64_t*) * h_dense.size()));
             CK(cudaMemcpyAsync(d_ptrs, h_dense.data(), sizeof(int64_t*) * h_dense.size(), cudaMemcpyHostToDevice, E.stream));
             rq_group_table_compact<<<(kGroupTableCap + 255) / 256, 256, 0, E.stream>>>(
-                E.g_state, E.g_keys, E.g_acc, pl.n_keys, nuniq, d_ptrs, dense->d_n_rows);
+                E.g_state, E.g_keys, E.g_acc, ku, nuniq, d_ptrs, dense->d_n_rows);
             if (tm) tm->kernel_launches++;
             CK(cudaGetLastError());
             check_flags("aggregation pipeline");
             cudaFree(d_ptrs);
-            if (E.h_flags[0]) continue;   // more groups than the low-cardinality path tracks
+            if (E.h_flags[0]) continue;   // more groups than this path tracks: next implementation
             // expand duplicates by aliasing: copy the columns (tiny)
             for (int k = 0; k < pl.n_keys; k++)
                 CK(cudaMemcpyAsync(out->cols[k].d, dense->cols[k].d, (size_t)kGroupTableCap * 8, cudaMemcpyDeviceToDevice, E.stream));
@@ -594,7 +784,7 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
                 }
                 P.ht = ht->d;
                 CK(cudaMemsetAsync(E.flags, 0, 24, E.stream));
-                launch_pipeline(P, rows_bound, tm, is_scan, ev_idx, ev_used);
+                launch_pipeline(P, 0, rows_bound, tm, is_scan, ev_idx, ev_used);
                 check_flags(impl == IMPL_BUILD ? "join build pipeline" : "hash aggregation pipeline");
                 if (!E.h_flags[1]) break;
                 if (cap >= cap_max) raise(RQ_ERR_RUNTIME, "pipeline %d: hash table overflow at capacity %llu", pi, (unsigned long long)cap);
@@ -649,7 +839,7 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
                 P.out_cap = out->cap_rows;
                 P.out_count = (unsigned long long*)out->d_n_rows;
                 for (int k = 0; k < pl.n_vals; k++) P.out_col[k] = (int64_t*)out->cols[k].d;
-                launch_pipeline(P, src->n_rows >= 0 ? src->n_rows : src->cap_rows, tm, is_scan, ev_idx, ev_used);
+                launch_pipeline(P, 0, src_rows, tm, is_scan, ev_idx, ev_used);
                 check_flags("materialize pipeline");
                 int64_t produced = 0;
                 CK(cudaMemcpy(&produced, out->d_n_rows, 8, cudaMemcpyDeviceToHost));
@@ -876,9 +1066,20 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
         AggDedup ad;
         if (sp.pl.sink_kind == RQ_SINK_AGG) ad = dedup_aggs(sp.pl);
         emit_program(L, impl, ad);
+        // the device encoding must succeed as well (layout + fusion), even though the model
+        // executes the host-level form
+        P.na = (int)ad.kind.size();
+        KeyUnpack ku;
+        const bool packed = pack_group_key(L, P, ku);
+        const int gr = impl == IMPL_REGAGG ? (sp.pl.n_keys == 0 ? 1 : kRegGroups) : 0;
+        if (!layout_smem(P, L.n_slots, impl == IMPL_LOWAGG ? P.na * 32 * 8 : 0, max_warps_of(gr)))
+            raise(RQ_ERR_UNSUPPORTED, "pipeline does not fit in shared memory");
+        encode_program(L, P);
         std::string s;
         char line[256];
-        snprintf(line, sizeof line, "cols %d strcols %d slots %d insn %d nk %d nout %d\n", P.n_cols, P.n_strcols, P.n_slots, P.n_insn, P.nk, P.n_out);
+        snprintf(line, sizeof line, "cols %d strcols %d slots %d insn %d nk %d nout %d uinsn %d warps %d stages %d packed %d\n",
+                 P.n_cols, P.n_strcols, L.n_slots, (int)L.prog.size(), (int)L.hkey.size(), (int)L.hout.size(),
+                 P.n_insn, P.warps, P.stages, packed ? 1 : 0);
         s += line;
         for (int c = 0; c < P.n_cols; c++) {
             int srccol = -1;
@@ -894,13 +1095,18 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
             snprintf(line, sizeof line, "strcol %d src %d w %u\n", c, srccol, P.str_w[c]);
             s += line;
         }
-        for (int i = 0; i < P.n_insn; i++) {
-            const DInsn& in = P.insn[i];
+        for (size_t i = 0; i < L.prog.size(); i++) {
+            const DInsn& in = L.prog[i];
             snprintf(line, sizeof line, "insn %d %d %d %d %d %d %lld\n", in.op, in.src, in.flags, in.dst, in.idx, in.aux, (long long)in.imm);
             s += line;
         }
-        for (int k = 0; k < P.nk; k++) { snprintf(line, sizeof line, "key %d %d\n", P.key[k].kind, P.key[k].idx); s += line; }
-        for (int k = 0; k < P.n_out; k++) { snprintf(line, sizeof line, "out %d %d\n", P.out[k].kind, P.out[k].idx); s += line; }
+        for (int i = 0; i < P.n_insn; i++) {
+            const UInsn& u = P.insn[i];
+            snprintf(line, sizeof line, "uinsn %d %d %d %d %d %d %d %lld\n", u.code, u.flags, u.dst, u.aux, u.gop, u.gsrc, u.off16, (long long)u.imm);
+            s += line;
+        }
+        for (size_t k = 0; k < L.hkey.size(); k++) { snprintf(line, sizeof line, "key %d %d\n", L.hkey[k].kind, L.hkey[k].idx); s += line; }
+        for (size_t k = 0; k < L.hout.size(); k++) { snprintf(line, sizeof line, "out %d %d\n", L.hout[k].kind, L.hout[k].idx); s += line; }
         for (int k = 0; k < kMaxImm; k++) { snprintf(line, sizeof line, "imm %d %lld\n", k, (long long)P.imm[k]); s += line; }
         for (size_t u = 0; u < ad.kind.size(); u++) { snprintf(line, sizeof line, "agg %d %d\n", (int)u, ad.kind[u]); s += line; }
         for (size_t k = 0; k < ad.uniq_of.size(); k++) { snprintf(line, sizeof line, "aggmap %d %d\n", (int)k, ad.uniq_of[k]); s += line; }

@@ -4,12 +4,16 @@
 
 namespace rq {
 
-// ---- tile geometry of the pipeline kernel ------------------------------------------------
-constexpr int kThreads       = 256;                 // threads per CTA (8 warps)
-constexpr int kRowsPerThread = 4;                   // register tile: 4 tuples per thread
-constexpr int kTileRows      = kThreads * kRowsPerThread;   // 1024 tuples per staged tile
-constexpr int kStages        = 2;                   // TMA double buffering
-constexpr int kWarps         = kThreads / 32;
+// ---- geometry of the scan kernel ------------------------------------------------------------
+// Every WARP is an independent pipeline: it owns a ring of TMA stages in shared memory, each
+// holding one warp tile (256 tuples of every scanned column), and interprets the program over
+// a register tile of 8 tuples per lane. Lane l owns tuples {64k + 2l, 64k + 2l + 1 : k=0..3} of
+// the tile, so every operand fetch is a conflict-free 16/8/2-byte vector load.
+constexpr int kR          = 8;                  // tuples per lane per tile
+constexpr int kTile       = 32 * kR;            // 256 tuples per warp tile
+constexpr int kPadRows    = 1024;               // owned tables are padded to this many rows
+constexpr int kMaxStages  = 4;                  // TMA ring depth per warp
+constexpr int kMaxWarps   = 16;                 // warps per CTA (one persistent CTA per SM)
 
 constexpr int kMaxStagedCols = 16;
 constexpr int kMaxStrCols    = 8;
@@ -20,14 +24,16 @@ constexpr int kMaxOut        = 24;
 constexpr int kMaxImm        = 32;
 constexpr int kMaxProbes     = 4;
 constexpr int kMaxSlots      = 12;
-constexpr int kLowCardMaxGroups = 8;    // groups a warp can track with lane-private accumulators
-constexpr int kGroupTableCap = 2048;    // global table of the low-cardinality aggregate path
+constexpr int kNAR           = 6;      // aggregates held in registers per group (register path)
+constexpr int kRegGroups     = 4;      // groups held in registers per warp (register path)
+constexpr int kLowCardMaxGroups = 8;   // groups per warp with lane-private shared-memory accumulators
+constexpr int kGroupTableCap = 2048;   // global table of the low-cardinality aggregate paths
 
-// ---- device instruction: accumulator machine ----------------------------------------------
+// ---- host-level instruction: accumulator machine ----------------------------------------------
 // The ABI-level postfix program (rq_node) is linearised on the host into instructions of the
-// form   acc = acc OP operand   over a register tile of kRowsPerThread tuples per thread.
-// Values used more than once or not consumed by the next instruction are kept in shared-memory
-// slots (one int64 per tuple of the tile).
+// form   acc = acc OP operand   over the register tile. Values used more than once or not
+// consumed by the next instruction are kept in shared-memory slots (one int64 per tuple).
+// This is the form tests/vm_model.py executes; encode_program() then fuses it into UInsn.
 enum DOp : uint8_t {
     D_LD = 1, D_ADD, D_SUB, D_RSUB, D_MUL, D_DIV, D_RDIV, D_AND, D_OR,
     D_LT, D_LE, D_GT, D_GE, D_EQ, D_NE,
@@ -40,7 +46,10 @@ enum DOp : uint8_t {
     D_HAGG,           // hash aggregate sink
     D_BUILD,          // hash-join build sink
     D_EMIT,           // materialize sink
-    D_NOP
+    D_NOP,
+    // valid &= (operand CMP imm): a compare whose only consumer is the selection; the
+    // accumulator is left untouched (selection.h:52-70 + the compare emitters fused)
+    D_FLT, D_FLE, D_FGT, D_FGE, D_FEQ, D_FNE
 };
 
 enum DSrc : uint8_t { S_NONE = 0, S_COL = 1, S_SLOT = 2, S_IMM = 3, S_STR = 4 };
@@ -48,7 +57,7 @@ enum DSrc : uint8_t { S_NONE = 0, S_COL = 1, S_SLOT = 2, S_IMM = 3, S_STR = 4 };
 struct DInsn {
     uint8_t  op;
     uint8_t  src;       // DSrc
-    uint8_t  flags;     // bit0: store acc to slot `dst` after the op
+    uint8_t  flags;     // bit0: store acc to slot `dst` after the op; bit1: SEL else is imm[aux]
     uint8_t  dst;
     uint16_t idx;       // column / slot index of the operand
     uint16_t aux;
@@ -56,16 +65,64 @@ struct DInsn {
 };
 static_assert(sizeof(DInsn) == 16, "DInsn must be 16 bytes");
 
+// ---- device-level instruction -------------------------------------------------------------------
+// One switch per instruction: opcode and operand form are fused into `code`, operands are byte
+// offsets into the warp's shared-memory region (stage-relative for columns, region-relative for
+// slots), so the interpreter does no address bookkeeping per tuple.
+enum UKind : uint8_t {             // operand kinds
+    K_NONE = 0, K_M64, K_M32, K_M8, K_IMM, K_STR
+};
+
+#define RQ_BINOPS(X) X(ADD) X(SUB) X(RSUB) X(MUL) X(AND) X(OR) X(LT) X(LE) X(GT) X(GE) X(EQ) X(NE)
+
+enum UCode : uint8_t {
+    U_END = 0,
+    U_LD_M64, U_LD_M32, U_LD_M8, U_LD_IMM, U_LD_STR,
+    // acc = acc OP m64 | acc OP imm | m64 OP imm | m64 OP m64'
+#define RQ_X(N) U_##N##_AM, U_##N##_AI, U_##N##_MI, U_##N##_MM,
+    RQ_BINOPS(RQ_X)
+#undef RQ_X
+    U_GEN,                         // gop/gsrc: any DOp with any operand kind (rare forms)
+    U_FILTER_A,                    // valid &= acc
+    U_FILTER_O,                    // valid &= operand (kind in gsrc)
+    // valid &= (column CMP imm)
+    U_FLT_M64, U_FLE_M64, U_FGT_M64, U_FGE_M64, U_FEQ_M64, U_FNE_M64,
+    U_FLT_M32, U_FLE_M32, U_FGT_M32, U_FGE_M32, U_FEQ_M32, U_FNE_M32,
+    U_FLT_M8,  U_FLE_M8,  U_FGT_M8,  U_FGE_M8,  U_FEQ_M8,  U_FNE_M8,
+    U_GROUP,
+    U_AGG_SUM_A, U_AGG_SUM_M,      // aux = aggregate index; operand = acc | m64
+    U_AGG_COUNT,
+    U_AGG_GEN,                     // gop = D_AGG_SUM/MIN/MAX, gsrc = operand kind (K_NONE: acc)
+    U_PROBE, U_HAGG, U_BUILD, U_EMIT
+};
+
+constexpr uint8_t UF_STORE    = 1;   // store acc to slot `dst` after the op
+constexpr uint8_t UF_ELSE_IMM = 2;   // SEL: else value is imm[aux]
+constexpr uint8_t UF_SLOT     = 4;   // operand offset is relative to the warp region (a slot)
+constexpr uint8_t UF_SLOT2    = 8;   // MM forms: second operand likewise
+
+struct UInsn {
+    uint8_t  code;
+    uint8_t  flags;
+    uint8_t  dst;       // slot index for UF_STORE
+    uint8_t  aux;       // aggregate / probe index, SEL else slot or imm index
+    uint8_t  gop;       // U_GEN / U_AGG_GEN: DOp
+    uint8_t  gsrc;      // U_GEN / U_FILTER_O / U_AGG_GEN: UKind of the operand
+    uint16_t off16;     // operand byte offset >> 4 (string columns: column index)
+    int64_t  imm;       // immediate; MM forms: byte offset of the second operand
+};
+static_assert(sizeof(UInsn) == 16, "UInsn must be 16 bytes");
+
 struct VRef {           // value reference used by sinks (keys, payloads, outputs)
-    uint8_t  kind;      // DSrc
-    uint8_t  pad;
-    uint16_t idx;       // S_IMM: index into KParams::imm
+    uint8_t  kind;      // UKind
+    uint8_t  slot;      // 1: offset relative to the warp region
+    uint16_t off16;     // byte offset >> 4; K_IMM: index into KParams::imm; K_STR: string column
 };
 
 // hash table used by joins (build then probe in separate kernels) and by hash aggregation
 struct DHashTable {
     uint64_t  cap_mask;     // capacity - 1 (power of two)
-    uint64_t* tags;         // 0 = empty; else fingerprint | 1
+    uint64_t* tags;         // 0 = empty; else fingerprint | 2
     int64_t*  keys;         // [nk][capacity]
     int64_t*  vals;         // [nv][capacity]  payload / accumulators
     int32_t   nk, nv;
@@ -93,27 +150,35 @@ struct KParams {
     int32_t        n_strcols;
     const unsigned char* str_ptr[kMaxStrCols];
     uint32_t       str_w[kMaxStrCols];
-    uint32_t       stage_bytes;
-    int32_t        stages;              // 2 = double buffered, 1 when shared memory is short
-    // shared memory carve-up (byte offsets)
-    uint32_t       slots_off, acc_off, dict_off, smem_bytes;
+    uint32_t       stage_bytes;         // kTile * sum(col_w)
+    int32_t        stages;              // TMA ring depth per warp
+    // shared memory carve-up: [mbarriers][warp 0 region][warp 1 region]...
+    uint32_t       warp_off;            // byte offset of warp 0's region
+    uint32_t       warp_bytes;          // bytes per warp region
+    uint32_t       slots_rel;           // slots, relative to the warp region
+    uint32_t       acc_rel;             // lane-private accumulators (shared-memory path)
+    uint32_t       smem_bytes;          // total dynamic shared memory of the CTA
     int32_t        n_slots;
+    int32_t        warps;               // warps per CTA
     // program
     int32_t        n_insn;
-    DInsn          insn[kMaxInsn];
+    UInsn          insn[kMaxInsn];
     int64_t        imm[kMaxImm];
     // grouping / aggregation
     int32_t        nk;
     VRef           key[kMaxKeys];
+    uint8_t        key_shift[kMaxKeys]; // packed group key: sum((value & mask) << shift)
+    uint8_t        key_bits[kMaxKeys];
+    int32_t        key32;               // the packed key fits in 32 bits
     int32_t        na;
     uint8_t        agg_kind[kMaxAggs];
     VRef           agg_src[kMaxAggs];    // hash aggregate only
-    int32_t        G;                    // lane-private groups per warp (low-card path)
-    // low-card global table
+    int32_t        G;                    // lane-private groups per warp (shared-memory path)
+    // low-card global table (packed key)
     uint32_t*      g_state;              // [kGroupTableCap]
-    int64_t*       g_keys;               // [kGroupTableCap][nk]
-    int64_t*       g_acc;                // [kGroupTableCap][na]
-    int32_t*       overflow;             // set when a warp meets more than G groups
+    int64_t*       g_keys;               // [kGroupTableCap]
+    int64_t*       g_acc;                // [kGroupTableCap][kMaxAggs]
+    int32_t*       overflow;             // set when a warp meets more groups than its path tracks
     // hash aggregate / build
     DHashTable     ht;
     int32_t*       ht_full;              // set when the table is full

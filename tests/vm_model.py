@@ -9,9 +9,10 @@ from resql_b200 import native as N
 
 (D_LD, D_ADD, D_SUB, D_RSUB, D_MUL, D_DIV, D_RDIV, D_AND, D_OR, D_LT, D_LE, D_GT, D_GE, D_EQ, D_NE,
  D_EQC, D_EQV, D_NEC, D_NEV, D_LIKE, D_RLIKE, D_SEL, D_FILTER, D_GROUP, D_AGG_SUM, D_AGG_COUNT,
- D_AGG_MIN, D_AGG_MAX, D_PROBE, D_HAGG, D_BUILD, D_EMIT, D_NOP) = range(1, 34)
+ D_AGG_MIN, D_AGG_MAX, D_PROBE, D_HAGG, D_BUILD, D_EMIT, D_NOP,
+ D_FLT, D_FLE, D_FGT, D_FGE, D_FEQ, D_FNE) = range(1, 40)
 S_NONE, S_COL, S_SLOT, S_IMM, S_STR = range(5)
-IMPL_LOWAGG, IMPL_HASHAGG, IMPL_BUILD, IMPL_EMIT = 1, 2, 3, 4
+IMPL_LOWAGG, IMPL_HASHAGG, IMPL_BUILD, IMPL_EMIT, IMPL_REGAGG = 1, 2, 3, 4, 5
 
 
 def phys_of(arr):
@@ -41,11 +42,11 @@ def parse(text):
     return prog
 
 
-def run_pipeline_vm(plan, pi, src_cols, pool_strings):
+def run_pipeline_vm(plan, pi, src_cols, pool_strings, agg_impl=IMPL_LOWAGG):
     """src_cols: list of numpy arrays (physical dtypes; intermediates int64/object).
     Returns the list of output columns of the pipeline (evaluation form)."""
     p = plan.pipelines[pi]
-    impl = IMPL_LOWAGG if p["sink_kind"] == 1 else IMPL_EMIT
+    impl = agg_impl if p["sink_kind"] == 1 else IMPL_EMIT
     types, widths = [], []
     for a in src_cols:
         if a.dtype == object:
@@ -65,7 +66,7 @@ def run_pipeline_vm(plan, pi, src_cols, pool_strings):
 
     def operand(src, idx, imm):
         if src == S_COL:
-            return vals[prog["cols"][idx]]
+            return vals[prog["cols"][idx]]       # (fused compares carry the constant in imm)
         if src == S_STR:
             return vals[prog["strcols"][idx]]
         if src == S_SLOT:
@@ -109,6 +110,12 @@ def run_pipeline_vm(plan, pi, src_cols, pool_strings):
         elif op == D_RLIKE: acc = np.array([PO._like(v, u) for u, v in zip(acc, b)], dtype=np.int64)
         elif op == D_SEL: acc = np.where((acc & 0xFF) != 0, b, (np.full(n, prog['imm'][aux], dtype=np.int64) if flags & 2 else slots[aux]))
         elif op == D_FILTER: valid = valid & (((b if src != S_NONE else acc) & 0xFF) != 0)
+        elif op == D_FLT: valid = valid & (b < imm)
+        elif op == D_FLE: valid = valid & (b <= imm)
+        elif op == D_FGT: valid = valid & (b > imm)
+        elif op == D_FGE: valid = valid & (b >= imm)
+        elif op == D_FEQ: valid = valid & (b == imm)
+        elif op == D_FNE: valid = valid & (b != imm)
         elif op == D_GROUP:
             keys = [vref(k, i) for k, i in prog["key"]]
             groups = {}
