@@ -329,7 +329,7 @@ uint8_t dop_left(int op) {
         case RQ_OP_NEQ_CHAR: return D_NEC; case RQ_OP_NEQ_VARCHAR: return D_NEV;
         case RQ_OP_LIKE: return D_LIKE;
     }
-    return D_NOP;
+    return 0;
 }
 uint8_t dop_right(int op) {
     switch (op) {
@@ -341,37 +341,49 @@ uint8_t dop_right(int op) {
         case RQ_OP_NEQ_CHAR: return D_NEC; case RQ_OP_NEQ_VARCHAR: return D_NEV;
         case RQ_OP_LIKE: return D_RLIKE;
     }
-    return D_NOP;
+    return 0;
 }
 // selection-fused compare: column CMP constant (constant on the right / on the left)
 uint8_t fcmp_left(int op) {
     switch (op) {
-        case RQ_OP_LT: return D_FLT; case RQ_OP_LE: return D_FLE; case RQ_OP_GT: return D_FGT;
-        case RQ_OP_GE: return D_FGE; case RQ_OP_EQ: return D_FEQ; case RQ_OP_NEQ: return D_FNE;
+        case RQ_OP_LT: return D_LT; case RQ_OP_LE: return D_LE; case RQ_OP_GT: return D_GT;
+        case RQ_OP_GE: return D_GE; case RQ_OP_EQ: return D_EQ; case RQ_OP_NEQ: return D_NE;
     }
     return 0;
 }
 uint8_t fcmp_right(int op) {
     switch (op) {
-        case RQ_OP_LT: return D_FGT; case RQ_OP_LE: return D_FGE; case RQ_OP_GT: return D_FLT;
-        case RQ_OP_GE: return D_FLE; case RQ_OP_EQ: return D_FEQ; case RQ_OP_NEQ: return D_FNE;
+        case RQ_OP_LT: return D_GT; case RQ_OP_LE: return D_GE; case RQ_OP_GT: return D_LT;
+        case RQ_OP_GE: return D_LE; case RQ_OP_EQ: return D_EQ; case RQ_OP_NEQ: return D_NE;
     }
     return 0;
 }
 
-struct Operand {
-    uint8_t src = S_NONE;
-    uint16_t idx = 0;
+struct HOpnd {           // host-level operand of a unit / value reference of a sink
+    uint8_t kind = S_NONE;   // DSrc
+    uint16_t idx = 0;        // staged column / slot / string column (sinks: imm-table index)
     int64_t imm = 0;
 };
+typedef HOpnd HRef;
 
-struct HRef {            // host-level value reference of a sink (resolved to VRef by encode)
-    uint8_t kind = S_NONE;   // DSrc
-    uint16_t idx = 0;        // staged column / slot / imm-table index / string column
+enum HOp : uint8_t { H_FCMP = 1, H_BIN = 2, H_MULI = 3, H_SEL = 4, H_PROBE = 5 };
+
+// One unit of the host-level program (what tests/vm_model.py executes):
+//   H_FCMP  valid &= (x GOP imm)                      gop in D_LT..D_NE, x a column
+//   H_BIN   t = x GOP y  (GOP = D_LD: t = x)
+//   H_MULI  t = (x GOP imm) * y                       gop in D_ADD / D_SUB / D_RSUB
+//   H_SEL   t = (x & 0xff) ? y : z
+//   H_PROBE hash-join probe number aux
+// then  slot[dst] = t  if dst >= 0, and  valid &= (t & 0xff) != 0  if filt.
+struct HUnit {
+    uint8_t op = 0, gop = 0;
+    HOpnd x, y, z;
+    int64_t imm = 0;
+    int dst = -1;
+    bool filt = false;
+    int aux = 0;
 };
 
-// Host-level program of one pipeline (what tests/vm_model.py executes) plus the pieces of
-// KParams that do not depend on the shared-memory layout.
 struct Lowerer {
     const rq_plan& plan;
     const rq_pipeline& pl;
@@ -381,7 +393,7 @@ struct Lowerer {
     KParams& P;
 
     int n;
-    std::vector<DInsn> prog;
+    std::vector<HUnit> prog;
     std::vector<HRef> hkey, hout;
     HRef hagg_src[kMaxAggs];
     HRef hprobe_key[kMaxProbes][kMaxKeys];
@@ -389,13 +401,12 @@ struct Lowerer {
 
     std::vector<int> uses;            // consumers per node
     std::vector<int> last_use;        // last consuming node index (n = sink)
-    std::vector<char> sink_ref;       // referenced by the sink (needs a slot unless leaf)
+    std::vector<char> sink_ref;       // referenced by the sink or a probe key
     std::vector<int> slot;            // assigned slot or -1
-    std::vector<Operand> leaf_op;     // operand descriptor of leaves
+    std::vector<HOpnd> leaf_op;       // operand descriptor of leaves
     std::vector<int> staged_of_col;   // source column -> staged index / str index
     std::vector<int> free_slots;
-    std::vector<char> fused;          // FILTER nodes folded into a selection-fused compare
-    int acc_node = -1;
+    std::vector<char> fused;          // node produces no unit of its own (folded into a consumer)
     int n_imm = 0;
 
     Lowerer(const rq_plan& plan, const rq_pipeline& pl, const rq_table& src,
@@ -406,33 +417,33 @@ struct Lowerer {
         if (ref < 0 || ref >= i) raise(RQ_ERR_INVALID, "node %d refers to node %d (must be an earlier node)", i, ref);
     }
 
-    void emit(uint8_t op, Operand o = Operand(), uint16_t aux = 0) {
-        if ((int)prog.size() >= kMaxInsn - 1) raise(RQ_ERR_UNSUPPORTED, "program longer than %d instructions", kMaxInsn - 1);
-        DInsn in;
-        in.op = op; in.src = o.src; in.flags = 0; in.dst = 0; in.idx = o.idx; in.aux = aux; in.imm = o.imm;
-        prog.push_back(in);
+    HUnit& emit(uint8_t op, uint8_t gop) {
+        if ((int)prog.size() >= kMaxInsn) raise(RQ_ERR_UNSUPPORTED, "program longer than %d units", kMaxInsn);
+        HUnit u;
+        u.op = op; u.gop = gop;
+        prog.push_back(u);
+        return prog.back();
     }
 
-    Operand operand_of(int node) {
+    HOpnd operand_of(int node) {
         if (is_leaf(pl.nodes[node].op)) return leaf_op[node];
         if (slot[node] < 0) raise(RQ_ERR_INVALID, "internal: node %d has no slot", node);
-        Operand o; o.src = S_SLOT; o.idx = (uint16_t)slot[node];
+        HOpnd o; o.kind = S_SLOT; o.idx = (uint16_t)slot[node];
         return o;
     }
     HRef href_of(int node) {
-        HRef v;
-        if (is_leaf(pl.nodes[node].op)) {
-            Operand o = leaf_op[node];
-            if (o.src == S_IMM) {
-                if (n_imm >= kMaxImm) raise(RQ_ERR_UNSUPPORTED, "too many constants in sink");
-                P.imm[n_imm] = o.imm;
-                v.kind = S_IMM; v.idx = (uint16_t)n_imm++;
-            } else { v.kind = o.src; v.idx = o.idx; }
-            return v;
+        HRef v = operand_of(node);
+        if (v.kind == S_IMM) {
+            if (n_imm >= kMaxImm) raise(RQ_ERR_UNSUPPORTED, "too many constants in sink");
+            P.imm[n_imm] = v.imm;
+            v.idx = (uint16_t)n_imm++;
         }
-        if (slot[node] < 0) raise(RQ_ERR_INVALID, "internal: sink node %d has no slot", node);
-        v.kind = S_SLOT; v.idx = (uint16_t)slot[node];
         return v;
+    }
+    int imm_index(int64_t v) {
+        if (n_imm >= kMaxImm) raise(RQ_ERR_UNSUPPORTED, "too many constants");
+        P.imm[n_imm] = v;
+        return n_imm++;
     }
 
     int alloc_slot() {
@@ -447,7 +458,7 @@ struct Lowerer {
 
     void prepare() {
         uses.assign(n, 0); last_use.assign(n, -1); sink_ref.assign(n, 0); slot.assign(n, -1);
-        leaf_op.assign(n, Operand()); fused.assign(n, 0);
+        leaf_op.assign(n, HOpnd()); fused.assign(n, 0);
         staged_of_col.assign(src.cols.size(), -1);
         auto use = [&](int i, int ref) { check_ref(i, ref); uses[ref]++; last_use[ref] = std::max(last_use[ref], i); };
         for (int i = 0; i < n; i++) {
@@ -456,30 +467,30 @@ struct Lowerer {
                 case RQ_OP_COL: {
                     if (nd.a < 0 || nd.a >= (int)src.cols.size()) raise(RQ_ERR_INVALID, "node %d: column %d out of range", i, nd.a);
                     const DevColumn& dc = src.cols[nd.a];
-                    Operand o;
+                    HOpnd o;
                     if (dc.type == RQ_STR) {
                         if (staged_of_col[nd.a] < 0) {
                             if (P.n_strcols >= kMaxStrCols) raise(RQ_ERR_UNSUPPORTED, "too many string columns");
                             P.str_ptr[P.n_strcols] = dc.d; P.str_w[P.n_strcols] = dc.width;
                             staged_of_col[nd.a] = P.n_strcols++;
                         }
-                        o.src = S_STR;
+                        o.kind = S_STR;
                     } else {
                         if (staged_of_col[nd.a] < 0) {
                             if (P.n_cols >= kMaxStagedCols) raise(RQ_ERR_UNSUPPORTED, "more than %d columns in one pipeline", kMaxStagedCols);
                             P.col_ptr[P.n_cols] = dc.d; P.col_w[P.n_cols] = (uint8_t)dc.width;
                             staged_of_col[nd.a] = P.n_cols++;
                         }
-                        o.src = S_COL;
+                        o.kind = S_COL;
                     }
                     o.idx = (uint16_t)staged_of_col[nd.a];
                     leaf_op[i] = o;
                     break;
                 }
-                case RQ_OP_CONST: { Operand o; o.src = S_IMM; o.imm = nd.imm; leaf_op[i] = o; break; }
+                case RQ_OP_CONST: { HOpnd o; o.kind = S_IMM; o.imm = nd.imm; leaf_op[i] = o; break; }
                 case RQ_OP_CONST_STR: {
                     if (nd.imm < 0 || nd.imm >= plan.strpool_bytes) raise(RQ_ERR_INVALID, "node %d: string offset out of range", i);
-                    Operand o; o.src = S_IMM; o.imm = (int64_t)(d_strpool + nd.imm); leaf_op[i] = o; break;
+                    HOpnd o; o.kind = S_IMM; o.imm = (int64_t)(d_strpool + nd.imm); leaf_op[i] = o; break;
                 }
                 case RQ_OP_FILTER: use(i, nd.a); break;
                 case RQ_OP_SELECT: use(i, nd.a); use(i, nd.b); use(i, nd.c); break;
@@ -505,13 +516,26 @@ struct Lowerer {
         uint32_t off = 0;
         for (int c = 0; c < P.n_cols; c++) { P.col_off[c] = off; off += kTile * P.col_w[c]; }
         P.stage_bytes = off;
-        mark_fused_filters();
+        // fusion marks
+        for (int f = 0; f < n; f++) {
+            HOpnd o; int64_t k;
+            if (fcmp_of(f, &o, &k)) fused[pl.nodes[f].a] = 1;
+        }
+        for (int i = 0; i < n; i++) {
+            int inner, other; uint8_t gop; int64_t k; HOpnd x;
+            if (muli_of(i, &inner, &other, &gop, &k, &x)) fused[inner] = 1;
+        }
     }
 
-    // FILTER(COL cmp CONST) where the compare has no other consumer becomes one instruction that
-    // leaves the accumulator alone. 4- and 1-byte columns compare in 32 bits, so the constant
-    // must fit (it always does for dates / flags; otherwise the generic form is used).
-    int fcmp_of(int f, Operand* col, int64_t* imm) const {
+    bool is_col8(int node) const {
+        return pl.nodes[node].op == RQ_OP_COL && leaf_op[node].kind == S_COL && P.col_w[leaf_op[node].idx] == 8;
+    }
+
+    // FILTER(COL cmp CONST) where the compare has no other consumer: one unit that only narrows
+    // the selection mask. 4- and 1-byte columns compare in 32 bits, so the constant must fit (it
+    // always does for dates / flags; otherwise the generic form is used). Returns the D_LT..D_NE
+    // compare with the column on the left.
+    int fcmp_of(int f, HOpnd* col, int64_t* imm) const {
         const rq_node& fl = pl.nodes[f];
         if (fl.op != RQ_OP_FILTER) return 0;
         const rq_node& cm = pl.nodes[fl.a];
@@ -522,75 +546,32 @@ struct Lowerer {
         if (xo == RQ_OP_COL && yo == RQ_OP_CONST) { code = fcmp_left(cm.op); cn = cm.a; kn = cm.b; }
         else if (xo == RQ_OP_CONST && yo == RQ_OP_COL) { code = fcmp_right(cm.op); cn = cm.b; kn = cm.a; }
         else return 0;
-        const Operand o = leaf_op[cn];
-        if (o.src != S_COL) return 0;
+        const HOpnd o = leaf_op[cn];
+        if (o.kind != S_COL) return 0;
         const int64_t k = leaf_op[kn].imm;
         if (P.col_w[o.idx] != 8 && (k < INT32_MIN || k > INT32_MAX)) return 0;
         *col = o; *imm = k;
         return code;
     }
-    void mark_fused_filters() {
-        for (int f = 0; f < n; f++) {
-            Operand o; int64_t k;
-            if (fcmp_of(f, &o, &k)) { fused[f] = 1; fused[pl.nodes[f].a] = 1; }
-        }
-    }
 
-    // ---- slot decision -------------------------------------------------------------------
-    // A computed value sits in the accumulator until the next clobbering instruction. A consumer
-    // can take it from there if it is a FILTER inside that window or the clobbering node itself
-    // (using it as exactly one operand), or an aggregate fused right behind its input.
-    bool clobbers(int j) const {
-        const int op = pl.nodes[j].op;
-        return !is_leaf(op) && op != RQ_OP_FILTER && op != RQ_OP_PAYLOAD && !fused[j];
-    }
-    int gpos = -1;                 // GROUP is emitted right after node gpos
-    std::vector<std::vector<int>> aggs_of;   // node -> aggregate indices fed by it
-    bool lowagg = false;
-
-    void decide_slots() {
-        std::vector<std::vector<int>> cons(n);
-        for (int j = 0; j < n; j++) {
-            const rq_node& nd = pl.nodes[j];
-            if (is_binary(nd.op)) { cons[nd.a].push_back(j); cons[nd.b].push_back(j); }
-            else if (nd.op == RQ_OP_FILTER) cons[nd.a].push_back(j);
-            else if (nd.op == RQ_OP_SELECT) { cons[nd.a].push_back(j); cons[nd.b].push_back(j); cons[nd.c].push_back(j); }
+    // MUL(ADD/SUB(col8, const), other) where the inner node has no other consumer:
+    // t = (x GOP imm) * other in one unit (TPC-H's  price * (1 - discount) * (1 + tax)  shapes)
+    bool muli_of(int i, int* inner, int* other, uint8_t* gop, int64_t* k, HOpnd* x) const {
+        const rq_node& nd = pl.nodes[i];
+        if (nd.op != RQ_OP_MUL || nd.a == nd.b) return false;
+        for (int side = 0; side < 2; side++) {
+            const int j = side == 0 ? nd.a : nd.b, o = side == 0 ? nd.b : nd.a;
+            const rq_node& in = pl.nodes[j];
+            if ((in.op != RQ_OP_ADD && in.op != RQ_OP_SUB) || uses[j] != 1 || sink_ref[j]) continue;
+            if (is_leaf(pl.nodes[o].op) && !is_col8(o)) continue;     // other side: 64-bit column or a slot
+            uint8_t g = 0; int cn = -1, kn = -1;
+            if (is_col8(in.a) && pl.nodes[in.b].op == RQ_OP_CONST) { cn = in.a; kn = in.b; g = in.op == RQ_OP_ADD ? D_ADD : D_SUB; }
+            else if (pl.nodes[in.a].op == RQ_OP_CONST && is_col8(in.b)) { cn = in.b; kn = in.a; g = in.op == RQ_OP_ADD ? D_ADD : D_RSUB; }
+            else continue;
+            *inner = j; *other = o; *gop = g; *k = leaf_op[kn].imm; *x = leaf_op[cn];
+            return true;
         }
-        for (int i = 0; i < n; i++) {
-            const int op = pl.nodes[i].op;
-            if (is_leaf(op) || op == RQ_OP_FILTER || op == RQ_OP_PROBE || fused[i]) continue;
-            if (op == RQ_OP_PAYLOAD) continue;   // slot handed out when the PROBE is emitted
-            bool need = false;
-            if (sink_ref[i]) {
-                // only a low-card aggregate fused behind its input reads the accumulator
-                bool all_fused = lowagg && i > gpos && !aggs_of[i].empty();
-                for (int k = 0; k < pl.n_keys; k++) if (pl.keys[k].node == i) all_fused = false;
-                for (int j = 0; j < n; j++)
-                    if (pl.nodes[j].op == RQ_OP_PROBE)
-                        for (int k = 0; k < pl.nodes[j].c; k++) if (pl.args[pl.nodes[j].b + k] == i) all_fused = false;
-                if (!all_fused) need = true;
-            }
-            int wend = -1;
-            for (int j = i + 1; j < n; j++) if (clobbers(j)) { wend = j; break; }
-            for (int j : cons[i]) {
-                if (wend >= 0 && j > wend) need = true;
-                if (j == wend) {
-                    const rq_node& nd = pl.nodes[j];
-                    int cnt = 0;
-                    if (is_binary(nd.op)) cnt = (nd.a == i) + (nd.b == i);
-                    else if (nd.op == RQ_OP_SELECT) {
-                        cnt = (nd.a == i) ? 1 : 2;
-                        if (nd.b == i || nd.c == i) cnt = 2;
-                        // a non-constant leaf else is staged through the accumulator first
-                        const int co = pl.nodes[nd.c].op;
-                        if (is_leaf(co) && co != RQ_OP_CONST && co != RQ_OP_CONST_STR) cnt = 2;
-                    }
-                    else cnt = 2;
-                    if (cnt != 1) need = true;
-                }
-            }
-            if (need) slot[i] = -3;   // marker: allocate at emission
-        }
+        return false;
     }
 };
 

@@ -214,105 +214,73 @@ static void simplify_pipeline(const rq_pipeline& in, SimplePipe& sp) {
     sp.pl.keys = sp.keys.data();          sp.pl.vals = sp.vals.data();
 }
 
-enum SinkImpl { IMPL_LOWAGG = 1, IMPL_HASHAGG = 2, IMPL_BUILD = 3, IMPL_EMIT = 4, IMPL_REGAGG = 5 };
-
-static uint8_t agg_dop(int kind) {
-    switch (kind) {
-        case RQ_AGG_SUM: return D_AGG_SUM;
-        case RQ_AGG_COUNT: return D_AGG_COUNT;
-        case RQ_AGG_MIN: return D_AGG_MIN;
-        default: return D_AGG_MAX;
-    }
-}
-
-// Emits the host-level program for one pipeline.
+// Emits the host-level program (units) for one pipeline.
 static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
     KParams& P = L.P;
     const rq_pipeline& pl = L.pl;
     const int n = L.n;
-    L.lowagg = (impl == IMPL_LOWAGG || impl == IMPL_REGAGG);
-    L.aggs_of.assign(n, {});
-    L.gpos = -1;
-    for (int i = 0; i < n; i++) {
-        const int op = pl.nodes[i].op;
-        if (op == RQ_OP_FILTER || op == RQ_OP_PROBE || op == RQ_OP_PAYLOAD) L.gpos = i;
-    }
-    if (L.lowagg) {
-        for (int k = 0; k < pl.n_keys; k++) L.gpos = std::max(L.gpos, pl.keys[k].node);
-        for (size_t u = 0; u < ad.kind.size(); u++)
-            if (ad.node[u] >= 0) L.aggs_of[ad.node[u]].push_back((int)u);
-    }
-    L.decide_slots();
 
-    auto emit_group = [&]() {
-        if (!L.lowagg) return;
-        L.emit(D_GROUP);
-        for (int k = 0; k < pl.n_keys; k++) L.hkey.push_back(L.href_of(pl.keys[k].node));
-        for (size_t u = 0; u < ad.kind.size(); u++) {
-            if (ad.kind[u] == RQ_AGG_COUNT) { L.emit(D_AGG_COUNT, Operand(), (uint16_t)u); continue; }
-            const int nd = ad.node[u];
-            if (is_leaf(pl.nodes[nd].op) || nd <= L.gpos || pl.nodes[nd].op == RQ_OP_PAYLOAD)
-                L.emit(agg_dop(ad.kind[u]), L.operand_of(nd), (uint16_t)u);
+    // a value needs a slot when somebody other than a selection directly behind it reads it
+    auto needs_slot = [&](int i) -> bool {
+        if (L.sink_ref[i]) return true;
+        for (int j = i + 1; j < n; j++) {
+            const rq_node& nd = pl.nodes[j];
+            if (L.fused[j] && nd.op != RQ_OP_FILTER) {
+                // a folded inner node reads only leaves
+                continue;
+            }
+            if (is_binary(nd.op) && (nd.a == i || nd.b == i)) return true;
+            if (nd.op == RQ_OP_SELECT && (nd.a == i || nd.b == i || nd.c == i)) return true;
         }
+        return false;
+    };
+    auto filter_behind = [&](int i) -> int {     // FILTER node testing value i right behind it
+        for (int j = i + 1; j < n && pl.nodes[j].op == RQ_OP_FILTER; j++)
+            if (pl.nodes[j].a == i) return j;
+        return -1;
+    };
+    auto finish_value = [&](int i) {
+        HUnit& u = L.prog.back();
+        if (needs_slot(i)) {
+            const int s = L.alloc_slot();
+            L.slot[i] = s;
+            u.dst = s;
+        }
+        if (filter_behind(i) >= 0) u.filt = true;
     };
 
-    if (L.gpos == -1) emit_group();
     for (int i = 0; i < n; i++) {
         const rq_node& nd = pl.nodes[i];
-        bool computed = false;
         if (is_leaf(nd.op) || nd.op == RQ_OP_PAYLOAD) {
-            // no instruction
-        } else if (L.fused[i] && nd.op != RQ_OP_FILTER) {
-            // compare folded into the selection that follows
+            // no unit
         } else if (nd.op == RQ_OP_FILTER) {
-            Operand col; int64_t k;
-            const int fc = L.fused[i] ? L.fcmp_of(i, &col, &k) : 0;
+            HOpnd col; int64_t k;
+            const int fc = L.fcmp_of(i, &col, &k);
             if (fc) {
-                col.imm = k;
-                L.emit((uint8_t)fc, col);
-            } else if (L.acc_node != nd.a || is_leaf(pl.nodes[nd.a].op)) {
-                // tests an operand without disturbing the accumulator
-                L.emit(D_FILTER, L.operand_of(nd.a));
-            } else {
-                L.emit(D_FILTER);
+                HUnit& u = L.emit(H_FCMP, (uint8_t)fc);
+                u.x = col; u.imm = k;
+            } else if (is_leaf(pl.nodes[nd.a].op)) {
+                HUnit& u = L.emit(H_BIN, D_LD);      // selection on a plain (BOOL) operand
+                u.x = L.operand_of(nd.a);
+                u.filt = true;
             }
+            // otherwise folded into the unit that computed the value (finish_value)
+        } else if (L.fused[i]) {
+            // folded into its consumer
         } else if (is_binary(nd.op)) {
-            const int x = nd.a, y = nd.b;
-            if (L.acc_node == x && x != y && !is_leaf(pl.nodes[x].op)) {
-                L.emit(dop_left(nd.op), L.operand_of(y));
-            } else if (L.acc_node == y && x != y && !is_leaf(pl.nodes[y].op)) {
-                L.emit(dop_right(nd.op), L.operand_of(x));
+            int inner, other; uint8_t gop; int64_t k; HOpnd x;
+            if (L.muli_of(i, &inner, &other, &gop, &k, &x)) {
+                HUnit& u = L.emit(H_MULI, gop);
+                u.x = x; u.imm = k; u.y = L.operand_of(other);
             } else {
-                L.emit(D_LD, L.operand_of(x));
-                L.emit(dop_left(nd.op), L.operand_of(y));
+                HUnit& u = L.emit(H_BIN, dop_left(nd.op));
+                u.x = L.operand_of(nd.a); u.y = L.operand_of(nd.b);
             }
-            computed = true;
+            finish_value(i);
         } else if (nd.op == RQ_OP_SELECT) {
-            // acc = cond ? then : else. A constant else travels in the immediate table
-            // (flags bit1), anything else in a slot.
-            int tmp = -1, else_ref;
-            bool else_imm = false;
-            if (pl.nodes[nd.c].op == RQ_OP_CONST || pl.nodes[nd.c].op == RQ_OP_CONST_STR) {
-                if (L.n_imm >= kMaxImm) raise(RQ_ERR_UNSUPPORTED, "too many constants");
-                P.imm[L.n_imm] = L.leaf_op[nd.c].imm;
-                else_ref = L.n_imm++;
-                else_imm = true;
-            } else if (is_leaf(pl.nodes[nd.c].op)) {
-                tmp = L.alloc_slot();
-                L.emit(D_LD, L.operand_of(nd.c));
-                L.prog.back().flags |= 1;
-                L.prog.back().dst = (uint8_t)tmp;
-                L.acc_node = -1;
-                else_ref = tmp;
-            } else {
-                if (L.slot[nd.c] < 0) raise(RQ_ERR_INVALID, "internal: SELECT else operand has no slot");
-                else_ref = L.slot[nd.c];
-            }
-            if (L.acc_node != nd.a || is_leaf(pl.nodes[nd.a].op)) L.emit(D_LD, L.operand_of(nd.a));
-            L.emit(D_SEL, L.operand_of(nd.b), (uint16_t)else_ref);
-            if (else_imm) L.prog.back().flags |= 2;
-            if (tmp >= 0) L.free_slots.push_back(tmp);
-            computed = true;
+            HUnit& u = L.emit(H_SEL, D_SEL);
+            u.x = L.operand_of(nd.a); u.y = L.operand_of(nd.b); u.z = L.operand_of(nd.c);
+            finish_value(i);
         } else if (nd.op == RQ_OP_PROBE) {
             if (P.n_probes >= kMaxProbes) raise(RQ_ERR_UNSUPPORTED, "more than %d joins in one pipeline", kMaxProbes);
             if (nd.a < 0 || nd.a >= (int)L.outs.size() || !L.outs[nd.a].ht)
@@ -333,45 +301,27 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
                 L.slot[j] = sl;
                 pr.out_slot[b] = (uint8_t)sl;
             }
-            L.emit(D_PROBE, Operand(), (uint16_t)P.n_probes);
+            HUnit& u = L.emit(H_PROBE, 0);
+            u.aux = P.n_probes;
             P.n_probes++;
         }
-        if (computed) {
-            L.acc_node = i;
-            if (L.slot[i] == -3) {
-                const int s = L.alloc_slot();
-                L.slot[i] = s;
-                L.prog.back().flags |= 1;
-                L.prog.back().dst = (uint8_t)s;
-            }
-            if (L.lowagg && i > L.gpos)
-                for (int u : L.aggs_of[i]) L.emit(agg_dop(ad.kind[u]), Operand(), (uint16_t)u);
-        }
         L.release_dead(i);
-        if (i == L.gpos) emit_group();
     }
 
-    if (impl == IMPL_BUILD || impl == IMPL_HASHAGG) {
-        if (pl.n_keys > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
-        for (int k = 0; k < pl.n_keys; k++) L.hkey.push_back(L.href_of(pl.keys[k].node));
-        if (impl == IMPL_BUILD) {
-            if (pl.n_vals > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d payload columns", kMaxOut);
-            for (int k = 0; k < pl.n_vals; k++) L.hout.push_back(L.href_of(pl.vals[k].node));
-            L.emit(D_BUILD);
-        } else {
-            P.na = (int)ad.kind.size();
-            for (int u = 0; u < P.na; u++) {
-                P.agg_kind[u] = (uint8_t)ad.kind[u];
-                if (ad.kind[u] != RQ_AGG_COUNT) L.hagg_src[u] = L.href_of(ad.node[u]);
-            }
-            L.emit(D_HAGG);
-        }
-    }
-    if (impl == IMPL_EMIT) {
+    // sinks
+    if (pl.n_keys > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
+    for (int k = 0; k < pl.n_keys; k++) L.hkey.push_back(L.href_of(pl.keys[k].node));
+    if (impl == IMPL_BUILD || impl == IMPL_EMIT) {
         if (pl.n_vals > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d output columns", kMaxOut);
         for (int k = 0; k < pl.n_vals; k++) L.hout.push_back(L.href_of(pl.vals[k].node));
-        L.emit(D_EMIT);
+    } else {
+        P.na = (int)ad.kind.size();
+        for (int u = 0; u < P.na; u++) {
+            P.agg_kind[u] = (uint8_t)ad.kind[u];
+            if (ad.kind[u] != RQ_AGG_COUNT) L.hagg_src[u] = L.href_of(ad.node[u]);
+        }
     }
+    P.sink = impl;
 }
 
 // ---- shared-memory layout and launch geometry --------------------------------------------
@@ -409,19 +359,19 @@ static bool layout_smem(KParams& P, int n_slots, int acc_bytes, int max_warps) {
     return true;
 }
 
-// ---- encode: host-level program -> fused device instructions (needs the layout) -------------
+// ---- encode: host-level units -> fused device instructions (needs the layout) -----------------
 struct UOperand { uint8_t kind; uint8_t slot; uint32_t off; };
 
-static UOperand resolve(const KParams& P, uint8_t src, uint16_t idx) {
+static UOperand resolve(const KParams& P, const HOpnd& h) {
     UOperand u{K_NONE, 0, 0};
-    switch (src) {
+    switch (h.kind) {
         case S_COL:
-            u.kind = P.col_w[idx] == 8 ? K_M64 : (P.col_w[idx] == 4 ? K_M32 : K_M8);
-            u.off = P.col_off[idx];
+            u.kind = P.col_w[h.idx] == 8 ? K_M64 : (P.col_w[h.idx] == 4 ? K_M32 : K_M8);
+            u.off = P.col_off[h.idx];
             break;
-        case S_SLOT: u.kind = K_M64; u.slot = 1; u.off = P.slots_rel + (uint32_t)idx * kTile * 8; break;
+        case S_SLOT: u.kind = K_M64; u.slot = 1; u.off = P.slots_rel + (uint32_t)h.idx * kTile * 8; break;
         case S_IMM: u.kind = K_IMM; break;
-        case S_STR: u.kind = K_STR; u.off = (uint32_t)idx << 4; break;
+        case S_STR: u.kind = K_STR; u.off = (uint32_t)h.idx << 4; break;
         default: break;
     }
     return u;
@@ -429,7 +379,7 @@ static UOperand resolve(const KParams& P, uint8_t src, uint16_t idx) {
 static VRef to_vref(const KParams& P, const HRef& h) {
     VRef v; v.kind = K_NONE; v.slot = 0; v.off16 = 0;
     if (h.kind == S_IMM) { v.kind = K_IMM; v.off16 = h.idx; return v; }
-    const UOperand u = resolve(P, h.kind, h.idx);
+    const UOperand u = resolve(P, h);
     v.kind = u.kind; v.slot = u.slot; v.off16 = (uint16_t)(u.off >> 4);
     return v;
 }
@@ -443,89 +393,64 @@ static int bin_index(uint8_t op) {   // position in RQ_BINOPS, -1 if not a fusab
     return -1;
 }
 
-static void encode_program(const Lowerer& L, KParams& P) {
+static void encode_program(Lowerer& L, KParams& P) {
     P.n_insn = 0;
-    auto push = [&](const UInsn& u) -> UInsn& {
-        if (P.n_insn >= kMaxInsn) raise(RQ_ERR_UNSUPPORTED, "program longer than %d instructions", kMaxInsn);
-        P.insn[P.n_insn] = u;
-        return P.insn[P.n_insn++];
-    };
     for (size_t i = 0; i < L.prog.size(); i++) {
-        const DInsn& d = L.prog[i];
-        const UOperand o = resolve(P, d.src, d.idx);
+        const HUnit& h = L.prog[i];
+        const UOperand x = resolve(P, h.x), y = resolve(P, h.y), z = resolve(P, h.z);
         UInsn u;
         memset(&u, 0, sizeof(u));
-        u.flags = (d.flags & 1) ? UF_STORE : 0;
-        if (d.flags & 2) u.flags |= UF_ELSE_IMM;
-        if (o.slot) u.flags |= UF_SLOT;
-        u.dst = d.dst;
-        u.aux = (uint8_t)d.aux;
-        u.off16 = (uint16_t)(o.off >> 4);
-        u.imm = d.imm;
-        u.gop = d.op;
-        u.gsrc = o.kind;
-        const int bi = bin_index(d.op);
-        if (d.op == D_LD) {
-            u.code = o.kind == K_M64 ? U_LD_M64 : o.kind == K_M32 ? U_LD_M32 : o.kind == K_M8 ? U_LD_M8
-                   : o.kind == K_STR ? U_LD_STR : U_LD_IMM;
-        } else if (bi >= 0 && (o.kind == K_M64 || o.kind == K_IMM)) {
-            const int form = (o.kind == K_M64) ? 0 : 1;      // AM / AI
-            u.code = (uint8_t)(U_ADD_AM + 4 * bi + form);
-            // fuse a preceding plain 64-bit load: acc = m64 OP imm | m64 OP m64'
-            if (P.n_insn > 0) {
-                UInsn& pv = P.insn[P.n_insn - 1];
-                if (pv.code == U_LD_IMM && !(pv.flags & UF_STORE) && form == 0) {
-                    // acc = imm OP m64  ==  m64 OP' imm with the operands swapped
-                    static const int swapped[12] = {0, 2, 1, 3, 4, 5, 8, 9, 6, 7, 10, 11};
-                    UInsn f = u;
-                    f.code = (uint8_t)(U_ADD_AM + 4 * swapped[bi] + 2);   // MI
-                    f.imm = pv.imm;
-                    pv = f;
-                    continue;
-                }
-                if (pv.code == U_LD_M64 && !(pv.flags & UF_STORE)) {
-                    UInsn f = u;
-                    f.code = (uint8_t)(U_ADD_AM + 4 * bi + (form == 0 ? 3 : 2));   // MM / MI
-                    f.flags = (uint8_t)((u.flags & (UF_STORE | UF_ELSE_IMM)) | (pv.flags & UF_SLOT));
-                    f.off16 = pv.off16;
-                    if (form == 0) {
-                        f.imm = (int64_t)o.off;
-                        if (o.slot) f.flags |= UF_SLOT2;
-                    }
-                    pv = f;
-                    continue;
-                }
-            }
-        } else if (d.op == D_FILTER) {
-            u.code = (d.src == S_NONE) ? U_FILTER_A : U_FILTER_O;
-        } else if (d.op >= D_FLT && d.op <= D_FNE) {
-            const int ci = d.op - D_FLT;
-            if (o.kind == K_M64) u.code = (uint8_t)(U_FLT_M64 + ci);
-            else if (o.kind == K_M32) u.code = (uint8_t)(U_FLT_M32 + ci);
-            else if (o.kind == K_M8) u.code = (uint8_t)(U_FLT_M8 + ci);
+        u.dst = h.dst >= 0 ? (uint8_t)h.dst : kNoDst;
+        if (h.filt) u.flags |= UF_FILTER;
+        if (x.slot) u.flags |= UF_XSLOT;
+        if (y.slot) u.flags |= UF_YSLOT;
+        if (z.slot) u.flags |= UF_ZSLOT;
+        u.aux = (uint8_t)h.aux;
+        u.gop = h.gop;
+        u.xkind = x.kind; u.ykind = y.kind; u.zkind = z.kind;
+        u.xoff16 = (uint16_t)(x.off >> 4); u.yoff16 = (uint16_t)(y.off >> 4); u.zoff16 = (uint16_t)(z.off >> 4);
+        u.imm = h.imm;
+        if (h.op == H_FCMP) {
+            const int ci = h.gop - D_LT;
+            if (ci < 0 || ci > 5) raise(RQ_ERR_INVALID, "internal: bad fused compare");
+            if (x.kind == K_M64) u.code = (uint8_t)(U_FLT_M64 + ci);
+            else if (x.kind == K_M32) u.code = (uint8_t)(U_FLT_M32 + ci);
+            else if (x.kind == K_M8) u.code = (uint8_t)(U_FLT_M8 + ci);
             else raise(RQ_ERR_INVALID, "internal: fused compare on a non-column operand");
-        } else if (d.op == D_GROUP) {
-            u.code = U_GROUP;
-        } else if (d.op == D_AGG_SUM && d.src == S_NONE) {
-            u.code = U_AGG_SUM_A;
-        } else if (d.op == D_AGG_SUM && o.kind == K_M64) {
-            u.code = U_AGG_SUM_M;
-        } else if (d.op == D_AGG_COUNT) {
-            u.code = U_AGG_COUNT;
-        } else if (d.op == D_AGG_SUM || d.op == D_AGG_MIN || d.op == D_AGG_MAX) {
-            u.code = U_AGG_GEN;
-        } else if (d.op == D_PROBE) {
+        } else if (h.op == H_MULI) {
+            if (x.kind != K_M64 || y.kind != K_M64) raise(RQ_ERR_INVALID, "internal: MULI operands");
+            u.code = h.gop == D_ADD ? U_MULADDI : (h.gop == D_SUB ? U_MULSUBI : U_MULRSUBI);
+        } else if (h.op == H_PROBE) {
             u.code = U_PROBE;
-        } else if (d.op == D_HAGG) {
-            u.code = U_HAGG;
-        } else if (d.op == D_BUILD) {
-            u.code = U_BUILD;
-        } else if (d.op == D_EMIT) {
-            u.code = U_EMIT;
-        } else {
-            u.code = U_GEN;   // DIV, string compares, SEL, binary ops on narrow / string operands
+        } else if (h.op == H_SEL) {
+            u.code = U_GEN;
+            if (y.kind == K_IMM) u.imm = h.y.imm;
+            if (x.kind == K_IMM) u.imm = h.x.imm;
+            if (z.kind == K_IMM) u.zoff16 = (uint16_t)L.imm_index(h.z.imm);
+        } else {   // H_BIN
+            const int bi = bin_index(h.gop);
+            static const int swapped[12] = {0, 2, 1, 3, 4, 5, 8, 9, 6, 7, 10, 11};
+            if (bi >= 0 && x.kind == K_M64 && y.kind == K_M64) {
+                u.code = (uint8_t)(U_ADD_MM + 2 * bi);
+            } else if (bi >= 0 && x.kind == K_M64 && y.kind == K_IMM) {
+                u.code = (uint8_t)(U_ADD_MM + 2 * bi + 1);
+                u.imm = h.y.imm;
+            } else if (bi >= 0 && x.kind == K_IMM && y.kind == K_M64) {
+                // imm OP m64  ==  m64 OP' imm
+                u.code = (uint8_t)(U_ADD_MM + 2 * swapped[bi] + 1);
+                u.imm = h.x.imm;
+                u.xkind = y.kind; u.xoff16 = u.yoff16;
+                u.flags = (uint8_t)((u.flags & ~(UF_XSLOT | UF_YSLOT)) | (y.slot ? UF_XSLOT : 0));
+            } else {
+                u.code = U_GEN;
+                if (x.kind == K_IMM && y.kind == K_IMM && h.gop != D_LD)
+                    raise(RQ_ERR_INVALID, "internal: constant expression reached the device program");
+                if (y.kind == K_IMM) u.imm = h.y.imm;
+                if (x.kind == K_IMM) u.imm = h.x.imm;
+            }
         }
-        push(u);
+        if (P.n_insn >= kMaxInsn) raise(RQ_ERR_UNSUPPORTED, "program longer than %d units", kMaxInsn);
+        P.insn[P.n_insn++] = u;
     }
     // sinks
     P.nk = (int)L.hkey.size();
@@ -615,6 +540,24 @@ static void launch_pipeline(const KParams& P, int gr, int64_t rows, rq_timings* 
     ev_used.push_back({ev_idx, is_scan});
     ev_idx++;
     if (tm) tm->kernel_launches++;
+}
+
+// hash-table capacities that worked, per pipeline shape and input size
+static std::map<uint64_t, uint64_t> g_ht_capacity;
+static uint64_t pipeline_signature(const rq_pipeline& pl, int64_t rows) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    auto mixin = [&](const void* p, size_t n) {
+        const unsigned char* b = (const unsigned char*)p;
+        for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 0x100000001b3ULL; }
+    };
+    mixin(&rows, sizeof rows);
+    mixin(&pl.sink_kind, sizeof pl.sink_kind);
+    mixin(&pl.source_kind, sizeof pl.source_kind);
+    mixin(&pl.source_id, sizeof pl.source_id);
+    for (int i = 0; i < pl.n_nodes; i++) mixin(&pl.nodes[i], sizeof(rq_node));
+    for (int i = 0; i < pl.n_keys; i++) mixin(&pl.keys[i], sizeof(rq_value));
+    for (int i = 0; i < pl.n_vals; i++) mixin(&pl.vals[i], sizeof(rq_value));
+    return h;
 }
 
 static bool has_str_key(const rq_pipeline& pl) {
@@ -760,10 +703,18 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
             while (cap < (uint64_t)(2 * want)) cap <<= 1;
             uint64_t cap_max = 4096;
             while (cap_max < (uint64_t)(2 * rows_bound)) cap_max <<= 1;
+            // capacities that worked for this pipeline on this many rows are remembered, so a
+            // repeated query does not pay for regrowth again
+            const uint64_t sig = pipeline_signature(pl_in, rows_bound);
+            auto known = g_ht_capacity.find(sig);
+            if (known != g_ht_capacity.end()) cap = std::min<uint64_t>(std::max(cap, known->second), cap_max);
             const int nk = pl.n_keys;
             if (nk > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
             const int nv = impl == IMPL_BUILD ? pl.n_vals : (int)ad.kind.size();
             std::unique_ptr<HashTableDev> ht;
+            unsigned long long* d_count = nullptr;
+            CK(cudaMalloc(&d_count, 8));
+            unsigned long long n_used = 0;
             for (;;) {
                 ht.reset(new HashTableDev());
                 ht->capacity = cap;
@@ -786,10 +737,24 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
                 CK(cudaMemsetAsync(E.flags, 0, 24, E.stream));
                 launch_pipeline(P, 0, rows_bound, tm, is_scan, ev_idx, ev_used);
                 check_flags(impl == IMPL_BUILD ? "join build pipeline" : "hash aggregation pipeline");
-                if (!E.h_flags[1]) break;
-                if (cap >= cap_max) raise(RQ_ERR_RUNTIME, "pipeline %d: hash table overflow at capacity %llu", pi, (unsigned long long)cap);
-                cap = std::min<uint64_t>(cap * 8, cap_max);
+                bool regrow = E.h_flags[1] != 0;
+                if (!regrow) {
+                    // keep the load factor at or below 1/2 (probe runs stay short)
+                    CK(cudaMemsetAsync(d_count, 0, 8, E.stream));
+                    rq_ht_count<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d.tags, cap, d_count);
+                    if (tm) tm->kernel_launches++;
+                    CK(cudaMemcpyAsync(&n_used, d_count, 8, cudaMemcpyDeviceToHost, E.stream));
+                    CK(cudaStreamSynchronize(E.stream));
+                    regrow = n_used * 2 > cap && cap < cap_max;
+                }
+                if (!regrow) break;
+                if (cap >= cap_max) { cudaFree(d_count); raise(RQ_ERR_RUNTIME, "pipeline %d: hash table overflow at capacity %llu", pi, (unsigned long long)cap); }
+                uint64_t next = cap * 8;
+                if (!E.h_flags[1]) { next = cap; while (next < 2 * n_used) next <<= 1; }
+                cap = std::min<uint64_t>(next, cap_max);
             }
+            cudaFree(d_count);
+            g_ht_capacity[sig] = cap;
             if (impl == IMPL_BUILD) {
                 for (int k = 0; k < pl.n_vals; k++) {
                     outs[pi].payload_sql_type.push_back(pl.vals[k].sql_type);
@@ -799,15 +764,7 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
                 return;
             }
             // dense relation out of the aggregation table
-            unsigned long long* d_count = nullptr;
-            CK(cudaMalloc(&d_count, 8));
-            CK(cudaMemsetAsync(d_count, 0, 8, E.stream));
-            rq_ht_count<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d.tags, cap, d_count);
-            if (tm) tm->kernel_launches++;
-            unsigned long long n_groups = 0;
-            CK(cudaMemcpyAsync(&n_groups, d_count, 8, cudaMemcpyDeviceToHost, E.stream));
-            CK(cudaStreamSynchronize(E.stream));
-            cudaFree(d_count);
+            const unsigned long long n_groups = n_used;
             const int ncols = pl.n_keys + pl.n_vals;
             out = new_intermediate(ncols, (int64_t)n_groups);
             std::vector<int> colmap(ncols);
@@ -1096,19 +1053,23 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
             s += line;
         }
         for (size_t i = 0; i < L.prog.size(); i++) {
-            const DInsn& in = L.prog[i];
-            snprintf(line, sizeof line, "insn %d %d %d %d %d %d %lld\n", in.op, in.src, in.flags, in.dst, in.idx, in.aux, (long long)in.imm);
+            const HUnit& h = L.prog[i];
+            snprintf(line, sizeof line, "unit %d %d %d %d %lld %d %d %lld %d %d %lld %lld %d %d %d\n", h.op, h.gop,
+                     h.x.kind, h.x.idx, (long long)h.x.imm, h.y.kind, h.y.idx, (long long)h.y.imm,
+                     h.z.kind, h.z.idx, (long long)h.z.imm, (long long)h.imm, h.dst, h.filt ? 1 : 0, h.aux);
             s += line;
         }
         for (int i = 0; i < P.n_insn; i++) {
             const UInsn& u = P.insn[i];
-            snprintf(line, sizeof line, "uinsn %d %d %d %d %d %d %d %lld\n", u.code, u.flags, u.dst, u.aux, u.gop, u.gsrc, u.off16, (long long)u.imm);
+            snprintf(line, sizeof line, "uinsn %d %d %d %d %d %d %d %d %d %d %d %lld\n", u.code, u.flags, u.dst, u.aux, u.gop,
+                     u.xkind, u.ykind, u.zkind, u.xoff16, u.yoff16, u.zoff16, (long long)u.imm);
             s += line;
         }
         for (size_t k = 0; k < L.hkey.size(); k++) { snprintf(line, sizeof line, "key %d %d\n", L.hkey[k].kind, L.hkey[k].idx); s += line; }
         for (size_t k = 0; k < L.hout.size(); k++) { snprintf(line, sizeof line, "out %d %d\n", L.hout[k].kind, L.hout[k].idx); s += line; }
         for (int k = 0; k < kMaxImm; k++) { snprintf(line, sizeof line, "imm %d %lld\n", k, (long long)P.imm[k]); s += line; }
         for (size_t u = 0; u < ad.kind.size(); u++) { snprintf(line, sizeof line, "agg %d %d\n", (int)u, ad.kind[u]); s += line; }
+        for (size_t u = 0; u < ad.kind.size(); u++) { snprintf(line, sizeof line, "aggsrc %d %d\n", L.hagg_src[u].kind, L.hagg_src[u].idx); s += line; }
         for (size_t k = 0; k < ad.uniq_of.size(); k++) { snprintf(line, sizeof line, "aggmap %d %d\n", (int)k, ad.uniq_of[k]); s += line; }
         if ((int64_t)s.size() + 1 > buflen) return fail(RQ_ERR_INVALID, "rq_debug_lower: buffer too small");
         memcpy(buf, s.c_str(), s.size() + 1);

@@ -21,6 +21,7 @@ struct HashTableDev {
 };
 
 constexpr uint64_t kTagLocked = 1ULL;
+constexpr uint64_t kMaxProbeLen = 2048;   // longer runs mean the table is (nearly) full: report and regrow
 
 // key kinds: 0 integer word, 1 CHAR (equality ignores trailing blanks), 2 VARCHAR (exact)
 __device__ __forceinline__ uint64_t hash_str(const unsigned char* s, bool strip) {
@@ -63,7 +64,8 @@ __device__ __forceinline__ bool ht_insert_dup(const DHashTable& ht, const int64_
     const uint64_t tag = h | 2ULL;
     const uint64_t cap = ht.cap_mask + 1;
     uint64_t i = h & ht.cap_mask;
-    for (uint64_t tries = 0; tries < cap; tries++) {
+    const uint64_t lim = cap < kMaxProbeLen ? cap : kMaxProbeLen;
+    for (uint64_t tries = 0; tries < lim; tries++) {
         const unsigned long long old = atomicCAS((unsigned long long*)&ht.tags[i], 0ULL, (unsigned long long)tag);
         if (old == 0ULL) {
             for (int j = 0; j < ht.nk; j++) ht.keys[(size_t)j * cap + i] = k[j];
@@ -81,7 +83,8 @@ __device__ __forceinline__ bool ht_find_or_insert(const DHashTable& ht, const in
     const uint64_t tag = h | 2ULL;
     const uint64_t cap = ht.cap_mask + 1;
     uint64_t i = h & ht.cap_mask;
-    for (uint64_t tries = 0; tries < cap; tries++) {
+    const uint64_t lim = cap < kMaxProbeLen ? cap : kMaxProbeLen;
+    for (uint64_t tries = 0; tries < lim; tries++) {
         uint64_t t = *(volatile uint64_t*)&ht.tags[i];
         if (t == 0ULL) {
             t = atomicCAS((unsigned long long*)&ht.tags[i], 0ULL, (unsigned long long)kTagLocked);

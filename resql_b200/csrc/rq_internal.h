@@ -17,7 +17,7 @@ constexpr int kMaxWarps   = 16;                 // warps per CTA (one persistent
 
 constexpr int kMaxStagedCols = 16;
 constexpr int kMaxStrCols    = 8;
-constexpr int kMaxInsn       = 160;
+constexpr int kMaxInsn       = 128;
 constexpr int kMaxKeys       = 8;
 constexpr int kMaxAggs       = 16;
 constexpr int kMaxOut        = 24;
@@ -29,46 +29,25 @@ constexpr int kRegGroups     = 4;      // groups held in registers per warp (reg
 constexpr int kLowCardMaxGroups = 8;   // groups per warp with lane-private shared-memory accumulators
 constexpr int kGroupTableCap = 2048;   // global table of the low-cardinality aggregate paths
 
-// ---- host-level instruction: accumulator machine ----------------------------------------------
-// The ABI-level postfix program (rq_node) is linearised on the host into instructions of the
-// form   acc = acc OP operand   over the register tile. Values used more than once or not
-// consumed by the next instruction are kept in shared-memory slots (one int64 per tuple).
-// This is the form tests/vm_model.py executes; encode_program() then fuses it into UInsn.
+enum SinkImpl { IMPL_LOWAGG = 1, IMPL_HASHAGG = 2, IMPL_BUILD = 3, IMPL_EMIT = 4, IMPL_REGAGG = 5 };
+
+// ---- operation codes shared by the host-level program and the device encoding ----------------
 enum DOp : uint8_t {
     D_LD = 1, D_ADD, D_SUB, D_RSUB, D_MUL, D_DIV, D_RDIV, D_AND, D_OR,
     D_LT, D_LE, D_GT, D_GE, D_EQ, D_NE,
     D_EQC, D_EQV, D_NEC, D_NEV, D_LIKE, D_RLIKE,
-    D_SEL,            // acc = (acc&0xff) ? operand : slot[aux]
-    D_FILTER,         // valid &= (acc & 0xff) != 0
-    D_GROUP,          // low-cardinality group lookup (keys via KParams::key)
-    D_AGG_SUM, D_AGG_COUNT, D_AGG_MIN, D_AGG_MAX,   // aux = aggregate index
-    D_PROBE,          // aux = probe index
-    D_HAGG,           // hash aggregate sink
-    D_BUILD,          // hash-join build sink
-    D_EMIT,           // materialize sink
-    D_NOP,
-    // valid &= (operand CMP imm): a compare whose only consumer is the selection; the
-    // accumulator is left untouched (selection.h:52-70 + the compare emitters fused)
-    D_FLT, D_FLE, D_FGT, D_FGE, D_FEQ, D_FNE
+    D_SEL
 };
 
 enum DSrc : uint8_t { S_NONE = 0, S_COL = 1, S_SLOT = 2, S_IMM = 3, S_STR = 4 };
 
-struct DInsn {
-    uint8_t  op;
-    uint8_t  src;       // DSrc
-    uint8_t  flags;     // bit0: store acc to slot `dst` after the op; bit1: SEL else is imm[aux]
-    uint8_t  dst;
-    uint16_t idx;       // column / slot index of the operand
-    uint16_t aux;
-    int64_t  imm;
-};
-static_assert(sizeof(DInsn) == 16, "DInsn must be 16 bytes");
-
 // ---- device-level instruction -------------------------------------------------------------------
-// One switch per instruction: opcode and operand form are fused into `code`, operands are byte
-// offsets into the warp's shared-memory region (stage-relative for columns, region-relative for
-// slots), so the interpreter does no address bookkeeping per tuple.
+// The program is a memory-to-memory vector VM over the warp's shared-memory region: every unit
+// reads its operands from staged columns / value slots (or an immediate), computes 8 tuples per
+// lane in registers and writes the result to a slot and/or folds it into the selection mask.
+// Nothing but the selection mask lives in registers across units, so the one big switch costs no
+// register shuffling. Opcode and operand form are fused into `code` on the host and operands are
+// precomputed byte offsets, so a unit does no address bookkeeping per tuple.
 enum UKind : uint8_t {             // operand kinds
     K_NONE = 0, K_M64, K_M32, K_M8, K_IMM, K_STR
 };
@@ -77,45 +56,41 @@ enum UKind : uint8_t {             // operand kinds
 
 enum UCode : uint8_t {
     U_END = 0,
-    U_LD_M64, U_LD_M32, U_LD_M8, U_LD_IMM, U_LD_STR,
-    // acc = acc OP m64 | acc OP imm | m64 OP imm | m64 OP m64'
-#define RQ_X(N) U_##N##_AM, U_##N##_AI, U_##N##_MI, U_##N##_MM,
+    // t = x OP y (64-bit operands in shared memory) | t = x OP imm
+#define RQ_X(N) U_##N##_MM, U_##N##_MI,
     RQ_BINOPS(RQ_X)
 #undef RQ_X
-    U_GEN,                         // gop/gsrc: any DOp with any operand kind (rare forms)
-    U_FILTER_A,                    // valid &= acc
-    U_FILTER_O,                    // valid &= operand (kind in gsrc)
-    // valid &= (column CMP imm)
+    U_MULADDI, U_MULSUBI, U_MULRSUBI,   // t = (x + imm) * y | (x - imm) * y | (imm - x) * y
+    U_GEN,                              // t = gop(x, y [, z]) with operands of any kind
+    // valid &= (column CMP imm): selection-fused compares, nothing stored
     U_FLT_M64, U_FLE_M64, U_FGT_M64, U_FGE_M64, U_FEQ_M64, U_FNE_M64,
     U_FLT_M32, U_FLE_M32, U_FGT_M32, U_FGE_M32, U_FEQ_M32, U_FNE_M32,
     U_FLT_M8,  U_FLE_M8,  U_FGT_M8,  U_FGE_M8,  U_FEQ_M8,  U_FNE_M8,
-    U_GROUP,
-    U_AGG_SUM_A, U_AGG_SUM_M,      // aux = aggregate index; operand = acc | m64
-    U_AGG_COUNT,
-    U_AGG_GEN,                     // gop = D_AGG_SUM/MIN/MAX, gsrc = operand kind (K_NONE: acc)
-    U_PROBE, U_HAGG, U_BUILD, U_EMIT
+    U_PROBE
 };
 
-constexpr uint8_t UF_STORE    = 1;   // store acc to slot `dst` after the op
-constexpr uint8_t UF_ELSE_IMM = 2;   // SEL: else value is imm[aux]
-constexpr uint8_t UF_SLOT     = 4;   // operand offset is relative to the warp region (a slot)
-constexpr uint8_t UF_SLOT2    = 8;   // MM forms: second operand likewise
+constexpr uint8_t UF_XSLOT  = 1;   // x offset is relative to the warp region (a slot), else the stage
+constexpr uint8_t UF_YSLOT  = 2;
+constexpr uint8_t UF_ZSLOT  = 4;
+constexpr uint8_t UF_FILTER = 8;   // valid &= (t & 0xff) != 0   (selection.h:62-66)
+constexpr uint8_t kNoDst = 0xff;
 
 struct UInsn {
     uint8_t  code;
     uint8_t  flags;
-    uint8_t  dst;       // slot index for UF_STORE
-    uint8_t  aux;       // aggregate / probe index, SEL else slot or imm index
-    uint8_t  gop;       // U_GEN / U_AGG_GEN: DOp
-    uint8_t  gsrc;      // U_GEN / U_FILTER_O / U_AGG_GEN: UKind of the operand
-    uint16_t off16;     // operand byte offset >> 4 (string columns: column index)
-    int64_t  imm;       // immediate; MM forms: byte offset of the second operand
+    uint8_t  dst;       // slot receiving t, kNoDst = none
+    uint8_t  aux;       // probe index
+    uint8_t  gop;       // U_GEN: DOp
+    uint8_t  xkind, ykind, zkind;   // U_GEN: UKind of the operands
+    uint16_t xoff16, yoff16, zoff16;   // byte offsets >> 4 (K_STR: string column; K_IMM: imm-table index)
+    uint16_t pad;
+    int64_t  imm;
 };
-static_assert(sizeof(UInsn) == 16, "UInsn must be 16 bytes");
+static_assert(sizeof(UInsn) == 24, "UInsn must be 24 bytes");
 
 struct VRef {           // value reference used by sinks (keys, payloads, outputs)
     uint8_t  kind;      // UKind
-    uint8_t  slot;      // 1: offset relative to the warp region
+    uint8_t  slot;      // bit0: offset relative to the warp region; bit1: value fits in unsigned 32 bits
     uint16_t off16;     // byte offset >> 4; K_IMM: index into KParams::imm; K_STR: string column
 };
 
@@ -172,7 +147,7 @@ struct KParams {
     int32_t        key32;               // the packed key fits in 32 bits
     int32_t        na;
     uint8_t        agg_kind[kMaxAggs];
-    VRef           agg_src[kMaxAggs];    // hash aggregate only
+    VRef           agg_src[kMaxAggs];    // aggregate inputs (COUNT has none)
     int32_t        G;                    // lane-private groups per warp (shared-memory path)
     // low-card global table (packed key)
     uint32_t*      g_state;              // [kGroupTableCap]
@@ -186,6 +161,7 @@ struct KParams {
     int32_t        n_probes;
     DProbe         probe[kMaxProbes];
     // materialize
+    int32_t        sink;                 // SinkImpl executed after the units of every tile
     int32_t        n_out;
     VRef           out[kMaxOut];
     int64_t*       out_col[kMaxOut];

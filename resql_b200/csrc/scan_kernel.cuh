@@ -2,18 +2,22 @@
 //
 // One persistent CTA per SM; every WARP is an independent pipeline. A warp owns a ring of TMA
 // stages in shared memory (cp.async.bulk + one mbarrier per stage); each stage holds one warp
-// tile = 256 tuples of every scanned column. The warp interprets the typed program over a
-// register tile of 8 tuples per lane with ONE switch per instruction (opcode and operand form are
-// fused on the host, operands are precomputed shared-memory offsets), then re-arms the stage. No
-// CTA-wide barrier exists in the steady state, so warps drift out of phase and the copy engine
-// always has work.
+// tile = 256 tuples of every scanned column. Per tile the warp
+//   1. runs the typed program: a memory-to-memory vector VM over its shared-memory region. Every
+//      unit reads operands from staged columns / value slots, computes 8 tuples per lane and
+//      writes a slot and/or narrows the selection mask. ONE switch per unit (opcode and operand
+//      form fused on the host, operands are precomputed offsets); only the selection mask lives in
+//      registers across units, so the switch causes no register shuffling;
+//   2. runs the sink as straight-line code: group match + aggregation, hash aggregation,
+//      hash-join build, or materialize;
+//   3. re-arms the stage. No CTA-wide barrier exists in the steady state.
 //
 // Aggregation (template parameter GR):
-//   GR = 1 / 4  register path: up to GR groups x kNAR aggregates live in registers; a tuple is
-//               added to every group accumulator through a 0/1 multiplier (two IMADs per 64-bit
-//               add, on the FMA pipe, no shared-memory traffic and no dependent memory chain).
-//   GR = 0      generic path: lane-private shared-memory accumulators for up to 8 groups per warp,
-//               HBM hash aggregation, hash-join build/probe, materialize.
+//   GR = 1 / 4  register path: up to GR groups x kNAR aggregates live in registers for the whole
+//               kernel; a tuple is added to every group accumulator through a 0/1 multiplier
+//               (IMAD.WIDE.U32 on the FMA pipe, no shared-memory traffic, no dependent chain).
+//   GR = 0      generic sinks: lane-private shared-memory accumulators for up to 8 groups per
+//               warp, HBM hash aggregation, hash-join build, materialize.
 //
 // Semantics restated from the reference (Henning1/resql):
 //   arithmetic / compares  src/ExpressionsJitFlounder.h:298-689
@@ -36,62 +40,76 @@ __device__ __forceinline__ int row_in_tile(int r, int lane) {
     return (r >> 1) * 64 + 2 * lane + (r & 1);
 }
 
-// ---- register tile <-> shared memory ---------------------------------------------------------
-__device__ __forceinline__ void ld_m64(const unsigned char* b, int lane, int64_t (&v)[kR]) {
-    const longlong2* p = reinterpret_cast<const longlong2*>(b) + lane;
-#pragma unroll
-    for (int k = 0; k < kR / 2; k++) {
-        const longlong2 x = p[k * 32];
-        v[2 * k] = x.x; v[2 * k + 1] = x.y;
-    }
+// ---- shared memory through 32-bit shared-space addresses --------------------------------------
+// (explicit ld.shared / st.shared: no generic-address arithmetic per access; volatile keeps the
+// program order between a slot store and the loads of later units)
+__device__ __forceinline__ void lds_v2b64(uint32_t a, int64_t& x, int64_t& y) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a));
 }
-__device__ __forceinline__ void st_m64(unsigned char* b, int lane, const int64_t (&v)[kR]) {
-    longlong2* p = reinterpret_cast<longlong2*>(b) + lane;
-#pragma unroll
-    for (int k = 0; k < kR / 2; k++) p[k * 32] = make_longlong2(v[2 * k], v[2 * k + 1]);
+__device__ __forceinline__ void sts_v2b64(uint32_t a, int64_t x, int64_t y) {
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(x), "l"(y) : "memory");
 }
-__device__ __forceinline__ void ld_m32(const unsigned char* b, int lane, int32_t (&v)[kR]) {
-    const int2* p = reinterpret_cast<const int2*>(b) + lane;
-#pragma unroll
-    for (int k = 0; k < kR / 2; k++) {
-        const int2 x = p[k * 32];
-        v[2 * k] = x.x; v[2 * k + 1] = x.y;
-    }
+__device__ __forceinline__ void lds_v2b32(uint32_t a, int32_t& x, int32_t& y) {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a));
 }
-__device__ __forceinline__ void ld_m8(const unsigned char* b, int lane, uint32_t (&v)[kR]) {
-    const uchar2* p = reinterpret_cast<const uchar2*>(b) + lane;
+__device__ __forceinline__ void lds_v2u8(uint32_t a, uint32_t& x, uint32_t& y) {
+    asm volatile("ld.shared.v2.u8 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a));
+}
+__device__ __forceinline__ int64_t lds_b64(uint32_t a) {
+    int64_t v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a)); return v;
+}
+__device__ __forceinline__ int32_t lds_s32(uint32_t a) {
+    int32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts_b64(uint32_t a, int64_t v) {
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// register tile <-> shared memory; `a` already includes the lane offset (16 / 8 / 2 bytes per lane)
+__device__ __forceinline__ void ld_m64(uint32_t a, int64_t (&v)[kR]) {
 #pragma unroll
-    for (int k = 0; k < kR / 2; k++) {
-        const uchar2 x = p[k * 32];
-        v[2 * k] = x.x; v[2 * k + 1] = x.y;
-    }
+    for (int k = 0; k < kR / 2; k++) lds_v2b64(a + k * 512, v[2 * k], v[2 * k + 1]);
+}
+__device__ __forceinline__ void st_m64(uint32_t a, const int64_t (&v)[kR]) {
+#pragma unroll
+    for (int k = 0; k < kR / 2; k++) sts_v2b64(a + k * 512, v[2 * k], v[2 * k + 1]);
+}
+__device__ __forceinline__ void ld_m32(uint32_t a, int32_t (&v)[kR]) {
+#pragma unroll
+    for (int k = 0; k < kR / 2; k++) lds_v2b32(a + k * 256, v[2 * k], v[2 * k + 1]);
+}
+__device__ __forceinline__ void ld_m8(uint32_t a, uint32_t (&v)[kR]) {
+#pragma unroll
+    for (int k = 0; k < kR / 2; k++) lds_v2u8(a + k * 64, v[2 * k], v[2 * k + 1]);
 }
 
 struct WarpCtx {
-    const unsigned char* stage;   // current stage (columns of the current tile)
-    unsigned char*       wbase;   // this warp's shared-memory region
-    int64_t              row0;    // first tuple of the tile in the source
-    int                  lane;
+    uint32_t stage;     // shared address of the current stage (columns of the current tile)
+    uint32_t wbase;     // shared address of this warp's region
+    int64_t  row0;      // first tuple of the tile in the source
+    int      lane;
 };
 
-__device__ __forceinline__ const unsigned char* opnd_base(const WarpCtx& c, bool slot, uint32_t off) {
-    return (slot ? c.wbase : c.stage) + off;
-}
-
-// any operand kind -> 8 int64 values (rare forms, group keys)
-__device__ __forceinline__ void fetch(const KParams& P, const WarpCtx& c, int kind,
-                                      const unsigned char* ob, int stridx, int64_t imm,
-                                      int64_t (&v)[kR]) {
+// any operand kind -> 8 int64 values (rare forms, group keys, aggregate inputs)
+__device__ __forceinline__ void fetch(const KParams& P, const WarpCtx& c, int kind, bool slot,
+                                      uint32_t off16, int64_t imm, int64_t (&v)[kR]) {
+    const uint32_t base = (slot ? c.wbase : c.stage) + (off16 << 4);
     switch (kind) {
-        case K_M64: ld_m64(ob, c.lane, v); break;
+        case K_M64: ld_m64(base + c.lane * 16, v); break;
         case K_M32: {
-            int32_t t[kR]; ld_m32(ob, c.lane, t);
+            int32_t t[kR]; ld_m32(base + c.lane * 8, t);
 #pragma unroll
             for (int r = 0; r < kR; r++) v[r] = t[r];
             break;
         }
         case K_M8: {
-            uint32_t t[kR]; ld_m8(ob, c.lane, t);
+            uint32_t t[kR]; ld_m8(base + c.lane * 2, t);
 #pragma unroll
             for (int r = 0; r < kR; r++) v[r] = t[r];
             break;
@@ -99,7 +117,7 @@ __device__ __forceinline__ void fetch(const KParams& P, const WarpCtx& c, int ki
         case K_STR:
 #pragma unroll
             for (int r = 0; r < kR; r++)
-                v[r] = (int64_t)(P.str_ptr[stridx] + (size_t)(c.row0 + row_in_tile(r, c.lane)) * P.str_w[stridx]);
+                v[r] = (int64_t)(P.str_ptr[off16] + (size_t)(c.row0 + row_in_tile(r, c.lane)) * P.str_w[off16]);
             break;
         default:
 #pragma unroll
@@ -107,25 +125,31 @@ __device__ __forceinline__ void fetch(const KParams& P, const WarpCtx& c, int ki
             break;
     }
 }
+__device__ __forceinline__ void fetch_vref(const KParams& P, const WarpCtx& c, VRef vr, int64_t (&v)[kR]) {
+    fetch(P, c, vr.kind, vr.slot & 1, vr.off16, vr.kind == K_IMM ? P.imm[vr.off16] : 0, v);
+}
 
 // one tuple of a sink value
 __device__ __forceinline__ int64_t ld_row(const KParams& P, const WarpCtx& c, VRef vr, int r) {
     const int row = row_in_tile(r, c.lane);
-    const unsigned char* b = (vr.slot ? c.wbase : c.stage) + ((uint32_t)vr.off16 << 4);
+    const uint32_t b = ((vr.slot & 1) ? c.wbase : c.stage) + ((uint32_t)vr.off16 << 4);
     switch (vr.kind) {
-        case K_M64: return reinterpret_cast<const int64_t*>(b)[row];
-        case K_M32: return reinterpret_cast<const int32_t*>(b)[row];
-        case K_M8:  return b[row];
+        case K_M64: return lds_b64(b + row * 8);
+        case K_M32: return lds_s32(b + row * 4);
+        case K_M8:  return lds_u8(b + row);
         case K_IMM: return P.imm[vr.off16];
         case K_STR: return (int64_t)(P.str_ptr[vr.off16] + (size_t)(c.row0 + row) * P.str_w[vr.off16]);
         default:    return 0;
     }
 }
 
-// acc += v * m for a 0/1 multiplier m (exact mod 2^64): IMAD.WIDE.U32 accumulates the low word
-// with carry, the high word is one more IMAD - FMA-pipe work, no shared memory, no branches.
+// acc += v * m for a 0/1 multiplier m (exact mod 2^64)
 __device__ __forceinline__ void macc(uint64_t& acc, int64_t v, uint32_t m) {
     acc += (uint64_t)v * (uint64_t)m;
+}
+// the same when v is known to fit in unsigned 32 bits: one IMAD.WIDE.U32
+__device__ __forceinline__ void macc32(uint64_t& acc, int64_t v, uint32_t m) {
+    acc += (uint64_t)(uint32_t)v * (uint64_t)m;
 }
 
 // ---- low-cardinality global group table (packed key) -----------------------------------------
@@ -184,12 +208,7 @@ extern __shared__ __align__(128) unsigned char rq_smem[];
 #define RQ_EX_EQ(x, y)   ((int64_t)((x) == (y)))
 #define RQ_EX_NE(x, y)   ((int64_t)((x) != (y)))
 
-// The aggregate-index switches must stay switches over compile-time register names: an inline
-// asm marker that differs per case keeps the compiler from merging the cases into one body that
-// indexes the accumulator array dynamically (which would demote it to local memory).
-#define RQ_NOMERGE(A) asm volatile("// agg case %0" ::"n"(A))
-
-static_assert(kNAR == 6, "the aggregate-index switches list cases 0..5");
+static_assert(kNAR == 6, "register accumulators are sized for 6 aggregates");
 template <int GR> struct ScanCfg;
 template <> struct ScanCfg<0> { static constexpr int kThreads = 512; };
 template <> struct ScanCfg<1> { static constexpr int kThreads = 512; };
@@ -205,39 +224,36 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     const int W = blockDim.x >> 5;
     const int S = P.stages;
 
-    uint64_t* bars = reinterpret_cast<uint64_t*>(rq_smem) + warp * kMaxStages;
-    unsigned char* wbase = rq_smem + P.warp_off + (size_t)warp * P.warp_bytes;
-    unsigned char* slot_base = wbase + P.slots_rel;
-    int64_t* sacc = reinterpret_cast<int64_t*>(wbase + P.acc_rel);   // GR == 0 low-card path
+    const uint32_t smem0 = smem_u32(rq_smem);
+    const uint32_t bars = smem0 + warp * (kMaxStages * 8);
+    const uint32_t wbase = smem0 + P.warp_off + warp * P.warp_bytes;
+    const uint32_t slot_base = wbase + P.slots_rel;
+    const uint32_t sacc = wbase + P.acc_rel;            // GR == 0 low-card path: [g][a][lane] int64
 
     const int64_t n_rows = P.n_rows_ptr ? *P.n_rows_ptr : P.n_rows;
     const int64_t n_tiles = (n_rows + kTile - 1) / kTile;
     const int64_t stride = (int64_t)gridDim.x * W;
     const int64_t first = (int64_t)blockIdx.x * W + warp;
     const int NA = P.na, NK = P.nk;
-    const bool lowagg = (GR > 0) || (P.G > 0);
+    const int sink = P.sink;
 
     if (lane == 0) {
-        for (int s = 0; s < S; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < S; s++) mbar_init_s(bars + s * 8, 1);
         fence_mbar_init();
     }
     // accumulators
     uint64_t racc[NG][kNAR];
-    uint32_t m[NG][kR];
     uint64_t dk[ND];
     int ngroups = 0;
     unsigned seen = 0;     // (no GROUP BY) did this lane aggregate at least one tuple
 #pragma unroll
-    for (int g = 0; g < NG; g++) {
+    for (int g = 0; g < NG; g++)
 #pragma unroll
         for (int a = 0; a < kNAR; a++) racc[g][a] = (uint64_t)agg_identity(a < NA ? P.agg_kind[a] : 0);
 #pragma unroll
-        for (int r = 0; r < kR; r++) m[g][r] = 0;
-    }
-#pragma unroll
     for (int e = 0; e < ND; e++) dk[e] = 0;
-    if (GR == 0 && P.G > 0) {
-        for (int i = lane; i < P.G * NA * 32; i += 32) sacc[i] = agg_identity(P.agg_kind[(i >> 5) % NA]);
+    if (GR == 0 && sink == IMPL_LOWAGG) {
+        for (int i = lane; i < P.G * NA * 32; i += 32) sts_b64(sacc + i * 8, agg_identity(P.agg_kind[(i >> 5) % NA]));
     }
     __syncwarp();
 
@@ -247,12 +263,12 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     };
     auto issue = [&](int64_t tile, int s) {
         if (is_guarded(tile)) return;
-        uint64_t* bar = &bars[s];
-        unsigned char* dst = wbase + (size_t)s * P.stage_bytes;
-        mbar_expect_tx(bar, P.stage_bytes);
+        const uint32_t bar = bars + s * 8;
+        const uint32_t dst = wbase + s * P.stage_bytes;
+        mbar_expect_tx_s(bar, P.stage_bytes);
         for (int c = 0; c < P.n_cols; c++) {
             const uint32_t bytes = kTile * P.col_w[c];
-            tma_bulk_g2s(dst + P.col_off[c], P.col_ptr[c] + (size_t)tile * bytes, bytes, bar);
+            tma_bulk_g2s_s(dst + P.col_off[c], P.col_ptr[c] + (size_t)tile * bytes, bytes, bar);
         }
     };
     if (lane == 0 && P.n_cols > 0) {
@@ -262,26 +278,28 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
 
     int s = 0;
     uint32_t phase = 0;
+    const bool hash_sink = (GR == 0) && (sink == IMPL_BUILD || sink == IMPL_HASHAGG);
     for (int64_t tile = first; tile < n_tiles; tile += stride) {
+        // a full hash table makes the host regrow it and rerun: stop early
+        if (hash_sink && *(volatile int32_t*)P.ht_full) break;
         WarpCtx c;
-        c.stage = wbase + (size_t)s * P.stage_bytes;
+        c.stage = wbase + s * P.stage_bytes;
         c.wbase = wbase;
         c.row0 = tile * (int64_t)kTile;
         c.lane = lane;
 
         if (P.n_cols > 0) {
             if (is_guarded(tile)) {
-                unsigned char* dst = wbase + (size_t)s * P.stage_bytes;
                 const int64_t rows = n_rows - c.row0;
                 for (int col = 0; col < P.n_cols; col++) {
                     const int w = P.col_w[col];
                     const unsigned char* src = P.col_ptr[col] + (size_t)c.row0 * w;
-                    for (int64_t i = lane; i < (int64_t)kTile * w; i += 32)
-                        dst[P.col_off[col] + i] = (i < rows * w) ? src[i] : (unsigned char)0;
+                    for (int i = lane; i < kTile * w; i += 32)
+                        sts_u8(c.stage + P.col_off[col] + i, (i < rows * w) ? src[i] : 0u);
                 }
                 __syncwarp();
             } else {
-                mbar_wait(&bars[s], phase);
+                mbar_wait_s(bars + s * 8, phase);
             }
         }
 
@@ -293,70 +311,66 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                 if (c.row0 + row_in_tile(r, lane) < n_rows) valid |= 1u << r;
         }
 
-        int64_t acc[kR];
-#pragma unroll
-        for (int r = 0; r < kR; r++) acc[r] = 0;
-        unsigned gid = 0;   // GR == 0 low-card path: 4 bits per tuple
-
+        // ---- 1. the program ---------------------------------------------------------------
         const int n_insn = P.n_insn;
         for (int pc = 0; pc < n_insn; pc++) {
             const UInsn in = P.insn[pc];
-            const unsigned char* ob = opnd_base(c, in.flags & UF_SLOT, (uint32_t)in.off16 << 4);
-            switch (in.code) {
-                case U_LD_M64: ld_m64(ob, lane, acc); break;
-                case U_LD_M32: {
-                    int32_t t[kR]; ld_m32(ob, lane, t);
-#pragma unroll
-                    for (int r = 0; r < kR; r++) acc[r] = t[r];
-                    break;
-                }
-                case U_LD_M8: {
-                    uint32_t t[kR]; ld_m8(ob, lane, t);
-#pragma unroll
-                    for (int r = 0; r < kR; r++) acc[r] = t[r];
-                    break;
-                }
-                case U_LD_IMM:
-#pragma unroll
-                    for (int r = 0; r < kR; r++) acc[r] = in.imm;
-                    break;
-                case U_LD_STR: fetch(P, c, K_STR, ob, in.off16, 0, acc); break;
+            const uint32_t xa = ((in.flags & UF_XSLOT) ? wbase : c.stage) + ((uint32_t)in.xoff16 << 4);
+            const uint32_t ya = ((in.flags & UF_YSLOT) ? wbase : c.stage) + ((uint32_t)in.yoff16 << 4);
+            // result handling, expanded inside every case so that t never crosses the switch
+#define RQ_FINISH(t)                                                                          \
+    do {                                                                                      \
+        if (in.dst != kNoDst) st_m64(slot_base + in.dst * (kTile * 8) + lane * 16, t);        \
+        if (in.flags & UF_FILTER) {                                                           \
+            _Pragma("unroll") for (int r = 0; r < kR; r++)                                    \
+                if ((t[r] & 0xff) == 0) valid &= ~(1u << r);                                  \
+            if (!__any_sync(kFull, valid != 0)) pc = n_insn;                                  \
+        }                                                                                     \
+    } while (0)
 
+            switch (in.code) {
 #define RQ_CASES(N)                                                                        \
-    case U_##N##_AM: {                                                                     \
-        int64_t b[kR]; ld_m64(ob, lane, b);                                                \
-        _Pragma("unroll") for (int r = 0; r < kR; r++) acc[r] = RQ_EX_##N(acc[r], b[r]);   \
-        break;                                                                             \
-    }                                                                                      \
-    case U_##N##_AI: {                                                                     \
-        const int64_t y = in.imm;                                                          \
-        _Pragma("unroll") for (int r = 0; r < kR; r++) acc[r] = RQ_EX_##N(acc[r], y);      \
+    case U_##N##_MM: {                                                                     \
+        int64_t a[kR], b[kR], t[kR];                                                       \
+        ld_m64(xa + lane * 16, a); ld_m64(ya + lane * 16, b);                              \
+        _Pragma("unroll") for (int r = 0; r < kR; r++) t[r] = RQ_EX_##N(a[r], b[r]);       \
+        RQ_FINISH(t);                                                                      \
         break;                                                                             \
     }                                                                                      \
     case U_##N##_MI: {                                                                     \
-        int64_t a[kR]; ld_m64(ob, lane, a);                                                \
+        int64_t a[kR], t[kR];                                                              \
+        ld_m64(xa + lane * 16, a);                                                         \
         const int64_t y = in.imm;                                                          \
-        _Pragma("unroll") for (int r = 0; r < kR; r++) acc[r] = RQ_EX_##N(a[r], y);        \
-        break;                                                                             \
-    }                                                                                      \
-    case U_##N##_MM: {                                                                     \
-        int64_t a[kR], b[kR]; ld_m64(ob, lane, a);                                         \
-        ld_m64(opnd_base(c, in.flags & UF_SLOT2, (uint32_t)in.imm), lane, b);              \
-        _Pragma("unroll") for (int r = 0; r < kR; r++) acc[r] = RQ_EX_##N(a[r], b[r]);     \
+        _Pragma("unroll") for (int r = 0; r < kR; r++) t[r] = RQ_EX_##N(a[r], y);          \
+        RQ_FINISH(t);                                                                      \
         break;                                                                             \
     }
                 RQ_BINOPS(RQ_CASES)
 #undef RQ_CASES
 
+#define RQ_MULI(CODE, EXPR)                                                                \
+    case CODE: {                                                                           \
+        int64_t a[kR], b[kR], t[kR];                                                       \
+        ld_m64(xa + lane * 16, a); ld_m64(ya + lane * 16, b);                              \
+        const uint64_t k = (uint64_t)in.imm;                                               \
+        _Pragma("unroll") for (int r = 0; r < kR; r++) {                                   \
+            const uint64_t x = (uint64_t)a[r];                                             \
+            t[r] = (int64_t)((EXPR) * (uint64_t)b[r]);                                     \
+        }                                                                                  \
+        RQ_FINISH(t);                                                                      \
+        break;                                                                             \
+    }
+                RQ_MULI(U_MULADDI, x + k)
+                RQ_MULI(U_MULSUBI, x - k)
+                RQ_MULI(U_MULRSUBI, k - x)
+#undef RQ_MULI
+
                 case U_GEN: {
-                    int64_t b[kR];
-                    fetch(P, c, in.gsrc, ob, in.off16, in.imm, b);
+                    int64_t t[kR], b[kR];
+                    fetch(P, c, in.xkind, in.flags & UF_XSLOT, in.xoff16, in.imm, t);
+                    if (in.gop != D_LD) fetch(P, c, in.ykind, in.flags & UF_YSLOT, in.yoff16, in.imm, b);
                     switch (in.gop) {
-#define RQ_GBIN(D, N) case D: _Pragma("unroll") for (int r = 0; r < kR; r++) acc[r] = RQ_EX_##N(acc[r], b[r]); break;
-                        case D_LD:
-#pragma unroll
-                            for (int r = 0; r < kR; r++) acc[r] = b[r];
-                            break;
+#define RQ_GBIN(D, N) case D: _Pragma("unroll") for (int r = 0; r < kR; r++) t[r] = RQ_EX_##N(t[r], b[r]); break;
                         RQ_GBIN(D_ADD, ADD) RQ_GBIN(D_SUB, SUB) RQ_GBIN(D_RSUB, RSUB) RQ_GBIN(D_MUL, MUL)
                         RQ_GBIN(D_AND, AND) RQ_GBIN(D_OR, OR) RQ_GBIN(D_LT, LT) RQ_GBIN(D_LE, LE)
                         RQ_GBIN(D_GT, GT) RQ_GBIN(D_GE, GE) RQ_GBIN(D_EQ, EQ) RQ_GBIN(D_NE, NE)
@@ -364,19 +378,19 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         case D_DIV:
 #pragma unroll
                             for (int r = 0; r < kR; r++)
-                                acc[r] = ((valid >> r) & 1) ? div_trunc(acc[r], b[r], P.err) : 0;
+                                t[r] = ((valid >> r) & 1) ? div_trunc(t[r], b[r], P.err) : 0;
                             break;
                         case D_RDIV:
 #pragma unroll
                             for (int r = 0; r < kR; r++)
-                                acc[r] = ((valid >> r) & 1) ? div_trunc(b[r], acc[r], P.err) : 0;
+                                t[r] = ((valid >> r) & 1) ? div_trunc(b[r], t[r], P.err) : 0;
                             break;
 #define RQ_STRBIN(D, EXPR)                                                       \
     case D:                                                                      \
         _Pragma("unroll") for (int r = 0; r < kR; r++) {                         \
-            const char* x = reinterpret_cast<const char*>(acc[r]);               \
+            const char* x = reinterpret_cast<const char*>(t[r]);                 \
             const char* y = reinterpret_cast<const char*>(b[r]);                 \
-            acc[r] = ((valid >> r) & 1) ? (EXPR) : 0;                            \
+            t[r] = ((valid >> r) & 1) ? (EXPR) : 0;                              \
         }                                                                        \
         break;
                         RQ_STRBIN(D_EQC, str_eq_char(x, y))
@@ -387,41 +401,23 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         RQ_STRBIN(D_RLIKE, str_like(y, x))
 #undef RQ_STRBIN
                         case D_SEL: {
+                            // t = (x & 0xff) ? y : z     (one WHEN/THEN arm of emitCase :720-754)
                             int64_t e[kR];
-                            if (in.flags & UF_ELSE_IMM) {
+                            fetch(P, c, in.zkind, in.flags & UF_ZSLOT, in.zoff16,
+                                  in.zkind == K_IMM ? P.imm[in.zoff16] : 0, e);
 #pragma unroll
-                                for (int r = 0; r < kR; r++) e[r] = P.imm[in.aux];
-                            } else {
-                                ld_m64(slot_base + (size_t)in.aux * (kTile * 8), lane, e);
-                            }
-#pragma unroll
-                            for (int r = 0; r < kR; r++) acc[r] = (acc[r] & 0xff) ? b[r] : e[r];
+                            for (int r = 0; r < kR; r++) t[r] = (t[r] & 0xff) ? b[r] : e[r];
                             break;
                         }
-                        default: break;
+                        default: break;   // D_LD: t = x
                     }
-                    break;
-                }
-
-                case U_FILTER_A:
-#pragma unroll
-                    for (int r = 0; r < kR; r++)
-                        if ((acc[r] & 0xff) == 0) valid &= ~(1u << r);
-                    if (!__any_sync(kFull, valid != 0)) pc = n_insn;
-                    break;
-                case U_FILTER_O: {
-                    int64_t b[kR];
-                    fetch(P, c, in.gsrc, ob, in.off16, in.imm, b);
-#pragma unroll
-                    for (int r = 0; r < kR; r++)
-                        if ((b[r] & 0xff) == 0) valid &= ~(1u << r);
-                    if (!__any_sync(kFull, valid != 0)) pc = n_insn;
+                    RQ_FINISH(t);
                     break;
                 }
 
 #define RQ_FCMP(N, OP)                                                                     \
     case U_F##N##_M64: {                                                                   \
-        int64_t b[kR]; ld_m64(ob, lane, b);                                                \
+        int64_t b[kR]; ld_m64(xa + lane * 16, b);                                          \
         const int64_t y = in.imm;                                                          \
         _Pragma("unroll") for (int r = 0; r < kR; r++)                                     \
             if (!(b[r] OP y)) valid &= ~(1u << r);                                         \
@@ -429,7 +425,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         break;                                                                             \
     }                                                                                      \
     case U_F##N##_M32: {                                                                   \
-        int32_t b[kR]; ld_m32(ob, lane, b);                                                \
+        int32_t b[kR]; ld_m32(xa + lane * 8, b);                                           \
         const int32_t y = (int32_t)in.imm;                                                 \
         _Pragma("unroll") for (int r = 0; r < kR; r++)                                     \
             if (!(b[r] OP y)) valid &= ~(1u << r);                                         \
@@ -437,7 +433,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         break;                                                                             \
     }                                                                                      \
     case U_F##N##_M8: {                                                                    \
-        uint32_t b[kR]; ld_m8(ob, lane, b);                                                \
+        uint32_t b[kR]; ld_m8(xa + lane * 2, b);                                           \
         const int32_t y = (int32_t)in.imm;                                                 \
         _Pragma("unroll") for (int r = 0; r < kR; r++)                                     \
             if (!((int32_t)b[r] OP y)) valid &= ~(1u << r);                                \
@@ -446,209 +442,6 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     }
                 RQ_FCMP(LT, <) RQ_FCMP(LE, <=) RQ_FCMP(GT, >) RQ_FCMP(GE, >=) RQ_FCMP(EQ, ==) RQ_FCMP(NE, !=)
 #undef RQ_FCMP
-
-                case U_GROUP: {
-                    if (!lowagg) break;
-                    if (NK == 0) {
-                        seen |= valid;
-                        if (GR > 0) {
-#pragma unroll
-                            for (int r = 0; r < kR; r++) m[0][r] = (valid >> r) & 1u;
-                        }
-                        break;
-                    }
-                    // packed group key
-                    uint64_t key[kR];
-#pragma unroll
-                    for (int r = 0; r < kR; r++) key[r] = 0;
-                    for (int j = 0; j < NK; j++) {
-                        const VRef vr = P.key[j];
-                        int64_t kv[kR];
-                        fetch(P, c, vr.kind, opnd_base(c, vr.slot, (uint32_t)vr.off16 << 4), 0,
-                              vr.kind == K_IMM ? P.imm[vr.off16] : 0, kv);
-                        const int sh = P.key_shift[j];
-                        const uint64_t mask = P.key_bits[j] >= 64 ? ~0ULL : ((1ULL << P.key_bits[j]) - 1);
-#pragma unroll
-                        for (int r = 0; r < kR; r++) key[r] |= ((uint64_t)kv[r] & mask) << sh;
-                    }
-                    unsigned unk = 0;
-                    if (GR > 0) {
-#pragma unroll
-                        for (int g = 0; g < NG; g++) {
-                            const bool act = g < ngroups;
-#pragma unroll
-                            for (int r = 0; r < kR; r++) {
-                                const bool hit = P.key32 ? ((uint32_t)key[r] == (uint32_t)dk[g]) : (key[r] == dk[g]);
-                                m[g][r] = (act && hit && ((valid >> r) & 1)) ? 1u : 0u;
-                            }
-                        }
-#pragma unroll
-                        for (int r = 0; r < kR; r++) {
-                            uint32_t any = 0;
-#pragma unroll
-                            for (int g = 0; g < NG; g++) any |= m[g][r];
-                            if (((valid >> r) & 1) && !any) unk |= 1u << r;
-                        }
-                    } else {
-                        gid = 0;
-#pragma unroll
-                        for (int r = 0; r < kR; r++) {
-                            unsigned g = 15;
-#pragma unroll
-                            for (int e = 0; e < ND; e++)
-                                if (e < ngroups && key[r] == dk[e]) g = e;
-                            if (!((valid >> r) & 1)) g = 0;
-                            else if (g == 15) { unk |= 1u << r; g = 0; }
-                            gid |= g << (4 * r);
-                        }
-                    }
-                    // slow path: a key this warp has not seen yet joins the dictionary
-                    while (__any_sync(kFull, unk != 0)) {
-                        const unsigned ball = __ballot_sync(kFull, unk != 0);
-                        const int leader = __ffs(ball) - 1;
-                        uint64_t lk = 0;
-                        const int rr = __ffs(unk) - 1;
-#pragma unroll
-                        for (int r = 0; r < kR; r++) if (r == rr) lk = key[r];
-                        lk = __shfl_sync(kFull, lk, leader);
-                        const int cap = GR > 0 ? NG : P.G;
-                        if (ngroups >= cap) {
-                            if (lane == 0) *P.overflow = 1;
-                            unk = 0;
-                            break;
-                        }
-#pragma unroll
-                        for (int e = 0; e < ND; e++) if (e == ngroups) dk[e] = lk;
-#pragma unroll
-                        for (int r = 0; r < kR; r++) {
-                            if (((unk >> r) & 1) && key[r] == lk) {
-                                unk &= ~(1u << r);
-                                if (GR > 0) {
-#pragma unroll
-                                    for (int g = 0; g < NG; g++) if (g == ngroups) m[g][r] = 1u;
-                                } else {
-                                    gid |= (unsigned)ngroups << (4 * r);
-                                }
-                            }
-                        }
-                        ngroups++;
-                    }
-                    break;
-                }
-
-                case U_AGG_SUM_A:
-                case U_AGG_SUM_M: {
-                    int64_t v[kR];
-                    if (in.code == U_AGG_SUM_M) ld_m64(ob, lane, v);
-                    else {
-#pragma unroll
-                        for (int r = 0; r < kR; r++) v[r] = acc[r];
-                    }
-                    if (GR > 0) {
-                        switch (in.aux) {
-#define RQ_SUMCASE(A)                                                                         \
-    case A:                                                                                   \
-        RQ_NOMERGE(A);                                                                        \
-        _Pragma("unroll") for (int g = 0; g < NG; g++)                                        \
-            _Pragma("unroll") for (int r = 0; r < kR; r++)                                    \
-                macc(racc[g][A], v[r], m[g][r]);                                             \
-        break;
-                            RQ_SUMCASE(0) RQ_SUMCASE(1) RQ_SUMCASE(2) RQ_SUMCASE(3)
-                            RQ_SUMCASE(4) RQ_SUMCASE(5)
-#undef RQ_SUMCASE
-                            default: break;
-                        }
-                    } else {
-                        int64_t* base = sacc + in.aux * 32 + lane;
-#pragma unroll
-                        for (int r = 0; r < kR; r++) {
-                            if ((valid >> r) & 1) {
-                                int64_t* p = base + ((gid >> (4 * r)) & 15) * NA * 32;
-                                *p = (int64_t)((uint64_t)*p + (uint64_t)v[r]);
-                            }
-                        }
-                    }
-                    break;
-                }
-                case U_AGG_COUNT: {
-                    if (GR > 0) {
-                        switch (in.aux) {
-#define RQ_CNTCASE(A)                                                                         \
-    case A:                                                                                   \
-        RQ_NOMERGE(A);                                                                        \
-        _Pragma("unroll") for (int g = 0; g < NG; g++) {                                      \
-            uint32_t cnt = 0;                                                                 \
-            _Pragma("unroll") for (int r = 0; r < kR; r++) cnt += m[g][r];                    \
-            racc[g][A] += cnt;                                                                \
-        }                                                                                     \
-        break;
-                            RQ_CNTCASE(0) RQ_CNTCASE(1) RQ_CNTCASE(2) RQ_CNTCASE(3)
-                            RQ_CNTCASE(4) RQ_CNTCASE(5)
-#undef RQ_CNTCASE
-                            default: break;
-                        }
-                    } else {
-                        int64_t* base = sacc + in.aux * 32 + lane;
-#pragma unroll
-                        for (int r = 0; r < kR; r++) {
-                            if ((valid >> r) & 1) {
-                                int64_t* p = base + ((gid >> (4 * r)) & 15) * NA * 32;
-                                *p = *p + 1;
-                            }
-                        }
-                    }
-                    break;
-                }
-                case U_AGG_GEN: {
-                    int64_t v[kR];
-                    if (in.gsrc == K_NONE) {
-#pragma unroll
-                        for (int r = 0; r < kR; r++) v[r] = acc[r];
-                    } else {
-                        fetch(P, c, in.gsrc, ob, in.off16, in.imm, v);
-                    }
-                    const int kind = in.gop == D_AGG_SUM ? 1 : (in.gop == D_AGG_MIN ? 3 : 4);
-                    if (GR > 0) {
-                        // reduce the lane's 8 tuples per group first, then fold into the accumulator
-                        int64_t cand[NG];
-#pragma unroll
-                        for (int g = 0; g < NG; g++) {
-                            cand[g] = agg_identity(kind);
-#pragma unroll
-                            for (int r = 0; r < kR; r++) {
-                                if (kind == 1) { uint64_t t = (uint64_t)cand[g]; macc(t, v[r], m[g][r]); cand[g] = (int64_t)t; }
-                                else if (m[g][r] && (kind == 3 ? v[r] < cand[g] : v[r] > cand[g])) cand[g] = v[r];
-                            }
-                        }
-                        switch (in.aux) {
-#define RQ_GENCASE(A)                                                                         \
-    case A:                                                                                   \
-        RQ_NOMERGE(A);                                                                        \
-        _Pragma("unroll") for (int g = 0; g < NG; g++) {                                      \
-            const int64_t cur = (int64_t)racc[g][A];                                          \
-            if (kind == 1) racc[g][A] = (uint64_t)cur + (uint64_t)cand[g];                    \
-            else if (kind == 3 ? cand[g] < cur : cand[g] > cur) racc[g][A] = (uint64_t)cand[g]; \
-        }                                                                                     \
-        break;
-                            RQ_GENCASE(0) RQ_GENCASE(1) RQ_GENCASE(2) RQ_GENCASE(3)
-                            RQ_GENCASE(4) RQ_GENCASE(5)
-#undef RQ_GENCASE
-                            default: break;
-                        }
-                    } else {
-                        int64_t* base = sacc + in.aux * 32 + lane;
-#pragma unroll
-                        for (int r = 0; r < kR; r++) {
-                            if ((valid >> r) & 1) {
-                                int64_t* p = base + ((gid >> (4 * r)) & 15) * NA * 32;
-                                const int64_t cur = *p;
-                                if (kind == 1) *p = (int64_t)((uint64_t)cur + (uint64_t)v[r]);
-                                else if (kind == 3 ? v[r] < cur : v[r] > cur) *p = v[r];
-                            }
-                        }
-                    }
-                    break;
-                }
 
                 case U_PROBE: {
                     if (GR > 0) break;
@@ -669,16 +462,14 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                             t0[r] = pr.ht.tags[h[r] & pr.ht.cap_mask];
                         }
                     }
-#pragma unroll 1
+#pragma unroll
                     for (int r = 0; r < kR; r++) {
                         if (!((valid >> r) & 1)) continue;
                         int64_t k[kMaxKeys];
                         for (int j = 0; j < pnk; j++) k[j] = ld_row(P, c, pr.key[j], r);
                         const uint64_t tag = h[r] | 2ULL;
                         uint64_t i = h[r] & pr.ht.cap_mask;
-                        uint64_t t = 0;
-#pragma unroll
-                        for (int q = 0; q < kR; q++) if (q == r) t = t0[q];
+                        uint64_t t = t0[r];
                         int64_t found = -1;
                         unsigned matches = 0;
                         for (uint64_t tries = 0; tries < cap; tries++) {
@@ -696,80 +487,253 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         const int row = row_in_tile(r, lane);
                         for (int q = 0; q < pr.n_out; q++)
                             if (pr.out_slot[q] != 0xff)
-                                reinterpret_cast<int64_t*>(slot_base + (size_t)pr.out_slot[q] * (kTile * 8))[row] =
-                                    pr.ht.vals[(size_t)q * cap + found];
+                                sts_b64(slot_base + pr.out_slot[q] * (kTile * 8) + row * 8,
+                                        pr.ht.vals[(size_t)q * cap + found]);
                     }
                     __syncwarp();
                     if (!__any_sync(kFull, valid != 0)) pc = n_insn;
                     break;
                 }
-                case U_BUILD: {
-                    if (GR > 0) break;
-                    const uint64_t cap = P.ht.cap_mask + 1;
-#pragma unroll 1
-                    for (int r = 0; r < kR; r++) {
-                        if (!((valid >> r) & 1)) continue;
-                        int64_t k[kMaxKeys];
-                        for (int j = 0; j < P.ht.nk; j++) k[j] = ld_row(P, c, P.key[j], r);
-                        const uint64_t hh = hash_typed(k, P.ht.key_kind, P.ht.nk);
-                        uint64_t slot;
-                        if (!ht_insert_dup(P.ht, k, hh, &slot)) { *P.ht_full = 1; continue; }
-                        for (int q = 0; q < P.n_out; q++)
-                            P.ht.vals[(size_t)q * cap + slot] = ld_row(P, c, P.out[q], r);
-                    }
-                    break;
-                }
-                case U_HAGG: {
-                    if (GR > 0) break;
-                    const uint64_t cap = P.ht.cap_mask + 1;
-#pragma unroll 1
-                    for (int r = 0; r < kR; r++) {
-                        if (!((valid >> r) & 1)) continue;
-                        int64_t k[kMaxKeys];
-                        for (int j = 0; j < P.ht.nk; j++) k[j] = ld_row(P, c, P.key[j], r);
-                        const uint64_t hh = hash_typed(k, P.ht.key_kind, P.ht.nk);
-                        uint64_t slot;
-                        if (!ht_find_or_insert(P.ht, k, hh, &slot)) { *P.ht_full = 1; continue; }
-                        for (int a = 0; a < P.na; a++) {
-                            int64_t* dst = &P.ht.vals[(size_t)a * cap + slot];
-                            const int kind = P.agg_kind[a];
-                            if (kind == 2) { atomicAdd((unsigned long long*)dst, 1ULL); continue; }
-                            const int64_t v = ld_row(P, c, P.agg_src[a], r);
-                            if (kind == 1) atomicAdd((unsigned long long*)dst, (unsigned long long)v);
-                            else if (kind == 3) atomicMin((long long*)dst, (long long)v);
-                            else atomicMax((long long*)dst, (long long)v);
-                        }
-                    }
-                    break;
-                }
-                case U_EMIT: {
-                    if (GR > 0) break;
-                    // one atomic per warp tile: lanes take consecutive output ranges
-                    const int cnt = __popc(valid);
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(kFull, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    const int total = __shfl_sync(kFull, incl, 31);
-                    if (total == 0) break;
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(P.out_count, (unsigned long long)total);
-                    base = __shfl_sync(kFull, base, 0);
-                    int64_t pos = (int64_t)base + (incl - cnt);
-#pragma unroll 1
-                    for (int r = 0; r < kR; r++) {
-                        if (!((valid >> r) & 1)) continue;
-                        if (pos < P.out_cap)
-                            for (int k = 0; k < P.n_out; k++) P.out_col[k][pos] = ld_row(P, c, P.out[k], r);
-                        pos++;
-                    }
-                    break;
-                }
                 default: break;
             }
-            if (in.flags & UF_STORE) st_m64(slot_base + (size_t)in.dst * (kTile * 8), lane, acc);
+#undef RQ_FINISH
+        }
+
+        // ---- 2. the sink --------------------------------------------------------------------
+        if (__any_sync(kFull, valid != 0)) {
+            if (GR > 0) {
+                // register path: group match -> 0/1 multipliers -> accumulate
+                uint32_t m[NG][kR];
+                if (NK == 0) {
+                    seen |= valid;
+#pragma unroll
+                    for (int r = 0; r < kR; r++) m[0][r] = (valid >> r) & 1u;
+#pragma unroll
+                    for (int g = 1; g < NG; g++)
+#pragma unroll
+                        for (int r = 0; r < kR; r++) m[g][r] = 0;
+                } else {
+                    uint64_t key[kR];
+#pragma unroll
+                    for (int r = 0; r < kR; r++) key[r] = 0;
+                    for (int j = 0; j < NK; j++) {
+                        int64_t kv[kR];
+                        fetch_vref(P, c, P.key[j], kv);
+                        const int sh = P.key_shift[j];
+                        const uint64_t mask = P.key_bits[j] >= 64 ? ~0ULL : ((1ULL << P.key_bits[j]) - 1);
+#pragma unroll
+                        for (int r = 0; r < kR; r++) key[r] |= ((uint64_t)kv[r] & mask) << sh;
+                    }
+                    unsigned unk = 0;
+#pragma unroll
+                    for (int g = 0; g < NG; g++) {
+                        const bool act = g < ngroups;
+#pragma unroll
+                        for (int r = 0; r < kR; r++) {
+                            const bool hit = P.key32 ? ((uint32_t)key[r] == (uint32_t)dk[g]) : (key[r] == dk[g]);
+                            m[g][r] = (act && hit && ((valid >> r) & 1)) ? 1u : 0u;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < kR; r++) {
+                        uint32_t any = 0;
+#pragma unroll
+                        for (int g = 0; g < NG; g++) any |= m[g][r];
+                        if (((valid >> r) & 1) && !any) unk |= 1u << r;
+                    }
+                    // slow path: a key this warp has not seen yet joins the dictionary
+                    while (__any_sync(kFull, unk != 0)) {
+                        const unsigned ball = __ballot_sync(kFull, unk != 0);
+                        const int leader = __ffs(ball) - 1;
+                        uint64_t lk = 0;
+                        const int rr = __ffs(unk) - 1;
+#pragma unroll
+                        for (int r = 0; r < kR; r++) if (r == rr) lk = key[r];
+                        lk = __shfl_sync(kFull, lk, leader);
+                        if (ngroups >= NG) {
+                            if (lane == 0) *P.overflow = 1;
+                            unk = 0;
+                            break;
+                        }
+#pragma unroll
+                        for (int e = 0; e < NG; e++) if (e == ngroups) dk[e] = lk;
+#pragma unroll
+                        for (int r = 0; r < kR; r++) {
+                            if (((unk >> r) & 1) && key[r] == lk) {
+                                unk &= ~(1u << r);
+#pragma unroll
+                                for (int g = 0; g < NG; g++) if (g == ngroups) m[g][r] = 1u;
+                            }
+                        }
+                        ngroups++;
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < kNAR; a++) {
+                    if (a >= NA) continue;
+                    const int kind = P.agg_kind[a];
+                    if (kind == 2) {                      // COUNT
+#pragma unroll
+                        for (int g = 0; g < NG; g++) {
+                            uint32_t cnt = 0;
+#pragma unroll
+                            for (int r = 0; r < kR; r++) cnt += m[g][r];
+                            racc[g][a] += cnt;
+                        }
+                        continue;
+                    }
+                    const VRef vr = P.agg_src[a];
+                    int64_t v[kR];
+                    fetch_vref(P, c, vr, v);
+                    if (kind == 1) {                      // SUM
+                        if (vr.slot & 2) {
+#pragma unroll
+                            for (int g = 0; g < NG; g++)
+#pragma unroll
+                                for (int r = 0; r < kR; r++) macc32(racc[g][a], v[r], m[g][r]);
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < NG; g++)
+#pragma unroll
+                                for (int r = 0; r < kR; r++) macc(racc[g][a], v[r], m[g][r]);
+                        }
+                    } else {                              // MIN / MAX
+#pragma unroll
+                        for (int g = 0; g < NG; g++)
+#pragma unroll
+                            for (int r = 0; r < kR; r++) {
+                                const int64_t cur = (int64_t)racc[g][a];
+                                if (m[g][r] && (kind == 3 ? v[r] < cur : v[r] > cur)) racc[g][a] = (uint64_t)v[r];
+                            }
+                    }
+                }
+            } else if (sink == IMPL_LOWAGG) {
+                // lane-private shared-memory accumulators [g][a][lane]
+                unsigned gid = 0;   // 4 bits per tuple
+                if (NK == 0) {
+                    seen |= valid;
+                } else {
+                    uint64_t key[kR];
+#pragma unroll
+                    for (int r = 0; r < kR; r++) key[r] = 0;
+                    for (int j = 0; j < NK; j++) {
+                        int64_t kv[kR];
+                        fetch_vref(P, c, P.key[j], kv);
+                        const int sh = P.key_shift[j];
+                        const uint64_t mask = P.key_bits[j] >= 64 ? ~0ULL : ((1ULL << P.key_bits[j]) - 1);
+#pragma unroll
+                        for (int r = 0; r < kR; r++) key[r] |= ((uint64_t)kv[r] & mask) << sh;
+                    }
+                    unsigned unk = 0;
+#pragma unroll
+                    for (int r = 0; r < kR; r++) {
+                        unsigned g = 15;
+#pragma unroll
+                        for (int e = 0; e < ND; e++)
+                            if (e < ngroups && key[r] == dk[e]) g = e;
+                        if (!((valid >> r) & 1)) g = 0;
+                        else if (g == 15) { unk |= 1u << r; g = 0; }
+                        gid |= g << (4 * r);
+                    }
+                    while (__any_sync(kFull, unk != 0)) {
+                        const unsigned ball = __ballot_sync(kFull, unk != 0);
+                        const int leader = __ffs(ball) - 1;
+                        uint64_t lk = 0;
+                        const int rr = __ffs(unk) - 1;
+#pragma unroll
+                        for (int r = 0; r < kR; r++) if (r == rr) lk = key[r];
+                        lk = __shfl_sync(kFull, lk, leader);
+                        if (ngroups >= P.G) {
+                            if (lane == 0) *P.overflow = 1;
+                            unk = 0;
+                            break;
+                        }
+#pragma unroll
+                        for (int e = 0; e < ND; e++) if (e == ngroups) dk[e] = lk;
+#pragma unroll
+                        for (int r = 0; r < kR; r++) {
+                            if (((unk >> r) & 1) && key[r] == lk) {
+                                unk &= ~(1u << r);
+                                gid |= (unsigned)ngroups << (4 * r);
+                            }
+                        }
+                        ngroups++;
+                    }
+                }
+                for (int a = 0; a < NA; a++) {
+                    const int kind = P.agg_kind[a];
+                    int64_t v[kR];
+                    if (kind != 2) fetch_vref(P, c, P.agg_src[a], v);
+                    const uint32_t base = sacc + (a * 32 + lane) * 8;
+#pragma unroll
+                    for (int r = 0; r < kR; r++) {
+                        if ((valid >> r) & 1) {
+                            const uint32_t p = base + ((gid >> (4 * r)) & 15) * NA * 256;
+                            const int64_t cur = lds_b64(p);
+                            int64_t nv;
+                            if (kind == 2) nv = cur + 1;
+                            else if (kind == 1) nv = (int64_t)((uint64_t)cur + (uint64_t)v[r]);
+                            else if (kind == 3) nv = v[r] < cur ? v[r] : cur;
+                            else nv = v[r] > cur ? v[r] : cur;
+                            sts_b64(p, nv);
+                        }
+                    }
+                }
+            } else if (sink == IMPL_BUILD) {
+                const uint64_t cap = P.ht.cap_mask + 1;
+#pragma unroll 1
+                for (int r = 0; r < kR; r++) {
+                    if (!((valid >> r) & 1)) continue;
+                    int64_t k[kMaxKeys];
+                    for (int j = 0; j < P.ht.nk; j++) k[j] = ld_row(P, c, P.key[j], r);
+                    const uint64_t hh = hash_typed(k, P.ht.key_kind, P.ht.nk);
+                    uint64_t slot;
+                    if (!ht_insert_dup(P.ht, k, hh, &slot)) { *P.ht_full = 1; continue; }
+                    for (int q = 0; q < P.n_out; q++)
+                        P.ht.vals[(size_t)q * cap + slot] = ld_row(P, c, P.out[q], r);
+                }
+            } else if (sink == IMPL_HASHAGG) {
+                const uint64_t cap = P.ht.cap_mask + 1;
+#pragma unroll 1
+                for (int r = 0; r < kR; r++) {
+                    if (!((valid >> r) & 1)) continue;
+                    int64_t k[kMaxKeys];
+                    for (int j = 0; j < P.ht.nk; j++) k[j] = ld_row(P, c, P.key[j], r);
+                    const uint64_t hh = hash_typed(k, P.ht.key_kind, P.ht.nk);
+                    uint64_t slot;
+                    if (!ht_find_or_insert(P.ht, k, hh, &slot)) { *P.ht_full = 1; continue; }
+                    for (int a = 0; a < NA; a++) {
+                        int64_t* dst = &P.ht.vals[(size_t)a * cap + slot];
+                        const int kind = P.agg_kind[a];
+                        if (kind == 2) { atomicAdd((unsigned long long*)dst, 1ULL); continue; }
+                        const int64_t v = ld_row(P, c, P.agg_src[a], r);
+                        if (kind == 1) atomicAdd((unsigned long long*)dst, (unsigned long long)v);
+                        else if (kind == 3) atomicMin((long long*)dst, (long long)v);
+                        else atomicMax((long long*)dst, (long long)v);
+                    }
+                }
+            } else if (sink == IMPL_EMIT) {
+                // one atomic per warp tile: lanes take consecutive output ranges
+                const int cnt = __popc(valid);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int total = __shfl_sync(kFull, incl, 31);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(P.out_count, (unsigned long long)total);
+                base = __shfl_sync(kFull, base, 0);
+                int64_t pos = (int64_t)base + (incl - cnt);
+#pragma unroll 1
+                for (int r = 0; r < kR; r++) {
+                    if (!((valid >> r) & 1)) continue;
+                    if (pos < P.out_cap)
+                        for (int k = 0; k < P.n_out; k++) P.out_col[k][pos] = ld_row(P, c, P.out[k], r);
+                    pos++;
+                }
+            }
         }
 
         // everyone is done with stage s (and the slots) before it is refilled
@@ -782,7 +746,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     }
 
     // ---- flush the per-warp accumulators of the low-cardinality aggregate -------------------
-    if (lowagg) {
+    if (GR > 0 || sink == IMPL_LOWAGG) {
         __syncwarp();
         int n = ngroups;
         if (NK == 0) n = __any_sync(kFull, seen != 0) ? 1 : 0;
@@ -805,8 +769,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                 }
             }
         } else {
-            const int cap = P.G;
-            if (n > cap) n = cap;
+            if (n > P.G) n = P.G;
             for (int e = 0; e < n; e++) {
                 uint64_t kk = 0;
 #pragma unroll
@@ -819,7 +782,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                 slot = __shfl_sync(kFull, slot, 0);
                 for (int a = 0; a < NA; a++) {
                     const int kind = P.agg_kind[a];
-                    const int64_t v = warp_reduce(sacc[(e * NA + a) * 32 + lane], kind);
+                    const int64_t v = warp_reduce(lds_b64(sacc + ((e * NA + a) * 32 + lane) * 8), kind);
                     if (lane == 0 && slot >= 0) group_table_add(P, slot, a, kind, v);
                 }
             }

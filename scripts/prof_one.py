@@ -1,0 +1,30 @@
+"""Runs one TPC-H plan fixture a few times on synthetic data generated in HBM (for ncu captures
+and quick timings):  python scripts/prof_one.py q1 10 3"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+from resql_b200 import Engine, Plan
+from resql_b200 import tpch_device as TD
+from common import load_plan_dict
+
+q = sys.argv[1]
+sf = float(sys.argv[2]) if len(sys.argv) > 2 else 10
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+dev = torch.device("cuda:0")
+eng = Engine(0)
+need_orders = q not in ("q1", "q6")
+orders, li, cust = TD.gen_orders_lineitem(sf, 42, dev, want_orders=need_orders)
+src = {"lineitem": li, "orders": orders, "customer": cust}
+d = load_plan_dict(q)
+tabs = {}
+for t in d["tables"]:
+    n = src[t["name"]][t["columns"][0]].shape[0]
+    tabs[t["name"]] = eng.upload_device(t["name"], TD.as_device_columns(src[t["name"]], t["columns"]), n, borrow=True)
+n = li["l_quantity"].numel()
+bpt = {"q1": 38, "q6": 28, "q3": 24}.get(q, 0)
+for i in range(reps):
+    res, tm = eng.execute(Plan(d), tabs)
+    print(q, "rows", n, "scan_ms", round(tm.scan_kernel_ms, 3), "Gtuples/s", round(n / tm.scan_kernel_ms / 1e6, 2),
+          "GB/s", round(n * bpt / tm.scan_kernel_ms / 1e6, 1), "launches", tm.kernel_launches, "kernel_ms", round(tm.kernel_ms, 3))
+print([c.tolist()[:4] for c in res.columns][:4])
