@@ -366,7 +366,7 @@ struct HOpnd {           // host-level operand of a unit / value reference of a 
 };
 typedef HOpnd HRef;
 
-enum HOp : uint8_t { H_FCMP = 1, H_BIN = 2, H_MULI = 3, H_SEL = 4, H_PROBE = 5 };
+enum HOp : uint8_t { H_FCMP = 1, H_BIN = 2, H_MULI = 3, H_SEL = 4, H_PROBE = 5, H_FRANGE = 6 };
 
 // One unit of the host-level program (what tests/vm_model.py executes):
 //   H_FCMP  valid &= (x GOP imm)                      gop in D_LT..D_NE, x a column
@@ -374,11 +374,12 @@ enum HOp : uint8_t { H_FCMP = 1, H_BIN = 2, H_MULI = 3, H_SEL = 4, H_PROBE = 5 }
 //   H_MULI  t = (x GOP imm) * y                       gop in D_ADD / D_SUB / D_RSUB
 //   H_SEL   t = (x & 0xff) ? y : z
 //   H_PROBE hash-join probe number aux
+//   H_FRANGE valid &= (imm <= x <= imm + imm2)         two H_FCMP on one column fused
 // then  slot[dst] = t  if dst >= 0, and  valid &= (t & 0xff) != 0  if filt.
 struct HUnit {
     uint8_t op = 0, gop = 0;
     HOpnd x, y, z;
-    int64_t imm = 0;
+    int64_t imm = 0, imm2 = 0;
     int dst = -1;
     bool filt = false;
     int aux = 0;

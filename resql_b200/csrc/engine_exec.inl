@@ -214,6 +214,54 @@ static void simplify_pipeline(const rq_pipeline& in, SimplePipe& sp) {
     sp.pl.keys = sp.keys.data();          sp.pl.vals = sp.vals.data();
 }
 
+// Selection compares on the same column intersect to one interval test (BETWEEN, date ranges):
+// lo <= x <= hi is a single unsigned compare of (x - lo) against (hi - lo). Selection compares
+// only narrow the mask and read columns, so the later one may move up to the earlier one.
+static void fuse_ranges(Lowerer& L) {
+    auto interval = [&](const HUnit& u, __int128* lo, __int128* hi) -> bool {
+        const __int128 NEG = -((__int128)1 << 100), POS = (__int128)1 << 100;
+        *lo = NEG; *hi = POS;
+        if (u.op == H_FRANGE) { *lo = u.imm; *hi = (__int128)u.imm + (__int128)(uint64_t)u.imm2; return true; }
+        if (u.op != H_FCMP) return false;
+        switch (u.gop) {
+            case D_GE: *lo = u.imm; return true;
+            case D_GT: *lo = (__int128)u.imm + 1; return true;
+            case D_LE: *hi = u.imm; return true;
+            case D_LT: *hi = (__int128)u.imm - 1; return true;
+            case D_EQ: *lo = *hi = u.imm; return true;
+            default: return false;
+        }
+    };
+    const __int128 NEG = -((__int128)1 << 100), POS = (__int128)1 << 100;
+    for (size_t i = 0; i < L.prog.size(); i++) {
+        __int128 lo, hi;
+        if (!interval(L.prog[i], &lo, &hi)) continue;
+        for (size_t j = i + 1; j < L.prog.size();) {
+            __int128 lo2, hi2;
+            const HUnit& v = L.prog[j];
+            if ((v.op == H_FCMP || v.op == H_FRANGE) && v.x.kind == L.prog[i].x.kind && v.x.idx == L.prog[i].x.idx &&
+                interval(v, &lo2, &hi2)) {
+                const __int128 nlo = lo > lo2 ? lo : lo2, nhi = hi < hi2 ? hi : hi2;
+                if (nlo <= nhi) {           // (an empty intersection is left to the two compares)
+                    lo = nlo; hi = nhi;
+                    L.prog.erase(L.prog.begin() + j);
+                    continue;
+                }
+            }
+            j++;
+        }
+        HUnit& u = L.prog[i];
+        if (lo != NEG && hi != POS) {
+            const int w = L.P.col_w[u.x.idx];
+            const bool fits = w == 8 || (lo >= INT32_MIN && hi <= INT32_MAX);
+            if (lo >= INT64_MIN && hi <= INT64_MAX && fits && (lo != hi || true)) {
+                u.op = H_FRANGE; u.gop = 0; u.imm = (int64_t)lo; u.imm2 = (int64_t)(uint64_t)(hi - lo);
+            }
+        } else if (lo != NEG) { u.op = H_FCMP; u.gop = D_GE; u.imm = (int64_t)lo; }
+        else if (hi != POS) { u.op = H_FCMP; u.gop = D_LE; u.imm = (int64_t)hi; }
+    }
+}
+
 // Emits the host-level program (units) for one pipeline.
 static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
     KParams& P = L.P;
@@ -308,6 +356,8 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
         L.release_dead(i);
     }
 
+    fuse_ranges(L);
+
     // sinks
     if (pl.n_keys > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
     for (int k = 0; k < pl.n_keys; k++) L.hkey.push_back(L.href_of(pl.keys[k].node));
@@ -329,7 +379,7 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
 // [stages][slots][lane-private accumulators]. As many warps as fit (latency hiding comes from
 // warps, bytes in flight from warps x stages), at least two stages when possible.
 static bool layout_smem(KParams& P, int n_slots, int acc_bytes, int max_warps) {
-    const uint32_t bars = kMaxWarps * kMaxStages * 8;
+    const uint32_t bars = kMaxWarps * kMaxStages * 8 + kMaxInsn * (uint32_t)sizeof(UInsn);   // + program copy
     int bestW = 0, bestS = 0;
     for (int S = 2; S <= kMaxStages; S++) {
         uint32_t wb = (uint32_t)S * P.stage_bytes + (uint32_t)n_slots * kTile * 8 + (uint32_t)acc_bytes;
@@ -351,6 +401,7 @@ static bool layout_smem(KParams& P, int n_slots, int acc_bytes, int max_warps) {
     uint32_t wb = (uint32_t)bestS * P.stage_bytes + (uint32_t)n_slots * kTile * 8 + (uint32_t)acc_bytes;
     wb = (wb + 127) & ~127u;
     if (wb == 0) wb = 128;
+    P.prog_off = kMaxWarps * kMaxStages * 8;
     P.warp_off = bars;
     P.warp_bytes = wb;
     P.slots_rel = (uint32_t)bestS * P.stage_bytes;
@@ -397,18 +448,13 @@ static void encode_program(Lowerer& L, KParams& P) {
     P.n_insn = 0;
     for (size_t i = 0; i < L.prog.size(); i++) {
         const HUnit& h = L.prog[i];
-        const UOperand x = resolve(P, h.x), y = resolve(P, h.y), z = resolve(P, h.z);
+        UOperand x = resolve(P, h.x), y = resolve(P, h.y), z = resolve(P, h.z);
         UInsn u;
         memset(&u, 0, sizeof(u));
-        u.dst = h.dst >= 0 ? (uint8_t)h.dst : kNoDst;
+        if (h.dst >= 0) { u.flags |= UF_STORE; u.dstrel = P.slots_rel + (uint32_t)h.dst * kTile * 8; }
         if (h.filt) u.flags |= UF_FILTER;
-        if (x.slot) u.flags |= UF_XSLOT;
-        if (y.slot) u.flags |= UF_YSLOT;
-        if (z.slot) u.flags |= UF_ZSLOT;
         u.aux = (uint8_t)h.aux;
         u.gop = h.gop;
-        u.xkind = x.kind; u.ykind = y.kind; u.zkind = z.kind;
-        u.xoff16 = (uint16_t)(x.off >> 4); u.yoff16 = (uint16_t)(y.off >> 4); u.zoff16 = (uint16_t)(z.off >> 4);
         u.imm = h.imm;
         if (h.op == H_FCMP) {
             const int ci = h.gop - D_LT;
@@ -417,6 +463,11 @@ static void encode_program(Lowerer& L, KParams& P) {
             else if (x.kind == K_M32) u.code = (uint8_t)(U_FLT_M32 + ci);
             else if (x.kind == K_M8) u.code = (uint8_t)(U_FLT_M8 + ci);
             else raise(RQ_ERR_INVALID, "internal: fused compare on a non-column operand");
+        } else if (h.op == H_FRANGE) {
+            u.code = x.kind == K_M64 ? U_FRANGE_M64 : (x.kind == K_M32 ? U_FRANGE_M32 : U_FRANGE_M8);
+            if (x.kind != K_M64 && x.kind != K_M32 && x.kind != K_M8) raise(RQ_ERR_INVALID, "internal: range compare on a non-column operand");
+            y = UOperand{K_NONE, 0, (uint32_t)((uint64_t)h.imm2 & 0xffffffffu)};
+            z = UOperand{K_NONE, 0, (uint32_t)((uint64_t)h.imm2 >> 32)};
         } else if (h.op == H_MULI) {
             if (x.kind != K_M64 || y.kind != K_M64) raise(RQ_ERR_INVALID, "internal: MULI operands");
             u.code = h.gop == D_ADD ? U_MULADDI : (h.gop == D_SUB ? U_MULSUBI : U_MULRSUBI);
@@ -426,7 +477,7 @@ static void encode_program(Lowerer& L, KParams& P) {
             u.code = U_GEN;
             if (y.kind == K_IMM) u.imm = h.y.imm;
             if (x.kind == K_IMM) u.imm = h.x.imm;
-            if (z.kind == K_IMM) u.zoff16 = (uint16_t)L.imm_index(h.z.imm);
+            if (z.kind == K_IMM) z.off = (uint32_t)L.imm_index(h.z.imm);
         } else {   // H_BIN
             const int bi = bin_index(h.gop);
             static const int swapped[12] = {0, 2, 1, 3, 4, 5, 8, 9, 6, 7, 10, 11};
@@ -439,8 +490,8 @@ static void encode_program(Lowerer& L, KParams& P) {
                 // imm OP m64  ==  m64 OP' imm
                 u.code = (uint8_t)(U_ADD_MM + 2 * swapped[bi] + 1);
                 u.imm = h.x.imm;
-                u.xkind = y.kind; u.xoff16 = u.yoff16;
-                u.flags = (uint8_t)((u.flags & ~(UF_XSLOT | UF_YSLOT)) | (y.slot ? UF_XSLOT : 0));
+                x = y;
+                y = UOperand{K_NONE, 0, 0};
             } else {
                 u.code = U_GEN;
                 if (x.kind == K_IMM && y.kind == K_IMM && h.gop != D_LD)
@@ -449,6 +500,13 @@ static void encode_program(Lowerer& L, KParams& P) {
                 if (x.kind == K_IMM) u.imm = h.x.imm;
             }
         }
+        if (x.slot) u.flags |= UF_XSLOT;
+        if (y.slot) u.flags |= UF_YSLOT;
+        if (z.slot) u.flags |= UF_ZSLOT;
+        u.xkind = x.kind; u.ykind = y.kind; u.zkind = z.kind;
+        u.xrel = x.kind == K_STR ? (x.off >> 4) : x.off;
+        u.yrel = y.kind == K_STR ? (y.off >> 4) : y.off;
+        u.zrel = z.kind == K_STR ? (z.off >> 4) : z.off;
         if (P.n_insn >= kMaxInsn) raise(RQ_ERR_UNSUPPORTED, "program longer than %d units", kMaxInsn);
         P.insn[P.n_insn++] = u;
     }
@@ -1054,15 +1112,16 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
         }
         for (size_t i = 0; i < L.prog.size(); i++) {
             const HUnit& h = L.prog[i];
-            snprintf(line, sizeof line, "unit %d %d %d %d %lld %d %d %lld %d %d %lld %lld %d %d %d\n", h.op, h.gop,
+            snprintf(line, sizeof line, "unit %d %d %d %d %lld %d %d %lld %d %d %lld %lld %d %d %d %lld\n", h.op, h.gop,
                      h.x.kind, h.x.idx, (long long)h.x.imm, h.y.kind, h.y.idx, (long long)h.y.imm,
-                     h.z.kind, h.z.idx, (long long)h.z.imm, (long long)h.imm, h.dst, h.filt ? 1 : 0, h.aux);
+                     h.z.kind, h.z.idx, (long long)h.z.imm, (long long)h.imm, h.dst, h.filt ? 1 : 0, h.aux,
+                     (long long)h.imm2);
             s += line;
         }
         for (int i = 0; i < P.n_insn; i++) {
             const UInsn& u = P.insn[i];
-            snprintf(line, sizeof line, "uinsn %d %d %d %d %d %d %d %d %d %d %d %lld\n", u.code, u.flags, u.dst, u.aux, u.gop,
-                     u.xkind, u.ykind, u.zkind, u.xoff16, u.yoff16, u.zoff16, (long long)u.imm);
+            snprintf(line, sizeof line, "uinsn %d %d %u %d %d %d %d %d %u %u %u %lld\n", u.code, u.flags, u.dstrel, u.aux, u.gop,
+                     u.xkind, u.ykind, u.zkind, u.xrel, u.yrel, u.zrel, (long long)u.imm);
             s += line;
         }
         for (size_t k = 0; k < L.hkey.size(); k++) { snprintf(line, sizeof line, "key %d %d\n", L.hkey[k].kind, L.hkey[k].idx); s += line; }

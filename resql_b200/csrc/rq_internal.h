@@ -66,6 +66,8 @@ enum UCode : uint8_t {
     U_FLT_M64, U_FLE_M64, U_FGT_M64, U_FGE_M64, U_FEQ_M64, U_FNE_M64,
     U_FLT_M32, U_FLE_M32, U_FGT_M32, U_FGE_M32, U_FEQ_M32, U_FNE_M32,
     U_FLT_M8,  U_FLE_M8,  U_FGT_M8,  U_FGE_M8,  U_FEQ_M8,  U_FNE_M8,
+    // valid &= (imm <= column <= imm + span): two selection compares on one column fused
+    U_FRANGE_M64, U_FRANGE_M32, U_FRANGE_M8,
     U_PROBE
 };
 
@@ -73,20 +75,23 @@ constexpr uint8_t UF_XSLOT  = 1;   // x offset is relative to the warp region (a
 constexpr uint8_t UF_YSLOT  = 2;
 constexpr uint8_t UF_ZSLOT  = 4;
 constexpr uint8_t UF_FILTER = 8;   // valid &= (t & 0xff) != 0   (selection.h:62-66)
-constexpr uint8_t kNoDst = 0xff;
+constexpr uint8_t UF_STORE  = 16;  // t goes to the slot at dstrel
 
+// Fully decoded on the host; the CTA copies the program to shared memory once and every unit is
+// fetched with two broadcast 128-bit loads.
 struct UInsn {
     uint8_t  code;
     uint8_t  flags;
-    uint8_t  dst;       // slot receiving t, kNoDst = none
-    uint8_t  aux;       // probe index
     uint8_t  gop;       // U_GEN: DOp
-    uint8_t  xkind, ykind, zkind;   // U_GEN: UKind of the operands
-    uint16_t xoff16, yoff16, zoff16;   // byte offsets >> 4 (K_STR: string column; K_IMM: imm-table index)
-    uint16_t pad;
-    int64_t  imm;
+    uint8_t  aux;       // probe index
+    uint8_t  xkind, ykind, zkind, pad;   // U_GEN: UKind of the operands
+    uint32_t xrel;      // byte offset of x (stage- or region-relative); K_STR: string column
+    uint32_t dstrel;    // byte offset of the destination slot inside the warp region
+    int64_t  imm;       // immediate operand / compare constant / range low bound
+    uint32_t yrel;      // byte offset of y                 } selection-fused range compare:
+    uint32_t zrel;      // byte offset of z; K_IMM: index   } yrel|zrel<<32 = span (unsigned)
 };
-static_assert(sizeof(UInsn) == 24, "UInsn must be 24 bytes");
+static_assert(sizeof(UInsn) == 32, "UInsn must be 32 bytes");
 
 struct VRef {           // value reference used by sinks (keys, payloads, outputs)
     uint8_t  kind;      // UKind
@@ -132,6 +137,7 @@ struct KParams {
     uint32_t       warp_bytes;          // bytes per warp region
     uint32_t       slots_rel;           // slots, relative to the warp region
     uint32_t       acc_rel;             // lane-private accumulators (shared-memory path)
+    uint32_t       prog_off;            // byte offset of the program copy
     uint32_t       smem_bytes;          // total dynamic shared memory of the CTA
     int32_t        n_slots;
     int32_t        warps;               // warps per CTA

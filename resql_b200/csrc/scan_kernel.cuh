@@ -55,6 +55,14 @@ __device__ __forceinline__ void lds_v2b32(uint32_t a, int32_t& x, int32_t& y) {
 __device__ __forceinline__ void lds_v2u8(uint32_t a, uint32_t& x, uint32_t& y) {
     asm volatile("ld.shared.v2.u8 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a));
 }
+__device__ __forceinline__ uint4 lds_v4b32(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_b32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ int64_t lds_b64(uint32_t a) {
     int64_t v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a)); return v;
 }
@@ -98,8 +106,8 @@ struct WarpCtx {
 
 // any operand kind -> 8 int64 values (rare forms, group keys, aggregate inputs)
 __device__ __forceinline__ void fetch(const KParams& P, const WarpCtx& c, int kind, bool slot,
-                                      uint32_t off16, int64_t imm, int64_t (&v)[kR]) {
-    const uint32_t base = (slot ? c.wbase : c.stage) + (off16 << 4);
+                                      uint32_t off, int64_t imm, int64_t (&v)[kR]) {
+    const uint32_t base = (slot ? c.wbase : c.stage) + off;
     switch (kind) {
         case K_M64: ld_m64(base + c.lane * 16, v); break;
         case K_M32: {
@@ -117,7 +125,7 @@ __device__ __forceinline__ void fetch(const KParams& P, const WarpCtx& c, int ki
         case K_STR:
 #pragma unroll
             for (int r = 0; r < kR; r++)
-                v[r] = (int64_t)(P.str_ptr[off16] + (size_t)(c.row0 + row_in_tile(r, c.lane)) * P.str_w[off16]);
+                v[r] = (int64_t)(P.str_ptr[off] + (size_t)(c.row0 + row_in_tile(r, c.lane)) * P.str_w[off]);
             break;
         default:
 #pragma unroll
@@ -126,7 +134,8 @@ __device__ __forceinline__ void fetch(const KParams& P, const WarpCtx& c, int ki
     }
 }
 __device__ __forceinline__ void fetch_vref(const KParams& P, const WarpCtx& c, VRef vr, int64_t (&v)[kR]) {
-    fetch(P, c, vr.kind, vr.slot & 1, vr.off16, vr.kind == K_IMM ? P.imm[vr.off16] : 0, v);
+    fetch(P, c, vr.kind, vr.slot & 1, vr.kind == K_STR ? (uint32_t)vr.off16 : ((uint32_t)vr.off16 << 4),
+          vr.kind == K_IMM ? P.imm[vr.off16] : 0, v);
 }
 
 // one tuple of a sink value
@@ -237,10 +246,17 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     const int NA = P.na, NK = P.nk;
     const int sink = P.sink;
 
+    // the program, decoded on the host, is copied to shared memory once per CTA
+    const uint32_t prog = smem0 + P.prog_off;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.insn);
+        for (int i = threadIdx.x; i < P.n_insn * 8; i += blockDim.x) sts_b32(prog + i * 4, src[i]);
+    }
     if (lane == 0) {
         for (int s = 0; s < S; s++) mbar_init_s(bars + s * 8, 1);
         fence_mbar_init();
     }
+    __syncthreads();
     // accumulators
     uint64_t racc[NG][kNAR];
     uint64_t dk[ND];
@@ -261,17 +277,23 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     auto is_guarded = [&](int64_t tile) -> bool {
         return P.borrowed && (tile + 1) * (int64_t)kTile > n_rows;
     };
-    auto issue = [&](int64_t tile, int s) {
-        if (is_guarded(tile)) return;
-        const uint32_t bar = bars + s * 8;
-        const uint32_t dst = wbase + s * P.stage_bytes;
-        mbar_expect_tx_s(bar, P.stage_bytes);
-        for (int c = 0; c < P.n_cols; c++) {
-            const uint32_t bytes = kTile * P.col_w[c];
-            tma_bulk_g2s_s(dst + P.col_off[c], P.col_ptr[c] + (size_t)tile * bytes, bytes, bar);
+    // lane c < n_cols owns column c's bulk copies: its source pointer advances by a fixed byte
+    // stride per tile, so re-arming a stage costs a handful of instructions per warp
+    const bool col_lane = lane < P.n_cols;
+    const uint32_t my_bytes = col_lane ? kTile * (uint32_t)P.col_w[lane] : 0;
+    const uint32_t my_off = col_lane ? P.col_off[lane] : 0;
+    const unsigned char* my_src = col_lane ? P.col_ptr[lane] + (size_t)first * my_bytes : nullptr;
+    const size_t my_step = (size_t)stride * my_bytes;
+    auto issue = [&](int64_t tile, int s) {      // called by the whole warp; my_src is at `tile`
+        if (!is_guarded(tile)) {
+            const uint32_t bar = bars + s * 8;
+            if (lane == 0) mbar_expect_tx_s(bar, P.stage_bytes);
+            __syncwarp();
+            if (col_lane) tma_bulk_g2s_s(wbase + s * P.stage_bytes + my_off, my_src, my_bytes, bar);
         }
+        my_src += my_step;
     };
-    if (lane == 0 && P.n_cols > 0) {
+    if (P.n_cols > 0) {
         for (int s = 0; s < S; s++)
             if (first + s * stride < n_tiles) issue(first + s * stride, s);
     }
@@ -314,13 +336,19 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         // ---- 1. the program ---------------------------------------------------------------
         const int n_insn = P.n_insn;
         for (int pc = 0; pc < n_insn; pc++) {
-            const UInsn in = P.insn[pc];
-            const uint32_t xa = ((in.flags & UF_XSLOT) ? wbase : c.stage) + ((uint32_t)in.xoff16 << 4);
-            const uint32_t ya = ((in.flags & UF_YSLOT) ? wbase : c.stage) + ((uint32_t)in.yoff16 << 4);
+            const uint4 w0 = lds_v4b32(prog + pc * 32), w1 = lds_v4b32(prog + pc * 32 + 16);
+            UInsn in;
+            in.code = (uint8_t)w0.x; in.flags = (uint8_t)(w0.x >> 8); in.gop = (uint8_t)(w0.x >> 16); in.aux = (uint8_t)(w0.x >> 24);
+            in.xkind = (uint8_t)w0.y; in.ykind = (uint8_t)(w0.y >> 8); in.zkind = (uint8_t)(w0.y >> 16);
+            in.xrel = w0.z; in.dstrel = w0.w;
+            in.imm = (int64_t)((uint64_t)w1.x | ((uint64_t)w1.y << 32));
+            in.yrel = w1.z; in.zrel = w1.w;
+            const uint32_t xa = ((in.flags & UF_XSLOT) ? wbase : c.stage) + in.xrel;
+            const uint32_t ya = ((in.flags & UF_YSLOT) ? wbase : c.stage) + in.yrel;
             // result handling, expanded inside every case so that t never crosses the switch
 #define RQ_FINISH(t)                                                                          \
     do {                                                                                      \
-        if (in.dst != kNoDst) st_m64(slot_base + in.dst * (kTile * 8) + lane * 16, t);        \
+        if (in.flags & UF_STORE) st_m64(wbase + in.dstrel + lane * 16, t);                    \
         if (in.flags & UF_FILTER) {                                                           \
             _Pragma("unroll") for (int r = 0; r < kR; r++)                                    \
                 if ((t[r] & 0xff) == 0) valid &= ~(1u << r);                                  \
@@ -367,8 +395,8 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
 
                 case U_GEN: {
                     int64_t t[kR], b[kR];
-                    fetch(P, c, in.xkind, in.flags & UF_XSLOT, in.xoff16, in.imm, t);
-                    if (in.gop != D_LD) fetch(P, c, in.ykind, in.flags & UF_YSLOT, in.yoff16, in.imm, b);
+                    fetch(P, c, in.xkind, in.flags & UF_XSLOT, in.xrel, in.imm, t);
+                    if (in.gop != D_LD) fetch(P, c, in.ykind, in.flags & UF_YSLOT, in.yrel, in.imm, b);
                     switch (in.gop) {
 #define RQ_GBIN(D, N) case D: _Pragma("unroll") for (int r = 0; r < kR; r++) t[r] = RQ_EX_##N(t[r], b[r]); break;
                         RQ_GBIN(D_ADD, ADD) RQ_GBIN(D_SUB, SUB) RQ_GBIN(D_RSUB, RSUB) RQ_GBIN(D_MUL, MUL)
@@ -403,8 +431,8 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         case D_SEL: {
                             // t = (x & 0xff) ? y : z     (one WHEN/THEN arm of emitCase :720-754)
                             int64_t e[kR];
-                            fetch(P, c, in.zkind, in.flags & UF_ZSLOT, in.zoff16,
-                                  in.zkind == K_IMM ? P.imm[in.zoff16] : 0, e);
+                            fetch(P, c, in.zkind, in.flags & UF_ZSLOT, in.zrel,
+                                  in.zkind == K_IMM ? P.imm[in.zrel] : 0, e);
 #pragma unroll
                             for (int r = 0; r < kR; r++) t[r] = (t[r] & 0xff) ? b[r] : e[r];
                             break;
@@ -415,33 +443,70 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     break;
                 }
 
+            // selection-fused compares: the 8 tuple tests are independent and combined by a tree,
+            // so the mask update is not a serial chain
+#define RQ_DROP(ok)                                                                        \
+    do {                                                                                   \
+        const unsigned f = (((ok[0] ? 0u : 1u) | (ok[1] ? 0u : 2u)) | ((ok[2] ? 0u : 4u) | (ok[3] ? 0u : 8u))) |       \
+                           (((ok[4] ? 0u : 16u) | (ok[5] ? 0u : 32u)) | ((ok[6] ? 0u : 64u) | (ok[7] ? 0u : 128u)));   \
+        valid &= ~f;                                                                       \
+        if (!__any_sync(kFull, valid != 0)) pc = n_insn;                                   \
+    } while (0)
 #define RQ_FCMP(N, OP)                                                                     \
     case U_F##N##_M64: {                                                                   \
         int64_t b[kR]; ld_m64(xa + lane * 16, b);                                          \
         const int64_t y = in.imm;                                                          \
-        _Pragma("unroll") for (int r = 0; r < kR; r++)                                     \
-            if (!(b[r] OP y)) valid &= ~(1u << r);                                         \
-        if (!__any_sync(kFull, valid != 0)) pc = n_insn;                                   \
+        bool ok[kR];                                                                       \
+        _Pragma("unroll") for (int r = 0; r < kR; r++) ok[r] = (b[r] OP y);                \
+        RQ_DROP(ok);                                                                       \
         break;                                                                             \
     }                                                                                      \
     case U_F##N##_M32: {                                                                   \
         int32_t b[kR]; ld_m32(xa + lane * 8, b);                                           \
         const int32_t y = (int32_t)in.imm;                                                 \
-        _Pragma("unroll") for (int r = 0; r < kR; r++)                                     \
-            if (!(b[r] OP y)) valid &= ~(1u << r);                                         \
-        if (!__any_sync(kFull, valid != 0)) pc = n_insn;                                   \
+        bool ok[kR];                                                                       \
+        _Pragma("unroll") for (int r = 0; r < kR; r++) ok[r] = (b[r] OP y);                \
+        RQ_DROP(ok);                                                                       \
         break;                                                                             \
     }                                                                                      \
     case U_F##N##_M8: {                                                                    \
         uint32_t b[kR]; ld_m8(xa + lane * 2, b);                                           \
         const int32_t y = (int32_t)in.imm;                                                 \
-        _Pragma("unroll") for (int r = 0; r < kR; r++)                                     \
-            if (!((int32_t)b[r] OP y)) valid &= ~(1u << r);                                \
-        if (!__any_sync(kFull, valid != 0)) pc = n_insn;                                   \
+        bool ok[kR];                                                                       \
+        _Pragma("unroll") for (int r = 0; r < kR; r++) ok[r] = ((int32_t)b[r] OP y);       \
+        RQ_DROP(ok);                                                                       \
         break;                                                                             \
     }
                 RQ_FCMP(LT, <) RQ_FCMP(LE, <=) RQ_FCMP(GT, >) RQ_FCMP(GE, >=) RQ_FCMP(EQ, ==) RQ_FCMP(NE, !=)
 #undef RQ_FCMP
+                case U_FRANGE_M64: {      // imm <= x <= imm + span, one unsigned compare
+                    int64_t b[kR]; ld_m64(xa + lane * 16, b);
+                    const uint64_t lo = (uint64_t)in.imm, span = (uint64_t)in.yrel | ((uint64_t)in.zrel << 32);
+                    bool ok[kR];
+#pragma unroll
+                    for (int r = 0; r < kR; r++) ok[r] = ((uint64_t)b[r] - lo) <= span;
+                    RQ_DROP(ok);
+                    break;
+                }
+                case U_FRANGE_M32: {
+                    int32_t b[kR]; ld_m32(xa + lane * 8, b);
+                    const uint32_t lo = (uint32_t)in.imm, span = in.yrel;
+                    bool ok[kR];
+#pragma unroll
+                    for (int r = 0; r < kR; r++) ok[r] = ((uint32_t)b[r] - lo) <= span;
+                    RQ_DROP(ok);
+                    break;
+                }
+                case U_FRANGE_M8: {
+                    uint32_t b[kR]; ld_m8(xa + lane * 2, b);
+                    const uint32_t lo = (uint32_t)in.imm, span = in.yrel;
+                    bool ok[kR];
+#pragma unroll
+                    for (int r = 0; r < kR; r++) ok[r] = (b[r] - lo) <= span;
+                    RQ_DROP(ok);
+                    break;
+                }
+#undef RQ_DROP
 
                 case U_PROBE: {
                     if (GR > 0) break;
@@ -738,7 +803,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
 
         // everyone is done with stage s (and the slots) before it is refilled
         __syncwarp();
-        if (lane == 0 && P.n_cols > 0) {
+        if (P.n_cols > 0) {
             const int64_t nt = tile + (int64_t)S * stride;
             if (nt < n_tiles) issue(nt, s);
         }

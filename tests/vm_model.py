@@ -10,7 +10,7 @@ from resql_b200 import native as N
 (D_LD, D_ADD, D_SUB, D_RSUB, D_MUL, D_DIV, D_RDIV, D_AND, D_OR, D_LT, D_LE, D_GT, D_GE, D_EQ, D_NE,
  D_EQC, D_EQV, D_NEC, D_NEV, D_LIKE, D_RLIKE, D_SEL) = range(1, 23)
 S_NONE, S_COL, S_SLOT, S_IMM, S_STR = range(5)
-H_FCMP, H_BIN, H_MULI, H_SEL, H_PROBE = range(1, 6)
+H_FCMP, H_BIN, H_MULI, H_SEL, H_PROBE, H_FRANGE = range(1, 7)
 IMPL_LOWAGG, IMPL_HASHAGG, IMPL_BUILD, IMPL_EMIT, IMPL_REGAGG = 1, 2, 3, 4, 5
 
 
@@ -105,10 +105,14 @@ def run_pipeline_vm(plan, pi, src_cols, pool_strings, agg_impl=IMPL_LOWAGG):
         return operand(kind, idx, 0)
 
     old = np.seterr(over="ignore")
-    for op, gop, xk, xi, ximm, yk, yi, yimm, zk, zi, zimm, imm, dst, filt, aux in prog["unit"]:
+    for op, gop, xk, xi, ximm, yk, yi, yimm, zk, zi, zimm, imm, dst, filt, aux, imm2 in prog["unit"]:
         x, y, z = operand(xk, xi, ximm), operand(yk, yi, yimm), operand(zk, zi, zimm)
         if op == H_FCMP:
             valid = valid & (_binop(gop, x, np.full(n, imm, dtype=np.int64), valid) != 0)
+            continue
+        if op == H_FRANGE:
+            xs = x.astype(object)
+            valid = valid & np.array([imm <= v <= imm + (imm2 & 0xFFFFFFFFFFFFFFFF) for v in xs], dtype=bool)
             continue
         if op == H_BIN: t = _binop(gop, x, y, valid)
         elif op == H_MULI: t = _binop(gop, x, np.full(n, imm, dtype=np.int64), valid) * y
