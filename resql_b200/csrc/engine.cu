@@ -67,6 +67,11 @@ struct DevColumn {
     int type = 0, width = 0;
     unsigned char* d = nullptr;
     bool owned = true;
+    // exact value bounds over all rows, taken once at upload (the data of a table never changes
+    // afterwards: the reference's tables are append-only and re-uploaded per version). They let the
+    // lowering prove that a value fits in 32 bits and pick the narrow instruction forms.
+    bool has_stats = false;
+    int64_t vmin = 0, vmax = 0;
 };
 struct rq_table {
     std::string name;
@@ -104,6 +109,9 @@ static Engine E;
 
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static constexpr int kSmemMax = 227 * 1024;
+
+struct rq_table;
+static void compute_stats(rq_table& t);
 
 // ------------------------------------------------------------------------------------------
 // lifecycle
@@ -214,6 +222,7 @@ extern "C" int rq_table_upload(const char* name, int32_t n_cols, const rq_column
             }
             t->cols.push_back(dc);
         }
+        compute_stats(*t);
         CK(cudaStreamSynchronize(E.stream));
     } catch (RqError& e) {
         return fail(e.code, "%s", e.msg.c_str());
@@ -273,6 +282,7 @@ extern "C" int rq_table_upload_rows(const char* name, int32_t n_cols, const int3
             CK(cudaEventRecord(done[s], E.stream));
             row0 += n;
         }
+        compute_stats(*t);
         CK(cudaStreamSynchronize(E.stream));
         CK(cudaGetLastError());
         cudaEventDestroy(done[0]);
@@ -286,6 +296,33 @@ extern "C" int rq_table_upload_rows(const char* name, int32_t n_cols, const int3
     }
     *out = t.release();
     return RQ_OK;
+}
+
+// min / max of every integer column (one pass over the resident data, on the engine stream)
+static void compute_stats(rq_table& t) {
+    if (t.n_rows <= 0) return;
+    std::vector<int> idx;
+    for (size_t c = 0; c < t.cols.size(); c++)
+        if (t.cols[c].type != RQ_STR) idx.push_back((int)c);
+    if (idx.empty()) return;
+    int64_t* d = nullptr;
+    CK(cudaMalloc(&d, idx.size() * 16));
+    std::vector<int64_t> h(idx.size() * 2);
+    for (size_t k = 0; k < idx.size(); k++) { h[2 * k] = INT64_MAX; h[2 * k + 1] = INT64_MIN; }
+    CK(cudaMemcpyAsync(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice, E.stream));
+    for (size_t k = 0; k < idx.size(); k++) {
+        const DevColumn& dc = t.cols[idx[k]];
+        const int grid = (int)std::min<int64_t>((t.n_rows + 256 * 16 - 1) / (256 * 16), (int64_t)E.sm_count * 8);
+        rq_col_minmax<<<std::max(grid, 1), 256, 0, E.stream>>>(dc.d, dc.width, t.n_rows, d + 2 * k);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    cudaFree(d);
+    for (size_t k = 0; k < idx.size(); k++) {
+        DevColumn& dc = t.cols[idx[k]];
+        dc.has_stats = true; dc.vmin = h[2 * k]; dc.vmax = h[2 * k + 1];
+    }
 }
 
 extern "C" int64_t rq_table_rows(const rq_table* t) { return t ? t->n_rows : -1; }
@@ -363,6 +400,8 @@ struct HOpnd {           // host-level operand of a unit / value reference of a 
     uint8_t kind = S_NONE;   // DSrc
     uint16_t idx = 0;        // staged column / slot / string column (sinks: imm-table index)
     int64_t imm = 0;
+    uint8_t u32 = 0;         // value proven to lie in [0, 2^32)
+    int64_t lo = INT64_MIN, hi = INT64_MAX;   // sinks: value bounds (group-key packing)
 };
 typedef HOpnd HRef;
 
@@ -383,6 +422,7 @@ struct HUnit {
     int dst = -1;
     bool filt = false;
     int aux = 0;
+    bool n32 = false;        // both multiplication factors proven to lie in [0, 2^32)
 };
 
 struct Lowerer {
@@ -408,6 +448,7 @@ struct Lowerer {
     std::vector<int> staged_of_col;   // source column -> staged index / str index
     std::vector<int> free_slots;
     std::vector<char> fused;          // node produces no unit of its own (folded into a consumer)
+    std::vector<__int128> vlo, vhi;   // value bounds per node (full int64 range when unknown)
     int n_imm = 0;
 
     Lowerer(const rq_plan& plan, const rq_pipeline& pl, const rq_table& src,
@@ -434,6 +475,8 @@ struct Lowerer {
     }
     HRef href_of(int node) {
         HRef v = operand_of(node);
+        v.u32 = is_u32(node) ? 1 : 0;
+        v.lo = (int64_t)vlo[node]; v.hi = (int64_t)vhi[node];
         if (v.kind == S_IMM) {
             if (n_imm >= kMaxImm) raise(RQ_ERR_UNSUPPORTED, "too many constants in sink");
             P.imm[n_imm] = v.imm;
@@ -517,6 +560,7 @@ struct Lowerer {
         uint32_t off = 0;
         for (int c = 0; c < P.n_cols; c++) { P.col_off[c] = off; off += kTile * P.col_w[c]; }
         P.stage_bytes = off;
+        derive_bounds();
         // fusion marks
         for (int f = 0; f < n; f++) {
             HOpnd o; int64_t k;
@@ -527,6 +571,48 @@ struct Lowerer {
             if (muli_of(i, &inner, &other, &gop, &k, &x)) fused[inner] = 1;
         }
     }
+
+    // Interval arithmetic over the typed program: column bounds come from the upload statistics,
+    // anything that may wrap around int64 becomes "unknown". A value proven to lie in [0, 2^32)
+    // has a zero high word, so the 32-bit instruction forms produce identical results.
+    void derive_bounds() {
+        const __int128 FMIN = INT64_MIN, FMAX = INT64_MAX;
+        vlo.assign(n, FMIN); vhi.assign(n, FMAX);
+        auto clampset = [&](int i, __int128 lo, __int128 hi) {
+            if (lo < FMIN || hi > FMAX) { vlo[i] = FMIN; vhi[i] = FMAX; } else { vlo[i] = lo; vhi[i] = hi; }
+        };
+        for (int i = 0; i < n; i++) {
+            const rq_node& nd = pl.nodes[i];
+            switch (nd.op) {
+                case RQ_OP_COL: {
+                    const DevColumn& dc = src.cols[nd.a];
+                    if (dc.type == RQ_STR) break;
+                    if (dc.has_stats) { vlo[i] = dc.vmin; vhi[i] = dc.vmax; }
+                    else if (dc.type == RQ_I8) { vlo[i] = 0; vhi[i] = 255; }
+                    else if (dc.type == RQ_I32) { vlo[i] = INT32_MIN; vhi[i] = INT32_MAX; }
+                    break;
+                }
+                case RQ_OP_CONST: vlo[i] = vhi[i] = nd.imm; break;
+                case RQ_OP_ADD: clampset(i, vlo[nd.a] + vlo[nd.b], vhi[nd.a] + vhi[nd.b]); break;
+                case RQ_OP_SUB: clampset(i, vlo[nd.a] - vhi[nd.b], vhi[nd.a] - vlo[nd.b]); break;
+                case RQ_OP_MUL: {
+                    const __int128 c[4] = {vlo[nd.a] * vlo[nd.b], vlo[nd.a] * vhi[nd.b], vhi[nd.a] * vlo[nd.b], vhi[nd.a] * vhi[nd.b]};
+                    clampset(i, std::min(std::min(c[0], c[1]), std::min(c[2], c[3])), std::max(std::max(c[0], c[1]), std::max(c[2], c[3])));
+                    break;
+                }
+                case RQ_OP_LT: case RQ_OP_LE: case RQ_OP_GT: case RQ_OP_GE: case RQ_OP_EQ: case RQ_OP_NEQ:
+                case RQ_OP_EQ_CHAR: case RQ_OP_EQ_VARCHAR: case RQ_OP_NEQ_CHAR: case RQ_OP_NEQ_VARCHAR: case RQ_OP_LIKE:
+                    vlo[i] = 0; vhi[i] = 1; break;
+                case RQ_OP_AND: case RQ_OP_OR:
+                    if (vlo[nd.a] >= 0 && vhi[nd.a] <= 1 && vlo[nd.b] >= 0 && vhi[nd.b] <= 1) { vlo[i] = 0; vhi[i] = 1; }
+                    break;
+                case RQ_OP_SELECT:
+                    vlo[i] = std::min(vlo[nd.b], vlo[nd.c]); vhi[i] = std::max(vhi[nd.b], vhi[nd.c]); break;
+                default: break;   // DIV, PROBE, PAYLOAD, strings: unknown
+            }
+        }
+    }
+    bool is_u32(int node) const { return vlo[node] >= 0 && vhi[node] <= 0xffffffffLL; }
 
     bool is_col8(int node) const {
         return pl.nodes[node].op == RQ_OP_COL && leaf_op[node].kind == S_COL && P.col_w[leaf_op[node].idx] == 8;

@@ -320,9 +320,11 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
             if (L.muli_of(i, &inner, &other, &gop, &k, &x)) {
                 HUnit& u = L.emit(H_MULI, gop);
                 u.x = x; u.imm = k; u.y = L.operand_of(other);
+                u.n32 = L.is_u32(inner) && L.is_u32(other) && k >= 0 && k <= 0xffffffffLL;
             } else {
                 HUnit& u = L.emit(H_BIN, dop_left(nd.op));
                 u.x = L.operand_of(nd.a); u.y = L.operand_of(nd.b);
+                u.n32 = nd.op == RQ_OP_MUL && L.is_u32(nd.a) && L.is_u32(nd.b);
             }
             finish_value(i);
         } else if (nd.op == RQ_OP_SELECT) {
@@ -375,32 +377,29 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
 }
 
 // ---- shared-memory layout and launch geometry --------------------------------------------
-// [mbarriers: kMaxWarps x kMaxStages][warp region 0][warp region 1]...; a warp region is
-// [stages][slots][lane-private accumulators]. As many warps as fit (latency hiding comes from
-// warps, bytes in flight from warps x stages), at least two stages when possible.
+// [mbarriers: kMaxWarps x kMaxStages][program][warp region 0][warp region 1]...; a warp region is
+// [stages][slots][lane-private accumulators].
 static bool layout_smem(KParams& P, int n_slots, int acc_bytes, int max_warps) {
     const uint32_t bars = kMaxWarps * kMaxStages * 8 + kMaxInsn * (uint32_t)sizeof(UInsn);   // + program copy
-    int bestW = 0, bestS = 0;
-    for (int S = 2; S <= kMaxStages; S++) {
+    auto warp_bytes = [&](int S) {
         uint32_t wb = (uint32_t)S * P.stage_bytes + (uint32_t)n_slots * kTile * 8 + (uint32_t)acc_bytes;
         wb = (wb + 127) & ~127u;
-        if (wb == 0) wb = 128;
-        const int W = (int)std::min<int64_t>(max_warps, ((int64_t)kSmemMax - bars) / wb);
-        if (W > bestW) { bestW = W; bestS = S; }
-        else if (W == bestW && W > 0 && S <= 3) bestS = S;   // a third stage when it is free
-    }
-    if (bestW == 0) {   // single buffered as the last resort
-        uint32_t wb = P.stage_bytes + (uint32_t)n_slots * kTile * 8 + (uint32_t)acc_bytes;
-        wb = (wb + 127) & ~127u;
-        if (bars + wb > (uint32_t)kSmemMax) return false;
-        bestW = 1; bestS = 1;
-    }
+        return wb == 0 ? 128u : wb;
+    };
+    auto fit = [&](int S) { return (int)std::min<int64_t>(max_warps, ((int64_t)kSmemMax - bars) / warp_bytes(S)); };
+    // Warps hide latency better than a second stage does (measured: throughput grows almost
+    // linearly with resident warps, single- and double-buffered runs tie at equal warp counts), so
+    // take the most warps; double buffering only when it costs no warp.
+    int bestW = fit(1), bestS = 1;
+    if (bestW < 1) return false;
+    if (fit(2) >= bestW) bestS = 2;
+    // tuning knobs for experiments (scripts/sweep.py): RQ_STAGES / RQ_WARPS override the choice
+    if (const char* e = getenv("RQ_STAGES")) { const int S = atoi(e); if (S >= 1 && S <= kMaxStages && fit(S) >= 1) { bestS = S; bestW = fit(S); } }
+    if (const char* e = getenv("RQ_WARPS")) { const int W = atoi(e); if (W >= 1 && W <= bestW) bestW = W; }
     P.stages = bestS;
     P.warps = bestW;
     P.n_slots = n_slots;
-    uint32_t wb = (uint32_t)bestS * P.stage_bytes + (uint32_t)n_slots * kTile * 8 + (uint32_t)acc_bytes;
-    wb = (wb + 127) & ~127u;
-    if (wb == 0) wb = 128;
+    const uint32_t wb = warp_bytes(bestS);
     P.prog_off = kMaxWarps * kMaxStages * 8;
     P.warp_off = bars;
     P.warp_bytes = wb;
@@ -431,7 +430,7 @@ static VRef to_vref(const KParams& P, const HRef& h) {
     VRef v; v.kind = K_NONE; v.slot = 0; v.off16 = 0;
     if (h.kind == S_IMM) { v.kind = K_IMM; v.off16 = h.idx; return v; }
     const UOperand u = resolve(P, h);
-    v.kind = u.kind; v.slot = u.slot; v.off16 = (uint16_t)(u.off >> 4);
+    v.kind = u.kind; v.slot = (uint8_t)(u.slot | (h.u32 ? 2 : 0)); v.off16 = (uint16_t)(u.off >> 4);
     return v;
 }
 
@@ -471,6 +470,7 @@ static void encode_program(Lowerer& L, KParams& P) {
         } else if (h.op == H_MULI) {
             if (x.kind != K_M64 || y.kind != K_M64) raise(RQ_ERR_INVALID, "internal: MULI operands");
             u.code = h.gop == D_ADD ? U_MULADDI : (h.gop == D_SUB ? U_MULSUBI : U_MULRSUBI);
+            if (h.n32) u.code = h.gop == D_ADD ? U_MULADDI32 : (h.gop == D_SUB ? U_MULSUBI32 : U_MULRSUBI32);
         } else if (h.op == H_PROBE) {
             u.code = U_PROBE;
         } else if (h.op == H_SEL) {
@@ -483,6 +483,7 @@ static void encode_program(Lowerer& L, KParams& P) {
             static const int swapped[12] = {0, 2, 1, 3, 4, 5, 8, 9, 6, 7, 10, 11};
             if (bi >= 0 && x.kind == K_M64 && y.kind == K_M64) {
                 u.code = (uint8_t)(U_ADD_MM + 2 * bi);
+                if (h.n32 && h.gop == D_MUL) u.code = U_MUL32_MM;
             } else if (bi >= 0 && x.kind == K_M64 && y.kind == K_IMM) {
                 u.code = (uint8_t)(U_ADD_MM + 2 * bi + 1);
                 u.imm = h.y.imm;
@@ -529,19 +530,23 @@ static bool pack_group_key(const Lowerer& L, KParams& P, KeyUnpack& ku) {
     for (int k = 0; k < ku.nk; k++) {
         const HRef& h = L.hkey[k];
         int bits = 64, sign = 1;
+        if (h.kind == S_STR) return false;
         if (h.kind == S_COL) {
             const int w = P.col_w[h.idx];
             bits = 8 * w;
             sign = (w == 1) ? 0 : 1;
-        } else if (h.kind == S_STR) {
-            return false;
+        }
+        if (h.lo >= 0) {        // non-negative values need no sign and only as many bits as the bound
+            int need = 1;
+            while (need < 63 && ((int64_t)1 << need) <= h.hi) need++;
+            if (need < bits) { bits = need; sign = 0; }
         }
         if (total + bits > 64) return false;
         P.key_shift[k] = (uint8_t)total; P.key_bits[k] = (uint8_t)bits;
         ku.shift[k] = (uint8_t)total; ku.bits[k] = (uint8_t)bits; ku.sign[k] = (uint8_t)sign;
         total += bits;
     }
-    P.key32 = total <= 32 ? 1 : 0;
+    P.key32 = total <= 31 ? 1 : 0;    // leaves room for the two sentinels of the register path
     return true;
 }
 
@@ -1061,7 +1066,8 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
 // is covered on CPU-only CI. Not part of the public ABI.
 // ------------------------------------------------------------------------------------------
 extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32_t* col_types,
-                              const int32_t* col_widths, int n_cols, char* buf, int64_t buflen) {
+                              const int32_t* col_widths, const int64_t* col_min, const int64_t* col_max,
+                              int n_cols, char* buf, int64_t buflen) {
     try {
         if (!plan || pi < 0 || pi >= plan->n_pipelines) return fail(RQ_ERR_INVALID, "rq_debug_lower: bad pipeline");
         SimplePipe sp;
@@ -1071,6 +1077,9 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
         for (int c = 0; c < n_cols; c++) {
             DevColumn dc;
             dc.type = col_types[c]; dc.width = col_widths[c]; dc.d = nullptr; dc.owned = false;
+            if (col_min && col_max && dc.type != RQ_STR && col_min[c] <= col_max[c]) {
+                dc.has_stats = true; dc.vmin = col_min[c]; dc.vmax = col_max[c];
+            }
             fake.cols.push_back(dc);
         }
         std::vector<PipeOut> outs(plan->n_pipelines);
@@ -1112,10 +1121,10 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
         }
         for (size_t i = 0; i < L.prog.size(); i++) {
             const HUnit& h = L.prog[i];
-            snprintf(line, sizeof line, "unit %d %d %d %d %lld %d %d %lld %d %d %lld %lld %d %d %d %lld\n", h.op, h.gop,
+            snprintf(line, sizeof line, "unit %d %d %d %d %lld %d %d %lld %d %d %lld %lld %d %d %d %lld %d\n", h.op, h.gop,
                      h.x.kind, h.x.idx, (long long)h.x.imm, h.y.kind, h.y.idx, (long long)h.y.imm,
                      h.z.kind, h.z.idx, (long long)h.z.imm, (long long)h.imm, h.dst, h.filt ? 1 : 0, h.aux,
-                     (long long)h.imm2);
+                     (long long)h.imm2, h.n32 ? 1 : 0);
             s += line;
         }
         for (int i = 0; i < P.n_insn; i++) {
@@ -1128,7 +1137,7 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
         for (size_t k = 0; k < L.hout.size(); k++) { snprintf(line, sizeof line, "out %d %d\n", L.hout[k].kind, L.hout[k].idx); s += line; }
         for (int k = 0; k < kMaxImm; k++) { snprintf(line, sizeof line, "imm %d %lld\n", k, (long long)P.imm[k]); s += line; }
         for (size_t u = 0; u < ad.kind.size(); u++) { snprintf(line, sizeof line, "agg %d %d\n", (int)u, ad.kind[u]); s += line; }
-        for (size_t u = 0; u < ad.kind.size(); u++) { snprintf(line, sizeof line, "aggsrc %d %d\n", L.hagg_src[u].kind, L.hagg_src[u].idx); s += line; }
+        for (size_t u = 0; u < ad.kind.size(); u++) { snprintf(line, sizeof line, "aggsrc %d %d %d\n", L.hagg_src[u].kind, L.hagg_src[u].idx, L.hagg_src[u].u32); s += line; }
         for (size_t k = 0; k < ad.uniq_of.size(); k++) { snprintf(line, sizeof line, "aggmap %d %d\n", (int)k, ad.uniq_of[k]); s += line; }
         if ((int64_t)s.size() + 1 > buflen) return fail(RQ_ERR_INVALID, "rq_debug_lower: buffer too small");
         memcpy(buf, s.c_str(), s.size() + 1);

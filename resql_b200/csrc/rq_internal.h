@@ -61,6 +61,8 @@ enum UCode : uint8_t {
     RQ_BINOPS(RQ_X)
 #undef RQ_X
     U_MULADDI, U_MULSUBI, U_MULRSUBI,   // t = (x + imm) * y | (x - imm) * y | (imm - x) * y
+    // the same, and x * y, when both factors are proven to lie in [0, 2^32): one IMAD.WIDE.U32
+    U_MULADDI32, U_MULSUBI32, U_MULRSUBI32, U_MUL32_MM,
     U_GEN,                              // t = gop(x, y [, z]) with operands of any kind
     // valid &= (column CMP imm): selection-fused compares, nothing stored
     U_FLT_M64, U_FLE_M64, U_FGT_M64, U_FGE_M64, U_FEQ_M64, U_FNE_M64,

@@ -152,13 +152,51 @@ __device__ __forceinline__ int64_t ld_row(const KParams& P, const WarpCtx& c, VR
     }
 }
 
-// acc += v * m for a 0/1 multiplier m (exact mod 2^64)
-__device__ __forceinline__ void macc(uint64_t& acc, int64_t v, uint32_t m) {
-    acc += (uint64_t)v * (uint64_t)m;
+// packed group key: every key is a bit field of one word (32-bit arithmetic when it fits)
+__device__ __forceinline__ void pack_keys(const KParams& P, const WarpCtx& c, uint64_t (&key)[kR]) {
+    if (P.key32) {
+        uint32_t k32[kR];
+#pragma unroll
+        for (int r = 0; r < kR; r++) k32[r] = 0;
+        for (int j = 0; j < P.nk; j++) {
+            const VRef vr = P.key[j];
+            const int sh = P.key_shift[j];
+            const uint32_t mask = P.key_bits[j] >= 32 ? ~0u : ((1u << P.key_bits[j]) - 1);
+            if (vr.kind == K_M8) {
+                uint32_t t[kR];
+                ld_m8(((vr.slot & 1) ? c.wbase : c.stage) + ((uint32_t)vr.off16 << 4) + c.lane * 2, t);
+#pragma unroll
+                for (int r = 0; r < kR; r++) k32[r] |= (t[r] & mask) << sh;
+            } else {
+                int64_t kv[kR];
+                fetch_vref(P, c, vr, kv);
+#pragma unroll
+                for (int r = 0; r < kR; r++) k32[r] |= ((uint32_t)kv[r] & mask) << sh;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kR; r++) key[r] = k32[r];
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < kR; r++) key[r] = 0;
+    for (int j = 0; j < P.nk; j++) {
+        int64_t kv[kR];
+        fetch_vref(P, c, P.key[j], kv);
+        const int sh = P.key_shift[j];
+        const uint64_t mask = P.key_bits[j] >= 64 ? ~0ULL : ((1ULL << P.key_bits[j]) - 1);
+#pragma unroll
+        for (int r = 0; r < kR; r++) key[r] |= ((uint64_t)kv[r] & mask) << sh;
+    }
 }
-// the same when v is known to fit in unsigned 32 bits: one IMAD.WIDE.U32
-__device__ __forceinline__ void macc32(uint64_t& acc, int64_t v, uint32_t m) {
-    acc += (uint64_t)(uint32_t)v * (uint64_t)m;
+
+// acc += (low word of v) * m : IMAD.WIDE.U32 with 64-bit accumulate, one FMA-pipe instruction
+__device__ __forceinline__ void mad_wide_u32(uint64_t& acc, uint32_t a, uint32_t m) {
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(m));
+}
+// acc += (signed high word of v) * m : IMAD.WIDE (signed) with 64-bit accumulate
+__device__ __forceinline__ void mad_wide_s32(int64_t& acc, int32_t a, int32_t m) {
+    asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(m));
 }
 
 // ---- low-cardinality global group table (packed key) -----------------------------------------
@@ -218,10 +256,14 @@ extern __shared__ __align__(128) unsigned char rq_smem[];
 #define RQ_EX_NE(x, y)   ((int64_t)((x) != (y)))
 
 static_assert(kNAR == 6, "register accumulators are sized for 6 aggregates");
+// The aggregate-index switch must stay a switch over compile-time register names: an inline asm
+// marker that differs per case keeps the compiler from merging the cases into one body that
+// indexes the accumulator array dynamically (which would demote it to local memory).
+#define RQ_NOMERGE(A) asm volatile("// agg case %0" ::"n"(A))
 template <int GR> struct ScanCfg;
 template <> struct ScanCfg<0> { static constexpr int kThreads = 512; };
 template <> struct ScanCfg<1> { static constexpr int kThreads = 512; };
-template <> struct ScanCfg<4> { static constexpr int kThreads = 384; };
+template <> struct ScanCfg<4> { static constexpr int kThreads = 512; };
 
 template <int GR>
 __global__ void __launch_bounds__(ScanCfg<GR>::kThreads, 1)
@@ -277,21 +319,16 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     auto is_guarded = [&](int64_t tile) -> bool {
         return P.borrowed && (tile + 1) * (int64_t)kTile > n_rows;
     };
-    // lane c < n_cols owns column c's bulk copies: its source pointer advances by a fixed byte
-    // stride per tile, so re-arming a stage costs a handful of instructions per warp
-    const bool col_lane = lane < P.n_cols;
-    const uint32_t my_bytes = col_lane ? kTile * (uint32_t)P.col_w[lane] : 0;
-    const uint32_t my_off = col_lane ? P.col_off[lane] : 0;
-    const unsigned char* my_src = col_lane ? P.col_ptr[lane] + (size_t)first * my_bytes : nullptr;
-    const size_t my_step = (size_t)stride * my_bytes;
-    auto issue = [&](int64_t tile, int s) {      // called by the whole warp; my_src is at `tile`
-        if (!is_guarded(tile)) {
-            const uint32_t bar = bars + s * 8;
-            if (lane == 0) mbar_expect_tx_s(bar, P.stage_bytes);
-            __syncwarp();
-            if (col_lane) tma_bulk_g2s_s(wbase + s * P.stage_bytes + my_off, my_src, my_bytes, bar);
+    // lane 0 issues the bulk copies of a tile, one per staged column
+    auto issue = [&](int64_t tile, int s) {
+        if (lane != 0 || is_guarded(tile)) return;
+        const uint32_t bar = bars + s * 8;
+        const uint32_t dst = wbase + s * P.stage_bytes;
+        mbar_expect_tx_s(bar, P.stage_bytes);
+        for (int c = 0; c < P.n_cols; c++) {
+            const uint32_t bytes = kTile * P.col_w[c];
+            tma_bulk_g2s_s(dst + P.col_off[c], P.col_ptr[c] + (size_t)tile * bytes, bytes, bar);
         }
-        my_src += my_step;
     };
     if (P.n_cols > 0) {
         for (int s = 0; s < S; s++)
@@ -392,6 +429,23 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                 RQ_MULI(U_MULSUBI, x - k)
                 RQ_MULI(U_MULRSUBI, k - x)
 #undef RQ_MULI
+#define RQ_MULI32(CODE, EXPR)                                                              \
+    case CODE: {                                                                           \
+        int64_t a[kR], b[kR], t[kR];                                                       \
+        ld_m64(xa + lane * 16, a); ld_m64(ya + lane * 16, b);                              \
+        const uint32_t k = (uint32_t)in.imm;                                               \
+        _Pragma("unroll") for (int r = 0; r < kR; r++) {                                   \
+            const uint32_t x = (uint32_t)a[r];                                             \
+            t[r] = (int64_t)((uint64_t)(uint32_t)(EXPR) * (uint64_t)(uint32_t)b[r]);       \
+        }                                                                                  \
+        RQ_FINISH(t);                                                                      \
+        break;                                                                             \
+    }
+                RQ_MULI32(U_MULADDI32, x + k)
+                RQ_MULI32(U_MULSUBI32, x - k)
+                RQ_MULI32(U_MULRSUBI32, k - x)
+                RQ_MULI32(U_MUL32_MM, x)
+#undef RQ_MULI32
 
                 case U_GEN: {
                     int64_t t[kR], b[kR];
@@ -579,24 +633,27 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         for (int r = 0; r < kR; r++) m[g][r] = 0;
                 } else {
                     uint64_t key[kR];
-#pragma unroll
-                    for (int r = 0; r < kR; r++) key[r] = 0;
-                    for (int j = 0; j < NK; j++) {
-                        int64_t kv[kR];
-                        fetch_vref(P, c, P.key[j], kv);
-                        const int sh = P.key_shift[j];
-                        const uint64_t mask = P.key_bits[j] >= 64 ? ~0ULL : ((1ULL << P.key_bits[j]) - 1);
-#pragma unroll
-                        for (int r = 0; r < kR; r++) key[r] |= ((uint64_t)kv[r] & mask) << sh;
-                    }
+                    pack_keys(P, c, key);
                     unsigned unk = 0;
+                    if (P.key32) {
+                        // packed keys use at most 31 bits: all-ones marks a dropped tuple, all-ones
+                        // minus one an unused dictionary entry, and neither equals a real key
+                        uint32_t k32[kR];
 #pragma unroll
-                    for (int g = 0; g < NG; g++) {
-                        const bool act = g < ngroups;
+                        for (int r = 0; r < kR; r++) k32[r] = ((valid >> r) & 1) ? (uint32_t)key[r] : 0xffffffffu;
 #pragma unroll
-                        for (int r = 0; r < kR; r++) {
-                            const bool hit = P.key32 ? ((uint32_t)key[r] == (uint32_t)dk[g]) : (key[r] == dk[g]);
-                            m[g][r] = (act && hit && ((valid >> r) & 1)) ? 1u : 0u;
+                        for (int g = 0; g < NG; g++) {
+                            const uint32_t d = g < ngroups ? (uint32_t)dk[g] : 0xfffffffeu;
+#pragma unroll
+                            for (int r = 0; r < kR; r++) m[g][r] = (k32[r] == d) ? 1u : 0u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < NG; g++) {
+                            const bool act = g < ngroups;
+#pragma unroll
+                            for (int r = 0; r < kR; r++)
+                                m[g][r] = (act && key[r] == dk[g] && ((valid >> r) & 1)) ? 1u : 0u;
                         }
                     }
 #pragma unroll
@@ -604,7 +661,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         uint32_t any = 0;
 #pragma unroll
                         for (int g = 0; g < NG; g++) any |= m[g][r];
-                        if (((valid >> r) & 1) && !any) unk |= 1u << r;
+                        unk |= (((valid >> r) & 1u) & ~any) << r;
                     }
                     // slow path: a key this warp has not seen yet joins the dictionary
                     while (__any_sync(kFull, unk != 0)) {
@@ -633,43 +690,74 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         ngroups++;
                     }
                 }
-#pragma unroll
-                for (int a = 0; a < kNAR; a++) {
-                    if (a >= NA) continue;
+                // One rolled loop over the aggregates: the tuple values are reduced into tile-local
+                // partials per group (two independent chains each), then folded into the register
+                // accumulator picked by a switch over compile-time names. The variant code exists
+                // once, so the hot path stays small.
+#pragma unroll 1
+                for (int a = 0; a < NA; a++) {
                     const int kind = P.agg_kind[a];
+                    uint64_t part[NG];
                     if (kind == 2) {                      // COUNT
 #pragma unroll
                         for (int g = 0; g < NG; g++) {
                             uint32_t cnt = 0;
 #pragma unroll
                             for (int r = 0; r < kR; r++) cnt += m[g][r];
-                            racc[g][a] += cnt;
+                            part[g] = cnt;
                         }
-                        continue;
-                    }
-                    const VRef vr = P.agg_src[a];
-                    int64_t v[kR];
-                    fetch_vref(P, c, vr, v);
-                    if (kind == 1) {                      // SUM
-                        if (vr.slot & 2) {
+                    } else {
+                        const VRef vr = P.agg_src[a];
+                        int64_t v[kR];
+                        if (vr.kind == K_M64) ld_m64(((vr.slot & 1) ? c.wbase : c.stage) + ((uint32_t)vr.off16 << 4) + lane * 16, v);
+                        else fetch_vref(P, c, vr, v);
+                        if (kind == 1 && (vr.slot & 2)) {   // SUM of values proven to fit 32 bits
 #pragma unroll
-                            for (int g = 0; g < NG; g++)
+                            for (int g = 0; g < NG; g++) {
+                                uint64_t p0 = 0, p1 = 0;
 #pragma unroll
-                                for (int r = 0; r < kR; r++) macc32(racc[g][a], v[r], m[g][r]);
-                        } else {
-#pragma unroll
-                            for (int g = 0; g < NG; g++)
-#pragma unroll
-                                for (int r = 0; r < kR; r++) macc(racc[g][a], v[r], m[g][r]);
-                        }
-                    } else {                              // MIN / MAX
-#pragma unroll
-                        for (int g = 0; g < NG; g++)
-#pragma unroll
-                            for (int r = 0; r < kR; r++) {
-                                const int64_t cur = (int64_t)racc[g][a];
-                                if (m[g][r] && (kind == 3 ? v[r] < cur : v[r] > cur)) racc[g][a] = (uint64_t)v[r];
+                                for (int r = 0; r < kR; r += 2) {
+                                    mad_wide_u32(p0, (uint32_t)v[r], m[g][r]);
+                                    mad_wide_u32(p1, (uint32_t)v[r + 1], m[g][r + 1]);
+                                }
+                                part[g] = p0 + p1;
                             }
+                        } else if (kind == 1) {             // SUM: low words unsigned, high words signed
+#pragma unroll
+                            for (int g = 0; g < NG; g++) {
+                                uint64_t lo = 0;
+                                int64_t hi = 0;
+#pragma unroll
+                                for (int r = 0; r < kR; r++) {
+                                    mad_wide_u32(lo, (uint32_t)v[r], m[g][r]);
+                                    mad_wide_s32(hi, (int32_t)((uint64_t)v[r] >> 32), (int32_t)m[g][r]);
+                                }
+                                part[g] = lo + ((uint64_t)hi << 32);
+                            }
+                        } else {                            // MIN / MAX
+#pragma unroll
+                            for (int g = 0; g < NG; g++) {
+                                int64_t best = agg_identity(kind);
+#pragma unroll
+                                for (int r = 0; r < kR; r++)
+                                    if (m[g][r] && (kind == 3 ? v[r] < best : v[r] > best)) best = v[r];
+                                part[g] = (uint64_t)best;
+                            }
+                        }
+                    }
+                    switch (a) {
+#define RQ_FOLD(A)                                                                            \
+    case A:                                                                                   \
+        RQ_NOMERGE(A);                                                                        \
+        _Pragma("unroll") for (int g = 0; g < NG; g++) {                                      \
+            const int64_t cur = (int64_t)racc[g][A], nv = (int64_t)part[g];                   \
+            if (kind <= 2) racc[g][A] = (uint64_t)cur + (uint64_t)nv;                         \
+            else if (kind == 3 ? nv < cur : nv > cur) racc[g][A] = (uint64_t)nv;              \
+        }                                                                                     \
+        break;
+                        RQ_FOLD(0) RQ_FOLD(1) RQ_FOLD(2) RQ_FOLD(3) RQ_FOLD(4) RQ_FOLD(5)
+#undef RQ_FOLD
+                        default: break;
                     }
                 }
             } else if (sink == IMPL_LOWAGG) {
@@ -679,16 +767,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     seen |= valid;
                 } else {
                     uint64_t key[kR];
-#pragma unroll
-                    for (int r = 0; r < kR; r++) key[r] = 0;
-                    for (int j = 0; j < NK; j++) {
-                        int64_t kv[kR];
-                        fetch_vref(P, c, P.key[j], kv);
-                        const int sh = P.key_shift[j];
-                        const uint64_t mask = P.key_bits[j] >= 64 ? ~0ULL : ((1ULL << P.key_bits[j]) - 1);
-#pragma unroll
-                        for (int r = 0; r < kR; r++) key[r] |= ((uint64_t)kv[r] & mask) << sh;
-                    }
+                    pack_keys(P, c, key);
                     unsigned unk = 0;
 #pragma unroll
                     for (int r = 0; r < kR; r++) {
@@ -891,6 +970,25 @@ __global__ void rq_group_table_compact(const uint32_t* state, const int64_t* key
             out_cols[j][pos] = (int64_t)f;
         }
         for (int a = 0; a < na; a++) out_cols[ku.nk + a][pos] = acc[(size_t)i * kMaxAggs + a];
+    }
+}
+
+// min / max of an integer column (upload-time statistics): out[0] = min, out[1] = max
+__global__ void rq_col_minmax(const unsigned char* col, int width, int64_t n, int64_t* out) {
+    int64_t lo = INT64_MAX, hi = INT64_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t v;
+        if (width == 8) v = reinterpret_cast<const int64_t*>(col)[i];
+        else if (width == 4) v = reinterpret_cast<const int32_t*>(col)[i];
+        else v = col[i];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+    lo = warp_reduce(lo, 3);
+    hi = warp_reduce(hi, 4);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin((long long*)&out[0], (long long)lo);
+        atomicMax((long long*)&out[1], (long long)hi);
     }
 }
 

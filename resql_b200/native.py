@@ -123,13 +123,15 @@ def load():
     lib.rq_dist_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     lib.rq_dist_init.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint8)]
     lib.rq_debug_lower.argtypes = [C.POINTER(rq_plan), C.c_int, C.c_int, C.POINTER(C.c_int32),
-                                   C.POINTER(C.c_int32), C.c_int, C.c_char_p, C.c_int64]
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                   C.c_int, C.c_char_p, C.c_int64]
     _lib = lib
     return lib
 
 
-def debug_lower(plan, pipeline, impl, col_types, col_widths):
-    """Host-side lowering of one pipeline to the device program, as text (no GPU needed)."""
+def debug_lower(plan, pipeline, impl, col_types, col_widths, col_min=None, col_max=None):
+    """Host-side lowering of one pipeline to the device program, as text (no GPU needed).
+    col_min/col_max: optional per-column value bounds (the upload statistics)."""
     lib = load()
 
     class _T:
@@ -141,7 +143,9 @@ def debug_lower(plan, pipeline, impl, col_types, col_widths):
     ty = (C.c_int32 * n)(*col_types)
     wi = (C.c_int32 * n)(*col_widths)
     buf = C.create_string_buffer(1 << 16)
-    rc = lib.rq_debug_lower(C.byref(cplan), pipeline, impl, ty, wi, n, buf, len(buf))
+    mn = (C.c_int64 * n)(*col_min) if col_min is not None else None
+    mx = (C.c_int64 * n)(*col_max) if col_max is not None else None
+    rc = lib.rq_debug_lower(C.byref(cplan), pipeline, impl, ty, wi, mn, mx, n, buf, len(buf))
     if rc != 0:
         raise EngineError(rc, lib.rq_last_error().decode())
     return buf.value.decode()

@@ -30,8 +30,10 @@ def parse(text):
             prog["strcols"][int(f[1])] = int(f[3])
         elif f[0] == "unit":
             prog["unit"].append([int(x) for x in f[1:]])
-        elif f[0] in ("key", "out", "aggsrc"):
+        elif f[0] in ("key", "out"):
             prog[f[0]].append((int(f[1]), int(f[2])))
+        elif f[0] == "aggsrc":
+            prog[f[0]].append((int(f[1]), int(f[2]), int(f[3])))
         elif f[0] == "imm":
             prog["imm"][int(f[1])] = int(f[2])
         elif f[0] == "agg":
@@ -68,19 +70,23 @@ def _binop(op, a, b, valid):
     raise NotImplementedError(op)
 
 
-def run_pipeline_vm(plan, pi, src_cols, pool_strings, agg_impl=IMPL_LOWAGG):
+def run_pipeline_vm(plan, pi, src_cols, pool_strings, agg_impl=IMPL_LOWAGG, with_stats=True):
     """src_cols: list of numpy arrays (physical dtypes; intermediates int64/object).
     Returns the list of output columns of the pipeline (evaluation form)."""
     p = plan.pipelines[pi]
     impl = agg_impl if p["sink_kind"] == 1 else IMPL_EMIT
-    types, widths = [], []
+    types, widths, mins, maxs = [], [], [], []
     for a in src_cols:
         if a.dtype == object:
             types.append(N.RQ_I64); widths.append(8)     # strings by reference inside intermediates
         else:
             t, w = phys_of(a)
             types.append(t); widths.append(w)
-    prog = parse(N.debug_lower(plan, pi, impl, types, widths))
+        if with_stats and a.dtype.kind in "iu" and len(a):
+            mins.append(int(a.min())); maxs.append(int(a.max()))
+        else:
+            mins.append(1); maxs.append(0)               # no statistics for this column
+    prog = parse(N.debug_lower(plan, pi, impl, types, widths, mins, maxs))
     vals = [PO._to_value(a) for a in src_cols]
     n = len(vals[0]) if vals else 0
     valid = np.ones(n, dtype=bool)
@@ -105,7 +111,7 @@ def run_pipeline_vm(plan, pi, src_cols, pool_strings, agg_impl=IMPL_LOWAGG):
         return operand(kind, idx, 0)
 
     old = np.seterr(over="ignore")
-    for op, gop, xk, xi, ximm, yk, yi, yimm, zk, zi, zimm, imm, dst, filt, aux, imm2 in prog["unit"]:
+    for op, gop, xk, xi, ximm, yk, yi, yimm, zk, zi, zimm, imm, dst, filt, aux, imm2, n32 in prog["unit"]:
         x, y, z = operand(xk, xi, ximm), operand(yk, yi, yimm), operand(zk, zi, zimm)
         if op == H_FCMP:
             valid = valid & (_binop(gop, x, np.full(n, imm, dtype=np.int64), valid) != 0)
@@ -114,8 +120,15 @@ def run_pipeline_vm(plan, pi, src_cols, pool_strings, agg_impl=IMPL_LOWAGG):
             xs = x.astype(object)
             valid = valid & np.array([imm <= v <= imm + (imm2 & 0xFFFFFFFFFFFFFFFF) for v in xs], dtype=bool)
             continue
-        if op == H_BIN: t = _binop(gop, x, y, valid)
-        elif op == H_MULI: t = _binop(gop, x, np.full(n, imm, dtype=np.int64), valid) * y
+        def narrow_ok(*vs):     # the 32-bit forms are only legal for values proven to be in [0, 2^32)
+            return all(len(v) == 0 or (int(v.min()) >= 0 and int(v.max()) < 2 ** 32) for v in vs)
+        if op == H_BIN:
+            t = _binop(gop, x, y, valid)
+            assert not n32 or narrow_ok(x, y), "narrow multiply on wide operands"
+        elif op == H_MULI:
+            inner = _binop(gop, x, np.full(n, imm, dtype=np.int64), valid)
+            assert not n32 or narrow_ok(inner, y), "narrow multiply on wide operands"
+            t = inner * y
         elif op == H_SEL: t = np.where((x & 0xFF) != 0, y, z)
         else: raise NotImplementedError(op)
         if dst >= 0:
@@ -140,7 +153,10 @@ def run_pipeline_vm(plan, pi, src_cols, pool_strings, agg_impl=IMPL_LOWAGG):
         if kind == 2:
             aggs.append(np.bincount(g, minlength=ng).astype(np.int64))
             continue
-        v = vref(*prog["aggsrc"][u])[valid].astype(np.int64)
+        ak, ai, a32 = prog["aggsrc"][u]
+        full = vref(ak, ai).astype(np.int64)
+        assert not a32 or len(full) == 0 or (int(full.min()) >= 0 and int(full.max()) < 2 ** 32), "narrow sum on wide values"
+        v = full[valid]
         if kind == 1:
             a = np.zeros(ng, dtype=np.uint64); np.add.at(a, g, v.view(np.uint64)); a = a.view(np.int64)
         elif kind == 3:
