@@ -226,6 +226,8 @@ typedef struct {
     double  scan_kernel_ms;  /* time of the table-scan pipeline kernels only (roofline)        */
     int32_t kernel_launches;
     int32_t reserved;
+    double  fact_scan_ms;    /* the last table-scan kernel of the plan: the probe/aggregate
+                                pipeline over the fact table (the roofline kernel)             */
 } rq_timings;
 
 int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings* timings);

@@ -7,6 +7,20 @@
 namespace rq {
 
 // ------------------------------------------------------------------------------------------
+// device memory: stream-ordered allocations from the default pool (release threshold raised at
+// rq_init), so that per-query hash tables and intermediates are recycled instead of going
+// through cudaMalloc / cudaFree every time
+// ------------------------------------------------------------------------------------------
+inline cudaStream_t& alloc_stream() { static cudaStream_t s = nullptr; return s; }
+template <typename T>
+inline cudaError_t dmalloc(T** p, size_t bytes) {
+    return cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 1, alloc_stream());
+}
+inline void dfree(void* p) {
+    if (p) cudaFreeAsync(p, alloc_stream());
+}
+
+// ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA bulk copy
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -55,6 +69,20 @@ __device__ __forceinline__ void tma_bulk_g2s_s(uint32_t dst, const void* src, ui
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+// L2 eviction policy for data that is streamed exactly once (scanned columns): evict first, so
+// that hash tables and Bloom filters stay resident in the 126 MB L2 under a multi-GB scan
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                                  uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {

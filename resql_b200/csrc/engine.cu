@@ -84,8 +84,8 @@ struct rq_table {
     std::vector<int> sql_type, sql_width;
     ~rq_table() {
         for (auto& c : cols)
-            if (c.owned && c.d) cudaFree(c.d);
-        if (d_n_rows) cudaFree(d_n_rows);
+            if (c.owned && c.d) dfree(c.d);
+        if (d_n_rows) dfree(d_n_rows);
     }
 };
 
@@ -132,12 +132,19 @@ extern "C" int rq_init(int device) {
         E.sm_count = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&E.copy_stream, cudaStreamNonBlocking));
+        alloc_stream() = E.stream;
+        {   // keep freed blocks in the pool: hash tables and intermediates are recycled across queries
+            cudaMemPool_t pool;
+            CK(cudaDeviceGetDefaultMemPool(&pool, device));
+            uint64_t keep = UINT64_MAX;
+            CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         for (auto& e : E.ev) CK(cudaEventCreate(&e));
-        CK(cudaMalloc(&E.g_state, sizeof(uint32_t) * kGroupTableCap));
-        CK(cudaMalloc(&E.g_keys, sizeof(int64_t) * kGroupTableCap));
-        CK(cudaMalloc(&E.g_acc, sizeof(int64_t) * kGroupTableCap * kMaxAggs));
-        CK(cudaMalloc(&E.g_kinds, kMaxAggs));
-        CK(cudaMalloc(&E.flags, 64));
+        CK(dmalloc(&E.g_state, sizeof(uint32_t) * kGroupTableCap));
+        CK(dmalloc(&E.g_keys, sizeof(int64_t) * kGroupTableCap));
+        CK(dmalloc(&E.g_acc, sizeof(int64_t) * kGroupTableCap * kMaxAggs));
+        CK(dmalloc(&E.g_kinds, kMaxAggs));
+        CK(dmalloc(&E.flags, 64));
         CK(cudaMallocHost(&E.h_flags, 64));
         CK(cudaFuncSetAttribute(rq_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         CK(cudaFuncSetAttribute(rq_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
@@ -153,11 +160,13 @@ extern "C" int rq_shutdown(void) {
     if (!E.init) return RQ_OK;
     cudaDeviceSynchronize();
     dist_shutdown(E.dist);
-    cudaFree(E.g_state); cudaFree(E.g_keys); cudaFree(E.g_acc); cudaFree(E.g_kinds);
-    cudaFree(E.flags); cudaFreeHost(E.h_flags);
+    dfree(E.g_state); dfree(E.g_keys); dfree(E.g_acc); dfree(E.g_kinds);
+    dfree(E.flags); cudaFreeHost(E.h_flags);
+    cudaStreamSynchronize(E.stream);
     for (auto& e : E.ev) cudaEventDestroy(e);
     cudaStreamDestroy(E.stream);
     cudaStreamDestroy(E.copy_stream);
+    alloc_stream() = nullptr;
     E = Engine();
     return RQ_OK;
 }
@@ -213,7 +222,7 @@ extern "C" int rq_table_upload(const char* name, int32_t n_cols, const rq_column
                 dc.owned = false;
             } else {
                 const size_t bytes = (size_t)t->cap_rows * dc.width;
-                CK(cudaMalloc(&dc.d, bytes));
+                CK(dmalloc(&dc.d, bytes));
                 const size_t used = (size_t)n_rows * dc.width;
                 if (used)
                     CK(cudaMemcpyAsync(dc.d, cols[c].data, used,
@@ -257,13 +266,13 @@ extern "C" int rq_table_upload_rows(const char* name, int32_t n_cols, const int3
             DevColumn dc;
             dc.type = types[c];
             dc.width = widths[c];
-            CK(cudaMalloc(&dc.d, (size_t)t->cap_rows * dc.width));
+            CK(dmalloc(&dc.d, (size_t)t->cap_rows * dc.width));
             CK(cudaMemsetAsync(dc.d, 0, (size_t)t->cap_rows * dc.width, E.stream));
             t->cols.push_back(dc);
         }
         if (max_block) {
-            CK(cudaMalloc(&d_rows[0], max_block));
-            CK(cudaMalloc(&d_rows[1], max_block));
+            CK(dmalloc(&d_rows[0], max_block));
+            CK(dmalloc(&d_rows[1], max_block));
         }
         int64_t row0 = 0;
         cudaEvent_t done[2];
@@ -287,11 +296,11 @@ extern "C" int rq_table_upload_rows(const char* name, int32_t n_cols, const int3
         CK(cudaGetLastError());
         cudaEventDestroy(done[0]);
         cudaEventDestroy(done[1]);
-        cudaFree(d_rows[0]);
-        cudaFree(d_rows[1]);
+        dfree(d_rows[0]);
+        dfree(d_rows[1]);
     } catch (RqError& e) {
-        cudaFree(d_rows[0]);
-        cudaFree(d_rows[1]);
+        dfree(d_rows[0]);
+        dfree(d_rows[1]);
         return fail(e.code, "%s", e.msg.c_str());
     }
     *out = t.release();
@@ -306,7 +315,7 @@ static void compute_stats(rq_table& t) {
         if (t.cols[c].type != RQ_STR) idx.push_back((int)c);
     if (idx.empty()) return;
     int64_t* d = nullptr;
-    CK(cudaMalloc(&d, idx.size() * 16));
+    CK(dmalloc(&d, idx.size() * 16));
     std::vector<int64_t> h(idx.size() * 2);
     for (size_t k = 0; k < idx.size(); k++) { h[2 * k] = INT64_MAX; h[2 * k + 1] = INT64_MIN; }
     CK(cudaMemcpyAsync(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice, E.stream));
@@ -318,7 +327,7 @@ static void compute_stats(rq_table& t) {
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, E.stream));
     CK(cudaStreamSynchronize(E.stream));
-    cudaFree(d);
+    dfree(d);
     for (size_t k = 0; k < idx.size(); k++) {
         DevColumn& dc = t.cols[idx[k]];
         dc.has_stats = true; dc.vmin = h[2 * k]; dc.vmax = h[2 * k + 1];

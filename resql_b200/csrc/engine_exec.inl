@@ -571,10 +571,10 @@ static std::unique_ptr<rq_table> new_intermediate(int n_cols, int64_t cap_rows) 
         DevColumn dc;
         dc.type = RQ_I64;
         dc.width = 8;
-        CK(cudaMalloc(&dc.d, (size_t)t->cap_rows * 8));
+        CK(dmalloc(&dc.d, (size_t)t->cap_rows * 8));
         t->cols.push_back(dc);
     }
-    CK(cudaMalloc(&t->d_n_rows, 8));
+    CK(dmalloc(&t->d_n_rows, 8));
     CK(cudaMemsetAsync(t->d_n_rows, 0, 8, E.stream));
     return t;
 }
@@ -686,6 +686,7 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
         P.n_rows = src->n_rows;
         P.n_rows_ptr = src->n_rows < 0 ? src->d_n_rows : nullptr;
         P.borrowed = src->borrowed ? 1 : 0;
+        P.stream_hint = getenv("RQ_NO_HINT") ? 0 : 1;
         P.overflow = E.flags + 0;
         P.ht_full = E.flags + 1;
         P.err = E.flags + 2;
@@ -737,14 +738,14 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
             std::vector<int64_t*> h_dense(pl.n_keys + nuniq);
             for (int c = 0; c < pl.n_keys + nuniq; c++) h_dense[c] = (int64_t*)dense->cols[c].d;
             int64_t** d_ptrs = nullptr;
-            CK(cudaMalloc(&d_ptrs, sizeof(int64_t*) * h_dense.size()));
+            CK(dmalloc(&d_ptrs, sizeof(int64_t*) * h_dense.size()));
             CK(cudaMemcpyAsync(d_ptrs, h_dense.data(), sizeof(int64_t*) * h_dense.size(), cudaMemcpyHostToDevice, E.stream));
             rq_group_table_compact<<<(kGroupTableCap + 255) / 256, 256, 0, E.stream>>>(
                 E.g_state, E.g_keys, E.g_acc, ku, nuniq, d_ptrs, dense->d_n_rows);
             if (tm) tm->kernel_launches++;
             CK(cudaGetLastError());
             check_flags("aggregation pipeline");
-            cudaFree(d_ptrs);
+            dfree(d_ptrs);
             if (E.h_flags[0]) continue;   // more groups than this path tracks: next implementation
             // expand duplicates by aliasing: copy the columns (tiny)
             for (int k = 0; k < pl.n_keys; k++)
@@ -764,8 +765,10 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
             if (pl.size_hint > 0) want = std::min<int64_t>(rows_bound, std::max<int64_t>(pl.size_hint, 2048));
             uint64_t cap = 4096;
             while (cap < (uint64_t)(2 * want)) cap <<= 1;
+            uint64_t max_load_den = impl == IMPL_BUILD ? 3 : 2;   // joins: load factor <= 1/3
+            if (const char* e = getenv("RQ_LOAD_DEN")) max_load_den = (uint64_t)std::max(2, atoi(e));
             uint64_t cap_max = 4096;
-            while (cap_max < (uint64_t)(2 * rows_bound)) cap_max <<= 1;
+            while (cap_max < (uint64_t)(max_load_den * rows_bound)) cap_max <<= 1;
             // capacities that worked for this pipeline on this many rows are remembered, so a
             // repeated query does not pay for regrowth again
             const uint64_t sig = pipeline_signature(pl_in, rows_bound);
@@ -776,26 +779,30 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
             const int nv = impl == IMPL_BUILD ? pl.n_vals : (int)ad.kind.size();
             std::unique_ptr<HashTableDev> ht;
             unsigned long long* d_count = nullptr;
-            CK(cudaMalloc(&d_count, 8));
+            CK(dmalloc(&d_count, 8));
             unsigned long long n_used = 0;
             for (;;) {
                 ht.reset(new HashTableDev());
                 ht->capacity = cap;
                 ht->d.cap_mask = cap - 1;
+                { uint32_t lg = 0; while ((1ULL << lg) < cap) lg++; ht->d.shift = 64 - lg; }
+                if (impl == IMPL_BUILD) {
+                    // 8 filter bits per slot (16+ per key at load factor <= 1/2), L2 resident
+                    const uint64_t words = std::max<uint64_t>(cap / 4, 1024);
+                    ht->d.bloom_mask = (uint32_t)(words - 1);
+                    CK(dmalloc(&ht->d.bloom, words * 4));
+                    CK(cudaMemsetAsync(ht->d.bloom, 0, words * 4, E.stream));
+                }
                 ht->d.nk = nk; ht->d.nv = nv;
                 for (int k = 0; k < nk && k < kMaxKeys; k++) {
                     const int st = pl.keys[k].sql_type;
                     ht->d.key_kind[k] = st == RQ_SQL_VARCHAR ? 2 : (st == RQ_SQL_CHAR && pl.keys[k].width > 1) ? 1 : 0;
                 }
-                CK(cudaMalloc(&ht->d.tags, cap * 8));
-                CK(cudaMalloc(&ht->d.keys, (size_t)std::max(nk, 1) * cap * 8));
-                CK(cudaMalloc(&ht->d.vals, (size_t)std::max(nv, 1) * cap * 8));
-                CK(cudaMemsetAsync(ht->d.tags, 0, cap * 8, E.stream));
-                if (impl == IMPL_HASHAGG) {
-                    CK(cudaMemcpyAsync(E.g_kinds, P.agg_kind, kMaxAggs, cudaMemcpyHostToDevice, E.stream));
-                    rq_ht_init_vals<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d.vals, cap, nv, E.g_kinds);
-                    if (tm) tm->kernel_launches++;
-                }
+                ht->d.stride = (uint32_t)((1 + nk + nv + 3) / 4 * 4);
+                CK(dmalloc(&ht->d.ent, cap * ht->d.stride * 8));
+                if (impl == IMPL_HASHAGG) CK(cudaMemcpyAsync(E.g_kinds, P.agg_kind, kMaxAggs, cudaMemcpyHostToDevice, E.stream));
+                rq_ht_init<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, E.g_kinds, impl == IMPL_HASHAGG ? 1 : 0);
+                if (tm) tm->kernel_launches++;
                 P.ht = ht->d;
                 CK(cudaMemsetAsync(E.flags, 0, 24, E.stream));
                 launch_pipeline(P, 0, rows_bound, tm, is_scan, ev_idx, ev_used);
@@ -804,19 +811,19 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
                 if (!regrow) {
                     // keep the load factor at or below 1/2 (probe runs stay short)
                     CK(cudaMemsetAsync(d_count, 0, 8, E.stream));
-                    rq_ht_count<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d.tags, cap, d_count);
+                    rq_ht_count<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, d_count);
                     if (tm) tm->kernel_launches++;
                     CK(cudaMemcpyAsync(&n_used, d_count, 8, cudaMemcpyDeviceToHost, E.stream));
                     CK(cudaStreamSynchronize(E.stream));
-                    regrow = n_used * 2 > cap && cap < cap_max;
+                    regrow = n_used * max_load_den > cap && cap < cap_max;
                 }
                 if (!regrow) break;
-                if (cap >= cap_max) { cudaFree(d_count); raise(RQ_ERR_RUNTIME, "pipeline %d: hash table overflow at capacity %llu", pi, (unsigned long long)cap); }
+                if (cap >= cap_max) { dfree(d_count); raise(RQ_ERR_RUNTIME, "pipeline %d: hash table overflow at capacity %llu", pi, (unsigned long long)cap); }
                 uint64_t next = cap * 8;
-                if (!E.h_flags[1]) { next = cap; while (next < 2 * n_used) next <<= 1; }
+                if (!E.h_flags[1]) { next = cap; while (next < max_load_den * n_used) next <<= 1; }
                 cap = std::min<uint64_t>(next, cap_max);
             }
-            cudaFree(d_count);
+            dfree(d_count);
             g_ht_capacity[sig] = cap;
             if (impl == IMPL_BUILD) {
                 for (int k = 0; k < pl.n_vals; k++) {
@@ -837,16 +844,16 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
             for (int c = 0; c < ncols; c++) h_cols[c] = (int64_t*)out->cols[c].d;
             int* d_map = nullptr;
             int64_t** d_ptrs = nullptr;
-            CK(cudaMalloc(&d_map, sizeof(int) * ncols));
-            CK(cudaMalloc(&d_ptrs, sizeof(int64_t*) * ncols));
+            CK(dmalloc(&d_map, sizeof(int) * ncols));
+            CK(dmalloc(&d_ptrs, sizeof(int64_t*) * ncols));
             CK(cudaMemcpyAsync(d_map, colmap.data(), sizeof(int) * ncols, cudaMemcpyHostToDevice, E.stream));
             CK(cudaMemcpyAsync(d_ptrs, h_cols.data(), sizeof(int64_t*) * ncols, cudaMemcpyHostToDevice, E.stream));
             rq_ht_compact<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, d_map, ncols, d_ptrs, (unsigned long long*)out->d_n_rows);
             if (tm) tm->kernel_launches++;
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(E.stream));
-            cudaFree(d_map);
-            cudaFree(d_ptrs);
+            dfree(d_map);
+            dfree(d_ptrs);
             set_types(*out, pl);
             outs[pi].table = std::move(out);
             return;
@@ -912,7 +919,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
     std::vector<void*> scratch;
     try {
         if (plan->strpool_bytes > 0) {
-            CK(cudaMalloc(&d_strpool, plan->strpool_bytes));
+            CK(dmalloc(&d_strpool, plan->strpool_bytes));
             CK(cudaMemcpyAsync(d_strpool, plan->strpool, plan->strpool_bytes, cudaMemcpyHostToDevice, E.stream));
         }
         std::vector<PipeOut> outs(plan->n_pipelines);
@@ -948,7 +955,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
                 K.desc[k] = plan->order[k].ascending ? 0 : 1;
             }
             uint32_t* perm = nullptr;
-            CK(cudaMalloc(&perm, sizeof(uint32_t) * std::max<int64_t>(n, kBitonicMax)));
+            CK(dmalloc(&perm, sizeof(uint32_t) * std::max<int64_t>(n, kBitonicMax)));
             scratch.push_back(perm);
             if (n <= kBitonicMax) {
                 rq_sort_small<<<1, 1024, 0, E.stream>>>(K, fin->d_n_rows, perm);
@@ -960,11 +967,11 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
                 unsigned long long* bits = nullptr;
                 const unsigned nb = (unsigned)((n + kRadixChunk - 1) / kRadixChunk);
                 const unsigned eb = (unsigned)((n + 255) / 256);
-                CK(cudaMalloc(&perm2, sizeof(uint32_t) * n)); scratch.push_back(perm2);
-                CK(cudaMalloc(&k1, sizeof(uint64_t) * n)); scratch.push_back(k1);
-                CK(cudaMalloc(&k2, sizeof(uint64_t) * n)); scratch.push_back(k2);
-                CK(cudaMalloc(&hist, sizeof(uint32_t) * 16 * nb)); scratch.push_back(hist);
-                CK(cudaMalloc(&bits, 16)); scratch.push_back(bits);
+                CK(dmalloc(&perm2, sizeof(uint32_t) * n)); scratch.push_back(perm2);
+                CK(dmalloc(&k1, sizeof(uint64_t) * n)); scratch.push_back(k1);
+                CK(dmalloc(&k2, sizeof(uint64_t) * n)); scratch.push_back(k2);
+                CK(dmalloc(&hist, sizeof(uint32_t) * 16 * nb)); scratch.push_back(hist);
+                CK(dmalloc(&bits, 16)); scratch.push_back(bits);
                 rq_sort_iota<<<eb, 256, 0, E.stream>>>(perm, n);
                 if (tm) tm->kernel_launches++;
                 for (int k = plan->n_order - 1; k >= 0; k--) {
@@ -995,7 +1002,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
             }
             for (int c = 0; c < ncols; c++) {
                 int64_t* sorted = nullptr;
-                CK(cudaMalloc(&sorted, sizeof(int64_t) * std::max<int64_t>(n_out, 1)));
+                CK(dmalloc(&sorted, sizeof(int64_t) * std::max<int64_t>(n_out, 1)));
                 scratch.push_back(sorted);
                 rq_apply_perm<<<(unsigned)((n_out + 255) / 256), 256, 0, E.stream>>>(cols[c], sorted, perm, fin->d_n_rows, plan->limit);
                 if (tm) tm->kernel_launches++;
@@ -1020,7 +1027,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
             const unsigned blocks = (unsigned)((n_out + 255) / 256);
             if (pt == RQ_I64) { d_out[c] = cols[c]; continue; }
             void* d = nullptr;
-            CK(cudaMalloc(&d, (size_t)n_out * w));
+            CK(dmalloc(&d, (size_t)n_out * w));
             scratch.push_back(d);
             d_out[c] = d;
             if (pt == RQ_I32) rq_narrow_i32<<<blocks, 256, 0, E.stream>>>(cols[c], (int32_t*)d, n_out);
@@ -1038,22 +1045,24 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         if (tm) {
             float ms = 0;
             tm->lower_ms = lower_ms;
+            const bool trace = getenv("RQ_TRACE") != nullptr;
             for (auto& u : ev_used) {
                 CK(cudaEventElapsedTime(&ms, g_event_pool[u.first].a, g_event_pool[u.first].b));
                 tm->kernel_ms += ms;
-                if (u.second) tm->scan_kernel_ms += ms;
+                if (u.second) { tm->scan_kernel_ms += ms; tm->fact_scan_ms = ms; }
+                if (trace) fprintf(stderr, "[rq] scan kernel launch %zu: %.3f ms%s\n", u.first, ms, u.second ? " (table scan)" : "");
             }
             CK(cudaEventElapsedTime(&ms, E.ev[1], E.ev[2]));
             tm->d2h_ms = ms;
         }
-        for (void* p : scratch) cudaFree(p);
-        if (d_strpool) cudaFree(d_strpool);
+        for (void* p : scratch) dfree(p);
+        if (d_strpool) dfree(d_strpool);
         *out = res;
         return RQ_OK;
     } catch (RqError& e) {
         cudaStreamSynchronize(E.stream);
-        for (void* p : scratch) cudaFree(p);
-        if (d_strpool) cudaFree(d_strpool);
+        for (void* p : scratch) dfree(p);
+        if (d_strpool) dfree(d_strpool);
         rq_result_free(res);
         return fail(e.code, "%s", e.msg.c_str());
     }

@@ -14,9 +14,7 @@ struct HashTableDev {
     DHashTable d{};
     uint64_t capacity = 0;
     ~HashTableDev() {
-        if (d.tags) cudaFree(d.tags);
-        if (d.keys) cudaFree(d.keys);
-        if (d.vals) cudaFree(d.vals);
+        dfree(d.ent); dfree(d.bloom);
     }
 };
 
@@ -45,16 +43,38 @@ __device__ __forceinline__ uint64_t hash_typed(const int64_t* k, const uint8_t* 
     return h;
 }
 
+// Hash of a key tuple. One integer key (the usual join / group key) takes a single 64-bit
+// multiply (Fibonacci hashing: the home slot comes from the HIGH bits); composite and string keys
+// go through the mixing hash.
+__device__ __forceinline__ uint64_t hash_int(int64_t k) { return (uint64_t)k * 0x9E3779B97F4A7C15ULL; }
+__device__ __forceinline__ uint64_t hash_keys(const int64_t* k, const uint8_t* kind, int nk) {
+    if (nk == 1 && kind[0] == 0) return hash_int(k[0]);
+    return hash_typed(k, kind, nk);
+}
+// blocked Bloom filter: word index and the two bits inside the 32-bit block
+__device__ __forceinline__ uint32_t bloom_word(uint64_t h, uint32_t mask) {
+    const uint64_t g = h ^ (h >> 29);
+    return (uint32_t)(g >> 10) & mask;
+}
+__device__ __forceinline__ uint32_t bloom_bits(uint64_t h) {
+    const uint64_t g = h ^ (h >> 29);
+    return (1u << ((uint32_t)g & 31)) | (1u << ((uint32_t)(g >> 5) & 31));
+}
+
 __device__ __forceinline__ bool key_word_equal(int64_t a, int64_t b, int kind) {
     if (kind == 0) return a == b;
     if (kind == 1) return str_eq_char(reinterpret_cast<const char*>(a), reinterpret_cast<const char*>(b)) != 0;
     return str_eq_varchar(reinterpret_cast<const char*>(a), reinterpret_cast<const char*>(b)) != 0;
 }
 
+__device__ __forceinline__ uint64_t* ht_entry(const DHashTable& ht, uint64_t i) {
+    return ht.ent + i * ht.stride;
+}
+
 __device__ __forceinline__ bool slot_keys_equal(const DHashTable& ht, uint64_t i, const int64_t* k) {
-    const uint64_t cap = ht.cap_mask + 1;
+    const volatile uint64_t* e = ht_entry(ht, i);
     for (int j = 0; j < ht.nk; j++)
-        if (!key_word_equal(((volatile int64_t*)ht.keys)[(size_t)j * cap + i], k[j], ht.key_kind[j])) return false;
+        if (!key_word_equal((int64_t)e[1 + j], k[j], ht.key_kind[j])) return false;
     return true;
 }
 
@@ -63,12 +83,13 @@ __device__ __forceinline__ bool ht_insert_dup(const DHashTable& ht, const int64_
                                               uint64_t* slot_out) {
     const uint64_t tag = h | 2ULL;
     const uint64_t cap = ht.cap_mask + 1;
-    uint64_t i = h & ht.cap_mask;
+    uint64_t i = h >> ht.shift;
     const uint64_t lim = cap < kMaxProbeLen ? cap : kMaxProbeLen;
     for (uint64_t tries = 0; tries < lim; tries++) {
-        const unsigned long long old = atomicCAS((unsigned long long*)&ht.tags[i], 0ULL, (unsigned long long)tag);
+        uint64_t* e = ht_entry(ht, i);
+        const unsigned long long old = atomicCAS((unsigned long long*)e, 0ULL, (unsigned long long)tag);
         if (old == 0ULL) {
-            for (int j = 0; j < ht.nk; j++) ht.keys[(size_t)j * cap + i] = k[j];
+            for (int j = 0; j < ht.nk; j++) e[1 + j] = (uint64_t)k[j];
             *slot_out = i;
             return true;
         }
@@ -82,21 +103,22 @@ __device__ __forceinline__ bool ht_find_or_insert(const DHashTable& ht, const in
                                                   uint64_t* slot_out) {
     const uint64_t tag = h | 2ULL;
     const uint64_t cap = ht.cap_mask + 1;
-    uint64_t i = h & ht.cap_mask;
+    uint64_t i = h >> ht.shift;
     const uint64_t lim = cap < kMaxProbeLen ? cap : kMaxProbeLen;
     for (uint64_t tries = 0; tries < lim; tries++) {
-        uint64_t t = *(volatile uint64_t*)&ht.tags[i];
+        volatile uint64_t* e = ht_entry(ht, i);
+        uint64_t t = e[0];
         if (t == 0ULL) {
-            t = atomicCAS((unsigned long long*)&ht.tags[i], 0ULL, (unsigned long long)kTagLocked);
+            t = atomicCAS((unsigned long long*)e, 0ULL, (unsigned long long)kTagLocked);
             if (t == 0ULL) {
-                for (int j = 0; j < ht.nk; j++) ((volatile int64_t*)ht.keys)[(size_t)j * cap + i] = k[j];
+                for (int j = 0; j < ht.nk; j++) e[1 + j] = (uint64_t)k[j];
                 __threadfence();
-                atomicExch((unsigned long long*)&ht.tags[i], (unsigned long long)tag);
+                atomicExch((unsigned long long*)e, (unsigned long long)tag);
                 *slot_out = i;
                 return true;
             }
         }
-        while (t == kTagLocked) t = *(volatile uint64_t*)&ht.tags[i];
+        while (t == kTagLocked) t = e[0];
         if (t == tag) {
             __threadfence();
             if (slot_keys_equal(ht, i, k)) { *slot_out = i; return true; }
@@ -107,15 +129,22 @@ __device__ __forceinline__ bool ht_find_or_insert(const DHashTable& ht, const in
 }
 
 // ---- helper kernels ------------------------------------------------------------------------
-__global__ void rq_ht_init_vals(int64_t* vals, uint64_t cap, int nv, const uint8_t* kinds) {
+// clear the tags and set the accumulators of a hash-aggregation table to their identities
+__global__ void rq_ht_init(DHashTable ht, const uint8_t* kinds, int init_vals) {
+    const uint64_t cap = ht.cap_mask + 1;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cap)
-        for (int a = 0; a < nv; a++) vals[(size_t)a * cap + i] = agg_identity(kinds[a]);
+    if (i < cap) {
+        uint64_t* e = ht_entry(ht, i);
+        e[0] = 0;
+        if (init_vals)
+            for (int a = 0; a < ht.nv; a++) e[1 + ht.nk + a] = (uint64_t)agg_identity(kinds[a]);
+    }
 }
 
-__global__ void rq_ht_count(const uint64_t* tags, uint64_t cap, unsigned long long* count) {
+__global__ void rq_ht_count(DHashTable ht, unsigned long long* count) {
+    const uint64_t cap = ht.cap_mask + 1;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool used = i < cap && tags[i] != 0ULL;
+    const bool used = i < cap && *ht_entry(ht, i) != 0ULL;
     const unsigned bal = __ballot_sync(0xffffffffu, used);
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, (unsigned long long)__popc(bal));
 }
@@ -126,7 +155,7 @@ __global__ void rq_ht_compact(DHashTable ht, const int* colmap, int n_out, int64
                               unsigned long long* count) {
     const uint64_t cap = ht.cap_mask + 1;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool used = i < cap && ht.tags[i] != 0ULL;
+    const bool used = i < cap && *ht_entry(ht, i) != 0ULL;
     const unsigned bal = __ballot_sync(0xffffffffu, used);
     if (!bal) return;
     const int lane = threadIdx.x & 31;
@@ -135,10 +164,8 @@ __global__ void rq_ht_compact(DHashTable ht, const int* colmap, int n_out, int64
     base = __shfl_sync(0xffffffffu, base, 0);
     if (used) {
         const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1));
-        for (int c = 0; c < n_out; c++) {
-            const int m = colmap[c];
-            out_cols[c][pos] = (m < ht.nk) ? ht.keys[(size_t)m * cap + i] : ht.vals[(size_t)(m - ht.nk) * cap + i];
-        }
+        const uint64_t* e = ht_entry(ht, i);
+        for (int c = 0; c < n_out; c++) out_cols[c][pos] = (int64_t)e[1 + colmap[c]];
     }
 }
 

@@ -104,9 +104,15 @@ struct VRef {           // value reference used by sinks (keys, payloads, output
 // hash table used by joins (build then probe in separate kernels) and by hash aggregation
 struct DHashTable {
     uint64_t  cap_mask;     // capacity - 1 (power of two)
-    uint64_t* tags;         // 0 = empty; else fingerprint | 2
-    int64_t*  keys;         // [nk][capacity]
-    int64_t*  vals;         // [nv][capacity]  payload / accumulators
+    uint32_t  shift;        // home slot = hash >> shift  (64 - log2(capacity): the high hash bits)
+    uint32_t  bloom_mask;   // words - 1 of the blocked Bloom filter (joins), 0 = none
+    uint32_t* bloom;        // 32-bit blocks, two bits per key; sized to stay L2 resident
+    // entries are packed rows: [tag][nk key words][nv payload / accumulator words], padded to a
+    // multiple of 4 words, so that a hit costs one memory round trip (tag 0 = empty, 1 = being
+    // written, else hash | 2)
+    uint64_t* ent;
+    uint32_t  stride;       // words per entry
+    uint32_t  pad_;
     int32_t   nk, nv;
     uint8_t   key_kind[kMaxKeys];   // 0 integer, 1 CHAR, 2 VARCHAR
 };
@@ -125,6 +131,7 @@ struct KParams {
     int64_t        n_rows;
     const int64_t* n_rows_ptr;          // if non-null the row count is read on the device
     int32_t        borrowed;            // source buffers may end exactly at n_rows (no padding)
+    int32_t        stream_hint;         // mark scanned data evict-first in L2
     int32_t        n_cols;              // staged (TMA) columns
     const unsigned char* col_ptr[kMaxStagedCols];
     uint32_t       col_off[kMaxStagedCols];   // byte offset inside a stage

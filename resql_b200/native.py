@@ -71,7 +71,7 @@ class rq_result(C.Structure):
 class rq_timings(C.Structure):
     _fields_ = [("lower_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double),
                 ("nccl_ms", C.c_double), ("d2h_ms", C.c_double), ("scan_kernel_ms", C.c_double),
-                ("kernel_launches", C.c_int32), ("reserved", C.c_int32)]
+                ("kernel_launches", C.c_int32), ("reserved", C.c_int32), ("fact_scan_ms", C.c_double)]
 
 
 class Timings:

@@ -47,17 +47,22 @@ class Plan:
     def to_c(self, tables, flags=0):
         keep = []
         handles = (C.c_void_p * len(self.tables))()
+        colmap = []     # per plan table: plan column index -> column index of the uploaded table
         for i, t in enumerate(self.tables):
             tab = tables[t["name"]]
-            if list(tab.names) != list(t["columns"]):
-                raise ValueError(f"table {t['name']}: uploaded columns {tab.names} != plan columns {t['columns']}")
+            missing = [c for c in t["columns"] if c not in tab.names]
+            if missing:
+                raise ValueError(f"table {t['name']}: uploaded columns {tab.names} lack {missing}")
+            colmap.append([list(tab.names).index(c) for c in t["columns"]])
             handles[i] = tab.handle
         pls = (N.rq_pipeline * len(self.pipelines))()
         for i, p in enumerate(self.pipelines):
             nodes = (N.rq_node * max(1, len(p["nodes"])))()
+            cm = colmap[p["source_id"]] if p["source_kind"] == SRC_TABLE else None
             for j, nd in enumerate(p["nodes"]):
                 op = nd[0] if isinstance(nd[0], int) else OP[nd[0]]
-                nodes[j].op, nodes[j].a, nodes[j].b, nodes[j].c, nodes[j].imm = op, nd[1], nd[2], nd[3], nd[4]
+                a = cm[nd[1]] if (cm is not None and op == OP["COL"]) else nd[1]
+                nodes[j].op, nodes[j].a, nodes[j].b, nodes[j].c, nodes[j].imm = op, a, nd[2], nd[3], nd[4]
             args = (C.c_int32 * max(1, len(p.get("args", []))))(*p.get("args", []))
             keys = (N.rq_value * max(1, len(p["keys"])))()
             for j, k in enumerate(p["keys"]):
