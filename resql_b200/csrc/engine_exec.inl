@@ -340,6 +340,8 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
             if (nd.c != pr.ht.nk) raise(RQ_ERR_INVALID, "PROBE has %d keys, the build side %d", nd.c, pr.ht.nk);
             for (int k = 0; k < nd.c; k++) L.hprobe_key[P.n_probes][k] = L.href_of(pl.args[nd.b + k]);
             pr.single = (int32_t)(nd.imm & 1);
+            pr.bloom_only = (int32_t)((nd.imm >> 1) & 1);     // internal: first pass of a split pipeline
+            if (pr.bloom_only && pr.ht.bloom == nullptr) raise(RQ_ERR_INVALID, "internal: semi-join pass without a Bloom filter");
             pr.n_out = pr.ht.nv;
             memset(pr.out_slot, 0xff, sizeof(pr.out_slot));
             pr.dup_counter = (unsigned long long*)(E.flags + 4);
@@ -550,6 +552,17 @@ static bool pack_group_key(const Lowerer& L, KParams& P, KeyUnpack& ku) {
     return true;
 }
 
+// ---- host-side trace (RQ_TRACE): wall-clock offsets since the plan started, after a stream sync --
+static std::chrono::steady_clock::time_point g_trace_t0;
+static bool g_trace = false;
+static void trace_point(const char* what, int pi = -1) {
+    if (!g_trace) return;
+    const double host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_trace_t0).count();
+    cudaStreamSynchronize(E.stream);
+    const double dev = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_trace_t0).count();
+    fprintf(stderr, "[rq] t=%8.3f ms (stream idle at %8.3f)  %s %d\n", host, dev, what, pi);
+}
+
 // ---- event pool -------------------------------------------------------------------------
 struct EventPair { cudaEvent_t a, b; };
 static std::vector<EventPair> g_event_pool;
@@ -630,7 +643,7 @@ static bool has_str_key(const rq_pipeline& pl) {
 }
 
 static void check_flags(const char* what) {
-    CK(cudaMemcpyAsync(E.h_flags, E.flags, 24, cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaMemcpyAsync(E.h_flags, E.flags, 32, cudaMemcpyDeviceToHost, E.stream));
     CK(cudaStreamSynchronize(E.stream));
     if (E.h_flags[2]) raise(RQ_ERR_RUNTIME, "division by zero in %s (the reference raises SIGFPE here)", what);
     if (*(unsigned long long*)(E.h_flags + 4) != 0)
@@ -639,15 +652,131 @@ static void check_flags(const char* what) {
 }
 
 // ---- one pipeline -------------------------------------------------------------------------
+struct SplitPipes {
+    std::vector<rq_node> a_nodes, b_nodes;
+    std::vector<int32_t> a_args, b_args;
+    std::vector<rq_value> a_vals, b_keys, b_vals;
+    std::vector<int> live_src_col;     // per materialized value: source column it copies, or -1
+    rq_pipeline a, b;
+};
+static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_table& src,
+                           const std::vector<PipeOut>& outs, SplitPipes& sp);
+static std::map<uint64_t, int64_t> g_emit_rows;    // rows a materialize pipeline produced last time
+
+static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
+                             const char* d_strpool, rq_timings* tm, size_t& ev_idx,
+                             std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
+                             bool is_fact_scan, const rq_table* src_override, PipeOut& result, bool allow_split);
+
+// ---- build-side pruning from probe-side statistics --------------------------------------------
+// An inner equi-join can only match build tuples whose key lies inside the value range of the
+// probe key. When every pipeline that probes build pipeline `pi` does so with a plain column whose
+// min/max were taken at upload, `lo <= key <= hi` is added to the build pipeline right behind the
+// key value (two selections the lowering fuses into one range compare). On one GPU the range is
+// usually the whole key domain; with a row-range sharded fact table that is clustered on the join
+// key (lineitem on l_orderkey) each rank builds only the slice of the build side it can ever probe,
+// so the build work shards with the fact table although the build table itself is replicated.
+struct PrunedBuild {
+    std::vector<rq_node> nodes;
+    std::vector<int32_t> args;
+    std::vector<rq_value> keys, vals;
+    rq_pipeline pl;
+};
+static bool prune_build_by_probe_stats(const rq_plan& plan, int pi, PrunedBuild& out) {
+    if (getenv("RQ_NO_PRUNE")) return false;
+    const rq_pipeline& b = plan.pipelines[pi];
+    const int nk = b.n_keys;
+    if (nk < 1 || nk > kMaxKeys) return false;
+    std::vector<int64_t> lo(nk, INT64_MAX), hi(nk, INT64_MIN);
+    std::vector<char> ok(nk, 1);
+    int probers = 0;
+    for (int q = pi + 1; q < plan.n_pipelines; q++) {
+        const rq_pipeline& pq = plan.pipelines[q];
+        for (int i = 0; i < pq.n_nodes; i++) {
+            const rq_node& nd = pq.nodes[i];
+            if (nd.op != RQ_OP_PROBE || nd.a != pi) continue;
+            probers++;
+            if (nd.c != nk || nd.b < 0 || nd.b + nd.c > pq.n_args) return false;
+            const rq_table* t = (pq.source_kind == RQ_SRC_TABLE && pq.source_id >= 0 && pq.source_id < plan.n_tables)
+                                    ? plan.tables[pq.source_id] : nullptr;
+            for (int k = 0; k < nk; k++) {
+                const int a = pq.args[nd.b + k];
+                const rq_node* kn = (a >= 0 && a < pq.n_nodes) ? &pq.nodes[a] : nullptr;
+                if (!t || !kn || kn->op != RQ_OP_COL || kn->a < 0 || kn->a >= (int)t->cols.size() ||
+                    !t->cols[kn->a].has_stats || t->cols[kn->a].type == RQ_STR) { ok[k] = 0; continue; }
+                lo[k] = std::min(lo[k], t->cols[kn->a].vmin);
+                hi[k] = std::max(hi[k], t->cols[kn->a].vmax);
+            }
+        }
+    }
+    if (probers == 0) return false;
+    bool any = false;
+    for (int k = 0; k < nk; k++) {
+        const int st = b.keys[k].sql_type;
+        if (st == RQ_SQL_VARCHAR || st == RQ_SQL_CHAR) ok[k] = 0;     // CHAR(1) included: keep it simple
+        if (ok[k] && lo[k] <= hi[k]) any = true; else ok[k] = 0;
+    }
+    if (!any) return false;
+    out.nodes.assign(b.nodes, b.nodes + b.n_nodes);
+    out.args.assign(b.args, b.args + b.n_args);
+    out.keys.assign(b.keys, b.keys + b.n_keys);
+    out.vals.assign(b.vals, b.vals + b.n_vals);
+    for (int k = 0; k < nk; k++) {
+        if (!ok[k]) continue;
+        const int pos = out.keys[k].node;                 // insert the six nodes right behind it
+        if (pos < 0 || pos >= (int)out.nodes.size()) return false;
+        const int K = 6;
+        auto mv = [&](int r) { return r > pos ? r + K : r; };
+        std::vector<rq_node> nn;
+        nn.reserve(out.nodes.size() + K);
+        for (int i = 0; i <= pos; i++) nn.push_back(out.nodes[i]);
+        nn.push_back(rq_node{RQ_OP_CONST, 0, 0, 0, lo[k]});
+        nn.push_back(rq_node{RQ_OP_GE, pos, pos + 1, 0, 0});
+        nn.push_back(rq_node{RQ_OP_FILTER, pos + 2, 0, 0, 0});
+        nn.push_back(rq_node{RQ_OP_CONST, 0, 0, 0, hi[k]});
+        nn.push_back(rq_node{RQ_OP_LE, pos, pos + 4, 0, 0});
+        nn.push_back(rq_node{RQ_OP_FILTER, pos + 5, 0, 0, 0});
+        for (int i = pos + 1; i < (int)out.nodes.size(); i++) {
+            rq_node nd = out.nodes[i];
+            if (is_binary(nd.op)) { nd.a = mv(nd.a); nd.b = mv(nd.b); }
+            else if (nd.op == RQ_OP_FILTER || nd.op == RQ_OP_PAYLOAD) nd.a = mv(nd.a);
+            else if (nd.op == RQ_OP_SELECT) { nd.a = mv(nd.a); nd.b = mv(nd.b); nd.c = mv(nd.c); }
+            nn.push_back(nd);
+        }
+        for (auto& a : out.args) a = mv(a);
+        for (auto& kk : out.keys) kk.node = mv(kk.node);
+        for (auto& v : out.vals) v.node = mv(v.node);
+        out.nodes.swap(nn);
+    }
+    out.pl = b;
+    out.pl.n_nodes = (int)out.nodes.size(); out.pl.nodes = out.nodes.data();
+    out.pl.n_args = (int)out.args.size(); out.pl.args = out.args.data();
+    out.pl.keys = out.keys.data(); out.pl.vals = out.vals.data();
+    return true;
+}
+
 static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs,
                          const char* d_strpool, rq_timings* tm, size_t& ev_idx,
-                         std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms) {
-    const rq_pipeline& pl_in = plan.pipelines[pi];
+                         std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
+                         bool is_fact_scan = true) {
+    PrunedBuild pb;
+    const rq_pipeline* pl = &plan.pipelines[pi];
+    if (pl->sink_kind == RQ_SINK_BUILD && prune_build_by_probe_stats(plan, pi, pb)) pl = &pb.pl;
+    run_pipeline_one(plan, *pl, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, is_fact_scan,
+                     nullptr, outs[pi], true);
+}
+
+static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
+                             const char* d_strpool, rq_timings* tm, size_t& ev_idx,
+                             std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
+                             bool is_fact_scan, const rq_table* src_override, PipeOut& result, bool allow_split) {
     SimplePipe sp;
     simplify_pipeline(pl_in, sp);
     const rq_pipeline& pl = sp.pl;
     const rq_table* src = nullptr;
-    if (pl.source_kind == RQ_SRC_TABLE) {
+    if (src_override) {
+        src = src_override;
+    } else if (pl.source_kind == RQ_SRC_TABLE) {
         if (pl.source_id < 0 || pl.source_id >= plan.n_tables || !plan.tables[pl.source_id])
             raise(RQ_ERR_INVALID, "pipeline %d: table %d out of range", pi, pl.source_id);
         src = plan.tables[pl.source_id];
@@ -658,7 +787,27 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
     } else {
         raise(RQ_ERR_INVALID, "pipeline %d: bad source kind %d", pi, pl.source_kind);
     }
-    const bool is_scan = pl.source_kind == RQ_SRC_TABLE;
+    const bool is_scan = pl.source_kind == RQ_SRC_TABLE && is_fact_scan && !src_override;
+
+    // A selective hash-join probe inside a big scan is run as two passes: scan -> filter -> Bloom
+    // test -> materialize the few survivors, then probe/aggregate/build over dense tiles of them.
+    if (allow_split && !src_override && pl.source_kind == RQ_SRC_TABLE) {
+        SplitPipes sx;
+        if (split_at_probe(plan, pl, *src, outs, sx)) {
+            PipeOut mid;
+            run_pipeline_one(plan, sx.a, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, is_fact_scan, nullptr, mid, false);
+            for (size_t c = 0; c < sx.live_src_col.size(); c++) {      // value bounds survive the copy
+                const int sc = sx.live_src_col[c];
+                if (sc >= 0 && src->cols[sc].has_stats) {
+                    mid.table->cols[c].has_stats = true;
+                    mid.table->cols[c].vmin = src->cols[sc].vmin;
+                    mid.table->cols[c].vmax = src->cols[sc].vmax;
+                }
+            }
+            run_pipeline_one(plan, sx.b, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, false, mid.table.get(), result, false);
+            return;
+        }
+    }
 
     auto t0 = std::chrono::steady_clock::now();
     std::vector<int> impls;
@@ -690,6 +839,7 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
         P.overflow = E.flags + 0;
         P.ht_full = E.flags + 1;
         P.err = E.flags + 2;
+        P.ht_entries = (unsigned long long*)(E.flags + 6);
         Lowerer L(plan, pl, *src, outs, d_strpool, P);
         L.prepare();
         emit_program(L, impl, ad);
@@ -724,7 +874,7 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
         encode_program(L, P);
         lower_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
-        CK(cudaMemsetAsync(E.flags, 0, 24, E.stream));
+        CK(cudaMemsetAsync(E.flags, 0, 32, E.stream));
         if (impl == IMPL_REGAGG || impl == IMPL_LOWAGG) {
             CK(cudaMemcpyAsync(E.g_kinds, P.agg_kind, kMaxAggs, cudaMemcpyHostToDevice, E.stream));
             rq_group_table_init<<<(kGroupTableCap + 255) / 256, 256, 0, E.stream>>>(E.g_state, E.g_acc, E.g_kinds, P.na);
@@ -756,7 +906,7 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
             CK(cudaMemcpyAsync(out->d_n_rows, dense->d_n_rows, 8, cudaMemcpyDeviceToDevice, E.stream));
             CK(cudaStreamSynchronize(E.stream));
             set_types(*out, pl);
-            outs[pi].table = std::move(out);
+            result.table = std::move(out);
             return;
         }
         if (impl == IMPL_BUILD || impl == IMPL_HASHAGG) {
@@ -801,22 +951,22 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
                 ht->d.stride = (uint32_t)((1 + nk + nv + 3) / 4 * 4);
                 CK(dmalloc(&ht->d.ent, cap * ht->d.stride * 8));
                 if (impl == IMPL_HASHAGG) CK(cudaMemcpyAsync(E.g_kinds, P.agg_kind, kMaxAggs, cudaMemcpyHostToDevice, E.stream));
-                rq_ht_init<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, E.g_kinds, impl == IMPL_HASHAGG ? 1 : 0);
-                if (tm) tm->kernel_launches++;
+                if (impl == IMPL_HASHAGG) {
+                    rq_ht_init<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, E.g_kinds, 1);
+                    if (tm) tm->kernel_launches++;
+                } else {
+                    // whole sectors are cleared (a tag-only clear is a partial write per sector)
+                    CK(cudaMemsetAsync(ht->d.ent, 0, cap * ht->d.stride * 8, E.stream));
+                }
                 P.ht = ht->d;
-                CK(cudaMemsetAsync(E.flags, 0, 24, E.stream));
+                CK(cudaMemsetAsync(E.flags, 0, 32, E.stream));
+                trace_point("hash table allocated + cleared", pi);
                 launch_pipeline(P, 0, rows_bound, tm, is_scan, ev_idx, ev_used);
                 check_flags(impl == IMPL_BUILD ? "join build pipeline" : "hash aggregation pipeline");
+                trace_point("hash sink kernel done", pi);
                 bool regrow = E.h_flags[1] != 0;
-                if (!regrow) {
-                    // keep the load factor at or below 1/2 (probe runs stay short)
-                    CK(cudaMemsetAsync(d_count, 0, 8, E.stream));
-                    rq_ht_count<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, d_count);
-                    if (tm) tm->kernel_launches++;
-                    CK(cudaMemcpyAsync(&n_used, d_count, 8, cudaMemcpyDeviceToHost, E.stream));
-                    CK(cudaStreamSynchronize(E.stream));
-                    regrow = n_used * max_load_den > cap && cap < cap_max;
-                }
+                n_used = *(unsigned long long*)(E.h_flags + 6);     // counted by the kernel itself
+                if (!regrow) regrow = n_used * max_load_den > cap && cap < cap_max;
                 if (!regrow) break;
                 if (cap >= cap_max) { dfree(d_count); raise(RQ_ERR_RUNTIME, "pipeline %d: hash table overflow at capacity %llu", pi, (unsigned long long)cap); }
                 uint64_t next = cap * 8;
@@ -827,10 +977,11 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
             g_ht_capacity[sig] = cap;
             if (impl == IMPL_BUILD) {
                 for (int k = 0; k < pl.n_vals; k++) {
-                    outs[pi].payload_sql_type.push_back(pl.vals[k].sql_type);
-                    outs[pi].payload_sql_width.push_back(pl.vals[k].width);
+                    result.payload_sql_type.push_back(pl.vals[k].sql_type);
+                    result.payload_sql_width.push_back(pl.vals[k].width);
                 }
-                outs[pi].ht = std::move(ht);
+                ht->entries = n_used;
+                result.ht = std::move(ht);
                 return;
             }
             // dense relation out of the aggregation table
@@ -855,31 +1006,269 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
             dfree(d_map);
             dfree(d_ptrs);
             set_types(*out, pl);
-            outs[pi].table = std::move(out);
+            result.table = std::move(out);
             return;
         }
         if (impl == IMPL_EMIT) {
             int64_t cap = src->n_rows >= 0 ? src->n_rows : src->cap_rows;
             cap = std::min<int64_t>(std::max<int64_t>(cap, 1), (int64_t)1 << 24);
+            const uint64_t esig = pipeline_signature(pl_in, src_rows) ^ 0x5bd1e995ULL;
+            {   // a repeated query sizes the output from what it produced last time
+                auto known = g_emit_rows.find(esig);
+                if (known != g_emit_rows.end())
+                    cap = std::min<int64_t>(std::max<int64_t>(src_rows, 1), known->second + known->second / 8 + 1024);
+            }
             for (int round = 0; round < 2; round++) {
                 out = new_intermediate(pl.n_vals, cap);
                 P.out_cap = out->cap_rows;
                 P.out_count = (unsigned long long*)out->d_n_rows;
                 for (int k = 0; k < pl.n_vals; k++) P.out_col[k] = (int64_t*)out->cols[k].d;
+                trace_point("materialize output allocated", pi);
                 launch_pipeline(P, 0, src_rows, tm, is_scan, ev_idx, ev_used);
                 check_flags("materialize pipeline");
+                trace_point("materialize kernel done", pi);
                 int64_t produced = 0;
                 CK(cudaMemcpy(&produced, out->d_n_rows, 8, cudaMemcpyDeviceToHost));
+                g_emit_rows[esig] = produced;
                 if (produced <= out->cap_rows) break;
                 if (round == 1) raise(RQ_ERR_RUNTIME, "materialize overflow");
                 cap = produced;
             }
             set_types(*out, pl);
-            outs[pi].table = std::move(out);
+            result.table = std::move(out);
             return;
         }
     }
     raise(RQ_ERR_UNSUPPORTED, "pipeline %d: no implementation fits", pi);
+}
+
+// ---- two-pass execution of a selective probe ---------------------------------------------------
+// pl is a simplified pipeline over a base table. If its first PROBE is selective (the build side
+// holds far fewer keys than the probe key's value domain, taken from the upload statistics), the
+// pipeline is cut in front of that PROBE:
+//   pass A  nodes[0 .. p0) + Bloom-only PROBE  -> MATERIALIZE(values that are still needed)
+//   pass B  source = pass A's relation: COL per value, then nodes[p0 .. n) and the original sink
+// The Bloom filter has no false negatives, so pass B sees every tuple the one-pass form would have
+// joined; results are identical. Pass A is a pure streaming kernel (no dependent table walks), pass
+// B runs the walks / atomics over dense tiles where every lane has work.
+static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_table& src,
+                           const std::vector<PipeOut>& outs, SplitPipes& sp) {
+    (void)plan;
+    int64_t min_rows = 4 << 20;
+    double max_frac = 0.3;
+    if (const char* e = getenv("RQ_SPLIT_MIN_ROWS")) min_rows = atoll(e);
+    if (const char* e = getenv("RQ_SPLIT_FRAC")) max_frac = atof(e);
+    if (src.n_rows < min_rows) return false;
+    const int n = pl.n_nodes;
+    int p0 = -1;
+    for (int i = 0; i < n && p0 < 0; i++) if (pl.nodes[i].op == RQ_OP_PROBE) p0 = i;
+    if (p0 < 0) return false;
+    const rq_node& pr = pl.nodes[p0];
+    if (pr.a < 0 || pr.a >= (int)outs.size() || !outs[pr.a].ht || !outs[pr.a].ht->d.bloom) return false;
+    // selectivity estimate: build entries / size of the probe key's value domain
+    double frac = 1.0;
+    if (pr.c == 1) {
+        const rq_node& kn = pl.nodes[pl.args[pr.b]];
+        if (kn.op == RQ_OP_COL && kn.a >= 0 && kn.a < (int)src.cols.size() && src.cols[kn.a].has_stats) {
+            const double dom = (double)src.cols[kn.a].vmax - (double)src.cols[kn.a].vmin + 1.0;
+            if (dom > 0) frac = (double)outs[pr.a].ht->entries / dom;
+        }
+    }
+    if (frac > max_frac) return false;
+
+    // values computed before the cut and read behind it
+    std::vector<char> need(n, 0);
+    auto mark = [&](int r) { if (r >= 0 && r < p0) need[r] = 1; };
+    for (int i = p0; i < n; i++) {
+        const rq_node& nd = pl.nodes[i];
+        if (is_binary(nd.op)) { mark(nd.a); mark(nd.b); }
+        else if (nd.op == RQ_OP_FILTER) mark(nd.a);
+        else if (nd.op == RQ_OP_SELECT) { mark(nd.a); mark(nd.b); mark(nd.c); }
+        else if (nd.op == RQ_OP_PROBE) for (int k = 0; k < nd.c; k++) mark(pl.args[nd.b + k]);
+    }
+    for (int k = 0; k < pl.n_keys; k++) mark(pl.keys[k].node);
+    for (int k = 0; k < pl.n_vals; k++)
+        if (!(pl.sink_kind == RQ_SINK_AGG && pl.vals[k].kind == RQ_AGG_COUNT)) mark(pl.vals[k].node);
+    for (int i = 0; i < p0; i++)
+        if (need[i] && (pl.nodes[i].op == RQ_OP_PAYLOAD || pl.nodes[i].op == RQ_OP_FILTER)) return false;
+
+    // pass A
+    sp.a_nodes.assign(pl.nodes, pl.nodes + p0);
+    rq_node semi = pr;
+    semi.imm |= 2;
+    sp.a_nodes.push_back(semi);
+    sp.a_args.assign(pl.args, pl.args + pl.n_args);
+    std::vector<int> newidx(n, -1);
+    for (int i = 0; i < p0; i++) {
+        const int op = pl.nodes[i].op;
+        if (!need[i] || op == RQ_OP_CONST || op == RQ_OP_CONST_STR) continue;
+        rq_value v;
+        v.node = i; v.kind = 0; v.sql_type = RQ_SQL_BIGINT; v.width = 0;
+        newidx[i] = (int)sp.a_vals.size();
+        sp.a_vals.push_back(v);
+        sp.live_src_col.push_back(op == RQ_OP_COL ? pl.nodes[i].a : -1);
+    }
+    if (sp.a_vals.empty() || (int)sp.a_vals.size() > kMaxOut || (int)sp.a_vals.size() > kMaxStagedCols) return false;
+    memset(&sp.a, 0, sizeof(sp.a));
+    sp.a.source_kind = pl.source_kind; sp.a.source_id = pl.source_id;
+    sp.a.n_nodes = (int)sp.a_nodes.size(); sp.a.nodes = sp.a_nodes.data();
+    sp.a.n_args = (int)sp.a_args.size(); sp.a.args = sp.a_args.data();
+    sp.a.sink_kind = RQ_SINK_MATERIALIZE;
+    sp.a.n_vals = (int)sp.a_vals.size(); sp.a.vals = sp.a_vals.data();
+
+    // pass B
+    for (size_t c = 0; c < sp.a_vals.size(); c++) sp.b_nodes.push_back(rq_node{RQ_OP_COL, (int)c, 0, 0, 0});
+    for (int i = 0; i < p0; i++) {
+        const int op = pl.nodes[i].op;
+        if (need[i] && (op == RQ_OP_CONST || op == RQ_OP_CONST_STR)) {
+            newidx[i] = (int)sp.b_nodes.size();
+            sp.b_nodes.push_back(pl.nodes[i]);
+        }
+    }
+    for (int i = p0; i < n; i++) {
+        rq_node nd = pl.nodes[i];
+        if (is_binary(nd.op)) { nd.a = newidx[nd.a]; nd.b = newidx[nd.b]; }
+        else if (nd.op == RQ_OP_FILTER) nd.a = newidx[nd.a];
+        else if (nd.op == RQ_OP_SELECT) { nd.a = newidx[nd.a]; nd.b = newidx[nd.b]; nd.c = newidx[nd.c]; }
+        else if (nd.op == RQ_OP_PAYLOAD) nd.a = newidx[nd.a];
+        else if (nd.op == RQ_OP_PROBE) {
+            const int b0 = (int)sp.b_args.size();
+            for (int k = 0; k < nd.c; k++) sp.b_args.push_back(newidx[pl.args[nd.b + k]]);
+            nd.b = b0;
+        }
+        newidx[i] = (int)sp.b_nodes.size();
+        sp.b_nodes.push_back(nd);
+    }
+    sp.b_keys.assign(pl.keys, pl.keys + pl.n_keys);
+    sp.b_vals.assign(pl.vals, pl.vals + pl.n_vals);
+    for (auto& k : sp.b_keys) k.node = newidx[k.node];
+    for (auto& v : sp.b_vals)
+        if (!(pl.sink_kind == RQ_SINK_AGG && v.kind == RQ_AGG_COUNT)) v.node = newidx[v.node];
+    sp.b = pl;
+    sp.b.source_kind = RQ_SRC_PIPELINE; sp.b.source_id = 0;
+    sp.b.n_nodes = (int)sp.b_nodes.size(); sp.b.nodes = sp.b_nodes.data();
+    sp.b.n_args = (int)sp.b_args.size(); sp.b.args = sp.b_args.data();
+    sp.b.keys = sp.b_keys.data(); sp.b.vals = sp.b_vals.data();
+    return true;
+}
+
+// ---- multi-GPU: merge of the per-rank partial results (RQ_PLAN_SHARDED) -----------------------
+// Fact tables are row-range sharded, one process per GPU. After the plan's last aggregation ran on
+// the local shard, every rank holds a dense group table (keys, partial SUM/COUNT/MIN/MAX). The
+// tables are exchanged with ONE ncclAllGather (padded to the largest rank) and re-aggregated on
+// every rank by the ordinary aggregation pipeline (SUM and COUNT partials add, MIN/MAX take
+// min/max). mod-2^64 addition is associative, so the merged sums are bit-identical to a single-GPU
+// run; AVG is finalised by the following pipeline, i.e. after the merge (aggregation.h:182-204).
+// A plan without aggregation concatenates the per-rank relations instead.
+static bool is_str_type(int sql_type, int sql_width) {
+    return sql_type == RQ_SQL_VARCHAR || (sql_type == RQ_SQL_CHAR && sql_width > 1);
+}
+
+static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timings* tm) {
+    Dist& D = E.dist;
+    const int W = D.world;
+    const int ncols = (int)local.cols.size();
+    for (int c = 0; c < ncols; c++)
+        if (c < (int)local.sql_type.size() && is_str_type(local.sql_type[c], local.sql_width[c]))
+            raise(RQ_ERR_UNSUPPORTED, "sharded plans cannot exchange string columns (strings are rank-local addresses)");
+    cudaEvent_t e0 = E.ev[3], e1 = E.ev[4];
+    CK(cudaEventRecord(e0, E.stream));
+    // 1. row counts
+    int64_t* d_counts = nullptr;
+    CK(dmalloc(&d_counts, sizeof(int64_t) * W));
+    const int64_t* d_n = local.d_n_rows;
+    int64_t* d_tmp = nullptr;
+    if (local.n_rows >= 0) {
+        CK(dmalloc(&d_tmp, 8));
+        CK(cudaMemcpyAsync(d_tmp, &local.n_rows, 8, cudaMemcpyHostToDevice, E.stream));
+        d_n = d_tmp;
+    }
+    auto nccl_ck = [&](int rc, const char* what) {
+        if (rc != 0) raise(RQ_ERR_NCCL, "%s failed: %s", what, D.get_error_string ? D.get_error_string(rc) : "?");
+    };
+    nccl_ck(D.all_gather(d_n, d_counts, 1, 4 /* ncclInt64 */, D.comm, E.stream), "ncclAllGather(counts)");
+    std::vector<int64_t> counts(W);
+    CK(cudaMemcpyAsync(counts.data(), d_counts, sizeof(int64_t) * W, cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    int64_t maxn = 0, total = 0;
+    for (int r = 0; r < W; r++) { maxn = std::max(maxn, counts[r]); total += counts[r]; }
+    std::unique_ptr<rq_table> all = new_intermediate(ncols, total);
+    all->sql_type = local.sql_type;
+    all->sql_width = local.sql_width;
+    if (maxn > 0 && ncols > 0) {
+        // 2. [ncols][maxn] per rank -> [world][ncols][maxn]
+        int64_t *send = nullptr, *recv = nullptr;
+        const size_t per_rank = (size_t)ncols * (size_t)maxn;
+        CK(dmalloc(&send, per_rank * 8));
+        CK(dmalloc(&recv, per_rank * 8 * W));
+        const int64_t mine = counts[D.rank];
+        for (int c = 0; c < ncols; c++)
+            if (mine > 0)
+                CK(cudaMemcpyAsync(send + (size_t)c * maxn, local.cols[c].d, (size_t)mine * 8, cudaMemcpyDeviceToDevice, E.stream));
+        nccl_ck(D.all_gather(send, recv, per_rank, 4, D.comm, E.stream), "ncclAllGather(partials)");
+        // 3. concatenate in rank order
+        int64_t off = 0;
+        for (int r = 0; r < W; r++) {
+            for (int c = 0; c < ncols && counts[r] > 0; c++)
+                CK(cudaMemcpyAsync(all->cols[c].d + (size_t)off * 8, recv + ((size_t)r * ncols + c) * maxn,
+                                   (size_t)counts[r] * 8, cudaMemcpyDeviceToDevice, E.stream));
+            off += counts[r];
+        }
+        dfree(send);
+        dfree(recv);
+    }
+    CK(cudaMemcpyAsync(all->d_n_rows, &total, 8, cudaMemcpyHostToDevice, E.stream));
+    CK(cudaEventRecord(e1, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    all->n_rows = total;
+    dfree(d_counts);
+    if (d_tmp) dfree(d_tmp);
+    if (tm) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        tm->nccl_ms += ms;
+    }
+    return all;
+}
+
+static void merge_sharded(const rq_plan& plan, int pi, std::vector<PipeOut>& outs, const char* d_strpool,
+                          rq_timings* tm, size_t& ev_idx, std::vector<std::pair<size_t, bool>>& ev_used,
+                          double& lower_ms) {
+    if (!outs[pi].table) raise(RQ_ERR_INVALID, "sharded merge: pipeline %d has no relation output", pi);
+    const rq_pipeline& pl = plan.pipelines[pi];
+    std::unique_ptr<rq_table> all = gather_relation(*outs[pi].table, tm);
+    if (pl.sink_kind != RQ_SINK_AGG) {       // no aggregation: the concatenation is the result
+        outs[pi].table = std::move(all);
+        return;
+    }
+    // re-aggregate: column i of the gathered table is node i
+    const int nk = pl.n_keys, nv = pl.n_vals;
+    std::vector<rq_node> nodes(nk + nv);
+    std::vector<rq_value> keys(pl.keys, pl.keys + nk), vals(pl.vals, pl.vals + nv);
+    for (int i = 0; i < nk + nv; i++) { nodes[i] = rq_node{RQ_OP_COL, i, 0, 0, 0}; }
+    for (int k = 0; k < nk; k++) keys[k].node = k;
+    for (int v = 0; v < nv; v++) {
+        vals[v].node = nk + v;
+        if (vals[v].kind == RQ_AGG_COUNT) vals[v].kind = RQ_AGG_SUM;     // partial counts add up
+    }
+    rq_pipeline mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.source_kind = RQ_SRC_TABLE; mp.source_id = 0;
+    mp.n_nodes = nk + nv; mp.nodes = nodes.data();
+    mp.sink_kind = RQ_SINK_AGG;
+    mp.n_keys = nk; mp.keys = keys.data();
+    mp.n_vals = nv; mp.vals = vals.data();
+    mp.size_hint = all->n_rows;
+    rq_table* tabs[1] = {all.get()};
+    rq_plan mplan;
+    memset(&mplan, 0, sizeof(mplan));
+    mplan.n_tables = 1; mplan.tables = tabs;
+    mplan.n_pipelines = 1; mplan.pipelines = &mp;
+    mplan.limit = -1;
+    mplan.strpool = plan.strpool; mplan.strpool_bytes = plan.strpool_bytes;
+    std::vector<PipeOut> mouts(1);
+    run_pipeline(mplan, 0, mouts, d_strpool, tm, ev_idx, ev_used, lower_ms, /*is_fact_scan=*/false);
+    outs[pi].table = std::move(mouts[0].table);
 }
 
 }  // namespace
@@ -926,9 +1315,22 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         size_t ev_idx = 0;
         std::vector<std::pair<size_t, bool>> ev_used;
         double lower_ms = 0;
+        g_trace = getenv("RQ_TRACE") != nullptr;
+        g_trace_t0 = std::chrono::steady_clock::now();
         CK(cudaEventRecord(E.ev[0], E.stream));
-        for (int pi = 0; pi < plan->n_pipelines; pi++)
+        // sharded plans: merge after the last aggregation (or concatenate the final relation)
+        int merge_after = -1;
+        if ((plan->flags & RQ_PLAN_SHARDED) && E.dist.comm && E.dist.world > 1) {
+            for (int pi = 0; pi < plan->n_pipelines; pi++)
+                if (plan->pipelines[pi].sink_kind == RQ_SINK_AGG) merge_after = pi;
+            if (merge_after < 0) merge_after = plan->n_pipelines - 1;
+        }
+        for (int pi = 0; pi < plan->n_pipelines; pi++) {
+            trace_point("pipeline start", pi);
             run_pipeline(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+            trace_point("pipeline done", pi);
+            if (pi == merge_after) merge_sharded(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+        }
 
         rq_table* fin = outs[plan->n_pipelines - 1].table.get();
         if (!fin) raise(RQ_ERR_INVALID, "last pipeline must produce a relation");
@@ -936,6 +1338,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         CK(cudaMemcpy(&n, fin->d_n_rows, 8, cudaMemcpyDeviceToHost));
         const int ncols = (int)fin->cols.size();
 
+        trace_point("row count read");
         // ORDER BY + LIMIT
         std::vector<int64_t*> cols(ncols);
         for (int c = 0; c < ncols; c++) cols[c] = (int64_t*)fin->cols[c].d;
@@ -1011,6 +1414,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
             CK(cudaGetLastError());
         }
 
+        trace_point("sorted");
         // narrow to the reference's physical widths on the device, then read back
         res = (rq_result*)calloc(1, sizeof(rq_result));
         res->n_rows = n_out;
@@ -1054,6 +1458,10 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
             }
             CK(cudaEventElapsedTime(&ms, E.ev[1], E.ev[2]));
             tm->d2h_ms = ms;
+            if (trace) {
+                CK(cudaEventElapsedTime(&ms, E.ev[0], E.ev[2]));
+                fprintf(stderr, "[rq] plan: %.3f ms on the stream from first launch to result read-back, %.3f ms in pipeline kernels\n", ms, tm->kernel_ms);
+            }
         }
         for (void* p : scratch) dfree(p);
         if (d_strpool) dfree(d_strpool);

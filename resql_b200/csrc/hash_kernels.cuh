@@ -13,6 +13,7 @@ namespace rq {
 struct HashTableDev {
     DHashTable d{};
     uint64_t capacity = 0;
+    uint64_t entries = 0;       // occupied slots after the build
     ~HashTableDev() {
         dfree(d.ent); dfree(d.bloom);
     }
@@ -98,9 +99,24 @@ __device__ __forceinline__ bool ht_insert_dup(const DHashTable& ht, const int64_
     return false;
 }
 
+// the same, starting the walk at slot `i` (the home slot was already found taken); keys are
+// written by the caller
+__device__ __forceinline__ bool ht_insert_dup_from(const DHashTable& ht, uint64_t h, uint64_t i,
+                                                   uint64_t* slot_out) {
+    const uint64_t tag = h | 2ULL;
+    const uint64_t cap = ht.cap_mask + 1;
+    const uint64_t lim = cap < kMaxProbeLen ? cap : kMaxProbeLen;
+    for (uint64_t tries = 1; tries < lim; tries++) {
+        const unsigned long long old = atomicCAS((unsigned long long*)ht_entry(ht, i), 0ULL, (unsigned long long)tag);
+        if (old == 0ULL) { *slot_out = i; return true; }
+        i = (i + 1) & ht.cap_mask;
+    }
+    return false;
+}
+
 // GROUP BY: find the slot of the key or claim a new one (aggregation.h:262-279)
 __device__ __forceinline__ bool ht_find_or_insert(const DHashTable& ht, const int64_t* k, uint64_t h,
-                                                  uint64_t* slot_out) {
+                                                  uint64_t* slot_out, bool* fresh) {
     const uint64_t tag = h | 2ULL;
     const uint64_t cap = ht.cap_mask + 1;
     uint64_t i = h >> ht.shift;
@@ -115,6 +131,7 @@ __device__ __forceinline__ bool ht_find_or_insert(const DHashTable& ht, const in
                 __threadfence();
                 atomicExch((unsigned long long*)e, (unsigned long long)tag);
                 *slot_out = i;
+                *fresh = true;
                 return true;
             }
         }

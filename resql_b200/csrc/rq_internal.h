@@ -123,6 +123,8 @@ struct DProbe {
     uint8_t    out_slot[kMaxOut];   // payload column k -> slot (0xff = not needed)
     int32_t    n_out;
     int32_t    single;
+    int32_t    bloom_only;          // semi-join reduction only: no table walk, no payload
+    int32_t    pad_;
     unsigned long long* dup_counter;   // counts tuples with more than one match (multi-match mode)
 };
 
@@ -172,6 +174,7 @@ struct KParams {
     // hash aggregate / build
     DHashTable     ht;
     int32_t*       ht_full;              // set when the table is full
+    unsigned long long* ht_entries;      // entries added by this launch
     // probes
     int32_t        n_probes;
     DProbe         probe[kMaxProbes];

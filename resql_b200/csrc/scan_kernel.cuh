@@ -304,6 +304,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     uint64_t dk[ND];
     int ngroups = 0;
     unsigned seen = 0;     // (no GROUP BY) did this lane aggregate at least one tuple
+    unsigned n_inserted = 0;   // hash sinks: entries this lane added to the table
 #pragma unroll
     for (int g = 0; g < NG; g++)
 #pragma unroll
@@ -319,18 +320,24 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     auto is_guarded = [&](int64_t tile) -> bool {
         return P.borrowed && (tile + 1) * (int64_t)kTile > n_rows;
     };
-    // lane 0 issues the bulk copies of a tile, one per staged column; scanned data is streamed
-    // once, so it is marked evict-first in L2
+    // Lane c issues the bulk copy of staged column c (all columns of a tile go out in one step);
+    // lane 0 arms the barrier with the stage's byte count first. Scanned data is streamed once, so
+    // it is marked evict-first in L2.
     const uint64_t stream_policy = l2_evict_first_policy();
+    const bool col_lane = lane < P.n_cols;
+    const unsigned char* const my_src = col_lane ? P.col_ptr[lane] : nullptr;
+    const uint32_t my_bytes = col_lane ? (uint32_t)kTile * P.col_w[lane] : 0u;
+    const uint32_t my_off = col_lane ? P.col_off[lane] : 0u;
     auto issue = [&](int64_t tile, int s) {
-        if (lane != 0 || is_guarded(tile)) return;
+        if (is_guarded(tile)) return;
         const uint32_t bar = bars + s * 8;
-        const uint32_t dst = wbase + s * P.stage_bytes;
-        mbar_expect_tx_s(bar, P.stage_bytes);
-        for (int c = 0; c < P.n_cols; c++) {
-            const uint32_t bytes = kTile * P.col_w[c];
-            if (P.stream_hint) tma_bulk_g2s_hint(dst + P.col_off[c], P.col_ptr[c] + (size_t)tile * bytes, bytes, bar, stream_policy);
-            else tma_bulk_g2s_s(dst + P.col_off[c], P.col_ptr[c] + (size_t)tile * bytes, bytes, bar);
+        if (lane == 0) mbar_expect_tx_s(bar, P.stage_bytes);
+        __syncwarp();
+        if (col_lane) {
+            const uint32_t dst = wbase + s * P.stage_bytes + my_off;
+            const unsigned char* src = my_src + (size_t)tile * my_bytes;
+            if (P.stream_hint) tma_bulk_g2s_hint(dst, src, my_bytes, bar, stream_policy);
+            else tma_bulk_g2s_s(dst, src, my_bytes, bar);
         }
     };
     if (P.n_cols > 0) {
@@ -343,7 +350,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     const bool hash_sink = (GR == 0) && (sink == IMPL_BUILD || sink == IMPL_HASHAGG);
     for (int64_t tile = first; tile < n_tiles; tile += stride) {
         // a full hash table makes the host regrow it and rerun: stop early
-        if (hash_sink && *(volatile int32_t*)P.ht_full) break;
+        if (hash_sink && ((tile - first) / stride & 15) == 0 && *(volatile int32_t*)P.ht_full) break;
         WarpCtx c;
         c.stage = wbase + s * P.stage_bytes;
         c.wbase = wbase;
@@ -575,21 +582,24 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     const DProbe& pr = P.probe[in.aux];
                     const uint64_t cap = pr.ht.cap_mask + 1;
                     const int pnk = pr.ht.nk;
+                    const bool k1 = pnk == 1 && pr.ht.key_kind[0] == 0;   // one integer key: the usual join
                     uint64_t h[kR];
-                    if (pnk == 1 && pr.ht.key_kind[0] == 0) {
-                        int64_t kv[kR];
+                    int64_t kv[kR];
+                    if (k1) {
                         fetch_vref(P, c, pr.key[0], kv);
 #pragma unroll
                         for (int r = 0; r < kR; r++) h[r] = hash_int(kv[r]);
                     } else {
 #pragma unroll
+                        for (int r = 0; r < kR; r++) { h[r] = 0; kv[r] = 0; }
+#pragma unroll 1
                         for (int r = 0; r < kR; r++) {
-                            h[r] = 0;
-                            if ((valid >> r) & 1) {
-                                int64_t k[kMaxKeys];
-                                for (int j = 0; j < pnk; j++) k[j] = ld_row(P, c, pr.key[j], r);
-                                h[r] = hash_typed(k, pr.ht.key_kind, pnk);
-                            }
+                            if (!((valid >> r) & 1)) continue;
+                            int64_t k[kMaxKeys];
+                            for (int j = 0; j < pnk; j++) k[j] = ld_row(P, c, pr.key[j], r);
+                            const uint64_t hv = hash_typed(k, pr.ht.key_kind, pnk);
+#pragma unroll
+                            for (int q = 0; q < kR; q++) if (q == r) h[q] = hv;
                         }
                     }
                     if (pr.ht.bloom != nullptr) {
@@ -603,36 +613,77 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                             if ((w[r] & bits) != bits) valid &= ~(1u << r);
                         }
                     }
-                    unsigned todo = valid;
-                    while (todo) {
-                        const int r = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        uint64_t hr = 0;
+                    if (pr.bloom_only) {
+                        // semi-join reduction pass of a split pipeline: survivors are materialized
+                        // and probed for real by the second pass (engine_exec.inl split_at_probe)
+                        if (!__any_sync(kFull, valid != 0)) pc = n_insn;
+                        break;
+                    }
+                    if (k1) {
+                        // The home-slot tags of all surviving tuples are fetched together (one memory
+                        // round trip per lane instead of one per tuple); a walk continues per tuple
+                        // only where the home slot holds another key.
+                        uint64_t tag0[kR];
 #pragma unroll
-                        for (int q = 0; q < kR; q++) if (q == r) hr = h[q];
-                        int64_t k[kMaxKeys];
-                        for (int j = 0; j < pnk; j++) k[j] = ld_row(P, c, pr.key[j], r);
-                        const uint64_t tag = hr | 2ULL;
-                        uint64_t i = hr >> pr.ht.shift;
-                        int64_t found = -1;
-                        unsigned matches = 0;
-                        for (uint64_t tries = 0; tries < cap; tries++) {
-                            const uint64_t t = *ht_entry(pr.ht, i);
-                            if (t == 0ULL) break;
-                            if (t == tag && slot_keys_equal(pr.ht, i, k)) {
-                                if (found < 0) found = (int64_t)i;
-                                matches++;
-                                if (pr.single) break;
+                        for (int r = 0; r < kR; r++)
+                            tag0[r] = ((valid >> r) & 1) ? *ht_entry(pr.ht, h[r] >> pr.ht.shift) : 0ULL;
+#pragma unroll
+                        for (int r = 0; r < kR; r++) {
+                            if (!((valid >> r) & 1)) continue;
+                            const uint64_t tag = h[r] | 2ULL;
+                            uint64_t i = h[r] >> pr.ht.shift;
+                            uint64_t t = tag0[r];
+                            int64_t found = -1;
+                            unsigned matches = 0;
+                            for (uint64_t tries = 0; tries < cap && t != 0ULL; tries++) {
+                                if (t == tag && (int64_t)ht_entry(pr.ht, i)[1] == kv[r]) {
+                                    if (found < 0) found = (int64_t)i;
+                                    matches++;
+                                    if (pr.single) break;
+                                }
+                                i = (i + 1) & pr.ht.cap_mask;
+                                t = *ht_entry(pr.ht, i);
                             }
-                            i = (i + 1) & pr.ht.cap_mask;
+                            if (found < 0) { valid &= ~(1u << r); continue; }
+                            if (matches > 1) atomicAdd(pr.dup_counter, (unsigned long long)(matches - 1));
+                            const int row = row_in_tile(r, lane);
+                            const uint64_t* pay = ht_entry(pr.ht, (uint64_t)found) + 2;
+                            for (int q = 0; q < pr.n_out; q++)
+                                if (pr.out_slot[q] != 0xff)
+                                    sts_b64(wbase + P.slots_rel + pr.out_slot[q] * (kTile * 8) + row * 8, (int64_t)pay[q]);
                         }
-                        if (found < 0) { valid &= ~(1u << r); continue; }
-                        if (matches > 1) atomicAdd(pr.dup_counter, (unsigned long long)(matches - 1));
-                        const int row = row_in_tile(r, lane);
-                        const uint64_t* pay = ht_entry(pr.ht, (uint64_t)found) + 1 + pnk;
-                        for (int q = 0; q < pr.n_out; q++)
-                            if (pr.out_slot[q] != 0xff)
-                                sts_b64(wbase + P.slots_rel + pr.out_slot[q] * (kTile * 8) + row * 8, (int64_t)pay[q]);
+                    } else {
+                        unsigned todo = valid;
+                        while (todo) {
+                            const int r = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            uint64_t hr = 0;
+#pragma unroll
+                            for (int q = 0; q < kR; q++) if (q == r) hr = h[q];
+                            int64_t k[kMaxKeys];
+                            for (int j = 0; j < pnk; j++) k[j] = ld_row(P, c, pr.key[j], r);
+                            const uint64_t tag = hr | 2ULL;
+                            uint64_t i = hr >> pr.ht.shift;
+                            int64_t found = -1;
+                            unsigned matches = 0;
+                            for (uint64_t tries = 0; tries < cap; tries++) {
+                                const uint64_t t = *ht_entry(pr.ht, i);
+                                if (t == 0ULL) break;
+                                if (t == tag && slot_keys_equal(pr.ht, i, k)) {
+                                    if (found < 0) found = (int64_t)i;
+                                    matches++;
+                                    if (pr.single) break;
+                                }
+                                i = (i + 1) & pr.ht.cap_mask;
+                            }
+                            if (found < 0) { valid &= ~(1u << r); continue; }
+                            if (matches > 1) atomicAdd(pr.dup_counter, (unsigned long long)(matches - 1));
+                            const int row = row_in_tile(r, lane);
+                            const uint64_t* pay = ht_entry(pr.ht, (uint64_t)found) + 1 + pnk;
+                            for (int q = 0; q < pr.n_out; q++)
+                                if (pr.out_slot[q] != 0xff)
+                                    sts_b64(wbase + P.slots_rel + pr.out_slot[q] * (kTile * 8) + row * 8, (int64_t)pay[q]);
+                        }
                     }
                     __syncwarp();
                     if (!__any_sync(kFull, valid != 0)) pc = n_insn;
@@ -849,20 +900,52 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     }
                 }
             } else if (sink == IMPL_BUILD) {
-                // hash-join build (hashjoin.h:226-256): every tuple claims its own entry
-                // (issuing the 8 claims of a lane back to back was measured slower: 9.7 vs 7.7 ms
-                // for the 14.6 M inserts of Q3 at SF100)
+                // hash-join build (hashjoin.h:226-256): every tuple claims its own entry.
+                const int bnk = P.ht.nk;
+                if (bnk == 1 && P.ht.key_kind[0] == 0) {
+                    // One integer key. The claims (atomicCAS on the home slot) of a lane's tuples
+                    // are issued together: a dense tile costs one atomic round trip per lane; a
+                    // tuple whose home slot is taken walks on alone.
+                    int64_t bk[kR];
+                    fetch_vref(P, c, P.key[0], bk);
+                    unsigned long long old[kR];
+#pragma unroll
+                    for (int r = 0; r < kR; r++) {
+                        old[r] = 1ULL;
+                        if ((valid >> r) & 1) {
+                            const uint64_t hh = hash_int(bk[r]);
+                            old[r] = atomicCAS((unsigned long long*)ht_entry(P.ht, hh >> P.ht.shift), 0ULL,
+                                               (unsigned long long)(hh | 2ULL));
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < kR; r++) {
+                        if (!((valid >> r) & 1)) continue;
+                        const uint64_t hh = hash_int(bk[r]);
+                        uint64_t slot = hh >> P.ht.shift;
+                        if (old[r] != 0ULL) {
+                            if (!ht_insert_dup_from(P.ht, hh, (slot + 1) & P.ht.cap_mask, &slot)) { *P.ht_full = 1; continue; }
+                        }
+                        uint64_t* e = ht_entry(P.ht, slot);
+                        e[1] = (uint64_t)bk[r];
+                        for (int q = 0; q < P.n_out; q++) e[2 + q] = (uint64_t)ld_row(P, c, P.out[q], r);
+                        if (P.ht.bloom != nullptr) atomicOr(&P.ht.bloom[bloom_word(hh, P.ht.bloom_mask)], bloom_bits(hh));
+                        n_inserted++;
+                    }
+                } else {
 #pragma unroll 1
-                for (int r = 0; r < kR; r++) {
-                    if (!((valid >> r) & 1)) continue;
-                    int64_t k[kMaxKeys];
-                    for (int j = 0; j < P.ht.nk; j++) k[j] = ld_row(P, c, P.key[j], r);
-                    const uint64_t hh = hash_keys(k, P.ht.key_kind, P.ht.nk);
-                    uint64_t slot;
-                    if (!ht_insert_dup(P.ht, k, hh, &slot)) { *P.ht_full = 1; continue; }
-                    uint64_t* e = ht_entry(P.ht, slot);
-                    for (int q = 0; q < P.n_out; q++) e[1 + P.ht.nk + q] = (uint64_t)ld_row(P, c, P.out[q], r);
-                    if (P.ht.bloom != nullptr) atomicOr(&P.ht.bloom[bloom_word(hh, P.ht.bloom_mask)], bloom_bits(hh));
+                    for (int r = 0; r < kR; r++) {
+                        if (!((valid >> r) & 1)) continue;
+                        int64_t k[kMaxKeys];
+                        for (int j = 0; j < bnk; j++) k[j] = ld_row(P, c, P.key[j], r);
+                        const uint64_t hh = hash_keys(k, P.ht.key_kind, bnk);
+                        uint64_t slot;
+                        if (!ht_insert_dup(P.ht, k, hh, &slot)) { *P.ht_full = 1; continue; }
+                        uint64_t* e = ht_entry(P.ht, slot);
+                        for (int q = 0; q < P.n_out; q++) e[1 + bnk + q] = (uint64_t)ld_row(P, c, P.out[q], r);
+                        if (P.ht.bloom != nullptr) atomicOr(&P.ht.bloom[bloom_word(hh, P.ht.bloom_mask)], bloom_bits(hh));
+                        n_inserted++;
+                    }
                 }
             } else if (sink == IMPL_HASHAGG) {
 #pragma unroll 1
@@ -872,7 +955,9 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     for (int j = 0; j < P.ht.nk; j++) k[j] = ld_row(P, c, P.key[j], r);
                     const uint64_t hh = hash_keys(k, P.ht.key_kind, P.ht.nk);
                     uint64_t slot;
-                    if (!ht_find_or_insert(P.ht, k, hh, &slot)) { *P.ht_full = 1; continue; }
+                    bool fresh = false;
+                    if (!ht_find_or_insert(P.ht, k, hh, &slot, &fresh)) { *P.ht_full = 1; continue; }
+                    if (fresh) n_inserted++;
                     uint64_t* acc = ht_entry(P.ht, slot) + 1 + P.ht.nk;
                     for (int a = 0; a < NA; a++) {
                         const int kind = P.agg_kind[a];
@@ -916,6 +1001,12 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         if (++s == S) { s = 0; phase ^= 1u; }
     }
 
+    if (hash_sink) {       // occupied entries of the table (replaces a counting pass over it)
+        unsigned tot = n_inserted;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
+        if (lane == 0 && tot) atomicAdd(P.ht_entries, (unsigned long long)tot);
+    }
     // ---- flush the per-warp accumulators of the low-cardinality aggregate -------------------
     if (GR > 0 || sink == IMPL_LOWAGG) {
         __syncwarp();

@@ -139,3 +139,21 @@ def test_host_front_end_end_to_end(sf001, tmp_path):
         got = [l for l in out.read_text().split("\n")[1:] if l]
         _, want = load_golden(q)
         assert_same_relation(got, want, load_plan_dict(q), q + " via resql-b200")
+
+
+def _join_plans():
+    return [n for n in plan_names() if any(p["sink_kind"] == 2 for p in load_plan_dict(n)["pipelines"])]
+
+
+@pytest.mark.parametrize("name", _join_plans())
+def test_two_pass_probe_matches_reference_engine(name, sf001, engine, monkeypatch):
+    """selective probes run as scan -> Bloom test -> materialize, then a dense probe pass
+    (engine_exec.inl split_at_probe); forced here for every join fixture regardless of size"""
+    monkeypatch.setenv("RQ_SPLIT_MIN_ROWS", "0")
+    monkeypatch.setenv("RQ_SPLIT_FRAC", "1e18")
+    d = load_plan_dict(name)
+    got, tm = _run(engine, d, plan_tables(d, sf001))
+    _, want = load_golden(name)
+    assert_same_relation(got, want, d, name + " (two-pass)")
+    n_scans = sum(1 for p in d["pipelines"] if p["source_kind"] == 1)
+    assert tm.kernel_launches > n_scans
