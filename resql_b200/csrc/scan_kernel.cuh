@@ -270,14 +270,20 @@ __global__ void __launch_bounds__(ScanCfg<GR>::kThreads, 1)
 rq_scan_kernel(const __grid_constant__ KParams P) {
     constexpr int NG = GR > 0 ? GR : 1;                 // register groups
     constexpr int ND = GR > 0 ? GR : kLowCardMaxGroups; // dictionary entries
-    const int lane = threadIdx.x & 31;
+    // lane / warp-region base are used everywhere; they are made opaque so that the compiler keeps
+    // them in registers instead of re-deriving them from S2R + parameter loads under register
+    // pressure (S2R has a long fixed latency and showed up as 'wait' stalls all over the tile loop)
+    int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int W = blockDim.x >> 5;
     const int S = P.stages;
 
     const uint32_t smem0 = smem_u32(rq_smem);
-    const uint32_t bars = smem0 + warp * (kMaxStages * 8);
-    const uint32_t wbase = smem0 + P.warp_off + warp * P.warp_bytes;
+    const uint32_t bars_ = smem0 + warp * (kMaxStages * 8);
+    uint32_t wbase = smem0 + P.warp_off + warp * P.warp_bytes;
+    uint32_t bars_o = bars_;
+    asm volatile("" : "+r"(lane), "+r"(wbase), "+r"(bars_o));
+    const uint32_t bars = bars_o;
     const uint32_t slot_base = wbase + P.slots_rel;
     const uint32_t sacc = wbase + P.acc_rel;            // GR == 0 low-card path: [g][a][lane] int64
 
@@ -766,74 +772,51 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         ngroups++;
                     }
                 }
-                // One rolled loop over the aggregates: the tuple values are reduced into tile-local
-                // partials per group (two independent chains each), then folded into the register
-                // accumulator picked by a switch over compile-time names. The variant code exists
-                // once, so the hot path stays small.
-#pragma unroll 1
-                for (int a = 0; a < NA; a++) {
+                // The aggregate loop is unrolled, so every accumulator is a fixed register and a
+                // tuple value goes into it with one multiply-add by the 0/1 group multiplier
+                // (IMAD.WIDE.U32 with 64-bit accumulate) - no tile-local partials, no fold step.
+                // Values proven to fit 32 bits take one instruction per (group, tuple), full 64-bit
+                // values a second IMAD on the high word (the low product of hi32(v) * m added to the
+                // accumulator's high word is exactly the wrap-around int64 sum).
+#pragma unroll
+                for (int a = 0; a < kNAR; a++) {
+                    if (a >= NA) continue;
                     const int kind = P.agg_kind[a];
-                    uint64_t part[NG];
                     if (kind == 2) {                      // COUNT
 #pragma unroll
                         for (int g = 0; g < NG; g++) {
-                            uint32_t cnt = 0;
-#pragma unroll
-                            for (int r = 0; r < kR; r++) cnt += m[g][r];
-                            part[g] = cnt;
+                            const uint32_t cnt = ((m[g][0] + m[g][1]) + (m[g][2] + m[g][3])) +
+                                                 ((m[g][4] + m[g][5]) + (m[g][6] + m[g][7]));
+                            racc[g][a] += cnt;
                         }
-                    } else {
-                        const VRef vr = P.agg_src[a];
-                        int64_t v[kR];
-                        if (vr.kind == K_M64) ld_m64(((vr.slot & 1) ? c.wbase : c.stage) + ((uint32_t)vr.off16 << 4) + lane * 16, v);
-                        else fetch_vref(P, c, vr, v);
-                        if (kind == 1 && (vr.slot & 2)) {   // SUM of values proven to fit 32 bits
-#pragma unroll
-                            for (int g = 0; g < NG; g++) {
-                                uint64_t p0 = 0, p1 = 0;
-#pragma unroll
-                                for (int r = 0; r < kR; r += 2) {
-                                    mad_wide_u32(p0, (uint32_t)v[r], m[g][r]);
-                                    mad_wide_u32(p1, (uint32_t)v[r + 1], m[g][r + 1]);
-                                }
-                                part[g] = p0 + p1;
-                            }
-                        } else if (kind == 1) {             // SUM: low words unsigned, high words signed
-#pragma unroll
-                            for (int g = 0; g < NG; g++) {
-                                uint64_t lo = 0;
-                                int64_t hi = 0;
-#pragma unroll
-                                for (int r = 0; r < kR; r++) {
-                                    mad_wide_u32(lo, (uint32_t)v[r], m[g][r]);
-                                    mad_wide_s32(hi, (int32_t)((uint64_t)v[r] >> 32), (int32_t)m[g][r]);
-                                }
-                                part[g] = lo + ((uint64_t)hi << 32);
-                            }
-                        } else {                            // MIN / MAX
-#pragma unroll
-                            for (int g = 0; g < NG; g++) {
-                                int64_t best = agg_identity(kind);
-#pragma unroll
-                                for (int r = 0; r < kR; r++)
-                                    if (m[g][r] && (kind == 3 ? v[r] < best : v[r] > best)) best = v[r];
-                                part[g] = (uint64_t)best;
-                            }
-                        }
+                        continue;
                     }
-                    switch (a) {
-#define RQ_FOLD(A)                                                                            \
-    case A:                                                                                   \
-        RQ_NOMERGE(A);                                                                        \
-        _Pragma("unroll") for (int g = 0; g < NG; g++) {                                      \
-            const int64_t cur = (int64_t)racc[g][A], nv = (int64_t)part[g];                   \
-            if (kind <= 2) racc[g][A] = (uint64_t)cur + (uint64_t)nv;                         \
-            else if (kind == 3 ? nv < cur : nv > cur) racc[g][A] = (uint64_t)nv;              \
-        }                                                                                     \
-        break;
-                        RQ_FOLD(0) RQ_FOLD(1) RQ_FOLD(2) RQ_FOLD(3) RQ_FOLD(4) RQ_FOLD(5)
-#undef RQ_FOLD
-                        default: break;
+                    const VRef vr = P.agg_src[a];
+                    int64_t v[kR];
+                    if (vr.kind == K_M64) ld_m64(((vr.slot & 1) ? c.wbase : c.stage) + ((uint32_t)vr.off16 << 4) + lane * 16, v);
+                    else fetch_vref(P, c, vr, v);
+                    if (kind == 1 && (vr.slot & 2)) {     // SUM of values proven to fit 32 bits
+#pragma unroll
+                        for (int r = 0; r < kR; r++)
+#pragma unroll
+                            for (int g = 0; g < NG; g++) mad_wide_u32(racc[g][a], (uint32_t)v[r], m[g][r]);
+                    } else if (kind == 1) {               // SUM, full width
+#pragma unroll
+                        for (int r = 0; r < kR; r++)
+#pragma unroll
+                            for (int g = 0; g < NG; g++) {
+                                mad_wide_u32(racc[g][a], (uint32_t)v[r], m[g][r]);
+                                racc[g][a] += (uint64_t)((uint32_t)((uint64_t)v[r] >> 32) * m[g][r]) << 32;
+                            }
+                    } else {                              // MIN / MAX
+#pragma unroll
+                        for (int g = 0; g < NG; g++) {
+                            int64_t best = (int64_t)racc[g][a];
+#pragma unroll
+                            for (int r = 0; r < kR; r++)
+                                if (m[g][r] && (kind == 3 ? v[r] < best : v[r] > best)) best = v[r];
+                            racc[g][a] = (uint64_t)best;
+                        }
                     }
                 }
             } else if (sink == IMPL_LOWAGG) {
