@@ -350,6 +350,12 @@ struct PipeOut {                    // what a finished pipeline left on the devi
     std::unique_ptr<rq_table> table;   // AGG / MATERIALIZE output (int64 columns)
     std::unique_ptr<HashTableDev> ht;  // BUILD output
     std::vector<int> payload_sql_type, payload_sql_width;
+    std::vector<uint8_t> pay_word;     // BUILD: payload index (as in the plan) -> entry word, 0xff = not stored
+    std::vector<void*> owned;          // device buffers the relation's string addresses point into
+    ~PipeOut() { for (void* p : owned) dfree(p); }
+    PipeOut() = default;
+    PipeOut(PipeOut&&) = default;
+    PipeOut& operator=(PipeOut&&) = default;
 };
 
 bool is_leaf(int op) { return op == RQ_OP_COL || op == RQ_OP_CONST || op == RQ_OP_CONST_STR; }

@@ -342,13 +342,18 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
             pr.single = (int32_t)(nd.imm & 1);
             pr.bloom_only = (int32_t)((nd.imm >> 1) & 1);     // internal: first pass of a split pipeline
             if (pr.bloom_only && pr.ht.bloom == nullptr) raise(RQ_ERR_INVALID, "internal: semi-join pass without a Bloom filter");
-            pr.n_out = pr.ht.nv;
+            const std::vector<uint8_t>& pw = L.outs[nd.a].pay_word;
+            pr.n_out = (int32_t)pw.size();
+            if (pr.n_out > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d payload columns", kMaxOut);
             memset(pr.out_slot, 0xff, sizeof(pr.out_slot));
+            memset(pr.pay_word, 0, sizeof(pr.pay_word));
             pr.dup_counter = (unsigned long long*)(E.flags + 4);
             for (int j = i + 1; j < n; j++) {
                 if (pl.nodes[j].op != RQ_OP_PAYLOAD || pl.nodes[j].a != i) continue;
                 const int b = pl.nodes[j].b;
-                if (b < 0 || b >= pr.ht.nv || b >= kMaxOut) raise(RQ_ERR_INVALID, "PAYLOAD %d out of range", b);
+                if (b < 0 || b >= pr.n_out) raise(RQ_ERR_INVALID, "PAYLOAD %d out of range", b);
+                if (pw[b] == 0xff) raise(RQ_ERR_INVALID, "internal: payload %d was not stored by the build", b);
+                pr.pay_word[b] = pw[b];
                 const int sl = L.alloc_slot();
                 L.slot[j] = sl;
                 pr.out_slot[b] = (uint8_t)sl;
@@ -682,6 +687,56 @@ struct PrunedBuild {
     std::vector<rq_value> keys, vals;
     rq_pipeline pl;
 };
+
+// Which payload columns of build pipeline `pi` does the rest of the plan read, and where do they
+// live in a hash-table entry? A payload that repeats a join key (the reference stores the join
+// keys AND all requested build attributes, hashjoin.h:233-236) is read from the key word; a payload
+// no later PAYLOAD node reads is not stored at all. Returns the build pipeline with the stored
+// payloads only; pay_word[q] = entry word of the plan's payload q (0xff = not stored).
+struct BuildLayout {
+    std::vector<rq_value> vals;
+    std::vector<uint8_t> pay_word;
+    std::vector<int> sql_type, sql_width;
+    rq_pipeline pl;
+};
+static void layout_build_payload(const rq_plan& plan, int pi, const rq_pipeline& b, BuildLayout& out) {
+    const int nv = b.n_vals, nk = b.n_keys;
+    std::vector<char> needed(nv, 0);
+    for (int q = pi + 1; q < plan.n_pipelines; q++) {
+        const rq_pipeline& pq = plan.pipelines[q];
+        std::vector<char> used(pq.n_nodes, 0);
+        auto use = [&](int r) { if (r >= 0 && r < pq.n_nodes) used[r] = 1; };
+        for (int i = 0; i < pq.n_nodes; i++) {
+            const rq_node& nd = pq.nodes[i];
+            if (is_binary(nd.op)) { use(nd.a); use(nd.b); }
+            else if (nd.op == RQ_OP_FILTER) use(nd.a);
+            else if (nd.op == RQ_OP_SELECT) { use(nd.a); use(nd.b); use(nd.c); }
+            else if (nd.op == RQ_OP_PROBE) for (int k = 0; k < nd.c && nd.b + k < pq.n_args; k++) use(pq.args[nd.b + k]);
+        }
+        for (int k = 0; k < pq.n_keys; k++) use(pq.keys[k].node);
+        for (int k = 0; k < pq.n_vals; k++) use(pq.vals[k].node);
+        for (int i = 0; i < pq.n_nodes; i++) {
+            const rq_node& nd = pq.nodes[i];
+            if (nd.op != RQ_OP_PAYLOAD || !used[i]) continue;
+            if (nd.a < 0 || nd.a >= pq.n_nodes || pq.nodes[nd.a].op != RQ_OP_PROBE || pq.nodes[nd.a].a != pi) continue;
+            if (nd.b >= 0 && nd.b < nv) needed[nd.b] = 1;
+        }
+    }
+    out.pay_word.assign(nv, 0xff);
+    for (int q = 0; q < nv; q++) {
+        out.sql_type.push_back(b.vals[q].sql_type);
+        out.sql_width.push_back(b.vals[q].width);
+        if (!needed[q]) continue;
+        int alias = -1;
+        for (int k = 0; k < nk; k++) if (b.keys[k].node == b.vals[q].node) alias = k;
+        if (alias >= 0) { out.pay_word[q] = (uint8_t)(1 + alias); continue; }
+        out.pay_word[q] = (uint8_t)(1 + nk + out.vals.size());
+        out.vals.push_back(b.vals[q]);
+    }
+    out.pl = b;
+    out.pl.n_vals = (int)out.vals.size();
+    out.pl.vals = out.vals.data();
+}
 static bool prune_build_by_probe_stats(const rq_plan& plan, int pi, PrunedBuild& out) {
     if (getenv("RQ_NO_PRUNE")) return false;
     const rq_pipeline& b = plan.pipelines[pi];
@@ -760,10 +815,20 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
                          std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
                          bool is_fact_scan = true) {
     PrunedBuild pb;
+    BuildLayout bl;
     const rq_pipeline* pl = &plan.pipelines[pi];
-    if (pl->sink_kind == RQ_SINK_BUILD && prune_build_by_probe_stats(plan, pi, pb)) pl = &pb.pl;
+    if (pl->sink_kind == RQ_SINK_BUILD) {
+        if (prune_build_by_probe_stats(plan, pi, pb)) pl = &pb.pl;
+        layout_build_payload(plan, pi, *pl, bl);
+        pl = &bl.pl;
+    }
     run_pipeline_one(plan, *pl, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, is_fact_scan,
                      nullptr, outs[pi], true);
+    if (pl->sink_kind == RQ_SINK_BUILD) {
+        outs[pi].pay_word = bl.pay_word;
+        outs[pi].payload_sql_type = bl.sql_type;
+        outs[pi].payload_sql_width = bl.sql_width;
+    }
 }
 
 static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
@@ -976,10 +1041,6 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
             dfree(d_count);
             g_ht_capacity[sig] = cap;
             if (impl == IMPL_BUILD) {
-                for (int k = 0; k < pl.n_vals; k++) {
-                    result.payload_sql_type.push_back(pl.vals[k].sql_type);
-                    result.payload_sql_width.push_back(pl.vals[k].width);
-                }
                 ht->entries = n_used;
                 result.ht = std::move(ht);
                 return;
@@ -1164,13 +1225,10 @@ static bool is_str_type(int sql_type, int sql_width) {
     return sql_type == RQ_SQL_VARCHAR || (sql_type == RQ_SQL_CHAR && sql_width > 1);
 }
 
-static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timings* tm) {
+static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timings* tm, std::vector<void*>& owned) {
     Dist& D = E.dist;
     const int W = D.world;
     const int ncols = (int)local.cols.size();
-    for (int c = 0; c < ncols; c++)
-        if (c < (int)local.sql_type.size() && is_str_type(local.sql_type[c], local.sql_width[c]))
-            raise(RQ_ERR_UNSUPPORTED, "sharded plans cannot exchange string columns (strings are rank-local addresses)");
     cudaEvent_t e0 = E.ev[3], e1 = E.ev[4];
     CK(cudaEventRecord(e0, E.stream));
     // 1. row counts
@@ -1217,6 +1275,31 @@ static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timin
         dfree(send);
         dfree(recv);
     }
+    // string columns hold rank-local addresses: ship the bytes (sql_width + 1 per row) and point the
+    // gathered column at the received copies
+    for (int c = 0; c < ncols && maxn > 0; c++) {
+        if (!(c < (int)local.sql_type.size() && is_str_type(local.sql_type[c], local.sql_width[c]))) continue;
+        const int w = local.sql_width[c] + 1;
+        unsigned char *sb = nullptr, *rb = nullptr, *cat = nullptr;
+        CK(dmalloc(&sb, (size_t)maxn * w));
+        CK(dmalloc(&rb, (size_t)maxn * w * W));
+        CK(dmalloc(&cat, (size_t)std::max<int64_t>(total, 1) * w));
+        owned.push_back(cat);
+        const int64_t mine = counts[D.rank];
+        if (mine > 0) rq_gather_str<<<(unsigned)((mine + 255) / 256), 256, 0, E.stream>>>((const int64_t*)local.cols[c].d, sb, w, mine);
+        nccl_ck(D.all_gather(sb, rb, (size_t)maxn * w, 0 /* ncclInt8 */, D.comm, E.stream), "ncclAllGather(strings)");
+        int64_t off = 0;
+        for (int r = 0; r < W; r++) {
+            if (counts[r] > 0)
+                CK(cudaMemcpyAsync(cat + (size_t)off * w, rb + (size_t)r * maxn * w, (size_t)counts[r] * w, cudaMemcpyDeviceToDevice, E.stream));
+            off += counts[r];
+        }
+        if (total > 0) rq_str_addrs<<<(unsigned)((total + 255) / 256), 256, 0, E.stream>>>(cat, w, total, (int64_t*)all->cols[c].d);
+        if (tm) tm->kernel_launches += 2;
+        dfree(sb);
+        dfree(rb);
+    }
+    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(all->d_n_rows, &total, 8, cudaMemcpyHostToDevice, E.stream));
     CK(cudaEventRecord(e1, E.stream));
     CK(cudaStreamSynchronize(E.stream));
@@ -1236,7 +1319,7 @@ static void merge_sharded(const rq_plan& plan, int pi, std::vector<PipeOut>& out
                           double& lower_ms) {
     if (!outs[pi].table) raise(RQ_ERR_INVALID, "sharded merge: pipeline %d has no relation output", pi);
     const rq_pipeline& pl = plan.pipelines[pi];
-    std::unique_ptr<rq_table> all = gather_relation(*outs[pi].table, tm);
+    std::unique_ptr<rq_table> all = gather_relation(*outs[pi].table, tm, outs[pi].owned);
     if (pl.sink_kind != RQ_SINK_AGG) {       // no aggregation: the concatenation is the result
         outs[pi].table = std::move(all);
         return;
@@ -1360,8 +1443,44 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
             uint32_t* perm = nullptr;
             CK(dmalloc(&perm, sizeof(uint32_t) * std::max<int64_t>(n, kBitonicMax)));
             scratch.push_back(perm);
-            if (n <= kBitonicMax) {
-                rq_sort_small<<<1, 1024, 0, E.stream>>>(K, fin->d_n_rows, perm);
+            bool sorted_by_topk = false;
+            if (n > kBitonicMax && plan->limit >= 0 && plan->limit <= kBitonicMax / 2 && n <= 0xffffffffLL && !getenv("RQ_NO_TOPK")) {
+                // ORDER BY ... LIMIT k: radix select of the k-th smallest first-key value (6 passes of
+                // 11 bits, all on the device), keep the rows up to it (ties included), sort those.
+                uint64_t* k1 = nullptr; uint32_t* hist = nullptr; unsigned long long* st = nullptr; uint32_t* cand = nullptr;
+                CK(dmalloc(&k1, sizeof(uint64_t) * n)); scratch.push_back(k1);
+                CK(dmalloc(&hist, sizeof(uint32_t) * kSelBins)); scratch.push_back(hist);
+                CK(dmalloc(&st, 32)); scratch.push_back(st);
+                CK(dmalloc(&cand, sizeof(uint32_t) * kBitonicMax)); scratch.push_back(cand);
+                const unsigned eb = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
+                rq_sort_iota<<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(perm, n);
+                rq_sort_make_keys<<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(K.col[0], perm, k1, n, K.is_str[0], 0, K.desc[0]);
+                const unsigned long long init[4] = {0ULL, (unsigned long long)std::max<int64_t>(plan->limit, 1), 0ULL, 0ULL};
+                CK(cudaMemcpyAsync(st, init, 32, cudaMemcpyHostToDevice, E.stream));
+                CK(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * kSelBins, E.stream));
+                int shift = 64;
+                while (shift > 0) {
+                    const int bits = std::min(kSelBits, shift);
+                    shift -= bits;
+                    rq_topk_hist<<<eb, 256, 0, E.stream>>>(k1, n, st, shift, bits, hist);
+                    rq_topk_pick<<<1, 1024, 0, E.stream>>>(hist, st, bits);
+                    if (tm) tm->kernel_launches += 2;
+                }
+                rq_topk_compact<<<eb, 256, 0, E.stream>>>(k1, n, st, cand, kBitonicMax, st + 2);
+                if (tm) tm->kernel_launches += 3;
+                unsigned long long n_cand = 0;
+                CK(cudaMemcpyAsync(&n_cand, st + 2, 8, cudaMemcpyDeviceToHost, E.stream));
+                CK(cudaStreamSynchronize(E.stream));
+                if (n_cand <= (unsigned long long)kBitonicMax) {
+                    rq_sort_small<<<1, 1024, 0, E.stream>>>(K, (const int64_t*)(st + 2), perm, cand);
+                    if (tm) tm->kernel_launches++;
+                    sorted_by_topk = true;
+                }
+            }
+            if (sorted_by_topk) {
+                // perm holds the first rows of the order; LIMIT cuts it below
+            } else if (n <= kBitonicMax) {
+                rq_sort_small<<<1, 1024, 0, E.stream>>>(K, fin->d_n_rows, perm, nullptr);
                 if (tm) tm->kernel_launches++;
             } else {
                 // LSD radix sort, least significant ORDER BY key first; every pass is stable

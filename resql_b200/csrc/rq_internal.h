@@ -121,6 +121,8 @@ struct DProbe {
     DHashTable ht;
     VRef       key[kMaxKeys];
     uint8_t    out_slot[kMaxOut];   // payload column k -> slot (0xff = not needed)
+    uint8_t    pay_word[kMaxOut];   // payload column k -> word of the entry that holds it (a key word when the
+                                    // payload repeats a join key)
     int32_t    n_out;
     int32_t    single;
     int32_t    bloom_only;          // semi-join reduction only: no table walk, no payload

@@ -653,10 +653,10 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                             if (found < 0) { valid &= ~(1u << r); continue; }
                             if (matches > 1) atomicAdd(pr.dup_counter, (unsigned long long)(matches - 1));
                             const int row = row_in_tile(r, lane);
-                            const uint64_t* pay = ht_entry(pr.ht, (uint64_t)found) + 2;
+                            const uint64_t* ent = ht_entry(pr.ht, (uint64_t)found);
                             for (int q = 0; q < pr.n_out; q++)
                                 if (pr.out_slot[q] != 0xff)
-                                    sts_b64(wbase + P.slots_rel + pr.out_slot[q] * (kTile * 8) + row * 8, (int64_t)pay[q]);
+                                    sts_b64(wbase + P.slots_rel + pr.out_slot[q] * (kTile * 8) + row * 8, (int64_t)ent[pr.pay_word[q]]);
                         }
                     } else {
                         unsigned todo = valid;
@@ -685,10 +685,10 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                             if (found < 0) { valid &= ~(1u << r); continue; }
                             if (matches > 1) atomicAdd(pr.dup_counter, (unsigned long long)(matches - 1));
                             const int row = row_in_tile(r, lane);
-                            const uint64_t* pay = ht_entry(pr.ht, (uint64_t)found) + 1 + pnk;
+                            const uint64_t* ent = ht_entry(pr.ht, (uint64_t)found);
                             for (int q = 0; q < pr.n_out; q++)
                                 if (pr.out_slot[q] != 0xff)
-                                    sts_b64(wbase + P.slots_rel + pr.out_slot[q] * (kTile * 8) + row * 8, (int64_t)pay[q]);
+                                    sts_b64(wbase + P.slots_rel + pr.out_slot[q] * (kTile * 8) + row * 8, (int64_t)ent[pr.pay_word[q]]);
                         }
                     }
                     __syncwarp();
@@ -1111,6 +1111,12 @@ __global__ void rq_gather_str(const int64_t* addrs, unsigned char* out, int widt
         for (; k < width - 1 && s[k] != 0; k++) d[k] = s[k];
         for (; k < width; k++) d[k] = 0;
     }
+}
+
+// addresses of the rows of a by-value string column (sharded merge: strings arrive by value)
+__global__ void rq_str_addrs(const unsigned char* bytes, int width, int64_t n, int64_t* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int64_t)(bytes + (size_t)i * width);
 }
 
 // row store (reference DataBlocks, dbdata.h:23-102) -> columns

@@ -40,12 +40,13 @@ __device__ __forceinline__ bool row_less(const SortKeys& K, uint32_t i, uint32_t
 
 // single-CTA bitonic sort of row indices (n <= kBitonicMax), perm[] receives the order
 __global__ void __launch_bounds__(1024)
-rq_sort_small(const __grid_constant__ SortKeys K, const int64_t* n_ptr, uint32_t* perm) {
+rq_sort_small(const __grid_constant__ SortKeys K, const int64_t* n_ptr, uint32_t* perm, const uint32_t* cand) {
     __shared__ uint32_t idx[kBitonicMax];
     const int n = (int)*n_ptr;
     int m = 1;
     while (m < n) m <<= 1;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) idx[i] = (i < n) ? (uint32_t)i : 0xffffffffu;
+    // rows to sort: all of 0..n-1, or the n candidate rows a top-k pre-selection left over
+    for (int i = threadIdx.x; i < m; i += blockDim.x) idx[i] = (i < n) ? (cand ? cand[i] : (uint32_t)i) : 0xffffffffu;
     __syncthreads();
     for (int k = 2; k <= m; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -73,6 +74,47 @@ __global__ void rq_apply_perm(const int64_t* in, int64_t* out, const uint32_t* p
     if (limit >= 0 && limit < n) n = limit;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[perm[i]];
+}
+
+// ---- ORDER BY ... LIMIT k over many rows: radix select on the first key, then a small sort ------
+// state[0] = key prefix decided so far, state[1] = rank still to find inside that prefix.
+constexpr int kSelBits = 11;
+constexpr int kSelBins = 1 << kSelBits;
+__global__ void rq_topk_hist(const uint64_t* keys, int64_t n, const unsigned long long* state, int shift, int bits,
+                             uint32_t* hist) {
+    const uint64_t prefix = state[0];
+    const int hs = shift + bits;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        const bool in = hs >= 64 ? true : (k >> hs) == prefix;
+        if (in) atomicAdd(&hist[(k >> shift) & ((1u << bits) - 1)], 1u);
+    }
+}
+__global__ void __launch_bounds__(1024) rq_topk_pick(uint32_t* hist, unsigned long long* state, int bits) {
+    __shared__ uint32_t s[kSelBins];
+    const int nb = 1 << bits;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s[i] = hist[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long want = state[1], cum = 0;
+        int b = 0;
+        for (; b < nb - 1; b++) { if (cum + s[b] >= want) break; cum += s[b]; }
+        state[0] = (state[0] << bits) | (unsigned long long)b;
+        state[1] = want - cum;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
+}
+// rows whose first-key value is not larger than the k-th smallest one (ties included)
+__global__ void rq_topk_compact(const uint64_t* keys, int64_t n, const unsigned long long* state, uint32_t* cand,
+                                int64_t cap, unsigned long long* count) {
+    const uint64_t thr = state[0];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (keys[i] <= thr) {
+            const unsigned long long pos = atomicAdd(count, 1ULL);
+            if ((int64_t)pos < cap) cand[pos] = (uint32_t)i;
+        }
+    }
 }
 
 // ---- LSD radix sort (n > kBitonicMax): 4-bit digits over order-preserving 64-bit keys -------

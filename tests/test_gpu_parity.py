@@ -157,3 +157,18 @@ def test_two_pass_probe_matches_reference_engine(name, sf001, engine, monkeypatc
     assert_same_relation(got, want, d, name + " (two-pass)")
     n_scans = sum(1 for p in d["pipelines"] if p["source_kind"] == 1)
     assert tm.kernel_launches > n_scans
+
+
+@pytest.mark.parametrize("limit", [1, 10, 100, 2048])
+@pytest.mark.parametrize("name", ["sort_large", "sort_strings_large", "agg_many_groups"])
+def test_order_by_limit_selects_top_k(name, limit, sf001, engine):
+    """ORDER BY ... LIMIT k over more than 4096 rows takes the radix-select path (k-th smallest first
+    key on the device, then a small sort of the candidates); the ORDER BY keys of these fixtures
+    form a total order, so the first k rows are unique and must equal the oracle's"""
+    d = dict(load_plan_dict(name))
+    d["limit"] = limit
+    tabs = plan_tables(d, sf001)
+    got, _ = _run(engine, d, tabs)
+    want = serialize_columns(*run_plan(d, tabs))
+    assert len(got) == limit
+    assert got == want
