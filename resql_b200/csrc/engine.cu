@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <set>
 #include <memory>
 #include <algorithm>
 #include <chrono>

@@ -337,11 +337,20 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
                 raise(RQ_ERR_INVALID, "PROBE refers to pipeline %d which built no hash table", nd.a);
             DProbe& pr = P.probe[P.n_probes];
             pr.ht = L.outs[nd.a].ht->d;
-            if (nd.c != pr.ht.nk) raise(RQ_ERR_INVALID, "PROBE has %d keys, the build side %d", nd.c, pr.ht.nk);
+            // internal modes (set by split_at_probe, never by the ABI caller): bit1 = Bloom-only
+            // semi-join pass, bit2 = expansion pass (Bloom test here, one output row per match in
+            // the materialize sink), bit3 = fetch the payload of the entry a previous pass found
+            pr.fetch = (int32_t)((nd.imm >> 3) & 1);
+            if (!pr.fetch && nd.c != pr.ht.nk) raise(RQ_ERR_INVALID, "PROBE has %d keys, the build side %d", nd.c, pr.ht.nk);
+            if (pr.fetch && nd.c != 1) raise(RQ_ERR_INVALID, "internal: fetch probe needs exactly the entry index");
             for (int k = 0; k < nd.c; k++) L.hprobe_key[P.n_probes][k] = L.href_of(pl.args[nd.b + k]);
             pr.single = (int32_t)(nd.imm & 1);
-            pr.bloom_only = (int32_t)((nd.imm >> 1) & 1);     // internal: first pass of a split pipeline
+            pr.bloom_only = (int32_t)(((nd.imm >> 1) | (nd.imm >> 2)) & 1);
             if (pr.bloom_only && pr.ht.bloom == nullptr) raise(RQ_ERR_INVALID, "internal: semi-join pass without a Bloom filter");
+            if ((nd.imm >> 2) & 1) {
+                if (impl != IMPL_EMIT || i != n - 1) raise(RQ_ERR_INVALID, "internal: expansion probe must end a materialize pipeline");
+                P.expand_probe = P.n_probes;
+            }
             const std::vector<uint8_t>& pw = L.outs[nd.a].pay_word;
             pr.n_out = (int32_t)pw.size();
             if (pr.n_out > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d payload columns", kMaxOut);
@@ -525,7 +534,7 @@ static void encode_program(Lowerer& L, KParams& P) {
     for (int k = 0; k < P.n_out; k++) P.out[k] = to_vref(P, L.hout[k]);
     for (int u = 0; u < kMaxAggs; u++) P.agg_src[u] = to_vref(P, L.hagg_src[u]);
     for (int p = 0; p < P.n_probes; p++)
-        for (int k = 0; k < P.probe[p].ht.nk; k++) P.probe[p].key[k] = to_vref(P, L.hprobe_key[p][k]);
+        for (int k = 0; k < (P.probe[p].fetch ? 1 : P.probe[p].ht.nk); k++) P.probe[p].key[k] = to_vref(P, L.hprobe_key[p][k]);
 }
 
 // packed group key of the low-cardinality paths: every key is a bit field of one 64-bit word
@@ -647,13 +656,15 @@ static bool has_str_key(const rq_pipeline& pl) {
     return false;
 }
 
+// thrown when a multi-match probe met a tuple with several matches: the pipeline is rerun in its
+// expanded two-pass form (split_at_probe, mode SPLIT_EXPAND)
+struct NeedExpand {};
+
 static void check_flags(const char* what) {
     CK(cudaMemcpyAsync(E.h_flags, E.flags, 32, cudaMemcpyDeviceToHost, E.stream));
     CK(cudaStreamSynchronize(E.stream));
     if (E.h_flags[2]) raise(RQ_ERR_RUNTIME, "division by zero in %s (the reference raises SIGFPE here)", what);
-    if (*(unsigned long long*)(E.h_flags + 4) != 0)
-        raise(RQ_ERR_UNSUPPORTED, "%s: a probe tuple matches several build tuples; multi-match expansion "
-              "(hashjoin.h:118-165) is not available in this build", what);
+    if (*(unsigned long long*)(E.h_flags + 4) != 0) throw NeedExpand{};
 }
 
 // ---- one pipeline -------------------------------------------------------------------------
@@ -664,8 +675,9 @@ struct SplitPipes {
     std::vector<int> live_src_col;     // per materialized value: source column it copies, or -1
     rq_pipeline a, b;
 };
+enum SplitMode { SPLIT_SEMI = 0, SPLIT_EXPAND = 1 };
 static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_table& src,
-                           const std::vector<PipeOut>& outs, SplitPipes& sp);
+                           const std::vector<PipeOut>& outs, SplitPipes& sp, SplitMode mode);
 static std::map<uint64_t, int64_t> g_emit_rows;    // rows a materialize pipeline produced last time
 
 static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
@@ -831,10 +843,40 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
     }
 }
 
+static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
+                              const char* d_strpool, rq_timings* tm, size_t& ev_idx,
+                              std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
+                              bool is_fact_scan, const rq_table* src_override, PipeOut& result, bool allow_split,
+                              bool expand);
+
+// pipelines that met duplicate matches once are run in expanded form straight away afterwards
+static std::set<uint64_t> g_needs_expand;
+
 static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
                              const char* d_strpool, rq_timings* tm, size_t& ev_idx,
                              std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
                              bool is_fact_scan, const rq_table* src_override, PipeOut& result, bool allow_split) {
+    const uint64_t sig = pipeline_signature(pl_in, src_override ? -2 : -1) ^ 0x9e3779b97f4a7c15ULL;
+    if (!g_needs_expand.count(sig)) {
+        try {
+            run_pipeline_impl(plan, pl_in, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, is_fact_scan,
+                              src_override, result, allow_split, false);
+            return;
+        } catch (NeedExpand&) {
+            cudaStreamSynchronize(E.stream);
+            result = PipeOut();
+            g_needs_expand.insert(sig);
+        }
+    }
+    run_pipeline_impl(plan, pl_in, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, is_fact_scan,
+                      src_override, result, allow_split, true);
+}
+
+static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
+                              const char* d_strpool, rq_timings* tm, size_t& ev_idx,
+                              std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
+                              bool is_fact_scan, const rq_table* src_override, PipeOut& result, bool allow_split,
+                              bool expand) {
     SimplePipe sp;
     simplify_pipeline(pl_in, sp);
     const rq_pipeline& pl = sp.pl;
@@ -856,9 +898,18 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
 
     // A selective hash-join probe inside a big scan is run as two passes: scan -> filter -> Bloom
     // test -> materialize the few survivors, then probe/aggregate/build over dense tiles of them.
+    if (expand) {
+        SplitPipes sx;
+        if (!split_at_probe(plan, pl, *src, outs, sx, SPLIT_EXPAND))
+            raise(RQ_ERR_INVALID, "pipeline %d: duplicate matches reported but no multi-match probe found", pi);
+        PipeOut mid;
+        run_pipeline_one(plan, sx.a, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, is_fact_scan, src_override, mid, false);
+        run_pipeline_one(plan, sx.b, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, false, mid.table.get(), result, false);
+        return;
+    }
     if (allow_split && !src_override && pl.source_kind == RQ_SRC_TABLE) {
         SplitPipes sx;
-        if (split_at_probe(plan, pl, *src, outs, sx)) {
+        if (split_at_probe(plan, pl, *src, outs, sx, SPLIT_SEMI)) {
             PipeOut mid;
             run_pipeline_one(plan, sx.a, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, is_fact_scan, nullptr, mid, false);
             for (size_t c = 0; c < sx.live_src_col.size(); c++) {      // value bounds survive the copy
@@ -897,6 +948,7 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
         const int impl = impls[attempt];
         KParams P;
         memset(&P, 0, sizeof(P));
+        P.expand_probe = -1;
         P.n_rows = src->n_rows;
         P.n_rows_ptr = src->n_rows < 0 ? src->d_n_rows : nullptr;
         P.borrowed = src->borrowed ? 1 : 0;
@@ -959,8 +1011,8 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
                 E.g_state, E.g_keys, E.g_acc, ku, nuniq, d_ptrs, dense->d_n_rows);
             if (tm) tm->kernel_launches++;
             CK(cudaGetLastError());
-            check_flags("aggregation pipeline");
             dfree(d_ptrs);
+            check_flags("aggregation pipeline");
             if (E.h_flags[0]) continue;   // more groups than this path tracks: next implementation
             // expand duplicates by aliasing: copy the columns (tiny)
             for (int k = 0; k < pl.n_keys; k++)
@@ -993,8 +1045,6 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
             if (nk > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
             const int nv = impl == IMPL_BUILD ? pl.n_vals : (int)ad.kind.size();
             std::unique_ptr<HashTableDev> ht;
-            unsigned long long* d_count = nullptr;
-            CK(dmalloc(&d_count, 8));
             unsigned long long n_used = 0;
             for (;;) {
                 ht.reset(new HashTableDev());
@@ -1033,12 +1083,11 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
                 n_used = *(unsigned long long*)(E.h_flags + 6);     // counted by the kernel itself
                 if (!regrow) regrow = n_used * max_load_den > cap && cap < cap_max;
                 if (!regrow) break;
-                if (cap >= cap_max) { dfree(d_count); raise(RQ_ERR_RUNTIME, "pipeline %d: hash table overflow at capacity %llu", pi, (unsigned long long)cap); }
+                if (cap >= cap_max) { raise(RQ_ERR_RUNTIME, "pipeline %d: hash table overflow at capacity %llu", pi, (unsigned long long)cap); }
                 uint64_t next = cap * 8;
                 if (!E.h_flags[1]) { next = cap; while (next < max_load_den * n_used) next <<= 1; }
                 cap = std::min<uint64_t>(next, cap_max);
             }
-            dfree(d_count);
             g_ht_capacity[sig] = cap;
             if (impl == IMPL_BUILD) {
                 ht->entries = n_used;
@@ -1080,10 +1129,12 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
                     cap = std::min<int64_t>(std::max<int64_t>(src_rows, 1), known->second + known->second / 8 + 1024);
             }
             for (int round = 0; round < 2; round++) {
-                out = new_intermediate(pl.n_vals, cap);
+                const int n_emit = pl.n_vals + (P.expand_probe >= 0 ? 1 : 0);     // + entry index of the match
+                if (n_emit > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d output columns", kMaxOut);
+                out = new_intermediate(n_emit, cap);
                 P.out_cap = out->cap_rows;
                 P.out_count = (unsigned long long*)out->d_n_rows;
-                for (int k = 0; k < pl.n_vals; k++) P.out_col[k] = (int64_t*)out->cols[k].d;
+                for (int k = 0; k < n_emit; k++) P.out_col[k] = (int64_t*)out->cols[k].d;
                 trace_point("materialize output allocated", pi);
                 launch_pipeline(P, 0, src_rows, tm, is_scan, ev_idx, ev_used);
                 check_flags("materialize pipeline");
@@ -1096,6 +1147,7 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
                 cap = produced;
             }
             set_types(*out, pl);
+            if (P.expand_probe >= 0) { out->sql_type.push_back(RQ_SQL_BIGINT); out->sql_width.push_back(0); }
             result.table = std::move(out);
             return;
         }
@@ -1113,29 +1165,41 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
 // joined; results are identical. Pass A is a pure streaming kernel (no dependent table walks), pass
 // B runs the walks / atomics over dense tiles where every lane has work.
 static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_table& src,
-                           const std::vector<PipeOut>& outs, SplitPipes& sp) {
+                           const std::vector<PipeOut>& outs, SplitPipes& sp, SplitMode mode) {
     (void)plan;
-    int64_t min_rows = 4 << 20;
-    double max_frac = 0.3;
-    if (const char* e = getenv("RQ_SPLIT_MIN_ROWS")) min_rows = atoll(e);
-    if (const char* e = getenv("RQ_SPLIT_FRAC")) max_frac = atof(e);
-    if (src.n_rows < min_rows) return false;
     const int n = pl.n_nodes;
     int p0 = -1;
-    for (int i = 0; i < n && p0 < 0; i++) if (pl.nodes[i].op == RQ_OP_PROBE) p0 = i;
-    if (p0 < 0) return false;
-    const rq_node& pr = pl.nodes[p0];
-    if (pr.a < 0 || pr.a >= (int)outs.size() || !outs[pr.a].ht || !outs[pr.a].ht->d.bloom) return false;
-    // selectivity estimate: build entries / size of the probe key's value domain
-    double frac = 1.0;
-    if (pr.c == 1) {
-        const rq_node& kn = pl.nodes[pl.args[pr.b]];
-        if (kn.op == RQ_OP_COL && kn.a >= 0 && kn.a < (int)src.cols.size() && src.cols[kn.a].has_stats) {
-            const double dom = (double)src.cols[kn.a].vmax - (double)src.cols[kn.a].vmin + 1.0;
-            if (dom > 0) frac = (double)outs[pr.a].ht->entries / dom;
+    if (mode == SPLIT_EXPAND) {
+        // multi-match expansion (hashjoin.h:118-165): cut at the first probe that may match more than
+        // one build tuple. Pass A emits one row per match together with the entry index, pass B
+        // fetches the payload through that index.
+        for (int i = 0; i < n && p0 < 0; i++)
+            if (pl.nodes[i].op == RQ_OP_PROBE && (pl.nodes[i].imm & (1 | 8)) == 0) p0 = i;
+        if (p0 < 0) return false;
+        const rq_node& pr = pl.nodes[p0];
+        if (pr.a < 0 || pr.a >= (int)outs.size() || !outs[pr.a].ht) return false;
+    } else {
+        int64_t min_rows = 4 << 20;
+        double max_frac = 0.3;
+        if (const char* e = getenv("RQ_SPLIT_MIN_ROWS")) min_rows = atoll(e);
+        if (const char* e = getenv("RQ_SPLIT_FRAC")) max_frac = atof(e);
+        if (src.n_rows < min_rows) return false;
+        for (int i = 0; i < n && p0 < 0; i++) if (pl.nodes[i].op == RQ_OP_PROBE) p0 = i;
+        if (p0 < 0 || (pl.nodes[p0].imm & ~1LL) != 0) return false;
+        const rq_node& pr = pl.nodes[p0];
+        if (pr.a < 0 || pr.a >= (int)outs.size() || !outs[pr.a].ht || !outs[pr.a].ht->d.bloom) return false;
+        // selectivity estimate: build entries / size of the probe key's value domain
+        double frac = 1.0;
+        if (pr.c == 1) {
+            const rq_node& kn = pl.nodes[pl.args[pr.b]];
+            if (kn.op == RQ_OP_COL && kn.a >= 0 && kn.a < (int)src.cols.size() && src.cols[kn.a].has_stats) {
+                const double dom = (double)src.cols[kn.a].vmax - (double)src.cols[kn.a].vmin + 1.0;
+                if (dom > 0) frac = (double)outs[pr.a].ht->entries / dom;
+            }
         }
+        if (frac > max_frac) return false;
     }
-    if (frac > max_frac) return false;
+    const rq_node& pr = pl.nodes[p0];
 
     // values computed before the cut and read behind it
     std::vector<char> need(n, 0);
@@ -1145,7 +1209,8 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
         if (is_binary(nd.op)) { mark(nd.a); mark(nd.b); }
         else if (nd.op == RQ_OP_FILTER) mark(nd.a);
         else if (nd.op == RQ_OP_SELECT) { mark(nd.a); mark(nd.b); mark(nd.c); }
-        else if (nd.op == RQ_OP_PROBE) for (int k = 0; k < nd.c; k++) mark(pl.args[nd.b + k]);
+        else if (nd.op == RQ_OP_PROBE && !(i == p0 && mode == SPLIT_EXPAND))
+            for (int k = 0; k < nd.c; k++) mark(pl.args[nd.b + k]);
     }
     for (int k = 0; k < pl.n_keys; k++) mark(pl.keys[k].node);
     for (int k = 0; k < pl.n_vals; k++)
@@ -1156,7 +1221,7 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
     // pass A
     sp.a_nodes.assign(pl.nodes, pl.nodes + p0);
     rq_node semi = pr;
-    semi.imm |= 2;
+    semi.imm |= (mode == SPLIT_EXPAND ? 4 : 2);
     sp.a_nodes.push_back(semi);
     sp.a_args.assign(pl.args, pl.args + pl.n_args);
     std::vector<int> newidx(n, -1);
@@ -1169,7 +1234,11 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
         sp.a_vals.push_back(v);
         sp.live_src_col.push_back(op == RQ_OP_COL ? pl.nodes[i].a : -1);
     }
-    if (sp.a_vals.empty() || (int)sp.a_vals.size() > kMaxOut || (int)sp.a_vals.size() > kMaxStagedCols) return false;
+    if (mode == SPLIT_SEMI && sp.a_vals.empty()) return false;
+    if ((int)sp.a_vals.size() + 1 > kMaxOut || (int)sp.a_vals.size() + 1 > kMaxStagedCols) {
+        if (mode == SPLIT_EXPAND) raise(RQ_ERR_UNSUPPORTED, "multi-match join carries more than %d live values", kMaxStagedCols - 1);
+        return false;
+    }
     memset(&sp.a, 0, sizeof(sp.a));
     sp.a.source_kind = pl.source_kind; sp.a.source_id = pl.source_id;
     sp.a.n_nodes = (int)sp.a_nodes.size(); sp.a.nodes = sp.a_nodes.data();
@@ -1179,6 +1248,11 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
 
     // pass B
     for (size_t c = 0; c < sp.a_vals.size(); c++) sp.b_nodes.push_back(rq_node{RQ_OP_COL, (int)c, 0, 0, 0});
+    int slot_col_node = -1;
+    if (mode == SPLIT_EXPAND) {          // the entry index pass A appended as its last column
+        slot_col_node = (int)sp.b_nodes.size();
+        sp.b_nodes.push_back(rq_node{RQ_OP_COL, (int)sp.a_vals.size(), 0, 0, 0});
+    }
     for (int i = 0; i < p0; i++) {
         const int op = pl.nodes[i].op;
         if (need[i] && (op == RQ_OP_CONST || op == RQ_OP_CONST_STR)) {
@@ -1194,7 +1268,13 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
         else if (nd.op == RQ_OP_PAYLOAD) nd.a = newidx[nd.a];
         else if (nd.op == RQ_OP_PROBE) {
             const int b0 = (int)sp.b_args.size();
-            for (int k = 0; k < nd.c; k++) sp.b_args.push_back(newidx[pl.args[nd.b + k]]);
+            if (i == p0 && mode == SPLIT_EXPAND) {
+                sp.b_args.push_back(slot_col_node);
+                nd.c = 1;
+                nd.imm |= 8;
+            } else {
+                for (int k = 0; k < nd.c; k++) sp.b_args.push_back(newidx[pl.args[nd.b + k]]);
+            }
             nd.b = b0;
         }
         newidx[i] = (int)sp.b_nodes.size();
@@ -1621,6 +1701,7 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
         std::vector<PipeOut> outs(plan->n_pipelines);
         KParams P;
         memset(&P, 0, sizeof(P));
+        P.expand_probe = -1;
         Lowerer L(*plan, sp.pl, fake, outs, (const char*)0, P);
         L.prepare();
         AggDedup ad;

@@ -126,7 +126,7 @@ struct DProbe {
     int32_t    n_out;
     int32_t    single;
     int32_t    bloom_only;          // semi-join reduction only: no table walk, no payload
-    int32_t    pad_;
+    int32_t    fetch;               // key[0] is the entry index of a match found by an expansion pass
     unsigned long long* dup_counter;   // counts tuples with more than one match (multi-match mode)
 };
 
@@ -182,6 +182,8 @@ struct KParams {
     DProbe         probe[kMaxProbes];
     // materialize
     int32_t        sink;                 // SinkImpl executed after the units of every tile
+    int32_t        expand_probe;         // IMPL_EMIT: >= 0 = emit one row per match of this probe, with the
+                                         // entry index of the match as an extra last column
     int32_t        n_out;
     VRef           out[kMaxOut];
     int64_t*       out_col[kMaxOut];

@@ -586,6 +586,26 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     // resident 32-bit word each, 8 loads in flight); only the survivors walk the
                     // hash table.
                     const DProbe& pr = P.probe[in.aux];
+                    if (pr.fetch) {
+                        // second pass of a multi-match expansion: the entry was found (and the tuple
+                        // multiplied) by the first pass, only the payload is read here
+                        int64_t ei[kR];
+                        fetch_vref(P, c, pr.key[0], ei);
+#pragma unroll 1
+                        for (int r = 0; r < kR; r++) {
+                            if (!((valid >> r) & 1)) continue;
+                            int64_t e = 0;
+#pragma unroll
+                            for (int q = 0; q < kR; q++) if (q == r) e = ei[q];
+                            const uint64_t* ent = ht_entry(pr.ht, (uint64_t)e);
+                            const int row = row_in_tile(r, lane);
+                            for (int q = 0; q < pr.n_out; q++)
+                                if (pr.out_slot[q] != 0xff)
+                                    sts_b64(wbase + P.slots_rel + pr.out_slot[q] * (kTile * 8) + row * 8, (int64_t)ent[pr.pay_word[q]]);
+                        }
+                        __syncwarp();
+                        break;
+                    }
                     const uint64_t cap = pr.ht.cap_mask + 1;
                     const int pnk = pr.ht.nk;
                     const bool k1 = pnk == 1 && pr.ht.key_kind[0] == 0;   // one integer key: the usual join
@@ -949,6 +969,35 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         if (kind == 1) atomicAdd((unsigned long long*)&acc[a], (unsigned long long)v);
                         else if (kind == 3) atomicMin((long long*)&acc[a], (long long)v);
                         else atomicMax((long long*)&acc[a], (long long)v);
+                    }
+                }
+            } else if (sink == IMPL_EMIT && P.expand_probe >= 0) {
+                // multi-match hash join (hashjoin.h:118-165): one output row per key-equal entry.
+                // The probe unit in front only applied the Bloom filter; here every surviving tuple
+                // walks its chain and emits (its values, entry index) once per match.
+                const DProbe& pr = P.probe[P.expand_probe];
+                const uint64_t cap = pr.ht.cap_mask + 1;
+                const int pnk = pr.ht.nk;
+#pragma unroll 1
+                for (int r = 0; r < kR; r++) {
+                    if (!((valid >> r) & 1)) continue;
+                    int64_t k[kMaxKeys];
+                    for (int j = 0; j < pnk; j++) k[j] = ld_row(P, c, pr.key[j], r);
+                    const uint64_t hr = hash_keys(k, pr.ht.key_kind, pnk);
+                    const uint64_t tag = hr | 2ULL;
+                    uint64_t i = hr >> pr.ht.shift;
+                    for (uint64_t tries = 0; tries < cap; tries++) {
+                        const uint64_t t = *ht_entry(pr.ht, i);
+                        if (t == 0ULL) break;
+                        if (t == tag && slot_keys_equal(pr.ht, i, k)) {
+                            const unsigned long long pos = atomicAdd(P.out_count, 1ULL);
+                            if ((int64_t)pos < P.out_cap) {
+                                for (int q = 0; q < P.n_out; q++) P.out_col[q][pos] = ld_row(P, c, P.out[q], r);
+                                P.out_col[P.n_out][pos] = (int64_t)i;
+                            }
+                            if (pr.single) break;
+                        }
+                        i = (i + 1) & pr.ht.cap_mask;
                     }
                 }
             } else if (sink == IMPL_EMIT) {

@@ -50,6 +50,15 @@ QUERIES = {
         where c_custkey = o_custkey and o_orderdate >= date '1998-01-01' group by c_mktsegment order by c_mktsegment""",
     "join_rows": """select o_orderkey, o_orderdate, c_name, c_nationkey from customer, orders
         where c_custkey = o_custkey and o_orderkey < 200 order by o_orderkey""",
+    # multi-match hash join (hashjoin.h:118-165; test_operators.h "hash join, duplicates on both sides"):
+    # the build side (customer, the smaller table) has many tuples per join key
+    "join_dups_rows": """select c_custkey, o_orderkey, o_totalprice from customer, orders
+        where c_nationkey = o_custkey order by o_orderkey, c_custkey""",
+    "join_dups_agg": """select c_mktsegment, count(*) as c, sum(o_totalprice) as s from customer, orders
+        where c_nationkey = o_custkey group by c_mktsegment order by c_mktsegment""",
+    "join_dups_both": """select o_orderpriority, count(*) as c, max(c_acctbal) as m from customer, orders
+        where c_nationkey = o_shippriority and c_acctbal > 9000.00 and o_orderkey < 3000
+        group by o_orderpriority order by o_orderpriority""",
     "case_sum": """select l_shipmode, sum(case when l_quantity > 25 then 1 else 0 end) as hi,
         sum(case when l_quantity <= 25 then l_extendedprice else 0 end) as lo
         from lineitem group by l_shipmode order by l_shipmode""",

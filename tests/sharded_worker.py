@@ -13,7 +13,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 CASES = [("q1", "lineitem"), ("q6", "lineitem"), ("q3", "lineitem"), ("agg_nogroup_minmax", "lineitem"),
          ("agg_many_groups", "lineitem"), ("agg_empty", "lineitem"), ("agg_linenumber", "lineitem"),
          ("agg_wrap", "lineitem"), ("case_sum", "lineitem"), ("sel_or", "lineitem"),
-         ("join_orders_lineitem", "lineitem"), ("sort_large", "lineitem")]
+         ("join_orders_lineitem", "lineitem"), ("sort_large", "lineitem"), ("join_dups_agg", "orders"),
+         ("join_dups_rows", "orders")]
 
 
 def main():
