@@ -1400,6 +1400,7 @@ static void merge_sharded(const rq_plan& plan, int pi, std::vector<PipeOut>& out
     if (!outs[pi].table) raise(RQ_ERR_INVALID, "sharded merge: pipeline %d has no relation output", pi);
     const rq_pipeline& pl = plan.pipelines[pi];
     std::unique_ptr<rq_table> all = gather_relation(*outs[pi].table, tm, outs[pi].owned);
+    trace_point("partials gathered", pi);
     if (pl.sink_kind != RQ_SINK_AGG) {       // no aggregation: the concatenation is the result
         outs[pi].table = std::move(all);
         return;
@@ -1478,7 +1479,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         size_t ev_idx = 0;
         std::vector<std::pair<size_t, bool>> ev_used;
         double lower_ms = 0;
-        g_trace = getenv("RQ_TRACE") != nullptr;
+        g_trace = getenv("RQ_TRACE") != nullptr && E.dist.rank == 0;
         g_trace_t0 = std::chrono::steady_clock::now();
         CK(cudaEventRecord(E.ev[0], E.stream));
         // sharded plans: merge after the last aggregation (or concatenate the final relation)
@@ -1492,7 +1493,10 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
             trace_point("pipeline start", pi);
             run_pipeline(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
             trace_point("pipeline done", pi);
-            if (pi == merge_after) merge_sharded(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+            if (pi == merge_after) {
+                merge_sharded(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+                trace_point("sharded merge done", pi);
+            }
         }
 
         rq_table* fin = outs[plan->n_pipelines - 1].table.get();
@@ -1648,7 +1652,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         if (tm) {
             float ms = 0;
             tm->lower_ms = lower_ms;
-            const bool trace = getenv("RQ_TRACE") != nullptr;
+            const bool trace = g_trace;
             for (auto& u : ev_used) {
                 CK(cudaEventElapsedTime(&ms, g_event_pool[u.first].a, g_event_pool[u.first].b));
                 tm->kernel_ms += ms;

@@ -80,15 +80,35 @@ __global__ void rq_apply_perm(const int64_t* in, int64_t* out, const uint32_t* p
 // state[0] = key prefix decided so far, state[1] = rank still to find inside that prefix.
 constexpr int kSelBits = 11;
 constexpr int kSelBins = 1 << kSelBits;
-__global__ void rq_topk_hist(const uint64_t* keys, int64_t n, const unsigned long long* state, int shift, int bits,
-                             uint32_t* hist) {
+__global__ void __launch_bounds__(256)
+rq_topk_hist(const uint64_t* keys, int64_t n, const unsigned long long* state, int shift, int bits,
+             uint32_t* hist) {
+    // block-private histogram in shared memory; lanes of a warp that hit the same bin (the usual case
+    // in the first passes, where the high bits of all keys agree) are combined before the atomic
+    __shared__ uint32_t sh[kSelBins];
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
     const uint64_t prefix = state[0];
     const int hs = shift + bits;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint64_t k = keys[i];
-        const bool in = hs >= 64 ? true : (k >> hs) == prefix;
-        if (in) atomicAdd(&hist[(k >> shift) & ((1u << bits) - 1)], 1u);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_pad = (n + stride - 1) / stride * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        bool in = false;
+        uint32_t bin = 0;
+        if (i < n) {
+            const uint64_t k = keys[i];
+            in = hs >= 64 ? true : (k >> hs) == prefix;
+            bin = (uint32_t)(k >> shift) & ((1u << bits) - 1);
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, in);
+        if (in) {
+            const unsigned peers = __match_any_sync(act, bin);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bin], (uint32_t)__popc(peers));
+        }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 __global__ void __launch_bounds__(1024) rq_topk_pick(uint32_t* hist, unsigned long long* state, int bits) {
     __shared__ uint32_t s[kSelBins];
