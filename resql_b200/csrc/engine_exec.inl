@@ -1029,7 +1029,9 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
         if (impl == IMPL_BUILD || impl == IMPL_HASHAGG) {
             const int64_t rows_bound = std::max<int64_t>(1, src->n_rows >= 0 ? src->n_rows : src->cap_rows);
             int64_t want = rows_bound;
-            if (pl.size_hint > 0) want = std::min<int64_t>(rows_bound, std::max<int64_t>(pl.size_hint, 2048));
+            // the planner's cardinality guess (RelOperator::getSize) sizes the first attempt of a table
+            // scan; the dense second pass of a split pipeline inserts (nearly) every row it reads
+            if (pl.size_hint > 0 && !src_override) want = std::min<int64_t>(rows_bound, std::max<int64_t>(pl.size_hint, 2048));
             uint64_t cap = 4096;
             while (cap < (uint64_t)(2 * want)) cap <<= 1;
             uint64_t max_load_den = impl == IMPL_BUILD ? 3 : 2;   // joins: load factor <= 1/3
@@ -1040,7 +1042,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             // repeated query does not pay for regrowth again
             const uint64_t sig = pipeline_signature(pl_in, rows_bound);
             auto known = g_ht_capacity.find(sig);
-            if (known != g_ht_capacity.end()) cap = std::min<uint64_t>(std::max(cap, known->second), cap_max);
+            if (known != g_ht_capacity.end()) cap = std::min<uint64_t>(known->second, cap_max);
             const int nk = pl.n_keys;
             if (nk > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
             const int nv = impl == IMPL_BUILD ? pl.n_vals : (int)ad.kind.size();
@@ -1088,7 +1090,11 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 if (!E.h_flags[1]) { next = cap; while (next < max_load_den * n_used) next <<= 1; }
                 cap = std::min<uint64_t>(next, cap_max);
             }
-            g_ht_capacity[sig] = cap;
+            {   // remember the capacity this pipeline needs, not the one the search happened to end at
+                uint64_t ideal = 4096;
+                while (ideal < max_load_den * n_used) ideal <<= 1;
+                g_ht_capacity[sig] = std::min<uint64_t>(ideal, cap_max);
+            }
             if (impl == IMPL_BUILD) {
                 ht->entries = n_used;
                 result.ht = std::move(ht);
@@ -1142,7 +1148,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 int64_t produced = 0;
                 CK(cudaMemcpy(&produced, out->d_n_rows, 8, cudaMemcpyDeviceToHost));
                 g_emit_rows[esig] = produced;
-                if (produced <= out->cap_rows) break;
+                if (produced <= out->cap_rows) { out->n_rows = produced; break; }
                 if (round == 1) raise(RQ_ERR_RUNTIME, "materialize overflow");
                 cap = produced;
             }

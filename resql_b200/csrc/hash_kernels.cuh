@@ -20,7 +20,7 @@ struct HashTableDev {
 };
 
 constexpr uint64_t kTagLocked = 1ULL;
-constexpr uint64_t kMaxProbeLen = 2048;   // longer runs mean the table is (nearly) full: report and regrow
+constexpr uint64_t kMaxProbeLen = 256;    // longer runs mean the table is (nearly) full: report and regrow
 
 // key kinds: 0 integer word, 1 CHAR (equality ignores trailing blanks), 2 VARCHAR (exact)
 __device__ __forceinline__ uint64_t hash_str(const unsigned char* s, bool strip) {

@@ -356,7 +356,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     const bool hash_sink = (GR == 0) && (sink == IMPL_BUILD || sink == IMPL_HASHAGG);
     for (int64_t tile = first; tile < n_tiles; tile += stride) {
         // a full hash table makes the host regrow it and rerun: stop early
-        if (hash_sink && ((tile - first) / stride & 15) == 0 && *(volatile int32_t*)P.ht_full) break;
+        if (hash_sink && *(volatile int32_t*)P.ht_full) break;
         WarpCtx c;
         c.stage = wbase + s * P.stage_bytes;
         c.wbase = wbase;
