@@ -85,6 +85,10 @@ __device__ __forceinline__ void tma_bulk_g2s_hint(uint32_t dst, const void* src,
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
         : "memory");
 }
+// bring a global range into L2 ahead of the bulk copy that will stage it (no shared memory needed)
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"

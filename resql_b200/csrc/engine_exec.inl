@@ -660,8 +660,9 @@ static bool has_str_key(const rq_pipeline& pl) {
 // expanded two-pass form (split_at_probe, mode SPLIT_EXPAND)
 struct NeedExpand {};
 
-static void check_flags(const char* what) {
+static void check_flags(const char* what, const void* d_extra = nullptr) {
     CK(cudaMemcpyAsync(E.h_flags, E.flags, 32, cudaMemcpyDeviceToHost, E.stream));
+    if (d_extra) CK(cudaMemcpyAsync(E.h_flags + 8, d_extra, 8, cudaMemcpyDeviceToHost, E.stream));   // same round trip
     CK(cudaStreamSynchronize(E.stream));
     if (E.h_flags[2]) raise(RQ_ERR_RUNTIME, "division by zero in %s (the reference raises SIGFPE here)", what);
     if (*(unsigned long long*)(E.h_flags + 4) != 0) throw NeedExpand{};
@@ -989,6 +990,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 raise(RQ_ERR_UNSUPPORTED, "pipeline %d does not fit in shared memory", pi);
         }
         encode_program(L, P);
+        P.l2_prefetch = (P.n_cols > 0 && P.n_probes == 0 && impl != IMPL_BUILD && impl != IMPL_HASHAGG && !getenv("RQ_NO_PREFETCH")) ? 1 : 0;
         lower_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
         CK(cudaMemsetAsync(E.flags, 0, 32, E.stream));
@@ -1012,7 +1014,8 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             if (tm) tm->kernel_launches++;
             CK(cudaGetLastError());
             dfree(d_ptrs);
-            check_flags("aggregation pipeline");
+            check_flags("aggregation pipeline", dense->d_n_rows);
+            const int64_t n_groups_host = *(const int64_t*)(E.h_flags + 8);
             if (E.h_flags[0]) continue;   // more groups than this path tracks: next implementation
             // expand duplicates by aliasing: copy the columns (tiny)
             for (int k = 0; k < pl.n_keys; k++)
@@ -1021,7 +1024,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 CK(cudaMemcpyAsync(out->cols[pl.n_keys + k].d, dense->cols[pl.n_keys + ad.uniq_of[k]].d,
                                    (size_t)kGroupTableCap * 8, cudaMemcpyDeviceToDevice, E.stream));
             CK(cudaMemcpyAsync(out->d_n_rows, dense->d_n_rows, 8, cudaMemcpyDeviceToDevice, E.stream));
-            CK(cudaStreamSynchronize(E.stream));
+            out->n_rows = n_groups_host;      // (the copies above are stream-ordered; no host wait needed)
             set_types(*out, pl);
             result.table = std::move(out);
             return;
@@ -1118,9 +1121,9 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             rq_ht_compact<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, d_map, ncols, d_ptrs, (unsigned long long*)out->d_n_rows);
             if (tm) tm->kernel_launches++;
             CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(E.stream));
-            dfree(d_map);
+            dfree(d_map);                 // stream-ordered: freed after the compaction kernel ran
             dfree(d_ptrs);
+            out->n_rows = (int64_t)n_groups;
             set_types(*out, pl);
             result.table = std::move(out);
             return;
@@ -1143,10 +1146,9 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 for (int k = 0; k < n_emit; k++) P.out_col[k] = (int64_t*)out->cols[k].d;
                 trace_point("materialize output allocated", pi);
                 launch_pipeline(P, 0, src_rows, tm, is_scan, ev_idx, ev_used);
-                check_flags("materialize pipeline");
+                check_flags("materialize pipeline", out->d_n_rows);
                 trace_point("materialize kernel done", pi);
-                int64_t produced = 0;
-                CK(cudaMemcpy(&produced, out->d_n_rows, 8, cudaMemcpyDeviceToHost));
+                const int64_t produced = *(const int64_t*)(E.h_flags + 8);
                 g_emit_rows[esig] = produced;
                 if (produced <= out->cap_rows) { out->n_rows = produced; break; }
                 if (round == 1) raise(RQ_ERR_RUNTIME, "materialize overflow");
@@ -1507,8 +1509,8 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
 
         rq_table* fin = outs[plan->n_pipelines - 1].table.get();
         if (!fin) raise(RQ_ERR_INVALID, "last pipeline must produce a relation");
-        int64_t n = 0;
-        CK(cudaMemcpy(&n, fin->d_n_rows, 8, cudaMemcpyDeviceToHost));
+        int64_t n = fin->n_rows;
+        if (n < 0) CK(cudaMemcpy(&n, fin->d_n_rows, 8, cudaMemcpyDeviceToHost));
         const int ncols = (int)fin->cols.size();
 
         trace_point("row count read");

@@ -136,6 +136,9 @@ struct KParams {
     const int64_t* n_rows_ptr;          // if non-null the row count is read on the device
     int32_t        borrowed;            // source buffers may end exactly at n_rows (no padding)
     int32_t        stream_hint;         // mark scanned data evict-first in L2
+    int32_t        l2_prefetch;         // pull the next tile into L2 while the current one is processed
+                                        // (pure scans only: pipelines with hash structures want L2 for those)
+    int32_t        pad0_;
     int32_t        n_cols;              // staged (TMA) columns
     const unsigned char* col_ptr[kMaxStagedCols];
     uint32_t       col_off[kMaxStagedCols];   // byte offset inside a stage

@@ -199,6 +199,11 @@ __device__ __forceinline__ void mad_wide_s32(int64_t& acc, int32_t a, int32_t m)
     asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(m));
 }
 
+// acc.hi += a * m (low 32 bits of the product): the high-word half of acc += (a << 32) * m
+__device__ __forceinline__ void mad_hi_word(uint64_t& acc, uint32_t a, uint32_t m) {
+    asm("{\n.reg .u32 lo, hi;\nmov.b64 {lo, hi}, %0;\nmad.lo.u32 hi, %1, %2, hi;\nmov.b64 %0, {lo, hi};\n}" : "+l"(acc) : "r"(a), "r"(m));
+}
+
 // ---- low-cardinality global group table (packed key) -----------------------------------------
 __device__ __forceinline__ int group_table_slot(const KParams& P, uint64_t key) {
     uint64_t hh = mix64(key ^ 0x9E3779B97F4A7C15ULL);
@@ -376,6 +381,14 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
             } else {
                 mbar_wait_s(bars + s * 8, phase);
             }
+        }
+
+        // the tile this warp stages next is pulled into L2 while the current one is processed, so
+        // the bulk copy issued at the end of the tile is served from L2 (one stage per warp cannot
+        // hide the DRAM latency otherwise)
+        if (P.l2_prefetch && col_lane) {
+            const int64_t nt = tile + (int64_t)S * stride;
+            if (nt < n_tiles && !is_guarded(nt)) tma_prefetch_l2(my_src + (size_t)nt * my_bytes, my_bytes);
         }
 
         unsigned valid = 0xffu;
@@ -826,7 +839,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
 #pragma unroll
                             for (int g = 0; g < NG; g++) {
                                 mad_wide_u32(racc[g][a], (uint32_t)v[r], m[g][r]);
-                                racc[g][a] += (uint64_t)((uint32_t)((uint64_t)v[r] >> 32) * m[g][r]) << 32;
+                                mad_hi_word(racc[g][a], (uint32_t)((uint64_t)v[r] >> 32), m[g][r]);
                             }
                     } else {                              // MIN / MAX
 #pragma unroll
