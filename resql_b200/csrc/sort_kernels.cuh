@@ -111,19 +111,41 @@ rq_topk_hist(const uint64_t* keys, int64_t n, const unsigned long long* state, i
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 __global__ void __launch_bounds__(1024) rq_topk_pick(uint32_t* hist, unsigned long long* state, int bits) {
-    __shared__ uint32_t s[kSelBins];
+    // block-wide prefix sum over the bins (two per thread); the thread whose pair of bins contains
+    // the wanted rank publishes the digit and the rank inside that bin
+    __shared__ unsigned long long warp_tot[32];
     const int nb = 1 << bits;
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) s[i] = hist[i];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned long long a = (2 * t < nb) ? hist[2 * t] : 0ULL;
+    const unsigned long long b = (2 * t + 1 < nb) ? hist[2 * t + 1] : 0ULL;
+    const unsigned long long s = a + b;
+    unsigned long long inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long want = state[1], cum = 0;
-        int b = 0;
-        for (; b < nb - 1; b++) { if (cum + s[b] >= want) break; cum += s[b]; }
-        state[0] = (state[0] << bits) | (unsigned long long)b;
-        state[1] = want - cum;
+    if (warp == 0) {
+        unsigned long long w = warp_tot[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        warp_tot[lane] = wi - w;      // exclusive offset of the warp
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
+    const unsigned long long want = state[1];
+    const unsigned long long excl = warp_tot[warp] + inc - s;
+    __syncthreads();
+    if (excl < want && want <= excl + s) {
+        const bool first = want <= excl + a;
+        state[0] = (state[0] << bits) | (unsigned long long)(first ? 2 * t : 2 * t + 1);
+        state[1] = want - (first ? excl : excl + a);
+    }
+    for (int i = t; i < nb; i += blockDim.x) hist[i] = 0;
 }
 // rows whose first-key value is not larger than the k-th smallest one (ties included)
 __global__ void rq_topk_compact(const uint64_t* keys, int64_t n, const unsigned long long* state, uint32_t* cand,
