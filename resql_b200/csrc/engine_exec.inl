@@ -664,6 +664,7 @@ static void check_flags(const char* what, const void* d_extra = nullptr) {
     CK(cudaMemcpyAsync(E.h_flags, E.flags, 32, cudaMemcpyDeviceToHost, E.stream));
     if (d_extra) CK(cudaMemcpyAsync(E.h_flags + 8, d_extra, 8, cudaMemcpyDeviceToHost, E.stream));   // same round trip
     CK(cudaStreamSynchronize(E.stream));
+    if (E.h_flags[2] == 2) raise(RQ_ERR_INVALID, "internal: %s was lowered for a kernel variant without probe support", what);
     if (E.h_flags[2]) raise(RQ_ERR_RUNTIME, "division by zero in %s (the reference raises SIGFPE here)", what);
     if (*(unsigned long long*)(E.h_flags + 4) != 0) throw NeedExpand{};
 }
@@ -932,7 +933,11 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
     if (pl.sink_kind == RQ_SINK_AGG) {
         ad = dedup_aggs(pl);
         if (!has_str_key(pl)) {
-            if ((int)ad.kind.size() <= kNAR) impls.push_back(IMPL_REGAGG);
+            // the register-aggregation kernels (GR > 0) carry no probe code: pipelines that join
+            // take the shared-memory accumulator path of the generic kernel
+            bool has_probe = false;
+            for (int i = 0; i < pl.n_nodes; i++) has_probe |= pl.nodes[i].op == RQ_OP_PROBE;
+            if ((int)ad.kind.size() <= kNAR && !has_probe) impls.push_back(IMPL_REGAGG);
             impls.push_back(IMPL_LOWAGG);
         }
         impls.push_back(IMPL_HASHAGG);

@@ -592,7 +592,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
 #undef RQ_DROP
 
                 case U_PROBE: {
-                    if (GR > 0) break;
+                    if (GR > 0) { *P.err = 2; break; }     // never lowered for these kernels (host checks)
                     // hash-join probe (hashjoin.h:118-214): tuples without a match are dropped, the
                     // matching entry's payload words land in value slots. All 8 tuples of a lane
                     // are hashed and tested against the build side's Bloom filter first (one L2

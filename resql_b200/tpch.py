@@ -22,6 +22,9 @@ SCHEMAS = {
     "part": [("p_partkey", "int", 0), ("p_name", "char", 55), ("p_mfgr", "char", 55), ("p_brand", "char", 10),
              ("p_type", "varchar", 25), ("p_size", "int", 0), ("p_container", "char", 10),
              ("p_retailprice", "dec", 2), ("p_comment", "varchar", 23)],
+    # README microbenchmark of the reference (README:69): select c, avg(d * a) from foo, bar where a = d group by c
+    "foo": [("a", "bigint", 0), ("c", "bigint", 0)],
+    "bar": [("d", "bigint", 0)],
 }
 
 SQL_VARCHAR, SQL_CHAR, SQL_BOOL, SQL_INT, SQL_BIGINT, SQL_DECIMAL, SQL_FLOAT, SQL_DATE = range(8)
@@ -127,8 +130,17 @@ INSTRUCT = ["DELIVER IN PERSON", "COLLECT COD", "NONE", "TAKE BACK RETURN"]
 MODES = ["REG AIR", "AIR", "RAIL", "SHIP", "TRUCK", "MAIL", "FOB"]
 
 
-def generate(sf, seed=42, tables=("lineitem", "orders", "customer")):
-    """TPC-H-shaped tables at scale factor `sf` (lineitem ~ 6 000 000 * sf rows)."""
+def generate_micro(n, groups, seed=42):
+    """foo(a bigint, c bigint), bar(d bigint): a and d are permutations of 1..n, c is uniform in
+    [0, groups) (columns must be BIGINT - INT has no arithmetic in the reference)."""
+    rng = np.random.default_rng(seed * 7919 + 13)
+    return {"foo": {"a": (rng.permutation(n) + 1).astype(np.int64), "c": rng.integers(0, groups, n).astype(np.int64)},
+            "bar": {"d": (rng.permutation(n) + 1).astype(np.int64)}}
+
+
+def generate(sf, seed=42, tables=("lineitem", "orders", "customer", "foo", "bar")):
+    """TPC-H-shaped tables at scale factor `sf` (lineitem ~ 6 000 000 * sf rows); foo/bar: the
+    microbenchmark tables with 2 000 000 * sf rows and 1000 groups."""
     rng = np.random.default_rng(seed)
     n_orders = max(1, int(round(1_500_000 * sf)))
     n_cust = max(3, int(round(150_000 * sf)))
@@ -206,6 +218,11 @@ def generate(sf, seed=42, tables=("lineitem", "orders", "customer")):
             "c_mktsegment": _pick(rng, SEGMENTS, n_cust, 10),
             "c_comment": _pick(rng, ["ironic epitaphs nag", "regular platelets", "blithely final"], n_cust, 117),
         }
+    if "foo" in tables or "bar" in tables:
+        micro = generate_micro(max(8, int(round(2_000_000 * sf))), 1000, seed)
+        for t in ("foo", "bar"):
+            if t in tables:
+                out[t] = micro[t]
     return out
 
 
@@ -215,6 +232,8 @@ def sql_type_of(kind, arg):
         return SQL_INT, 0
     if kind == "date":
         return SQL_DATE, 0
+    if kind == "bigint":
+        return SQL_BIGINT, 0
     if kind == "dec":
         return SQL_DECIMAL, (12 << 8) | arg
     if kind == "char":

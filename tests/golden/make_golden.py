@@ -32,7 +32,7 @@ def main():
     os.makedirs(plan_dir, exist_ok=True)
     with tempfile.TemporaryDirectory() as tmp:
         data = tpch.generate(0.01, seed=42)
-        loads = ["exec tpch/create.sql"]
+        loads = ["exec tpch/create.sql", "create table foo ( a bigint, c bigint )", "create table bar ( d bigint )"]
         for name, cols in data.items():
             path = os.path.join(tmp, name + ".bin")
             tpch.to_rows(name, cols).tofile(path)

@@ -59,6 +59,9 @@ QUERIES = {
     "join_dups_both": """select o_orderpriority, count(*) as c, max(c_acctbal) as m from customer, orders
         where c_nationkey = o_shippriority and c_acctbal > 9000.00 and o_orderkey < 3000
         group by o_orderpriority order by o_orderpriority""",
+    # the reference's README microbenchmark (README:69; BASELINE config 5): bigint join + avg + group by
+    "micro_join_avg": "select c, avg(d * a) from foo, bar where a = d group by c order by c",
+    "micro_join_few_groups": "select c * 0 as g, avg(d * a), count(*), max(a) from foo, bar where a = d group by c * 0",
     "case_sum": """select l_shipmode, sum(case when l_quantity > 25 then 1 else 0 end) as hi,
         sum(case when l_quantity <= 25 then l_extendedprice else 0 end) as lo
         from lineitem group by l_shipmode order by l_shipmode""",

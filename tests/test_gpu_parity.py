@@ -122,7 +122,7 @@ def test_host_front_end_end_to_end(sf001, tmp_path):
             continue
         fields = []
         for c, k, a in schema:
-            ty = {"int": "int", "date": "date"}.get(k) or (f"decimal(12,{a})" if k == "dec" else f"{k}({a})")
+            ty = {"int": "int", "date": "date", "bigint": "bigint"}.get(k) or (f"decimal(12,{a})" if k == "dec" else f"{k}({a})")
             fields.append(f"{c} {ty}")
         stm.append(f"create table {name} ( " + ", ".join(fields) + " )")
     create.write_text(";\n".join(stm) + ";\n")
@@ -131,7 +131,7 @@ def test_host_front_end_end_to_end(sf001, tmp_path):
         p = tmp_path / f"{name}.bin"
         tpch.to_rows(name, cols).tofile(p)
         loads.append(f"binload {name} {p}")
-    for q in ("q6", "q1", "sel_or", "agg_neg_avg"):
+    for q in ("q6", "q1", "sel_or", "agg_neg_avg", "micro_join_avg"):
         out = tmp_path / f"{q}.out"
         sql = " ".join(QUERIES[q].split())
         r = subprocess.run([exe, "--quiet"] + loads + [f"out {out}", sql], capture_output=True, text=True, timeout=300)
