@@ -183,14 +183,17 @@ static void simplify_pipeline(const rq_pipeline& in, SimplePipe& sp) {
     // hoist every FILTER to right behind the value it tests: the value is still in the
     // accumulator and later work is skipped for dropped tuples (expressions are side-effect free)
     {
+        // Source columns come first (they depend on nothing): the pipeline splitters cut in front of
+        // a probe and rely on every column read sitting before the cut.
         const int k = (int)sp.nodes.size();
         std::vector<int> order_, pos(k, -1);
-        for (int i = 0; i < k; i++) {
-            if (sp.nodes[i].op == RQ_OP_FILTER) continue;
-            order_.push_back(i);
-            for (int f = 0; f < k; f++)
-                if (sp.nodes[f].op == RQ_OP_FILTER && sp.nodes[f].a == i) order_.push_back(f);
-        }
+        for (int pass = 0; pass < 2; pass++)
+            for (int i = 0; i < k; i++) {
+                if (sp.nodes[i].op == RQ_OP_FILTER || (sp.nodes[i].op == RQ_OP_COL) != (pass == 0)) continue;
+                order_.push_back(i);
+                for (int f = 0; f < k; f++)
+                    if (sp.nodes[f].op == RQ_OP_FILTER && sp.nodes[f].a == i) order_.push_back(f);
+            }
         for (int i = 0; i < k; i++) pos[order_[i]] = i;
         std::vector<rq_node> re(k);
         for (int i = 0; i < k; i++) {
