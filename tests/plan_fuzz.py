@@ -62,7 +62,9 @@ class _Pipe:
             if rng.random() < 0.8 and nums:
                 return self.col(rng.choice(nums))
             return self.n("CONST", imm=rng.choice([0, 1, 2, 7, 100, 1000, -3, 123456789]))
-        op = rng.choice(["ADD", "SUB", "MUL", "MUL", "DIV"])
+        op = rng.choice(["ADD", "SUB", "MUL", "MUL", "DIV", "CASE"])
+        if op == "CASE":      # one WHEN/THEN arm with ELSE (emitCase, ExpressionsJitFlounder.h:720-754)
+            return self.n("SELECT", self.predicate(2), self.num_expr(depth + 1), self.num_expr(depth + 1))
         x = self.num_expr(depth + 1)
         if op == "DIV":
             return self.n("DIV", x, self.n("CONST", imm=rng.choice([1, 2, 3, 10, 100, -7])))

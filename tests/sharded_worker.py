@@ -51,6 +51,35 @@ def main():
         finally:
             for h in handles.values():
                 h.free()
+    # random plans (tests/plan_fuzz.py): the probe-side table of the main pipeline is the sharded fact table
+    from oracle.plan_oracle import run_plan
+    from plan_fuzz import random_plan
+    n_fuzz = 0
+    for seed in range(60):
+        d = random_plan(seed)
+        tabs = plan_tables(d, data)
+        try:
+            want = serialize_columns(*run_plan(d, tabs))
+        except ZeroDivisionError:
+            continue
+        fact = d["tables"][-1]["name"]
+        tabs[fact] = shard_columns(tabs[fact], rank, world)
+        handles = {n: eng.upload(n, c) for n, c in tabs.items()}
+        try:
+            res, tm = eng.execute(Plan(d), handles, N.RQ_PLAN_SHARDED)
+            assert_same_relation(serialize_columns(res.columns, res.sql_types, res.sql_widths), want, d,
+                                 f"random plan {seed} on {world} GPUs (rank {rank})")
+            n_fuzz += 1
+        except N.EngineError as e:
+            if e.code != 3:
+                failures.append(f"random plan {seed}: {e}")
+        except Exception as e:  # noqa: BLE001
+            failures.append(f"random plan {seed}: {e}")
+        finally:
+            for h in handles.values():
+                h.free()
+    if rank == 0:
+        print(f"sharded random plans: {n_fuzz} identical on {world} GPUs", flush=True)
     flags = [None] * world
     dist.all_gather_object(flags, failures)
     eng.shutdown()
