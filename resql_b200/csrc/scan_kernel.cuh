@@ -964,9 +964,8 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     }
                 }
             } else if (sink == IMPL_HASHAGG) {
-#pragma unroll 1
-                for (int r = 0; r < kR; r++) {
-                    if (!((valid >> r) & 1)) continue;
+                for (unsigned todo = valid; todo; todo &= todo - 1) {
+                    const int r = __ffs(todo) - 1;
                     int64_t k[kMaxKeys];
                     for (int j = 0; j < P.ht.nk; j++) k[j] = ld_row(P, c, P.key[j], r);
                     const uint64_t hh = hash_keys(k, P.ht.key_kind, P.ht.nk);
@@ -1027,9 +1026,9 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                 if (lane == 0) base = atomicAdd(P.out_count, (unsigned long long)total);
                 base = __shfl_sync(kFull, base, 0);
                 int64_t pos = (int64_t)base + (incl - cnt);
-#pragma unroll 1
-                for (int r = 0; r < kR; r++) {
-                    if (!((valid >> r) & 1)) continue;
+                // only the surviving tuples are visited (a selective pass leaves a few per warp tile)
+                for (unsigned todo = valid; todo; todo &= todo - 1) {
+                    const int r = __ffs(todo) - 1;
                     if (pos < P.out_cap)
                         for (int k = 0; k < P.n_out; k++) P.out_col[k][pos] = ld_row(P, c, P.out[k], r);
                     pos++;
