@@ -1349,25 +1349,28 @@ static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timin
     std::unique_ptr<rq_table> all = new_intermediate(ncols, total);
     all->sql_type = local.sql_type;
     all->sql_width = local.sql_width;
+    if (W > 64) raise(RQ_ERR_UNSUPPORTED, "sharded plans support up to 64 ranks");
+    if (ncols > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "sharded merge of more than %d columns", kMaxOut);
     if (maxn > 0 && ncols > 0) {
-        // 2. [ncols][maxn] per rank -> [world][ncols][maxn]
+        // 2. [ncols][maxn] per rank -> [world][ncols][maxn], one pack and one unpack kernel
         int64_t *send = nullptr, *recv = nullptr;
         const size_t per_rank = (size_t)ncols * (size_t)maxn;
         CK(dmalloc(&send, per_rank * 8));
         CK(dmalloc(&recv, per_rank * 8 * W));
-        const int64_t mine = counts[D.rank];
-        for (int c = 0; c < ncols; c++)
-            if (mine > 0)
-                CK(cudaMemcpyAsync(send + (size_t)c * maxn, local.cols[c].d, (size_t)mine * 8, cudaMemcpyDeviceToDevice, E.stream));
-        nccl_ck(D.all_gather(send, recv, per_rank, 4, D.comm, E.stream), "ncclAllGather(partials)");
-        // 3. concatenate in rank order
+        GatherCols gc;
+        memset(&gc, 0, sizeof(gc));
+        gc.ncols = ncols; gc.world = W;
+        for (int c = 0; c < ncols; c++) { gc.in[c] = (const int64_t*)local.cols[c].d; gc.out[c] = (int64_t*)all->cols[c].d; }
+        GatherCounts gn;
+        memset(&gn, 0, sizeof(gn));
         int64_t off = 0;
-        for (int r = 0; r < W; r++) {
-            for (int c = 0; c < ncols && counts[r] > 0; c++)
-                CK(cudaMemcpyAsync(all->cols[c].d + (size_t)off * 8, recv + ((size_t)r * ncols + c) * maxn,
-                                   (size_t)counts[r] * 8, cudaMemcpyDeviceToDevice, E.stream));
-            off += counts[r];
-        }
+        for (int r = 0; r < W; r++) { gn.count[r] = counts[r]; gn.off[r] = off; off += counts[r]; }
+        const unsigned pb = (unsigned)std::min<size_t>((per_rank + 255) / 256, 148 * 8);
+        rq_gather_pack<<<pb, 256, 0, E.stream>>>(gc, counts[D.rank], maxn, send);
+        nccl_ck(D.all_gather(send, recv, per_rank, 4, D.comm, E.stream), "ncclAllGather(partials)");
+        const unsigned ub = (unsigned)std::min<size_t>((per_rank * W + 255) / 256, 148 * 8);
+        rq_gather_unpack<<<ub, 256, 0, E.stream>>>(gc, gn, maxn, recv);
+        if (tm) tm->kernel_launches += 2;
         dfree(send);
         dfree(recv);
     }

@@ -1174,6 +1174,28 @@ __global__ void rq_gather_str(const int64_t* addrs, unsigned char* out, int widt
     }
 }
 
+// sharded merge: pack the local relation as [ncols][stride] for one all-gather, and unpack the
+// gathered [world][ncols][stride] into dense columns in rank order (one launch each instead of
+// world x ncols small copies)
+struct GatherCols { const int64_t* in[kMaxOut]; int64_t* out[kMaxOut]; int32_t ncols; int32_t world; };
+struct GatherCounts { int64_t count[64]; int64_t off[64]; };
+__global__ void rq_gather_pack(GatherCols gc, int64_t n, int64_t stride, int64_t* send) {
+    const int64_t total = (int64_t)gc.ncols * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = i / stride, j = i - c * stride;
+        if (j < n) send[i] = gc.in[c][j];
+    }
+}
+__global__ void rq_gather_unpack(GatherCols gc, GatherCounts cnt, int64_t stride, const int64_t* recv) {
+    const int64_t per_rank = (int64_t)gc.ncols * stride;
+    const int64_t total = per_rank * gc.world;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / per_rank, w = i - r * per_rank;
+        const int64_t c = w / stride, j = w - c * stride;
+        if (j < cnt.count[r]) gc.out[c][cnt.off[r] + j] = recv[i];
+    }
+}
+
 // addresses of the rows of a by-value string column (sharded merge: strings arrive by value)
 __global__ void rq_str_addrs(const unsigned char* bytes, int width, int64_t n, int64_t* out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
