@@ -856,6 +856,8 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
 
 // pipelines that met duplicate matches once are run in expanded form straight away afterwards
 static std::set<uint64_t> g_needs_expand;
+// join builds whose keys clustered under the order-preserving hash
+static std::set<uint64_t> g_no_monotone;
 
 static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
                              const char* d_strpool, rq_timings* tm, size_t& ev_idx,
@@ -1057,6 +1059,22 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             const int nk = pl.n_keys;
             if (nk > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
             const int nv = impl == IMPL_BUILD ? pl.n_vals : (int)ad.kind.size();
+            // A join build on one integer column whose value range is known (upload statistics) and
+            // dense relative to the table uses the order-preserving hash; if the keys turn out to
+            // cluster (long probe runs -> table-full flag) the pipeline falls back to Fibonacci hashing.
+            bool monotone = false;
+            int64_t key_lo = 0, key_hi = 0;
+            const uint64_t mono_sig = sig ^ 0x6d6f6e6fULL;
+            if (impl == IMPL_BUILD && nk == 1 && !getenv("RQ_NO_MONOTONE") && !g_no_monotone.count(mono_sig)) {
+                const rq_node& kn = pl.nodes[pl.keys[0].node];
+                const int st = pl.keys[0].sql_type;
+                const bool int_key = !(st == RQ_SQL_VARCHAR || (st == RQ_SQL_CHAR && pl.keys[0].width > 1));
+                if (int_key && kn.op == RQ_OP_COL && kn.a >= 0 && kn.a < (int)src->cols.size() && src->cols[kn.a].has_stats) {
+                    key_lo = src->cols[kn.a].vmin; key_hi = src->cols[kn.a].vmax;
+                    const double range = (double)key_hi - (double)key_lo + 1.0;
+                    monotone = range >= 1.0 && range <= 64.0 * (double)rows_bound && range < 9.0e18;
+                }
+            }
             std::unique_ptr<HashTableDev> ht;
             unsigned long long n_used = 0;
             for (;;) {
@@ -1072,6 +1090,15 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                     CK(cudaMemsetAsync(ht->d.bloom, 0, words * 4, E.stream));
                 }
                 ht->d.nk = nk; ht->d.nv = nv;
+                ht->d.hmul = 0x9E3779B97F4A7C15ULL; ht->d.hsub = 0; ht->d.bloom_shift = 0;
+                if (monotone) {
+                    // order-preserving hash over the dense key domain [key_lo, key_hi]
+                    const unsigned __int128 range = (unsigned __int128)((__int128)key_hi - (__int128)key_lo) + 1;
+                    ht->d.hsub = key_lo;
+                    ht->d.hmul = (uint64_t)(((unsigned __int128)UINT64_MAX) / range);
+                    // (the Bloom filter keeps its mixed word index: an order-preserving one was measured to
+                    // pass more false positives into the dense pass than it saved in locality)
+                }
                 for (int k = 0; k < nk && k < kMaxKeys; k++) {
                     const int st = pl.keys[k].sql_type;
                     ht->d.key_kind[k] = st == RQ_SQL_VARCHAR ? 2 : (st == RQ_SQL_CHAR && pl.keys[k].width > 1) ? 1 : 0;
@@ -1093,6 +1120,11 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 check_flags(impl == IMPL_BUILD ? "join build pipeline" : "hash aggregation pipeline");
                 trace_point("hash sink kernel done", pi);
                 bool regrow = E.h_flags[1] != 0;
+                if (regrow && monotone) {      // clustered keys: same capacity again with the mixing hash
+                    monotone = false;
+                    g_no_monotone.insert(mono_sig);
+                    continue;
+                }
                 n_used = *(unsigned long long*)(E.h_flags + 6);     // counted by the kernel itself
                 if (!regrow) regrow = n_used * max_load_den > cap && cap < cap_max;
                 if (!regrow) break;

@@ -20,7 +20,7 @@ struct HashTableDev {
 };
 
 constexpr uint64_t kTagLocked = 1ULL;
-constexpr uint64_t kMaxProbeLen = 256;    // longer runs mean the table is (nearly) full: report and regrow
+constexpr uint64_t kMaxProbeLen = 2048;   // longer runs mean the table is (nearly) full: report and regrow
 
 // key kinds: 0 integer word, 1 CHAR (equality ignores trailing blanks), 2 VARCHAR (exact)
 __device__ __forceinline__ uint64_t hash_str(const unsigned char* s, bool strip) {
@@ -45,19 +45,23 @@ __device__ __forceinline__ uint64_t hash_typed(const int64_t* k, const uint8_t* 
 }
 
 // Hash of a key tuple. One integer key (the usual join / group key) takes a single 64-bit
-// multiply (Fibonacci hashing: the home slot comes from the HIGH bits); composite and string keys
-// go through the mixing hash.
-__device__ __forceinline__ uint64_t hash_int(int64_t k) { return (uint64_t)k * 0x9E3779B97F4A7C15ULL; }
-__device__ __forceinline__ uint64_t hash_keys(const int64_t* k, const uint8_t* kind, int nk) {
-    if (nk == 1 && kind[0] == 0) return hash_int(k[0]);
-    return hash_typed(k, kind, nk);
+// multiply, (key - hsub) * hmul: Fibonacci hashing or the order-preserving scaling of a dense key
+// domain (see DHashTable); the home slot comes from the HIGH bits. Composite and string keys go
+// through the mixing hash.
+__device__ __forceinline__ uint64_t hash_int(const DHashTable& ht, int64_t k) {
+    return ((uint64_t)k - (uint64_t)ht.hsub) * ht.hmul;
+}
+__device__ __forceinline__ uint64_t hash_keys(const DHashTable& ht, const int64_t* k) {
+    if (ht.nk == 1 && ht.key_kind[0] == 0) return hash_int(ht, k[0]);
+    return hash_typed(k, ht.key_kind, ht.nk);
 }
 // blocked Bloom filter: word index and the two bits inside the 32-bit block
-__device__ __forceinline__ uint32_t bloom_word(uint64_t h, uint32_t mask) {
+__device__ __forceinline__ uint32_t bloom_word(const DHashTable& ht, uint64_t h) {
     const uint64_t g = h ^ (h >> 29);
-    return (uint32_t)(g >> 10) & mask;
+    return (uint32_t)(g >> 10) & ht.bloom_mask;
 }
-__device__ __forceinline__ uint32_t bloom_bits(uint64_t h) {
+__device__ __forceinline__ uint32_t bloom_bits(const DHashTable& ht, uint64_t h) {
+    (void)ht;
     const uint64_t g = h ^ (h >> 29);
     return (1u << ((uint32_t)g & 31)) | (1u << ((uint32_t)(g >> 5) & 31));
 }

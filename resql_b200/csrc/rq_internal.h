@@ -106,6 +106,15 @@ struct DHashTable {
     uint64_t  cap_mask;     // capacity - 1 (power of two)
     uint32_t  shift;        // home slot = hash >> shift  (64 - log2(capacity): the high hash bits)
     uint32_t  bloom_mask;   // words - 1 of the blocked Bloom filter (joins), 0 = none
+    // hash of a single integer key: (key - hsub) * hmul. Fibonacci hashing (hsub 0, hmul golden ratio)
+    // by default; for a dense key domain [lo, hi] known from the upload statistics the ORDER-PRESERVING
+    // form hsub = lo, hmul = floor((2^64 - 1) / (hi - lo + 1)): neighbouring keys land in neighbouring
+    // slots, so a build or probe that visits keys in (nearly) sorted order - orders by
+    // o_orderkey, lineitem by l_orderkey - streams through the table instead of hopping over HBM.
+    uint64_t  hmul;
+    int64_t   hsub;
+    uint32_t  bloom_shift;  // reserved (0): Bloom word index always comes from the mixed hash
+    uint32_t  pad2_;
     uint32_t* bloom;        // 32-bit blocks, two bits per key; sized to stay L2 resident
     // entries are packed rows: [tag][nk key words][nv payload / accumulator words], padded to a
     // multiple of 4 words, so that a hit costs one memory round trip (tag 0 = empty, 1 = being

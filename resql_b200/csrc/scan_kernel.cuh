@@ -627,7 +627,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     if (k1) {
                         fetch_vref(P, c, pr.key[0], kv);
 #pragma unroll
-                        for (int r = 0; r < kR; r++) h[r] = hash_int(kv[r]);
+                        for (int r = 0; r < kR; r++) h[r] = hash_int(pr.ht, kv[r]);
                     } else {
 #pragma unroll
                         for (int r = 0; r < kR; r++) { h[r] = 0; kv[r] = 0; }
@@ -645,10 +645,10 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         uint32_t w[kR];
 #pragma unroll
                         for (int r = 0; r < kR; r++)
-                            w[r] = ((valid >> r) & 1) ? pr.ht.bloom[bloom_word(h[r], pr.ht.bloom_mask)] : 0u;
+                            w[r] = ((valid >> r) & 1) ? pr.ht.bloom[bloom_word(pr.ht, h[r])] : 0u;
 #pragma unroll
                         for (int r = 0; r < kR; r++) {
-                            const uint32_t bits = bloom_bits(h[r]);
+                            const uint32_t bits = bloom_bits(pr.ht, h[r]);
                             if ((w[r] & bits) != bits) valid &= ~(1u << r);
                         }
                     }
@@ -929,7 +929,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     for (int r = 0; r < kR; r++) {
                         old[r] = 1ULL;
                         if ((valid >> r) & 1) {
-                            const uint64_t hh = hash_int(bk[r]);
+                            const uint64_t hh = hash_int(P.ht, bk[r]);
                             old[r] = atomicCAS((unsigned long long*)ht_entry(P.ht, hh >> P.ht.shift), 0ULL,
                                                (unsigned long long)(hh | 2ULL));
                         }
@@ -937,7 +937,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
 #pragma unroll
                     for (int r = 0; r < kR; r++) {
                         if (!((valid >> r) & 1)) continue;
-                        const uint64_t hh = hash_int(bk[r]);
+                        const uint64_t hh = hash_int(P.ht, bk[r]);
                         uint64_t slot = hh >> P.ht.shift;
                         if (old[r] != 0ULL) {
                             if (!ht_insert_dup_from(P.ht, hh, (slot + 1) & P.ht.cap_mask, &slot)) { *P.ht_full = 1; continue; }
@@ -945,7 +945,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         uint64_t* e = ht_entry(P.ht, slot);
                         e[1] = (uint64_t)bk[r];
                         for (int q = 0; q < P.n_out; q++) e[2 + q] = (uint64_t)ld_row(P, c, P.out[q], r);
-                        if (P.ht.bloom != nullptr) atomicOr(&P.ht.bloom[bloom_word(hh, P.ht.bloom_mask)], bloom_bits(hh));
+                        if (P.ht.bloom != nullptr) atomicOr(&P.ht.bloom[bloom_word(P.ht, hh)], bloom_bits(P.ht, hh));
                         n_inserted++;
                     }
                 } else {
@@ -954,12 +954,12 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         if (!((valid >> r) & 1)) continue;
                         int64_t k[kMaxKeys];
                         for (int j = 0; j < bnk; j++) k[j] = ld_row(P, c, P.key[j], r);
-                        const uint64_t hh = hash_keys(k, P.ht.key_kind, bnk);
+                        const uint64_t hh = hash_keys(P.ht, k);
                         uint64_t slot;
                         if (!ht_insert_dup(P.ht, k, hh, &slot)) { *P.ht_full = 1; continue; }
                         uint64_t* e = ht_entry(P.ht, slot);
                         for (int q = 0; q < P.n_out; q++) e[1 + bnk + q] = (uint64_t)ld_row(P, c, P.out[q], r);
-                        if (P.ht.bloom != nullptr) atomicOr(&P.ht.bloom[bloom_word(hh, P.ht.bloom_mask)], bloom_bits(hh));
+                        if (P.ht.bloom != nullptr) atomicOr(&P.ht.bloom[bloom_word(P.ht, hh)], bloom_bits(P.ht, hh));
                         n_inserted++;
                     }
                 }
@@ -968,7 +968,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     const int r = __ffs(todo) - 1;
                     int64_t k[kMaxKeys];
                     for (int j = 0; j < P.ht.nk; j++) k[j] = ld_row(P, c, P.key[j], r);
-                    const uint64_t hh = hash_keys(k, P.ht.key_kind, P.ht.nk);
+                    const uint64_t hh = hash_keys(P.ht, k);
                     uint64_t slot;
                     bool fresh = false;
                     if (!ht_find_or_insert(P.ht, k, hh, &slot, &fresh)) { *P.ht_full = 1; continue; }
@@ -995,7 +995,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     if (!((valid >> r) & 1)) continue;
                     int64_t k[kMaxKeys];
                     for (int j = 0; j < pnk; j++) k[j] = ld_row(P, c, pr.key[j], r);
-                    const uint64_t hr = hash_keys(k, pr.ht.key_kind, pnk);
+                    const uint64_t hr = hash_keys(pr.ht, k);
                     const uint64_t tag = hr | 2ULL;
                     uint64_t i = hr >> pr.ht.shift;
                     for (uint64_t tries = 0; tries < cap; tries++) {
