@@ -22,6 +22,10 @@ SCHEMAS = {
     "part": [("p_partkey", "int", 0), ("p_name", "char", 55), ("p_mfgr", "char", 55), ("p_brand", "char", 10),
              ("p_type", "varchar", 25), ("p_size", "int", 0), ("p_container", "char", 10),
              ("p_retailprice", "dec", 2), ("p_comment", "varchar", 23)],
+    "supplier": [("s_suppkey", "int", 0), ("s_name", "char", 25), ("s_address", "varchar", 40), ("s_nationkey", "int", 0),
+                 ("s_phone", "char", 15), ("s_acctbal", "dec", 2), ("s_comment", "varchar", 101)],
+    "nation": [("n_nationkey", "int", 0), ("n_name", "char", 25), ("n_regionkey", "int", 0), ("n_comment", "varchar", 152)],
+    "region": [("r_regionkey", "int", 0), ("r_name", "char", 25), ("r_comment", "varchar", 152)],
     # README microbenchmark of the reference (README:69): select c, avg(d * a) from foo, bar where a = d group by c
     "foo": [("a", "bigint", 0), ("c", "bigint", 0)],
     "bar": [("d", "bigint", 0)],
@@ -138,7 +142,60 @@ def generate_micro(n, groups, seed=42):
             "bar": {"d": (rng.permutation(n) + 1).astype(np.int64)}}
 
 
-def generate(sf, seed=42, tables=("lineitem", "orders", "customer", "foo", "bar")):
+NATIONS = [("ALGERIA", 0), ("ARGENTINA", 1), ("BRAZIL", 1), ("CANADA", 1), ("EGYPT", 4), ("ETHIOPIA", 0), ("FRANCE", 3),
+           ("GERMANY", 3), ("INDIA", 2), ("INDONESIA", 2), ("IRAN", 4), ("IRAQ", 4), ("JAPAN", 2), ("JORDAN", 4), ("KENYA", 0),
+           ("MOROCCO", 0), ("MOZAMBIQUE", 0), ("PERU", 1), ("CHINA", 2), ("ROMANIA", 3), ("SAUDI ARABIA", 4), ("VIETNAM", 2),
+           ("RUSSIA", 3), ("UNITED KINGDOM", 3), ("UNITED STATES", 1)]
+REGIONS = ["AFRICA", "AMERICA", "ASIA", "EUROPE", "MIDDLE EAST"]
+TYPE_1 = ["STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO"]
+TYPE_2 = ["ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED"]
+TYPE_3 = ["TIN", "NICKEL", "BRASS", "STEEL", "COPPER"]
+CONT_1 = ["SM", "LG", "MED", "JUMBO", "WRAP"]
+CONT_2 = ["CASE", "BOX", "BAG", "JAR", "PKG", "PACK", "CAN", "DRUM"]
+
+
+def _strs(values, width):
+    return np.array([v.encode() for v in values], dtype=f"S{width + 1}")
+
+
+def generate_dims(sf, seed=42):
+    """part, supplier, nation, region in the shapes of the TPC-H specification (values drawn uniformly)."""
+    rng = np.random.default_rng(seed * 104729 + 7)
+    n_part = max(1, int(round(200_000 * sf)))
+    n_supp = max(1, int(round(10_000 * sf)))
+    pk = np.arange(1, n_part + 1, dtype=np.int64)
+    part = {
+        "p_partkey": pk.astype(np.int32),
+        "p_name": _strs([f"part {i} almond antique" for i in pk], 55),
+        "p_mfgr": _strs([f"Manufacturer#{1 + int(i) % 5}" for i in pk], 55),
+        "p_brand": _strs([f"Brand#{a}{b}" for a, b in zip(rng.integers(1, 6, n_part), rng.integers(1, 6, n_part))], 10),
+        "p_type": _strs([f"{TYPE_1[a]} {TYPE_2[b]} {TYPE_3[c]}" for a, b, c in
+                         zip(rng.integers(0, 6, n_part), rng.integers(0, 5, n_part), rng.integers(0, 5, n_part))], 25),
+        "p_size": rng.integers(1, 51, n_part).astype(np.int32),
+        "p_container": _strs([f"{CONT_1[a]} {CONT_2[b]}" for a, b in zip(rng.integers(0, 5, n_part), rng.integers(0, 8, n_part))], 10),
+        "p_retailprice": (90000 + ((pk // 10) % 20001) + 100 * (pk % 1000)).astype(np.int64),
+        "p_comment": _pick(rng, ["carefully final", "slyly ironic", "furiously even"], n_part, 23),
+    }
+    sk = np.arange(1, n_supp + 1, dtype=np.int32)
+    snat = rng.integers(0, 25, n_supp).astype(np.int32)
+    supplier = {
+        "s_suppkey": sk,
+        "s_name": _strs([f"Supplier#{i:09d}" for i in sk], 25),
+        "s_address": _pick(rng, ["N kD4on9OM Ipw3,gf0J", "89eJ5ksX3ImxJQBvxObC,", "q1,G3Pj6OjIuUYfUoH18BFTKP5aU9bEV3"], n_supp, 40),
+        "s_nationkey": snat,
+        "s_phone": _strs([f"{10 + int(n)}-{int(k) % 900 + 100}-{int(k) % 9000 + 1000}" for n, k in zip(snat, sk)], 15),
+        "s_acctbal": rng.integers(-99999, 1000000, n_supp).astype(np.int64),
+        "s_comment": _pick(rng, ["blithely silent requests", "even, bold deposits", "Customer Complaints noted"], n_supp, 101),
+    }
+    nation = {"n_nationkey": np.arange(25, dtype=np.int32), "n_name": _strs([n for n, _ in NATIONS], 25),
+              "n_regionkey": np.array([r for _, r in NATIONS], dtype=np.int32),
+              "n_comment": _pick(rng, ["haggle carefully", "final deposits detect", "ironic foxes promise"], 25, 152)}
+    region = {"r_regionkey": np.arange(5, dtype=np.int32), "r_name": _strs(REGIONS, 25),
+              "r_comment": _pick(rng, ["lar deposits", "hs use ironic requests", "ges thinly even"], 5, 152)}
+    return {"part": part, "supplier": supplier, "nation": nation, "region": region}
+
+
+def generate(sf, seed=42, tables=("lineitem", "orders", "customer", "foo", "bar", "part", "supplier", "nation", "region")):
     """TPC-H-shaped tables at scale factor `sf` (lineitem ~ 6 000 000 * sf rows); foo/bar: the
     microbenchmark tables with 2 000 000 * sf rows and 1000 groups."""
     rng = np.random.default_rng(seed)
@@ -218,6 +275,11 @@ def generate(sf, seed=42, tables=("lineitem", "orders", "customer", "foo", "bar"
             "c_mktsegment": _pick(rng, SEGMENTS, n_cust, 10),
             "c_comment": _pick(rng, ["ironic epitaphs nag", "regular platelets", "blithely final"], n_cust, 117),
         }
+    if any(t in tables for t in ("part", "supplier", "nation", "region")):
+        dims = generate_dims(sf, seed)
+        for t in ("part", "supplier", "nation", "region"):
+            if t in tables:
+                out[t] = dims[t]
     if "foo" in tables or "bar" in tables:
         micro = generate_micro(max(8, int(round(2_000_000 * sf))), 1000, seed)
         for t in ("foo", "bar"):
