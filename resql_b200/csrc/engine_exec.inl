@@ -1113,6 +1113,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                     // whole sectors are cleared (a tag-only clear is a partial write per sector)
                     CK(cudaMemsetAsync(ht->d.ent, 0, cap * ht->d.stride * 8, E.stream));
                 }
+                ht->d.limit = cap / max_load_den + 1;      // beyond this load the table is regrown anyway
                 P.ht = ht->d;
                 CK(cudaMemsetAsync(E.flags, 0, 32, E.stream));
                 trace_point("hash table allocated + cleared", pi);

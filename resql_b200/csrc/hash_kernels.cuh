@@ -20,7 +20,11 @@ struct HashTableDev {
 };
 
 constexpr uint64_t kTagLocked = 1ULL;
-constexpr uint64_t kMaxProbeLen = 2048;   // longer runs mean the table is (nearly) full: report and regrow
+// A full table is detected by its LOAD (entries are counted per warp tile against DHashTable::limit,
+// scan_kernel.cuh), not by the length of a probe run: a join key with thousands of duplicates makes
+// long runs in a nearly empty table (hashjoin.h:226-256 keeps every duplicate). Walks only give up
+// when somebody raised the table-full flag.
+constexpr uint64_t kFullCheckEvery = 256;
 
 // key kinds: 0 integer word, 1 CHAR (equality ignores trailing blanks), 2 VARCHAR (exact)
 __device__ __forceinline__ uint64_t hash_str(const unsigned char* s, bool strip) {
@@ -85,12 +89,11 @@ __device__ __forceinline__ bool slot_keys_equal(const DHashTable& ht, uint64_t i
 
 // join build: every tuple gets its own slot (duplicates are kept, hashjoin.h:226-256)
 __device__ __forceinline__ bool ht_insert_dup(const DHashTable& ht, const int64_t* k, uint64_t h,
-                                              uint64_t* slot_out) {
+                                              uint64_t* slot_out, const int32_t* full) {
     const uint64_t tag = h | 2ULL;
     const uint64_t cap = ht.cap_mask + 1;
     uint64_t i = h >> ht.shift;
-    const uint64_t lim = cap < kMaxProbeLen ? cap : kMaxProbeLen;
-    for (uint64_t tries = 0; tries < lim; tries++) {
+    for (uint64_t tries = 0; tries < cap; tries++) {
         uint64_t* e = ht_entry(ht, i);
         const unsigned long long old = atomicCAS((unsigned long long*)e, 0ULL, (unsigned long long)tag);
         if (old == 0ULL) {
@@ -99,6 +102,7 @@ __device__ __forceinline__ bool ht_insert_dup(const DHashTable& ht, const int64_
             return true;
         }
         i = (i + 1) & ht.cap_mask;
+        if ((tries & (kFullCheckEvery - 1)) == kFullCheckEvery - 1 && *(volatile int32_t*)full) return false;
     }
     return false;
 }
@@ -106,26 +110,26 @@ __device__ __forceinline__ bool ht_insert_dup(const DHashTable& ht, const int64_
 // the same, starting the walk at slot `i` (the home slot was already found taken); keys are
 // written by the caller
 __device__ __forceinline__ bool ht_insert_dup_from(const DHashTable& ht, uint64_t h, uint64_t i,
-                                                   uint64_t* slot_out) {
+                                                   uint64_t* slot_out, const int32_t* full) {
     const uint64_t tag = h | 2ULL;
     const uint64_t cap = ht.cap_mask + 1;
-    const uint64_t lim = cap < kMaxProbeLen ? cap : kMaxProbeLen;
-    for (uint64_t tries = 1; tries < lim; tries++) {
+    for (uint64_t tries = 1; tries < cap; tries++) {
         const unsigned long long old = atomicCAS((unsigned long long*)ht_entry(ht, i), 0ULL, (unsigned long long)tag);
         if (old == 0ULL) { *slot_out = i; return true; }
         i = (i + 1) & ht.cap_mask;
+        if ((tries & (kFullCheckEvery - 1)) == kFullCheckEvery - 1 && *(volatile int32_t*)full) return false;
     }
     return false;
 }
 
 // GROUP BY: find the slot of the key or claim a new one (aggregation.h:262-279)
 __device__ __forceinline__ bool ht_find_or_insert(const DHashTable& ht, const int64_t* k, uint64_t h,
-                                                  uint64_t* slot_out, bool* fresh) {
+                                                  uint64_t* slot_out, bool* fresh, const int32_t* full) {
     const uint64_t tag = h | 2ULL;
     const uint64_t cap = ht.cap_mask + 1;
     uint64_t i = h >> ht.shift;
-    const uint64_t lim = cap < kMaxProbeLen ? cap : kMaxProbeLen;
-    for (uint64_t tries = 0; tries < lim; tries++) {
+    for (uint64_t tries = 0; tries < cap; tries++) {
+        if ((tries & (kFullCheckEvery - 1)) == kFullCheckEvery - 1 && *(volatile int32_t*)full) return false;
         volatile uint64_t* e = ht_entry(ht, i);
         uint64_t t = e[0];
         if (t == 0ULL) {

@@ -115,6 +115,7 @@ struct DHashTable {
     int64_t   hsub;
     uint32_t  bloom_shift;  // reserved (0): Bloom word index always comes from the mixed hash
     uint32_t  pad2_;
+    uint64_t  limit;        // entries a launch may add before it raises the table-full flag
     uint32_t* bloom;        // 32-bit blocks, two bits per key; sized to stay L2 resident
     // entries are packed rows: [tag][nk key words][nv payload / accumulator words], padded to a
     // multiple of 4 words, so that a hit costs one memory round trip (tag 0 = empty, 1 = being

@@ -940,7 +940,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         const uint64_t hh = hash_int(P.ht, bk[r]);
                         uint64_t slot = hh >> P.ht.shift;
                         if (old[r] != 0ULL) {
-                            if (!ht_insert_dup_from(P.ht, hh, (slot + 1) & P.ht.cap_mask, &slot)) { *P.ht_full = 1; continue; }
+                            if (!ht_insert_dup_from(P.ht, hh, (slot + 1) & P.ht.cap_mask, &slot, P.ht_full)) { *P.ht_full = 1; continue; }
                         }
                         uint64_t* e = ht_entry(P.ht, slot);
                         e[1] = (uint64_t)bk[r];
@@ -956,7 +956,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         for (int j = 0; j < bnk; j++) k[j] = ld_row(P, c, P.key[j], r);
                         const uint64_t hh = hash_keys(P.ht, k);
                         uint64_t slot;
-                        if (!ht_insert_dup(P.ht, k, hh, &slot)) { *P.ht_full = 1; continue; }
+                        if (!ht_insert_dup(P.ht, k, hh, &slot, P.ht_full)) { *P.ht_full = 1; continue; }
                         uint64_t* e = ht_entry(P.ht, slot);
                         for (int q = 0; q < P.n_out; q++) e[1 + bnk + q] = (uint64_t)ld_row(P, c, P.out[q], r);
                         if (P.ht.bloom != nullptr) atomicOr(&P.ht.bloom[bloom_word(P.ht, hh)], bloom_bits(P.ht, hh));
@@ -971,7 +971,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     const uint64_t hh = hash_keys(P.ht, k);
                     uint64_t slot;
                     bool fresh = false;
-                    if (!ht_find_or_insert(P.ht, k, hh, &slot, &fresh)) { *P.ht_full = 1; continue; }
+                    if (!ht_find_or_insert(P.ht, k, hh, &slot, &fresh, P.ht_full)) { *P.ht_full = 1; continue; }
                     if (fresh) n_inserted++;
                     uint64_t* acc = ht_entry(P.ht, slot) + 1 + P.ht.nk;
                     for (int a = 0; a < NA; a++) {
@@ -1036,6 +1036,18 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
             }
         }
 
+        // hash sinks: the entries this warp added go to the table's counter tile by tile; crossing the
+        // load limit raises the table-full flag (the host regrows and reruns)
+        if (hash_sink) {
+            unsigned tot = n_inserted;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
+            if (lane == 0 && tot) {
+                const unsigned long long before = atomicAdd(P.ht_entries, (unsigned long long)tot);
+                if (before + tot > P.ht.limit) *P.ht_full = 1;
+            }
+            n_inserted = 0;
+        }
         // everyone is done with stage s (and the slots) before it is refilled
         __syncwarp();
         if (P.n_cols > 0) {
@@ -1045,12 +1057,6 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         if (++s == S) { s = 0; phase ^= 1u; }
     }
 
-    if (hash_sink) {       // occupied entries of the table (replaces a counting pass over it)
-        unsigned tot = n_inserted;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
-        if (lane == 0 && tot) atomicAdd(P.ht_entries, (unsigned long long)tot);
-    }
     // ---- flush the per-warp accumulators of the low-cardinality aggregate -------------------
     if (GR > 0 || sink == IMPL_LOWAGG) {
         __syncwarp();
