@@ -25,6 +25,10 @@ constexpr uint64_t kTagLocked = 1ULL;
 // long runs in a nearly empty table (hashjoin.h:226-256 keeps every duplicate). Walks only give up
 // when somebody raised the table-full flag.
 constexpr uint64_t kFullCheckEvery = 256;
+// flags block of the engine: [0] group overflow, [1] table full, [2] runtime error, [3] long probe run
+// (a claim that had to walk this far: duplicates, or keys clustering under the order-preserving hash)
+constexpr uint64_t kLongRun = 1024;
+__device__ __forceinline__ void note_long_run(const int32_t* full) { *const_cast<int32_t*>(full + 2) = 1; }
 
 // key kinds: 0 integer word, 1 CHAR (equality ignores trailing blanks), 2 VARCHAR (exact)
 __device__ __forceinline__ uint64_t hash_str(const unsigned char* s, bool strip) {
@@ -117,6 +121,7 @@ __device__ __forceinline__ bool ht_insert_dup_from(const DHashTable& ht, uint64_
         const unsigned long long old = atomicCAS((unsigned long long*)ht_entry(ht, i), 0ULL, (unsigned long long)tag);
         if (old == 0ULL) { *slot_out = i; return true; }
         i = (i + 1) & ht.cap_mask;
+        if (tries == kLongRun) note_long_run(full);
         if ((tries & (kFullCheckEvery - 1)) == kFullCheckEvery - 1 && *(volatile int32_t*)full) return false;
     }
     return false;

@@ -316,6 +316,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     int ngroups = 0;
     unsigned seen = 0;     // (no GROUP BY) did this lane aggregate at least one tuple
     unsigned n_inserted = 0;   // hash sinks: entries this lane added to the table
+    unsigned long long acct_before = 0, acct_added = 0;   // lane 0: table counter before / by the previous tile
 #pragma unroll
     for (int g = 0; g < NG; g++)
 #pragma unroll
@@ -1042,9 +1043,11 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
             unsigned tot = n_inserted;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
-            if (lane == 0 && tot) {
-                const unsigned long long before = atomicAdd(P.ht_entries, (unsigned long long)tot);
-                if (before + tot > P.ht.limit) *P.ht_full = 1;
+            // (the counter's old value is only looked at one tile later, so nobody waits for the atomic)
+            if (lane == 0) {
+                if (acct_before + acct_added > P.ht.limit) *P.ht_full = 1;
+                acct_added = tot;
+                acct_before = tot ? atomicAdd(P.ht_entries, (unsigned long long)tot) : 0ULL;
             }
             n_inserted = 0;
         }
