@@ -74,8 +74,11 @@ void* rq_stream(void);
 
 /* Multi-GPU (one process per GPU). rank 0 calls rq_dist_unique_id, the harness broadcasts the
  * 128 bytes (torch.distributed / MPI / file), every rank calls rq_dist_init. After that, plans
- * executed with RQ_PLAN_SHARDED merge the partial aggregates of the last aggregation with one
- * NCCL all-reduce (SUM/COUNT: uint64 sum, MIN/MAX: min/max) before AVG finalisation. */
+ * executed with RQ_PLAN_SHARDED exchange the per-rank result of the last aggregation (NCCL
+ * all-gather of the group tables) and re-aggregate it on every rank (SUM/COUNT partials add,
+ * MIN/MAX take min/max) before AVG finalisation, ORDER BY and LIMIT; a plan without aggregation
+ * concatenates the per-rank relations. The table scanned by that aggregation's pipeline holds
+ * this rank's row range, all other tables are complete on every rank. */
 int rq_dist_unique_id(uint8_t out_id[128]);
 int rq_dist_init(int rank, int world_size, const uint8_t id[128]);
 
@@ -132,7 +135,8 @@ enum rq_op {
     RQ_OP_FILTER,       /* drop the tuple unless (a & 0xff) != 0        (selection.h:62-66)    */
     RQ_OP_PROBE,        /* a = index of the build pipeline; b = first entry, c = count in
                            rq_pipeline.args (probe key nodes). Drops tuples without a match.
-                           imm bit0 = single match (hashjoin.h:168-214) else multi (:118-165)  */
+                           imm bit0 = single match (hashjoin.h:168-214) else multi (:118-165);
+                           the other imm bits must be 0 (used inside the library)              */
     RQ_OP_PAYLOAD       /* a = PROBE node, b = payload column of that build                    */
 };
 

@@ -371,7 +371,7 @@ bool is_binary(int op) {
             return false;
     }
 }
-// opcode when the LEFT operand is in the accumulator / when the RIGHT operand is
+// device opcode of a binary ABI op
 uint8_t dop_left(int op) {
     switch (op) {
         case RQ_OP_ADD: return D_ADD; case RQ_OP_SUB: return D_SUB; case RQ_OP_MUL: return D_MUL;
@@ -381,18 +381,6 @@ uint8_t dop_left(int op) {
         case RQ_OP_EQ_CHAR: return D_EQC; case RQ_OP_EQ_VARCHAR: return D_EQV;
         case RQ_OP_NEQ_CHAR: return D_NEC; case RQ_OP_NEQ_VARCHAR: return D_NEV;
         case RQ_OP_LIKE: return D_LIKE;
-    }
-    return 0;
-}
-uint8_t dop_right(int op) {
-    switch (op) {
-        case RQ_OP_ADD: return D_ADD; case RQ_OP_SUB: return D_RSUB; case RQ_OP_MUL: return D_MUL;
-        case RQ_OP_DIV: return D_RDIV; case RQ_OP_AND: return D_AND; case RQ_OP_OR: return D_OR;
-        case RQ_OP_LT: return D_GT; case RQ_OP_LE: return D_GE; case RQ_OP_GT: return D_LT;
-        case RQ_OP_GE: return D_LE; case RQ_OP_EQ: return D_EQ; case RQ_OP_NEQ: return D_NE;
-        case RQ_OP_EQ_CHAR: return D_EQC; case RQ_OP_EQ_VARCHAR: return D_EQV;
-        case RQ_OP_NEQ_CHAR: return D_NEC; case RQ_OP_NEQ_VARCHAR: return D_NEV;
-        case RQ_OP_LIKE: return D_RLIKE;
     }
     return 0;
 }

@@ -1,8 +1,8 @@
 // Hash tables in HBM: join build/probe and high-cardinality GROUP BY.
 // Replaces src/qlib/hash.h of the reference (linear probing with a stored hash per entry,
-// :385-478) and its users hashjoin.h:118-279 / aggregation.h:240-295. Layout is columnar:
-// one 64-bit tag word per slot (0 = empty, 1 = being written, else hash|2), key words and
-// payload/accumulator words in separate arrays indexed by slot.
+// :385-478) and its users hashjoin.h:118-279 / aggregation.h:240-295. Entries are packed rows
+// [tag][key words][payload / accumulator words] padded to a multiple of 32 bytes; tag 0 = empty,
+// 1 = being written, else hash|2.
 #pragma once
 #include <cuda_runtime.h>
 #include "rq_internal.h"
@@ -169,14 +169,6 @@ __global__ void rq_ht_init(DHashTable ht, const uint8_t* kinds, int init_vals) {
         if (init_vals)
             for (int a = 0; a < ht.nv; a++) e[1 + ht.nk + a] = (uint64_t)agg_identity(kinds[a]);
     }
-}
-
-__global__ void rq_ht_count(DHashTable ht, unsigned long long* count) {
-    const uint64_t cap = ht.cap_mask + 1;
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool used = i < cap && *ht_entry(ht, i) != 0ULL;
-    const unsigned bal = __ballot_sync(0xffffffffu, used);
-    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, (unsigned long long)__popc(bal));
 }
 
 // occupied slots -> dense int64 columns. colmap[c] < nk selects key word colmap[c], otherwise

@@ -260,11 +260,6 @@ extern __shared__ __align__(128) unsigned char rq_smem[];
 #define RQ_EX_EQ(x, y)   ((int64_t)((x) == (y)))
 #define RQ_EX_NE(x, y)   ((int64_t)((x) != (y)))
 
-static_assert(kNAR == 6, "register accumulators are sized for 6 aggregates");
-// The aggregate-index switch must stay a switch over compile-time register names: an inline asm
-// marker that differs per case keeps the compiler from merging the cases into one body that
-// indexes the accumulator array dynamically (which would demote it to local memory).
-#define RQ_NOMERGE(A) asm volatile("// agg case %0" ::"n"(A))
 template <int GR> struct ScanCfg;
 template <> struct ScanCfg<0> { static constexpr int kThreads = 512; };
 template <> struct ScanCfg<1> { static constexpr int kThreads = 512; };
@@ -289,7 +284,6 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     uint32_t bars_o = bars_;
     asm volatile("" : "+r"(lane), "+r"(wbase), "+r"(bars_o));
     const uint32_t bars = bars_o;
-    const uint32_t slot_base = wbase + P.slots_rel;
     const uint32_t sacc = wbase + P.acc_rel;            // GR == 0 low-card path: [g][a][lane] int64
 
     const int64_t n_rows = P.n_rows_ptr ? *P.n_rows_ptr : P.n_rows;
@@ -474,7 +468,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                 RQ_MULI32(U_MULADDI32, x + k)
                 RQ_MULI32(U_MULSUBI32, x - k)
                 RQ_MULI32(U_MULRSUBI32, k - x)
-                RQ_MULI32(U_MUL32_MM, x)
+                RQ_MULI32(U_MUL32_MM, ((void)k, x))
 #undef RQ_MULI32
 
                 case U_GEN: {
