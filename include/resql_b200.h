@@ -156,6 +156,11 @@ typedef struct {
 
 #define RQ_SRC_TABLE     1   /* source_id indexes rq_plan.tables                               */
 #define RQ_SRC_PIPELINE  2   /* source_id = earlier pipeline whose sink is AGG or MATERIALIZE  */
+#define RQ_SRC_CROSS     3   /* cross product of two earlier materialized pipelines, source_id x
+                                source_id2 (NestedLoopsJoinOp, nestedloopsjoin.h:5-94: both children
+                                are materialized, every pair is produced, an optional condition
+                                follows as RQ_OP_FILTER). COL indices address the columns of
+                                source_id first, then those of source_id2.                       */
 
 #define RQ_SINK_AGG          1   /* GROUP BY keys + aggregates (aggregation.h:240-295)          */
 #define RQ_SINK_BUILD        2   /* hash-join build: keys + payload (hashjoin.h:226-256)        */
@@ -181,6 +186,8 @@ typedef struct {
     int32_t         n_vals;        /* AGG: aggregates; BUILD: payload; MATERIALIZE: columns    */
     const rq_value* vals;
     int64_t         size_hint;     /* expected sink cardinality (RelOperator::getSize), 0 = ?  */
+    int32_t         source_id2;    /* RQ_SRC_CROSS: the second materialized pipeline           */
+    int32_t         reserved;
 } rq_pipeline;
 /* Output column order of a pipeline: keys first, then vals (aggregation.h:326). */
 

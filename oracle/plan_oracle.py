@@ -126,6 +126,12 @@ def _run_pipeline(plan, p, tables, outs, pool):
     if p["source_kind"] == 1:
         t = plan["tables"][p["source_id"]]
         src = [_to_value(np.asarray(tables[t["name"]][c])) for c in t["columns"]]
+    elif p["source_kind"] == 3:
+        # NestedLoopsJoinOp (nestedloopsjoin.h:5-94): both children materialized, every pair produced
+        left, right = list(outs[p["source_id"]][0]), list(outs[p["source_id2"]][0])
+        nl = len(left[0]) if left else 0
+        nr = len(right[0]) if right else 0
+        src = [np.repeat(c, nr) for c in left] + [np.tile(c, nl) for c in right]
     else:
         src = list(outs[p["source_id"]][0])
     n = len(src[0]) if src else 0

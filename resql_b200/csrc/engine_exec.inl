@@ -888,12 +888,47 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
     simplify_pipeline(pl_in, sp);
     const rq_pipeline& pl = sp.pl;
     const rq_table* src = nullptr;
+    std::unique_ptr<rq_table> cross_holder;
     if (src_override) {
         src = src_override;
     } else if (pl.source_kind == RQ_SRC_TABLE) {
         if (pl.source_id < 0 || pl.source_id >= plan.n_tables || !plan.tables[pl.source_id])
             raise(RQ_ERR_INVALID, "pipeline %d: table %d out of range", pi, pl.source_id);
         src = plan.tables[pl.source_id];
+    } else if (pl.source_kind == RQ_SRC_CROSS) {
+        // NestedLoopsJoinOp: materialize the cross product of two earlier relations, then run the
+        // pipeline (condition, projection, sink) over it like over any other relation
+        const int a = pl.source_id, b = pl_in.source_id2;
+        if (a < 0 || a >= pi || b < 0 || b >= pi || !outs[a].table || !outs[b].table)
+            raise(RQ_ERR_INVALID, "pipeline %d: cross product needs two earlier relation outputs", pi);
+        const rq_table& L = *outs[a].table;
+        const rq_table& R = *outs[b].table;
+        int64_t nl = L.n_rows, nr = R.n_rows;
+        if (nl < 0 || nr < 0) CK(cudaStreamSynchronize(E.stream));
+        if (nl < 0) CK(cudaMemcpy(&nl, L.d_n_rows, 8, cudaMemcpyDeviceToHost));
+        if (nr < 0) CK(cudaMemcpy(&nr, R.d_n_rows, 8, cudaMemcpyDeviceToHost));
+        const int ncols = (int)(L.cols.size() + R.cols.size());
+        if (ncols > kMaxStagedCols) raise(RQ_ERR_UNSUPPORTED, "nested-loops join over more than %d columns", kMaxStagedCols);
+        if (nl > 0 && nr > ((int64_t)1 << 28) / nl)
+            raise(RQ_ERR_UNSUPPORTED, "nested-loops join of %lld x %lld tuples exceeds the materialization limit (2^28 pairs)",
+                  (long long)nl, (long long)nr);
+        cross_holder = new_intermediate(ncols, nl * nr);
+        CrossCols cc;
+        memset(&cc, 0, sizeof(cc));
+        cc.n_left = (int32_t)L.cols.size(); cc.n_right = (int32_t)R.cols.size();
+        for (int c = 0; c < cc.n_left; c++) cc.in[c] = (const int64_t*)L.cols[c].d;
+        for (int c = 0; c < cc.n_right; c++) cc.in[cc.n_left + c] = (const int64_t*)R.cols[c].d;
+        for (int c = 0; c < ncols; c++) cc.out[c] = (int64_t*)cross_holder->cols[c].d;
+        const int64_t total = nl * nr;
+        if (total > 0) {
+            rq_cross_product<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, E.stream>>>(cc, nl, nr);
+            if (tm) tm->kernel_launches++;
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(cross_holder->d_n_rows, &total, 8, cudaMemcpyHostToDevice, E.stream));
+        CK(cudaStreamSynchronize(E.stream));      // `total` is a stack variable
+        cross_holder->n_rows = total;
+        src = cross_holder.get();
     } else if (pl.source_kind == RQ_SRC_PIPELINE) {
         if (pl.source_id < 0 || pl.source_id >= pi || !outs[pl.source_id].table)
             raise(RQ_ERR_INVALID, "pipeline %d: source pipeline %d has no relation output", pi, pl.source_id);
@@ -1294,7 +1329,7 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
         return false;
     }
     memset(&sp.a, 0, sizeof(sp.a));
-    sp.a.source_kind = pl.source_kind; sp.a.source_id = pl.source_id;
+    sp.a.source_kind = pl.source_kind; sp.a.source_id = pl.source_id; sp.a.source_id2 = pl.source_id2;
     sp.a.n_nodes = (int)sp.a_nodes.size(); sp.a.nodes = sp.a_nodes.data();
     sp.a.n_args = (int)sp.a_args.size(); sp.a.args = sp.a_args.data();
     sp.a.sink_kind = RQ_SINK_MATERIALIZE;

@@ -1177,6 +1177,17 @@ __global__ void rq_gather_str(const int64_t* addrs, unsigned char* out, int widt
     }
 }
 
+// cross product of two materialized relations (NestedLoopsJoinOp): row i = (left i / nr, right i % nr)
+struct CrossCols { const int64_t* in[kMaxStagedCols]; int64_t* out[kMaxStagedCols]; int32_t n_left; int32_t n_right; };
+__global__ void rq_cross_product(CrossCols cc, int64_t nl, int64_t nr) {
+    const int64_t total = nl * nr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t li = i / nr, ri = i - li * nr;
+        for (int c = 0; c < cc.n_left; c++) cc.out[c][i] = cc.in[c][li];
+        for (int c = 0; c < cc.n_right; c++) cc.out[cc.n_left + c][i] = cc.in[cc.n_left + c][ri];
+    }
+}
+
 // sharded merge: pack the local relation as [ncols][stride] for one all-gather, and unpack the
 // gathered [world][ncols][stride] into dense columns in rank order (one launch each instead of
 // world x ncols small copies)

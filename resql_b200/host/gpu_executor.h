@@ -56,7 +56,7 @@ struct ValueInfo {
 };
 
 struct PipelineDesc {
-    int source_kind = 0, source_id = 0;
+    int source_kind = 0, source_id = 0, source_id2 = 0;
     std::vector<rq_node>  nodes;
     std::vector<int32_t>  args;
     int sink_kind = 0;
@@ -105,6 +105,7 @@ public:
     std::map<RelOperator*, SymbolSet> requests;
     std::map<RelOperator*, int> joinCalls;
     std::map<RelOperator*, int> joinBuildPipe;
+    std::map<RelOperator*, int> matPipe;        /* inner MaterializeOp -> pipeline that fills it */
     int exprIdGen = 1;                          /* RelationalContext::exprIdGen                  */
 
     Lowering ( Database& db, bool requestAll ) : db ( db ), requestAll ( requestAll ) {}
@@ -354,6 +355,13 @@ public:
             produce ( hj->_rChild, allReq );
             return;
         }
+        if ( auto* nlj = dynamic_cast<NestedLoopsJoinOp*> ( op ) ) {
+            /* nestedloopsjoin.h:53-67: both (materialized) children are produced with the parent's request */
+            joinCalls [ op ] = 0;
+            produce ( nlj->_lChild, request );
+            produce ( nlj->_rChild, request );
+            return;
+        }
         if ( dynamic_cast<OrderByOp*> ( op ) ) {
             auto* ob = static_cast<OrderByOp*> ( op );
             produce ( ob->_child, request );
@@ -461,7 +469,41 @@ public:
             }
             throw ResqlError ( "HashJoin::consumeFlounder(..) called more than 2 times." );
         }
+        if ( auto* nlj = dynamic_cast<NestedLoopsJoinOp*> ( op ) ) {
+            /* nestedloopsjoin.h:70-93: after both children are materialized every pair of tuples is
+             * produced (schema = left ++ right), the optional condition drops pairs */
+            int call = ++joinCalls [ op ];
+            if ( call < 2 ) return;
+            Schema ls = schemas [ nlj->_lChild ], rs = schemas [ nlj->_rChild ];
+            newPipeline ( RQ_SRC_CROSS, matPipe [ nlj->_lChild ] );
+            P().source_id2 = matPipe [ nlj->_rChild ];
+            int col = 0;
+            for ( auto& a : ls._attribs ) env [ a.name ] = { node ( RQ_OP_COL, col++ ), a.type };
+            for ( auto& a : rs._attribs ) env [ a.name ] = { node ( RQ_OP_COL, col++ ), a.type };
+            schemas [ op ] = ls.join ( rs );
+            if ( nlj->_condition != nullptr ) {
+                addIds ( nlj->_condition );
+                node ( RQ_OP_FILTER, lower ( nlj->_condition ) );
+            }
+            consume ( op->_parent, op );
+            return;
+        }
         if ( dynamic_cast<OrderByOp*> ( op ) ) return;
+        if ( op->isMaterializedOperator() && op->_parent != nullptr && dynamic_cast<NestedLoopsJoinOp*> ( op->_parent ) ) {
+            /* MaterializeOp wrapped around a nested-loops join child (nestedloopsjoin.h:25-26) */
+            Schema s = schemas [ op->_child ];
+            schemas [ op ] = s;
+            PipelineDesc& p = P();
+            p.sink_kind = RQ_SINK_MATERIALIZE;
+            for ( auto& a : s._attribs ) {
+                auto it = env.find ( a.name );
+                if ( it == env.end() ) throw ResqlError ( "GPU engine: attribute " + a.name + " not available" );
+                p.vals.push_back ( valueOf ( it->second.node, a.type ) );
+            }
+            matPipe [ op ] = cur;
+            consume ( op->_parent, op );
+            return;
+        }
         if ( op->isMaterializedOperator() ) {
             Schema s = schemas [ op->_child ];
             schemas [ op ] = s;
@@ -539,7 +581,7 @@ public:
         o << "],\n \"pipelines\": [\n";
         for ( size_t p = 0; p < pipelines.size(); p++ ) {
             PipelineDesc& pd = pipelines[p];
-            o << "  {\"source_kind\": " << pd.source_kind << ", \"source_id\": " << pd.source_id << ", \"sink_kind\": " << pd.sink_kind
+            o << "  {\"source_kind\": " << pd.source_kind << ", \"source_id\": " << pd.source_id << ", \"source_id2\": " << pd.source_id2 << ", \"sink_kind\": " << pd.sink_kind
               << ", \"size_hint\": " << pd.size_hint << ",\n   \"nodes\": [";
             for ( size_t i = 0; i < pd.nodes.size(); i++ ) {
                 rq_node& n = pd.nodes[i];
@@ -695,7 +737,7 @@ std::unique_ptr < SelectResult > executeSelectPlanGpu ( RelOperator*  root,
             for ( size_t i = 0; i < pls.size(); i++ ) {
                 rqshim::PipelineDesc& pd = low.pipelines[i];
                 rq_pipeline& p = pls[i];
-                p.source_kind = pd.source_kind; p.source_id = pd.source_id;
+                p.source_kind = pd.source_kind; p.source_id = pd.source_id; p.source_id2 = pd.source_id2; p.reserved = 0;
                 p.n_nodes = (int) pd.nodes.size(); p.nodes = pd.nodes.data();
                 p.n_args = (int) pd.args.size(); p.args = pd.args.data();
                 p.sink_kind = pd.sink_kind;

@@ -43,7 +43,7 @@ class rq_pipeline(C.Structure):
                 ("sink_kind", C.c_int32),
                 ("n_keys", C.c_int32), ("keys", C.POINTER(rq_value)),
                 ("n_vals", C.c_int32), ("vals", C.POINTER(rq_value)),
-                ("size_hint", C.c_int64)]
+                ("size_hint", C.c_int64), ("source_id2", C.c_int32), ("reserved", C.c_int32)]
 
 
 class rq_order_key(C.Structure):

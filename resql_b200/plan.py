@@ -14,7 +14,7 @@ OPS = ["", "COL", "CONST", "CONST_STR", "ADD", "SUB", "MUL", "DIV", "AND", "OR",
        "FILTER", "PROBE", "PAYLOAD"]
 OP = {n: i for i, n in enumerate(OPS) if n}
 AGG = {"SUM": 1, "COUNT": 2, "MIN": 3, "MAX": 4}
-SRC_TABLE, SRC_PIPELINE = 1, 2
+SRC_TABLE, SRC_PIPELINE, SRC_CROSS = 1, 2, 3
 SINK_AGG, SINK_BUILD, SINK_MATERIALIZE = 1, 2, 3
 
 
@@ -79,6 +79,7 @@ class Plan:
             pl.n_keys, pl.keys = len(p["keys"]), keys
             pl.n_vals, pl.vals = len(p["vals"]), vals
             pl.size_hint = p.get("size_hint", 0)
+            pl.source_id2 = p.get("source_id2", 0)
         order = (N.rq_order_key * max(1, len(self.order)))()
         for j, o in enumerate(self.order):
             order[j].column, order[j].ascending = o

@@ -68,6 +68,14 @@ QUERIES = {
     # the reference's README microbenchmark (README:69; BASELINE config 5): bigint join + avg + group by
     "micro_join_avg": "select c, avg(d * a) from foo, bar where a = d group by c order by c",
     "micro_join_few_groups": "select c * 0 as g, avg(d * a), count(*), max(a) from foo, bar where a = d group by c * 0",
+    # nested-loops join (nestedloopsjoin.h; the planner's fallback for cross products / non-equi joins,
+    # planner.h:453-463; test_operators.h has three NLJ shapes incl. a cross product)
+    "nlj_cross_filter": """select c_custkey, o_orderkey, c_acctbal, o_totalprice from customer, orders
+        where c_custkey < 10 and o_orderkey < 100 and c_acctbal < o_totalprice order by c_custkey, o_orderkey""",
+    "nlj_cross_agg": """select count(*) as n, sum(c_acctbal) as s, max(o_totalprice) as m from customer, orders
+        where c_custkey < 30 and o_orderkey < 300""",
+    "nlj_noneq_group": """select c_mktsegment, count(*) as c, min(o_orderdate) as d from customer, orders
+        where c_custkey < 50 and o_orderkey < 400 and c_acctbal * 20 > o_totalprice group by c_mktsegment order by c_mktsegment""",
     "case_sum": """select l_shipmode, sum(case when l_quantity > 25 then 1 else 0 end) as hi,
         sum(case when l_quantity <= 25 then l_extendedprice else 0 end) as lo
         from lineitem group by l_shipmode order by l_shipmode""",

@@ -131,7 +131,7 @@ def test_host_front_end_end_to_end(sf001, tmp_path):
         p = tmp_path / f"{name}.bin"
         tpch.to_rows(name, cols).tofile(p)
         loads.append(f"binload {name} {p}")
-    for q in ("q6", "q1", "q3", "q5", "q10", "q12", "q14", "sel_or", "agg_neg_avg", "micro_join_avg", "join_dups_agg"):
+    for q in ("q6", "q1", "q3", "q5", "q10", "q12", "q14", "sel_or", "agg_neg_avg", "micro_join_avg", "join_dups_agg", "nlj_cross_agg", "nlj_cross_filter"):
         out = tmp_path / f"{q}.out"
         sql = " ".join(QUERIES[q].split())
         r = subprocess.run([exe, "--quiet"] + loads + [f"out {out}", sql], capture_output=True, text=True, timeout=300)

@@ -12,7 +12,7 @@ import vm_model
 
 
 def _has_join(plan):
-    return any(p["sink_kind"] == 2 for p in plan["pipelines"])
+    return any(p["sink_kind"] == 2 or p["source_kind"] == 3 for p in plan["pipelines"])
 
 
 def _has_string_key(plan):
