@@ -43,6 +43,21 @@ def _worker(rank, world, port, failures):
                 assert_same_relation(got, want, d, f"{name} sharded over {world} ranks (rank {rank})")
             except AssertionError as e:
                 failures.put(str(e))
+        # random plans (tests/plan_fuzz.py): the probe-side table of the main pipeline is sharded
+        from oracle.plan_oracle import run_plan
+        from plan_fuzz import random_plan
+        for seed in range(40):
+            d = random_plan(seed)
+            tabs = plan_tables(d, data)
+            try:
+                want = serialize_columns(*run_plan(d, tabs))
+            except ZeroDivisionError:
+                continue
+            got = serialize_columns(*run_plan_sharded(d, tabs, d["tables"][-1]["name"], rank, world, all_gather))
+            try:
+                assert_same_relation(got, want, d, f"random plan {seed} sharded over {world} ranks (rank {rank})")
+            except AssertionError as e:
+                failures.put(str(e))
     finally:
         dist.destroy_process_group()
 
