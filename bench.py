@@ -36,8 +36,14 @@ def load_plan(name):
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        try:
+            with open(p) as f:
+                d = json.load(f)
+            for key in ("hbm_gbs", "hbm_gbs_burst", "hbm_gbs_sustained"):
+                if key in d and float(d[key]) > 0:
+                    return float(d[key]), f"measured (MEASURED_PEAKS.json {key})"
+        except (OSError, ValueError, TypeError):
+            pass
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
