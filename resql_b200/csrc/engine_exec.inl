@@ -1798,7 +1798,9 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
         KParams P;
         memset(&P, 0, sizeof(P));
         P.expand_probe = -1;
-        Lowerer L(*plan, sp.pl, fake, outs, (const char*)0, P);
+        // string constants are lowered to pool base + offset; a recognisable fake base lets the Python
+        // model of the VM (tests/vm_model.py) tell them from numeric constants
+        Lowerer L(*plan, sp.pl, fake, outs, (const char*)(uintptr_t)(1ULL << 44), P);
         L.prepare();
         AggDedup ad;
         if (sp.pl.sink_kind == RQ_SINK_AGG) ad = dedup_aggs(sp.pl);

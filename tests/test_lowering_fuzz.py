@@ -1,8 +1,7 @@
 """CPU-only: the host-side lowering (constant folding, CSE, fused compares / ranges / multiply-adds,
 32-bit forms from interval analysis, slot assignment) of RANDOM plans (tests/plan_fuzz.py), executed
 by the Python model of the device VM, must reproduce the plan oracle. Join plans and string group
-keys are lowered against device state and are covered by the GPU suite; plans with string constants
-are left out because the model cannot tell a pool offset from a numeric constant."""
+keys are lowered against device state and are covered by the GPU suite."""
 import numpy as np
 import pytest
 
@@ -14,8 +13,6 @@ import vm_model
 
 
 def _eligible(d):
-    if d.get("strpool"):
-        return False
     if any(p["sink_kind"] == 2 or p["source_kind"] == 3 for p in d["pipelines"]):
         return False
     return not any(PO._is_str(k[2], k[3]) for p in d["pipelines"] if p["sink_kind"] == 1 for k in p["keys"])
@@ -25,7 +22,7 @@ SEEDS = [s for s in range(160) if _eligible(random_plan(s))]
 
 
 def test_enough_random_plans_are_eligible():
-    assert len(SEEDS) >= 30
+    assert len(SEEDS) >= 50
 
 
 @pytest.mark.parametrize("agg_impl", [vm_model.IMPL_REGAGG, vm_model.IMPL_LOWAGG])
@@ -38,6 +35,7 @@ def test_lowered_random_plan_matches_oracle(seed, agg_impl, sf001):
     except ZeroDivisionError:
         pytest.skip("plan divides by zero")
     plan = Plan(d)
+    pool = d.get("strpool", "").encode("latin1")
     outs = []
     for pi, p in enumerate(d["pipelines"]):
         if p["source_kind"] == 1:
@@ -45,7 +43,8 @@ def test_lowered_random_plan_matches_oracle(seed, agg_impl, sf001):
             src = [np.asarray(tables[t["name"]][c]) for c in t["columns"]]
         else:
             src = outs[p["source_id"]]
-        outs.append(vm_model.run_pipeline_vm(plan, pi, src, {}, agg_impl, True))
+        pool_strings = {nd[4]: pool[nd[4]:].split(b"\0")[0] for nd in p["nodes"] if nd[0] == 3}
+        outs.append(vm_model.run_pipeline_vm(plan, pi, src, pool_strings, agg_impl, True))
     last = d["pipelines"][-1]
     st = [k[2] for k in last["keys"]] + [v[2] for v in last["vals"]]
     sw = [k[3] for k in last["keys"]] + [v[3] for v in last["vals"]]

@@ -12,6 +12,7 @@ from resql_b200 import native as N
 S_NONE, S_COL, S_SLOT, S_IMM, S_STR = range(5)
 H_FCMP, H_BIN, H_MULI, H_SEL, H_PROBE, H_FRANGE = range(1, 7)
 IMPL_LOWAGG, IMPL_HASHAGG, IMPL_BUILD, IMPL_EMIT, IMPL_REGAGG = 1, 2, 3, 4, 5
+STR_BASE = 1 << 44      # pool base rq_debug_lower lowers string constants against
 
 
 def phys_of(arr):
@@ -100,8 +101,8 @@ def run_pipeline_vm(plan, pi, src_cols, pool_strings, agg_impl=IMPL_LOWAGG, with
         if kind == S_SLOT:
             return slots[idx]
         if kind == S_IMM:
-            if imm in pool_strings:
-                return PO._bcast(pool_strings[imm], n)
+            if imm >= STR_BASE and (imm - STR_BASE) in pool_strings:     # rq_debug_lower's fake pool base
+                return PO._bcast(pool_strings[imm - STR_BASE], n)
             return np.full(n, imm, dtype=np.int64)
         return None
 
