@@ -259,46 +259,76 @@ def main():
     value = 3.0 * n_total * a.steps / dt
 
     # ---- independent check at full size: the same queries evaluated with torch int64 ops -------
+    # At N > 1 every rank evaluates its own row range and the partial values are all-reduced
+    # (mod-2^64 sums, aggregation.h:182-204: AVG only after the global merge), then compared with
+    # the merged result every rank got back from the library. A false check fails the run.
+    def allsum(x):
+        t = torch.tensor([x], device=dev, dtype=torch.int64) if not torch.is_tensor(x) else x.clone()
+        if world > 1:
+            dist.all_reduce(t)
+        return t
+
     checks = {}
-    if world == 1:
-        m = (li["l_shipdate"] >= 19940101) & (li["l_shipdate"] < 19950101) & (li["l_discount"] >= 5) & \
-            (li["l_discount"] <= 7) & (li["l_quantity"] < 24)
-        want = int((li["l_extendedprice"] * li["l_discount"])[m].sum().item())
-        got = int(last["q6"][0].columns[0][0]) if last["q6"][0].n_rows else None
-        checks["q6_vs_torch"] = (got == want)
-        m1 = li["l_shipdate"] <= 19980902
-        key = li["l_returnflag"].to(torch.int64) * 256 + li["l_linestatus"].to(torch.int64)
-        charge = li["l_extendedprice"] * (100 - li["l_discount"]) * (100 + li["l_tax"])
-        ok = True
-        res1 = last["q1"][0]
-        for i in range(res1.n_rows):
-            kk = int(res1.columns[0][i]) * 256 + int(res1.columns[1][i])
-            sel = m1 & (key == kk)
-            ok &= int(res1.columns[9][i]) == int(sel.sum().item())
-            ok &= int(res1.columns[5][i]) == int(charge[sel].sum().item())
-            ok &= int(res1.columns[2][i]) == int(li["l_quantity"][sel].sum().item())
-        checks["q1_vs_torch"] = bool(ok) and res1.n_rows > 0
-        del m, m1, key, charge
-        # Q3: top-10 revenue, recomputed with torch joins (searchsorted on the unique keys)
-        try:
-            cb = cust["c_custkey"][(cust["c_mktsegment"][:, :8] == torch.tensor(list(b"BUILDING"), device=dev, dtype=torch.uint8)).all(1)
-                                   & (cust["c_mktsegment"][:, 8] == 0)]
-            o_ok = (orders["o_orderdate"] < 19950315) & torch.isin(orders["o_custkey"], cb)
-            ok_keys, _ = torch.sort(orders["o_orderkey"][o_ok])
-            lm = li["l_shipdate"] > 19950315
-            lk = li["l_orderkey"][lm]
-            pos = torch.searchsorted(ok_keys, lk).clamp(max=max(ok_keys.numel() - 1, 0))
-            hit = ok_keys[pos] == lk if ok_keys.numel() else torch.zeros_like(lk, dtype=torch.bool)
-            rev = (li["l_extendedprice"][lm] * (100 - li["l_discount"][lm]))[hit]
-            uk, inv = torch.unique(lk[hit], return_inverse=True)
-            tot = torch.zeros(uk.numel(), dtype=torch.int64, device=dev).index_add_(0, inv, rev)
-            top = torch.sort(tot, descending=True).values[:10].tolist()
-            res3 = last["q3"][0]
-            checks["q3_top10_revenue_vs_torch"] = [int(x) for x in res3.columns[1]] == top
-            del o_ok, ok_keys, lm, lk, pos, hit, rev, uk, inv, tot
-        except Exception as e:       # the check is independent evidence, never part of the timed path
-            checks["q3_top10_revenue_vs_torch"] = f"not run: {e}"
-        torch.cuda.empty_cache()
+    m = (li["l_shipdate"] >= 19940101) & (li["l_shipdate"] < 19950101) & (li["l_discount"] >= 5) & \
+        (li["l_discount"] <= 7) & (li["l_quantity"] < 24)
+    want = int(allsum((li["l_extendedprice"] * li["l_discount"])[m].sum().reshape(1))[0].item())
+    got = int(last["q6"][0].columns[0][0]) if last["q6"][0].n_rows else None
+    checks["q6_vs_torch"] = (got == want)
+    m1 = li["l_shipdate"] <= 19980902
+    key = li["l_returnflag"].to(torch.int64) * 256 + li["l_linestatus"].to(torch.int64)
+    charge = li["l_extendedprice"] * (100 - li["l_discount"]) * (100 + li["l_tax"])
+    res1 = last["q1"][0]
+    n_groups_total = int(allsum(torch.unique(key[m1]).numel())[0].item()) if world == 1 else None
+    ok = res1.n_rows > 0 and (world > 1 or res1.n_rows == n_groups_total)
+    for i in range(res1.n_rows):
+        kk = int(res1.columns[0][i]) * 256 + int(res1.columns[1][i])
+        sel = m1 & (key == kk)
+        part = torch.stack([sel.sum(), charge[sel].sum(), li["l_quantity"][sel].sum(),
+                            (li["l_extendedprice"][sel] * (100 - li["l_discount"][sel])).sum(),
+                            li["l_discount"][sel].sum()])
+        tot = [int(x) for x in allsum(part).tolist()]
+        ok &= int(res1.columns[9][i]) == tot[0]
+        ok &= int(res1.columns[5][i]) == tot[1]
+        ok &= int(res1.columns[2][i]) == tot[2]
+        ok &= int(res1.columns[4][i]) == tot[3]
+        ok &= tot[0] > 0 and int(res1.columns[8][i]) == (tot[4] * 100) // tot[0]      # AVG after the merge, truncating
+    # every valid tuple belongs to exactly one reported group
+    ok &= int(sum(int(x) for x in res1.columns[9])) == int(allsum(m1.sum().reshape(1))[0].item())
+    checks["q1_vs_torch"] = bool(ok)
+    del m, m1, key, charge
+    # Q3: top-10 revenue recomputed with torch joins (searchsorted on the unique keys). Orders are
+    # range-partitioned with their lineitems (tpch_device), so every order's revenue is complete on
+    # one rank: the global top 10 is the top 10 of the ranks' top 10s.
+    try:
+        cb = cust["c_custkey"][(cust["c_mktsegment"][:, :8] == torch.tensor(list(b"BUILDING"), device=dev, dtype=torch.uint8)).all(1)
+                               & (cust["c_mktsegment"][:, 8] == 0)]
+        o_ok = (orders["o_orderdate"] < 19950315) & torch.isin(orders["o_custkey"], cb)
+        ok_keys, _ = torch.sort(orders["o_orderkey"][o_ok])
+        lm = li["l_shipdate"] > 19950315
+        lk = li["l_orderkey"][lm]
+        pos = torch.searchsorted(ok_keys, lk).clamp(max=max(ok_keys.numel() - 1, 0))
+        hit = ok_keys[pos] == lk if ok_keys.numel() else torch.zeros_like(lk, dtype=torch.bool)
+        rev = (li["l_extendedprice"][lm] * (100 - li["l_discount"][lm]))[hit]
+        uk, inv = torch.unique(lk[hit], return_inverse=True)
+        tot = torch.zeros(uk.numel(), dtype=torch.int64, device=dev).index_add_(0, inv, rev)
+        top = torch.sort(tot, descending=True).values[:10]
+        top = torch.cat([top, torch.full((10 - top.numel(),), -1, dtype=torch.int64, device=dev)])
+        if world > 1:
+            alltop = [torch.empty_like(top) for _ in range(world)]
+            dist.all_gather(alltop, top)
+            top = torch.sort(torch.cat(alltop), descending=True).values[:10]
+        top = [int(x) for x in top.tolist() if x >= 0]
+        res3 = last["q3"][0]
+        checks["q3_top10_revenue_vs_torch"] = [int(x) for x in res3.columns[1]] == top
+        del o_ok, ok_keys, lm, lk, pos, hit, rev, uk, inv, tot
+    except Exception as e:       # the check is independent evidence, never part of the timed path
+        checks["q3_top10_revenue_vs_torch"] = f"not run: {e}"
+    # all ranks must agree (every rank holds the merged result)
+    if world > 1:
+        flag = torch.tensor([int(all(v is True for v in checks.values()))], device=dev, dtype=torch.int64)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        checks["all_ranks_agree"] = bool(flag.item() == 1)
+    torch.cuda.empty_cache()
 
     # ---- e2e: host buffers through the C ABI, H2D inside the timed region -------------------------
     e2e = None
@@ -360,7 +390,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return 0
+        return 1 if any(v is False for v in checks.values()) else 0
 
     peak, peak_src = measured_peak()
     traffic_tab = {}
@@ -423,6 +453,10 @@ def main():
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    bad = [k for k, v in checks.items() if v is False]
+    if bad:
+        print(f"bench.py: result check(s) failed: {bad}", file=sys.stderr)
+        return 1
     return 0
 
 

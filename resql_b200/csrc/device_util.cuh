@@ -60,6 +60,13 @@ __device__ __forceinline__ void tma_bulk_g2s_hint(uint32_t dst, const void* src,
 __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
+// one lane of the (converged) warp; ptxas then issues a following bulk copy once instead of
+// looping over the active lanes
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"

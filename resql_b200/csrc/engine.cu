@@ -64,10 +64,19 @@ struct RqError {
 // ------------------------------------------------------------------------------------------
 // engine state
 // ------------------------------------------------------------------------------------------
+// Storage layout. Tables the engine owns are stored TILE-MAJOR: the table is a sequence of pages of
+// kTile (256) rows; a page holds the 256-row chunk of every fixed-width column back to back
+// ([col0: 256 x w0][col1: 256 x w1]...). A warp tile of the scan kernel is exactly one page, so the
+// chunks of all adjacent scanned columns arrive with ONE cp.async.bulk (every chunk is a multiple of
+// 256 bytes: source, destination and size are always 16-byte aligned). String columns (accessed by
+// address, never staged) stay plain arrays. Borrowed device columns and pipeline intermediates are
+// plain arrays: one copy per column per tile.
 struct DevColumn {
     int type = 0, width = 0;
-    unsigned char* d = nullptr;
+    unsigned char* d = nullptr;     // plain array, or the column's chunk in page 0 of a tile-major table
     bool owned = true;
+    int64_t tile_stride = 0;        // bytes from one tile's chunk to the next (plain: kTile * width)
+    uint32_t page_off = 0;          // tile-major: offset of the chunk inside a page
     // exact value bounds over all rows, taken once at upload (the data of a table never changes
     // afterwards: the reference's tables are append-only and re-uploaded per version). They let the
     // lowering prove that a value fits in 32 bits and pick the narrow instruction forms.
@@ -80,12 +89,15 @@ struct rq_table {
     int64_t cap_rows = 0;     // allocated rows (multiple of kTileRows for owned tables)
     int64_t* d_n_rows = nullptr;
     bool borrowed = false;
+    unsigned char* pax_base = nullptr;   // tile-major storage of the fixed-width columns (owned tables)
+    size_t page_bytes = 0;
     std::vector<DevColumn> cols;
     // logical type info for intermediates (per column)
     std::vector<int> sql_type, sql_width;
     ~rq_table() {
         for (auto& c : cols)
             if (c.owned && c.d) dfree(c.d);
+        if (pax_base) dfree(pax_base);
         if (d_n_rows) dfree(d_n_rows);
     }
 };
@@ -198,6 +210,40 @@ static bool valid_col(int type, int width) {
     return false;
 }
 
+// allocates the storage of an owned table (cap_rows must be set): fixed-width columns tile-major in
+// one block, strings as plain arrays; everything behind n_rows is zero
+template <typename FT, typename FW>
+static void alloc_tile_major(rq_table& t, int n_cols, FT type_of, FW width_of) {
+    size_t page = 0;
+    for (int c = 0; c < n_cols; c++) {
+        DevColumn dc;
+        dc.type = type_of(c);
+        dc.width = width_of(c);
+        if (dc.type != RQ_STR) { dc.page_off = (uint32_t)page; page += (size_t)kTile * dc.width; dc.owned = false; }
+        t.cols.push_back(dc);
+    }
+    t.page_bytes = page;
+    const int64_t pages = t.cap_rows / kTile;
+    if (page) {
+        CK(dmalloc(&t.pax_base, (size_t)pages * page));
+        // rows behind n_rows read as zero: clear from the page that holds row n_rows to the end
+        const int64_t first = std::max<int64_t>(t.n_rows, 0) / kTile;
+        CK(cudaMemsetAsync(t.pax_base + (size_t)first * page, 0, (size_t)(pages - first) * page, E.stream));
+    }
+    for (auto& dc : t.cols) {
+        if (dc.type != RQ_STR) {
+            dc.d = t.pax_base + dc.page_off;
+            dc.tile_stride = (int64_t)page;
+        } else {
+            const size_t bytes = (size_t)t.cap_rows * dc.width;
+            CK(dmalloc(&dc.d, bytes));
+            dc.tile_stride = (int64_t)kTile * dc.width;
+            const size_t used = (size_t)std::max<int64_t>(t.n_rows, 0) * dc.width;
+            CK(cudaMemsetAsync(dc.d + used, 0, bytes - used, E.stream));
+        }
+    }
+}
+
 extern "C" int rq_table_upload(const char* name, int32_t n_cols, const rq_column* cols,
                                int64_t n_rows, int32_t flags, rq_table** out) {
     if (!E.init) return fail(RQ_ERR_NOT_INIT, "rq_table_upload before rq_init");
@@ -210,27 +256,39 @@ extern "C" int rq_table_upload(const char* name, int32_t n_cols, const rq_column
         const bool borrow = dev && (flags & RQ_BORROW);
         t->borrowed = borrow;
         t->cap_rows = borrow ? n_rows : round_up(std::max<int64_t>(n_rows, 1), kPadRows);
-        for (int c = 0; c < n_cols; c++) {
+        for (int c = 0; c < n_cols; c++)
             if (!valid_col(cols[c].type, cols[c].width))
                 raise(RQ_ERR_INVALID, "rq_table_upload: column %d has bad type/width %d/%d", c, cols[c].type, cols[c].width);
-            DevColumn dc;
-            dc.type = cols[c].type;
-            dc.width = cols[c].width;
+        if (!borrow) alloc_tile_major(*t, n_cols, [&](int c) { return cols[c].type; }, [&](int c) { return cols[c].width; });
+        const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        for (int c = 0; c < n_cols; c++) {
             if (borrow) {
+                DevColumn dc;
+                dc.type = cols[c].type;
+                dc.width = cols[c].width;
                 if (((uintptr_t)cols[c].data & 15) != 0)
                     raise(RQ_ERR_INVALID, "rq_table_upload: borrowed column %d is not 16-byte aligned", c);
                 dc.d = (unsigned char*)cols[c].data;
                 dc.owned = false;
-            } else {
-                const size_t bytes = (size_t)t->cap_rows * dc.width;
-                CK(dmalloc(&dc.d, bytes));
-                const size_t used = (size_t)n_rows * dc.width;
-                if (used)
-                    CK(cudaMemcpyAsync(dc.d, cols[c].data, used,
-                                       dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, E.stream));
-                if (bytes > used) CK(cudaMemsetAsync(dc.d + used, 0, bytes - used, E.stream));
+                dc.tile_stride = (int64_t)kTile * dc.width;
+                t->cols.push_back(dc);
+                continue;
             }
-            t->cols.push_back(dc);
+            DevColumn& dc = t->cols[c];
+            const size_t used = (size_t)n_rows * dc.width;
+            if (dc.type == RQ_STR) {
+                if (used) CK(cudaMemcpyAsync(dc.d, cols[c].data, used, kind, E.stream));
+                continue;
+            }
+            // full pages with one pitched copy, the partial last page with a plain one
+            const size_t chunk = (size_t)kTile * dc.width;
+            const int64_t full = n_rows / kTile;
+            if (full > 0)
+                CK(cudaMemcpy2DAsync(dc.d, t->page_bytes, cols[c].data, chunk, chunk, (size_t)full, kind, E.stream));
+            const size_t rest = used - (size_t)full * chunk;
+            if (rest)
+                CK(cudaMemcpyAsync(dc.d + (size_t)full * t->page_bytes, (const unsigned char*)cols[c].data + (size_t)full * chunk,
+                                   rest, kind, E.stream));
         }
         compute_stats(*t);
         CK(cudaStreamSynchronize(E.stream));
@@ -261,16 +319,10 @@ extern "C" int rq_table_upload_rows(const char* name, int32_t n_cols, const int3
         t->name = name ? name : "";
         t->n_rows = n_rows;
         t->cap_rows = round_up(std::max<int64_t>(n_rows, 1), kPadRows);
-        for (int c = 0; c < n_cols; c++) {
+        for (int c = 0; c < n_cols; c++)
             if (!valid_col(types[c], widths[c]) || offsets[c] < 0 || offsets[c] + widths[c] > tuple_size)
                 raise(RQ_ERR_INVALID, "rq_table_upload_rows: column %d bad type/width/offset", c);
-            DevColumn dc;
-            dc.type = types[c];
-            dc.width = widths[c];
-            CK(dmalloc(&dc.d, (size_t)t->cap_rows * dc.width));
-            CK(cudaMemsetAsync(dc.d, 0, (size_t)t->cap_rows * dc.width, E.stream));
-            t->cols.push_back(dc);
-        }
+        alloc_tile_major(*t, n_cols, [&](int c) { return types[c]; }, [&](int c) { return widths[c]; });
         if (max_block) {
             CK(dmalloc(&d_rows[0], max_block));
             CK(dmalloc(&d_rows[1], max_block));
@@ -287,7 +339,7 @@ extern "C" int rq_table_upload_rows(const char* name, int32_t n_cols, const int3
             CK(cudaMemcpyAsync(d_rows[s], blocks[b], block_bytes[b], cudaMemcpyHostToDevice, E.stream));
             for (int c = 0; c < n_cols; c++) {
                 rq_transpose_rows<<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(
-                    d_rows[s], n, tuple_size, offsets[c], widths[c], t->cols[c].d, row0);
+                    d_rows[s], n, tuple_size, offsets[c], widths[c], t->cols[c].d, t->cols[c].tile_stride, row0);
             }
             CK(cudaEventRecord(done[s], E.stream));
             row0 += n;
@@ -323,7 +375,7 @@ static void compute_stats(rq_table& t) {
     for (size_t k = 0; k < idx.size(); k++) {
         const DevColumn& dc = t.cols[idx[k]];
         const int grid = (int)std::min<int64_t>((t.n_rows + 256 * 16 - 1) / (256 * 16), (int64_t)E.sm_count * 8);
-        rq_col_minmax<<<std::max(grid, 1), 256, 0, E.stream>>>(dc.d, dc.width, t.n_rows, d + 2 * k);
+        rq_col_minmax<<<std::max(grid, 1), 256, 0, E.stream>>>(dc.d, dc.width, dc.tile_stride, t.n_rows, d + 2 * k);
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, E.stream));
@@ -560,10 +612,37 @@ struct Lowerer {
         for (int k = 0; k < pl.n_keys; k++) sink_use(pl.keys[k].node);
         for (int k = 0; k < pl.n_vals; k++)
             if (!(pl.sink_kind == RQ_SINK_AGG && pl.vals[k].kind == RQ_AGG_COUNT)) sink_use(pl.vals[k].node);
-        // stage layout: one warp tile of every staged column
-        uint32_t off = 0;
-        for (int c = 0; c < P.n_cols; c++) { P.col_off[c] = off; off += kTile * P.col_w[c]; }
-        P.stage_bytes = off;
+        // stage layout: one warp tile of every staged column, in source order (tile-major tables:
+        // page order), so that adjacent columns of a page arrive with one bulk copy
+        {
+            std::vector<int> order;       // staged columns
+            for (int c = 0; c < P.n_cols; c++) order.push_back(c);
+            std::vector<int> src_of(P.n_cols, -1);
+            for (size_t k = 0; k < staged_of_col.size(); k++)
+                if (src.cols[k].type != RQ_STR && staged_of_col[k] >= 0) src_of[staged_of_col[k]] = (int)k;
+            const bool tile_major = src.pax_base != nullptr;
+            if (tile_major)
+                std::sort(order.begin(), order.end(), [&](int a, int b) { return src.cols[src_of[a]].page_off < src.cols[src_of[b]].page_off; });
+            uint32_t off = 0;
+            P.n_runs = 0;
+            for (int c : order) {
+                const DevColumn& dc = src.cols[src_of[c]];
+                const uint32_t bytes = (uint32_t)kTile * P.col_w[c];
+                P.col_off[c] = off;
+                const int r = P.n_runs - 1;
+                if (tile_major && r >= 0 && P.run_ptr[r] + P.run_bytes[r] == dc.d) {
+                    P.run_bytes[r] += bytes;              // adjacent in the page: same copy
+                } else {
+                    P.run_ptr[P.n_runs] = dc.d;
+                    P.run_bytes[P.n_runs] = bytes;
+                    P.run_stride[P.n_runs] = (uint32_t)(dc.tile_stride ? dc.tile_stride : (int64_t)bytes);
+                    P.run_off[P.n_runs] = off;
+                    P.n_runs++;
+                }
+                off += bytes;
+            }
+            P.stage_bytes = off;
+        }
         derive_bounds();
         // fusion marks
         for (int f = 0; f < n; f++) {

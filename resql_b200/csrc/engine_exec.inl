@@ -569,6 +569,44 @@ static bool pack_group_key(const Lowerer& L, KParams& P, KeyUnpack& ku) {
     return true;
 }
 
+// Register-aggregation path: accumulation form of every SUM (rq_internal.h AggMode) from the value
+// bounds, and how often the 32-bit piece sums must be flushed so that none can wrap. A lane adds
+// at most kR tuples per tile to an accumulator.
+static void choose_agg_modes(const Lowerer& L, KParams& P, int64_t src_rows) {
+    uint64_t flush = UINT64_MAX;          // tiles between two flushes
+    auto bound_tiles = [](uint64_t piece_max) -> uint64_t {
+        return 0xffffffffULL / ((uint64_t)kR * std::max<uint64_t>(piece_max, 1));
+    };
+    for (int u = 0; u < P.na; u++) {
+        P.agg_mode[u] = AM_FULL;
+        P.agg_shift[u] = 0;
+        if (P.agg_kind[u] != RQ_AGG_SUM) continue;
+        const HRef& h = L.hagg_src[u];
+        if (h.lo < 0) continue;
+        const uint64_t hi = (uint64_t)h.hi;
+        if (hi < (1ULL << 25)) {
+            P.agg_mode[u] = AM_P1;
+            flush = std::min(flush, bound_tiles(hi));
+        } else if (hi <= 0xffffffffULL) {
+            P.agg_mode[u] = AM_W64;
+        } else if (hi < (1ULL << 48)) {
+            int bits = 0;
+            while (bits < 63 && (1ULL << bits) <= hi) bits++;
+            const int sh = (bits + 1) / 2;
+            P.agg_mode[u] = AM_P2;
+            P.agg_shift[u] = (uint8_t)sh;
+            flush = std::min(flush, bound_tiles((1ULL << sh) - 1));
+            flush = std::min(flush, bound_tiles(hi >> sh));
+        }
+    }
+    // tuple counters are 32-bit as well: kR per tile
+    flush = std::min(flush, bound_tiles(1));
+    const int64_t tiles = std::max<int64_t>(1, (src_rows + kTile - 1) / kTile);
+    const int64_t grid = std::min<int64_t>((tiles + P.warps - 1) / P.warps, (int64_t)E.sm_count > 0 ? E.sm_count : 148);
+    const uint64_t per_warp = (uint64_t)((tiles + grid * P.warps - 1) / (grid * P.warps));
+    P.flush_tiles = flush >= per_warp ? 0 : (int32_t)std::min<uint64_t>(flush, 1u << 30);
+}
+
 // ---- host-side trace (RQ_TRACE): wall-clock offsets since the plan started, after a stream sync --
 static std::chrono::steady_clock::time_point g_trace_t0;
 static bool g_trace = false;
@@ -601,6 +639,7 @@ static std::unique_ptr<rq_table> new_intermediate(int n_cols, int64_t cap_rows) 
         DevColumn dc;
         dc.type = RQ_I64;
         dc.width = 8;
+        dc.tile_stride = (int64_t)kTile * 8;
         CK(dmalloc(&dc.d, (size_t)t->cap_rows * 8));
         t->cols.push_back(dc);
     }
@@ -1020,6 +1059,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 gr = pl.n_keys == 0 ? 1 : kRegGroups;
                 P.G = 0;
                 if (!layout_smem(P, L.n_slots, 0, max_warps_of(gr))) continue;
+                choose_agg_modes(L, P, src_rows);
             } else {
                 bool fits = false;
                 for (int G = (pl.n_keys == 0 ? 1 : kLowCardMaxGroups); G >= 1 && !fits; G >>= 1) {
@@ -1789,6 +1829,7 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
         for (int c = 0; c < n_cols; c++) {
             DevColumn dc;
             dc.type = col_types[c]; dc.width = col_widths[c]; dc.d = nullptr; dc.owned = false;
+            dc.tile_stride = (int64_t)kTile * dc.width;
             if (col_min && col_max && dc.type != RQ_STR && col_min[c] <= col_max[c]) {
                 dc.has_stats = true; dc.vmin = col_min[c]; dc.vmax = col_max[c];
             }

@@ -29,6 +29,9 @@ constexpr int kRegGroups     = 4;      // groups held in registers per warp (reg
 constexpr int kLowCardMaxGroups = 8;   // groups per warp with lane-private shared-memory accumulators
 constexpr int kGroupTableCap = 2048;   // global table of the low-cardinality aggregate paths
 
+// register-path accumulation forms of a SUM aggregate (chosen on the host from the value bounds)
+enum AggMode : uint8_t { AM_FULL = 0, AM_P1 = 1, AM_P2 = 2, AM_W64 = 3 };
+
 enum SinkImpl { IMPL_LOWAGG = 1, IMPL_HASHAGG = 2, IMPL_BUILD = 3, IMPL_EMIT = 4, IMPL_REGAGG = 5 };
 
 // ---- operation codes shared by the host-level program and the device encoding ----------------
@@ -150,7 +153,15 @@ struct KParams {
                                         // (pure scans only: pipelines with hash structures want L2 for those)
     int32_t        pad0_;
     int32_t        n_cols;              // staged (TMA) columns
-    const unsigned char* col_ptr[kMaxStagedCols];
+    // A tile is staged by one bulk copy per RUN: a contiguous byte range of the source that holds
+    // the tile's chunk of one column (plain column arrays) or of several adjacent columns (tables
+    // owned by the engine are stored tile-major, see engine.cu "storage layout").
+    int32_t        n_runs;
+    const unsigned char* run_ptr[kMaxStagedCols];   // the run of tile 0
+    uint32_t       run_bytes[kMaxStagedCols];       // bytes per tile
+    uint32_t       run_stride[kMaxStagedCols];      // distance between the runs of consecutive tiles
+    uint32_t       run_off[kMaxStagedCols];         // destination offset inside a stage
+    const unsigned char* col_ptr[kMaxStagedCols];   // plain column arrays only (guarded tail of borrowed sources)
     uint32_t       col_off[kMaxStagedCols];   // byte offset inside a stage
     uint8_t        col_w[kMaxStagedCols];     // 1, 4, 8
     int32_t        n_strcols;
@@ -180,6 +191,10 @@ struct KParams {
     int32_t        na;
     uint8_t        agg_kind[kMaxAggs];
     VRef           agg_src[kMaxAggs];    // aggregate inputs (COUNT has none)
+    uint8_t        agg_mode[kMaxAggs];   // register path: AggMode of a SUM
+    uint8_t        agg_shift[kMaxAggs];  // AM_P2: bits of the low piece
+    int32_t        flush_tiles;          // register path: flush the 32-bit piece sums every this many tiles (0 = never)
+    int32_t        pad1_;
     int32_t        G;                    // lane-private groups per warp (shared-memory path)
     // low-card global table (packed key)
     uint32_t*      g_state;              // [kGroupTableCap]

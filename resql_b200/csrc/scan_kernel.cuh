@@ -152,28 +152,38 @@ __device__ __forceinline__ int64_t ld_row(const KParams& P, const WarpCtx& c, VR
     }
 }
 
-// packed group key: every key is a bit field of one word (32-bit arithmetic when it fits)
+// packed group key: every key is a bit field of one word. In the 32-bit form (P.key32) every
+// field is wide enough for its value by construction (pack_group_key sizes it from the value bounds
+// or the physical width), so no masking is needed.
+__device__ __forceinline__ void pack_keys32(const KParams& P, const WarpCtx& c, uint32_t (&k32)[kR]) {
+#pragma unroll
+    for (int r = 0; r < kR; r++) k32[r] = 0;
+    for (int j = 0; j < P.nk; j++) {
+        const VRef vr = P.key[j];
+        const int sh = P.key_shift[j];
+        const uint32_t base = ((vr.slot & 1) ? c.wbase : c.stage) + ((uint32_t)vr.off16 << 4);
+        if (vr.kind == K_M8) {
+            uint32_t t[kR];
+            ld_m8(base + c.lane * 2, t);
+#pragma unroll
+            for (int r = 0; r < kR; r++) k32[r] |= t[r] << sh;
+        } else if (vr.kind == K_M32) {
+            int32_t t[kR];
+            ld_m32(base + c.lane * 8, t);
+#pragma unroll
+            for (int r = 0; r < kR; r++) k32[r] |= (uint32_t)t[r] << sh;
+        } else {
+            int64_t kv[kR];
+            fetch_vref(P, c, vr, kv);
+#pragma unroll
+            for (int r = 0; r < kR; r++) k32[r] |= (uint32_t)kv[r] << sh;
+        }
+    }
+}
 __device__ __forceinline__ void pack_keys(const KParams& P, const WarpCtx& c, uint64_t (&key)[kR]) {
     if (P.key32) {
         uint32_t k32[kR];
-#pragma unroll
-        for (int r = 0; r < kR; r++) k32[r] = 0;
-        for (int j = 0; j < P.nk; j++) {
-            const VRef vr = P.key[j];
-            const int sh = P.key_shift[j];
-            const uint32_t mask = P.key_bits[j] >= 32 ? ~0u : ((1u << P.key_bits[j]) - 1);
-            if (vr.kind == K_M8) {
-                uint32_t t[kR];
-                ld_m8(((vr.slot & 1) ? c.wbase : c.stage) + ((uint32_t)vr.off16 << 4) + c.lane * 2, t);
-#pragma unroll
-                for (int r = 0; r < kR; r++) k32[r] |= (t[r] & mask) << sh;
-            } else {
-                int64_t kv[kR];
-                fetch_vref(P, c, vr, kv);
-#pragma unroll
-                for (int r = 0; r < kR; r++) k32[r] |= ((uint32_t)kv[r] & mask) << sh;
-            }
-        }
+        pack_keys32(P, c, k32);
 #pragma unroll
         for (int r = 0; r < kR; r++) key[r] = k32[r];
         return;
@@ -274,16 +284,18 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     // them in registers instead of re-deriving them from S2R + parameter loads under register
     // pressure (S2R has a long fixed latency and showed up as 'wait' stalls all over the tile loop)
     int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    // The warp index is read through a lane-0 shuffle: the compiler then knows it is warp-uniform,
+    // so the tile counter, stage index and every TMA operand live in uniform registers and a bulk
+    // copy is issued straight from them (a per-lane address would be serialised by an
+    // elect / R2UR loop per copy - 18 instructions per tuple in the first version of this kernel).
+    const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
     const int W = blockDim.x >> 5;
     const int S = P.stages;
 
     const uint32_t smem0 = smem_u32(rq_smem);
-    const uint32_t bars_ = smem0 + warp * (kMaxStages * 8);
-    uint32_t wbase = smem0 + P.warp_off + warp * P.warp_bytes;
-    uint32_t bars_o = bars_;
-    asm volatile("" : "+r"(lane), "+r"(wbase), "+r"(bars_o));
-    const uint32_t bars = bars_o;
+    const uint32_t bars = smem0 + warp * (kMaxStages * 8);
+    const uint32_t wbase = smem0 + P.warp_off + warp * P.warp_bytes;
+    asm volatile("" : "+r"(lane));
     const uint32_t sacc = wbase + P.acc_rel;            // GR == 0 low-card path: [g][a][lane] int64
 
     const int64_t n_rows = P.n_rows_ptr ? *P.n_rows_ptr : P.n_rows;
@@ -304,49 +316,92 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         fence_mbar_init();
     }
     __syncthreads();
-    // accumulators
-    uint64_t racc[NG][kNAR];
+    // accumulators of the register path: per group 2 x kNAR 32-bit registers (an aggregate owns a
+    // pair: one or two 32-bit piece sums, or one 64-bit sum / min / max) and a tuple counter
+    uint32_t racc[NG][2 * kNAR];
+    uint32_t rcnt[NG];
     uint64_t dk[ND];
     int ngroups = 0;
     unsigned seen = 0;     // (no GROUP BY) did this lane aggregate at least one tuple
     unsigned n_inserted = 0;   // hash sinks: entries this lane added to the table
     unsigned long long acct_before = 0, acct_added = 0;   // lane 0: table counter before / by the previous tile
+    auto reset_racc = [&]() {
 #pragma unroll
-    for (int g = 0; g < NG; g++)
+        for (int g = 0; g < NG; g++) {
+            rcnt[g] = 0;
 #pragma unroll
-        for (int a = 0; a < kNAR; a++) racc[g][a] = (uint64_t)agg_identity(a < NA ? P.agg_kind[a] : 0);
+            for (int a = 0; a < kNAR; a++) {
+                const uint64_t id = (uint64_t)agg_identity(a < NA ? P.agg_kind[a] : 0);
+                racc[g][2 * a] = (uint32_t)id;
+                racc[g][2 * a + 1] = (uint32_t)(id >> 32);
+            }
+        }
+    };
+    reset_racc();
 #pragma unroll
     for (int e = 0; e < ND; e++) dk[e] = 0;
+    // register path: warp-reduce every (group, aggregate) partial and add it to the global group table
+    // (at the end of the scan, and every P.flush_tiles tiles so that 32-bit piece sums cannot wrap)
+    auto flush_regs = [&]() {
+        int n = ngroups;
+        if (NK == 0) n = __any_sync(kFull, seen != 0) ? 1 : 0;
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            if (g >= n) continue;
+            int slot = -1;
+            if (lane == 0) {
+                slot = group_table_slot(P, NK == 0 ? 0ULL : dk[g]);
+                if (slot < 0) *P.overflow = 1;
+            }
+            slot = __shfl_sync(kFull, slot, 0);
+#pragma unroll
+            for (int a = 0; a < kNAR; a++) {
+                if (a >= NA) continue;
+                const int kind = P.agg_kind[a];
+                const int mode = P.agg_mode[a];
+                uint64_t part;
+                if (kind == 2) part = rcnt[g];
+                else if (kind == 1 && mode == AM_P1) part = racc[g][2 * a];
+                else if (kind == 1 && mode == AM_P2) part = (uint64_t)racc[g][2 * a] + ((uint64_t)racc[g][2 * a + 1] << P.agg_shift[a]);
+                else part = (uint64_t)racc[g][2 * a] | ((uint64_t)racc[g][2 * a + 1] << 32);
+                const int64_t v = warp_reduce((int64_t)part, kind);
+                if (lane == 0 && slot >= 0) group_table_add(P, slot, a, kind, v);
+            }
+        }
+        reset_racc();
+    };
+    int tiles_to_flush = P.flush_tiles;
     if (GR == 0 && sink == IMPL_LOWAGG) {
         for (int i = lane; i < P.G * NA * 32; i += 32) sts_b64(sacc + i * 8, agg_identity(P.agg_kind[(i >> 5) % NA]));
     }
     __syncwarp();
 
     // a partial last tile of a borrowed (unpadded) source is staged with guarded plain loads
-    auto is_guarded = [&](int64_t tile) -> bool {
-        return P.borrowed && (tile + 1) * (int64_t)kTile > n_rows;
-    };
-    // Lane c issues the bulk copy of staged column c (all columns of a tile go out in one step);
-    // lane 0 arms the barrier with the stage's byte count first. Scanned data is streamed once, so
-    // it is marked evict-first in L2.
+    const int64_t guarded_tile = (P.borrowed && (n_rows % kTile) != 0) ? n_tiles - 1 : -1;
+    // One lane issues the bulk copies of all staged columns of a tile (uniform operands) after arming
+    // the barrier with the stage's byte count. Scanned data is streamed once, so it is marked
+    // evict-first in L2.
     const uint64_t stream_policy = l2_evict_first_policy();
-    const bool col_lane = lane < P.n_cols;
-    const unsigned char* const my_src = col_lane ? P.col_ptr[lane] : nullptr;
-    const uint32_t my_bytes = col_lane ? (uint32_t)kTile * P.col_w[lane] : 0u;
-    const uint32_t my_off = col_lane ? P.col_off[lane] : 0u;
+    const int n_cols = P.n_cols;
+    const int n_runs = P.n_runs;
+    const bool hint = P.stream_hint != 0;
     auto issue = [&](int64_t tile, int s) {
-        if (is_guarded(tile)) return;
-        const uint32_t bar = bars + s * 8;
-        if (lane == 0) mbar_expect_tx_s(bar, P.stage_bytes);
-        __syncwarp();
-        if (col_lane) {
-            const uint32_t dst = wbase + s * P.stage_bytes + my_off;
-            const unsigned char* src = my_src + (size_t)tile * my_bytes;
-            if (P.stream_hint) tma_bulk_g2s_hint(dst, src, my_bytes, bar, stream_policy);
-            else tma_bulk_g2s_s(dst, src, my_bytes, bar);
+        if (tile == guarded_tile) return;
+        if (elect_one()) {
+            const uint32_t bar = bars + s * 8;
+            const uint32_t dst0 = wbase + s * P.stage_bytes;
+            const uint32_t t32 = (uint32_t)tile;
+            mbar_expect_tx_s(bar, P.stage_bytes);
+            if (hint) {
+                for (int c = 0; c < n_runs; c++)
+                    tma_bulk_g2s_hint(dst0 + P.run_off[c], P.run_ptr[c] + (size_t)t32 * P.run_stride[c], P.run_bytes[c], bar, stream_policy);
+            } else {
+                for (int c = 0; c < n_runs; c++)
+                    tma_bulk_g2s_s(dst0 + P.run_off[c], P.run_ptr[c] + (size_t)t32 * P.run_stride[c], P.run_bytes[c], bar);
+            }
         }
     };
-    if (P.n_cols > 0) {
+    if (n_cols > 0) {
         for (int s = 0; s < S; s++)
             if (first + s * stride < n_tiles) issue(first + s * stride, s);
     }
@@ -363,8 +418,8 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         c.row0 = tile * (int64_t)kTile;
         c.lane = lane;
 
-        if (P.n_cols > 0) {
-            if (is_guarded(tile)) {
+        if (n_cols > 0) {
+            if (tile == guarded_tile) {
                 const int64_t rows = n_rows - c.row0;
                 for (int col = 0; col < P.n_cols; col++) {
                     const int w = P.col_w[col];
@@ -381,9 +436,11 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         // the tile this warp stages next is pulled into L2 while the current one is processed, so
         // the bulk copy issued at the end of the tile is served from L2 (one stage per warp cannot
         // hide the DRAM latency otherwise)
-        if (P.l2_prefetch && col_lane) {
+        if (P.l2_prefetch && elect_one()) {
             const int64_t nt = tile + (int64_t)S * stride;
-            if (nt < n_tiles && !is_guarded(nt)) tma_prefetch_l2(my_src + (size_t)nt * my_bytes, my_bytes);
+            if (nt < n_tiles && nt != guarded_tile)
+                for (int c = 0; c < n_runs; c++)
+                    tma_prefetch_l2(P.run_ptr[c] + (size_t)(uint32_t)nt * P.run_stride[c], P.run_bytes[c]);
         }
 
         unsigned valid = 0xffu;
@@ -733,6 +790,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
             if (GR > 0) {
                 // register path: group match -> 0/1 multipliers -> accumulate
                 uint32_t m[NG][kR];
+                const unsigned nvalid = __popc(valid & 0xffu);
                 if (NK == 0) {
                     seen |= valid;
 #pragma unroll
@@ -741,40 +799,63 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     for (int g = 1; g < NG; g++)
 #pragma unroll
                         for (int r = 0; r < kR; r++) m[g][r] = 0;
+                    rcnt[0] += nvalid;
                 } else {
+                    // packed 32-bit keys use at most 31 bits: all-ones marks a dropped tuple, all-ones
+                    // minus one an unused dictionary entry, and neither equals a real key
                     uint64_t key[kR];
-                    pack_keys(P, c, key);
-                    unsigned unk = 0;
+                    uint32_t k32[kR];
                     if (P.key32) {
-                        // packed keys use at most 31 bits: all-ones marks a dropped tuple, all-ones
-                        // minus one an unused dictionary entry, and neither equals a real key
-                        uint32_t k32[kR];
+                        pack_keys32(P, c, k32);
 #pragma unroll
-                        for (int r = 0; r < kR; r++) k32[r] = ((valid >> r) & 1) ? (uint32_t)key[r] : 0xffffffffu;
-#pragma unroll
-                        for (int g = 0; g < NG; g++) {
-                            const uint32_t d = g < ngroups ? (uint32_t)dk[g] : 0xfffffffeu;
-#pragma unroll
-                            for (int r = 0; r < kR; r++) m[g][r] = (k32[r] == d) ? 1u : 0u;
+                        for (int r = 0; r < kR; r++) {
+                            key[r] = k32[r];
+                            k32[r] = ((valid >> r) & 1) ? k32[r] : 0xffffffffu;
                         }
                     } else {
+                        pack_keys(P, c, key);
+                    }
+                    for (;;) {
+                        uint32_t ct[NG];
+                        if (P.key32) {
+#pragma unroll
+                            for (int g = 0; g < NG; g++) {
+                                const uint32_t d = g < ngroups ? (uint32_t)dk[g] : 0xfffffffeu;
+#pragma unroll
+                                for (int r = 0; r < kR; r++) m[g][r] = (k32[r] == d) ? 1u : 0u;
+                            }
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < NG; g++) {
+                                const bool act = g < ngroups;
+#pragma unroll
+                                for (int r = 0; r < kR; r++)
+                                    m[g][r] = (act && key[r] == dk[g] && ((valid >> r) & 1)) ? 1u : 0u;
+                            }
+                        }
+                        // tuples per group in this tile; a valid tuple that matched no dictionary
+                        // entry shows up as a shortfall against the number of valid tuples
+                        unsigned known = 0;
 #pragma unroll
                         for (int g = 0; g < NG; g++) {
-                            const bool act = g < ngroups;
-#pragma unroll
-                            for (int r = 0; r < kR; r++)
-                                m[g][r] = (act && key[r] == dk[g] && ((valid >> r) & 1)) ? 1u : 0u;
+                            ct[g] = ((m[g][0] + m[g][1]) + (m[g][2] + m[g][3])) + ((m[g][4] + m[g][5]) + (m[g][6] + m[g][7]));
+                            known += ct[g];
                         }
-                    }
+                        if (__all_sync(kFull, known == nvalid)) {
 #pragma unroll
-                    for (int r = 0; r < kR; r++) {
-                        uint32_t any = 0;
+                            for (int g = 0; g < NG; g++) rcnt[g] += ct[g];
+                            break;
+                        }
+                        // slow path (first tiles of a warp): the key of the first unmatched tuple of the
+                        // lowest lane joins the dictionary, then the multipliers are computed again
+                        unsigned unk = 0;
 #pragma unroll
-                        for (int g = 0; g < NG; g++) any |= m[g][r];
-                        unk |= (((valid >> r) & 1u) & ~any) << r;
-                    }
-                    // slow path: a key this warp has not seen yet joins the dictionary
-                    while (__any_sync(kFull, unk != 0)) {
+                        for (int r = 0; r < kR; r++) {
+                            uint32_t any = 0;
+#pragma unroll
+                            for (int g = 0; g < NG; g++) any |= m[g][r];
+                            unk |= (((valid >> r) & 1u) & ~any) << r;
+                        }
                         const unsigned ball = __ballot_sync(kFull, unk != 0);
                         const int leader = __ffs(ball) - 1;
                         uint64_t lk = 0;
@@ -783,67 +864,86 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         for (int r = 0; r < kR; r++) if (r == rr) lk = key[r];
                         lk = __shfl_sync(kFull, lk, leader);
                         if (ngroups >= NG) {
+                            // more groups than this path tracks: the host reruns with the next
+                            // implementation; the unmatched tuples are simply dropped here
                             if (lane == 0) *P.overflow = 1;
-                            unk = 0;
+                            valid &= ~unk;
+#pragma unroll
+                            for (int g = 0; g < NG; g++) rcnt[g] += ct[g];
                             break;
                         }
 #pragma unroll
                         for (int e = 0; e < NG; e++) if (e == ngroups) dk[e] = lk;
-#pragma unroll
-                        for (int r = 0; r < kR; r++) {
-                            if (((unk >> r) & 1) && key[r] == lk) {
-                                unk &= ~(1u << r);
-#pragma unroll
-                                for (int g = 0; g < NG; g++) if (g == ngroups) m[g][r] = 1u;
-                            }
-                        }
                         ngroups++;
                     }
                 }
-                // The aggregate loop is unrolled, so every accumulator is a fixed register and a
-                // tuple value goes into it with one multiply-add by the 0/1 group multiplier
-                // (IMAD.WIDE.U32 with 64-bit accumulate) - no tile-local partials, no fold step.
-                // Values proven to fit 32 bits take one instruction per (group, tuple), full 64-bit
-                // values a second IMAD on the high word (the low product of hi32(v) * m added to the
-                // accumulator's high word is exactly the wrap-around int64 sum).
+                // The aggregate loop is unrolled, so every accumulator is a fixed register. A tuple
+                // value goes into the accumulator of every group through the 0/1 group multiplier.
+                // sm_100a has no fused 64-bit multiply-add (IMAD.WIDE + IADD3 + IADD3.X), so the host
+                // picks the cheapest exact form per aggregate from the value bounds (upload
+                // statistics + interval arithmetic):
+                //   AM_P1   value < 2^24: one 32-bit accumulator, one IMAD per (group, tuple)
+                //   AM_P2   value < 2^48: two 32-bit accumulators for the low / high piece
+                //   AM_W64  value < 2^32: 64-bit accumulator, IMAD.WIDE.U32 + 64-bit add
+                //   AM_FULL any int64   : 64-bit accumulator, wide multiply of the low word plus the
+                //                         high word's low product (wrap-around int64 sum)
+                // 32-bit accumulators are flushed to the global group table before they can wrap
+                // (every P.flush_tiles tiles, see below).
 #pragma unroll
                 for (int a = 0; a < kNAR; a++) {
                     if (a >= NA) continue;
                     const int kind = P.agg_kind[a];
-                    if (kind == 2) {                      // COUNT
-#pragma unroll
-                        for (int g = 0; g < NG; g++) {
-                            const uint32_t cnt = ((m[g][0] + m[g][1]) + (m[g][2] + m[g][3])) +
-                                                 ((m[g][4] + m[g][5]) + (m[g][6] + m[g][7]));
-                            racc[g][a] += cnt;
-                        }
-                        continue;
-                    }
+                    if (kind == 2) continue;              // COUNT: rcnt
+                    const int mode = P.agg_mode[a];
                     const VRef vr = P.agg_src[a];
                     int64_t v[kR];
                     if (vr.kind == K_M64) ld_m64(((vr.slot & 1) ? c.wbase : c.stage) + ((uint32_t)vr.off16 << 4) + lane * 16, v);
                     else fetch_vref(P, c, vr, v);
-                    if (kind == 1 && (vr.slot & 2)) {     // SUM of values proven to fit 32 bits
+                    if (mode == AM_P1) {
 #pragma unroll
                         for (int r = 0; r < kR; r++)
 #pragma unroll
-                            for (int g = 0; g < NG; g++) mad_wide_u32(racc[g][a], (uint32_t)v[r], m[g][r]);
-                    } else if (kind == 1) {               // SUM, full width
+                            for (int g = 0; g < NG; g++) racc[g][2 * a] += (uint32_t)v[r] * m[g][r];
+                    } else if (mode == AM_P2) {
+                        const int sh = P.agg_shift[a];
+                        const uint32_t lomask = (1u << sh) - 1u;
 #pragma unroll
-                        for (int r = 0; r < kR; r++)
+                        for (int r = 0; r < kR; r++) {
+                            const uint32_t lo = (uint32_t)v[r] & lomask;
+                            const uint32_t hi = (uint32_t)((uint64_t)v[r] >> sh);
 #pragma unroll
                             for (int g = 0; g < NG; g++) {
-                                mad_wide_u32(racc[g][a], (uint32_t)v[r], m[g][r]);
-                                mad_hi_word(racc[g][a], (uint32_t)((uint64_t)v[r] >> 32), m[g][r]);
+                                racc[g][2 * a] += lo * m[g][r];
+                                racc[g][2 * a + 1] += hi * m[g][r];
                             }
+                        }
+                    } else if (mode == AM_W64) {
+#pragma unroll
+                        for (int g = 0; g < NG; g++) {
+                            uint64_t acc = (uint64_t)racc[g][2 * a] | ((uint64_t)racc[g][2 * a + 1] << 32);
+#pragma unroll
+                            for (int r = 0; r < kR; r++) acc += (uint64_t)(uint32_t)v[r] * (uint64_t)m[g][r];
+                            racc[g][2 * a] = (uint32_t)acc; racc[g][2 * a + 1] = (uint32_t)(acc >> 32);
+                        }
+                    } else if (kind == 1) {               // AM_FULL
+#pragma unroll
+                        for (int g = 0; g < NG; g++) {
+                            uint64_t acc = (uint64_t)racc[g][2 * a] | ((uint64_t)racc[g][2 * a + 1] << 32);
+#pragma unroll
+                            for (int r = 0; r < kR; r++) {
+                                acc += (uint64_t)(uint32_t)v[r] * (uint64_t)m[g][r];
+                                acc += (uint64_t)((uint32_t)((uint64_t)v[r] >> 32) * m[g][r]) << 32;
+                            }
+                            racc[g][2 * a] = (uint32_t)acc; racc[g][2 * a + 1] = (uint32_t)(acc >> 32);
+                        }
                     } else {                              // MIN / MAX
 #pragma unroll
                         for (int g = 0; g < NG; g++) {
-                            int64_t best = (int64_t)racc[g][a];
+                            int64_t best = (int64_t)((uint64_t)racc[g][2 * a] | ((uint64_t)racc[g][2 * a + 1] << 32));
 #pragma unroll
                             for (int r = 0; r < kR; r++)
                                 if (m[g][r] && (kind == 3 ? v[r] < best : v[r] > best)) best = v[r];
-                            racc[g][a] = (uint64_t)best;
+                            racc[g][2 * a] = (uint32_t)(uint64_t)best; racc[g][2 * a + 1] = (uint32_t)((uint64_t)best >> 32);
                         }
                     }
                 }
@@ -1047,11 +1147,15 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         }
         // everyone is done with stage s (and the slots) before it is refilled
         __syncwarp();
-        if (P.n_cols > 0) {
+        if (n_cols > 0) {
             const int64_t nt = tile + (int64_t)S * stride;
             if (nt < n_tiles) issue(nt, s);
         }
         if (++s == S) { s = 0; phase ^= 1u; }
+        if (GR > 0 && P.flush_tiles > 0 && --tiles_to_flush == 0) {
+            flush_regs();
+            tiles_to_flush = P.flush_tiles;
+        }
     }
 
     // ---- flush the per-warp accumulators of the low-cardinality aggregate -------------------
@@ -1060,23 +1164,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         int n = ngroups;
         if (NK == 0) n = __any_sync(kFull, seen != 0) ? 1 : 0;
         if (GR > 0) {
-#pragma unroll
-            for (int g = 0; g < NG; g++) {
-                if (g >= n) continue;
-                int slot = -1;
-                if (lane == 0) {
-                    slot = group_table_slot(P, NK == 0 ? 0ULL : dk[g]);
-                    if (slot < 0) *P.overflow = 1;
-                }
-                slot = __shfl_sync(kFull, slot, 0);
-#pragma unroll
-                for (int a = 0; a < kNAR; a++) {
-                    if (a >= NA) continue;
-                    const int kind = P.agg_kind[a];
-                    const int64_t v = warp_reduce((int64_t)racc[g][a], kind);
-                    if (lane == 0 && slot >= 0) group_table_add(P, slot, a, kind, v);
-                }
-            }
+            flush_regs();
         } else {
             if (n > P.G) n = P.G;
             for (int e = 0; e < n; e++) {
@@ -1138,14 +1226,21 @@ __global__ void rq_group_table_compact(const uint32_t* state, const int64_t* key
     }
 }
 
+// address of row i of a column: plain arrays have tile_stride == kTile * width, tile-major tables
+// the page size
+__device__ __forceinline__ const unsigned char* col_row(const unsigned char* col, int width, int64_t tile_stride, int64_t i) {
+    return col + (i / kTile) * tile_stride + (i % kTile) * width;
+}
+
 // min / max of an integer column (upload-time statistics): out[0] = min, out[1] = max
-__global__ void rq_col_minmax(const unsigned char* col, int width, int64_t n, int64_t* out) {
+__global__ void rq_col_minmax(const unsigned char* col, int width, int64_t tile_stride, int64_t n, int64_t* out) {
     int64_t lo = INT64_MAX, hi = INT64_MIN;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned char* p = col_row(col, width, tile_stride, i);
         int64_t v;
-        if (width == 8) v = reinterpret_cast<const int64_t*>(col)[i];
-        else if (width == 4) v = reinterpret_cast<const int32_t*>(col)[i];
-        else v = col[i];
+        if (width == 8) v = *reinterpret_cast<const int64_t*>(p);
+        else if (width == 4) v = *reinterpret_cast<const int32_t*>(p);
+        else v = *p;
         lo = v < lo ? v : lo;
         hi = v > hi ? v : hi;
     }
@@ -1218,11 +1313,11 @@ __global__ void rq_str_addrs(const unsigned char* bytes, int width, int64_t n, i
 
 // row store (reference DataBlocks, dbdata.h:23-102) -> columns
 __global__ void rq_transpose_rows(const unsigned char* rows, int64_t n, int tuple_size, int offset,
-                                  int width, unsigned char* col, int64_t col_row0) {
+                                  int width, unsigned char* col, int64_t tile_stride, int64_t col_row0) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const unsigned char* s = rows + (size_t)i * tuple_size + offset;
-        unsigned char* d = col + (size_t)(col_row0 + i) * width;
+        unsigned char* d = const_cast<unsigned char*>(col_row(col, width, tile_stride, col_row0 + i));
         for (int k = 0; k < width; k++) d[k] = s[k];
     }
 }

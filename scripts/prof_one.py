@@ -11,6 +11,7 @@ from common import load_plan_dict
 q = sys.argv[1]
 sf = float(sys.argv[2]) if len(sys.argv) > 2 else 10
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+mode = sys.argv[4] if len(sys.argv) > 4 else "owned"     # owned: engine storage (tile-major); borrow: plain torch columns
 dev = torch.device("cuda:0")
 eng = Engine(0)
 need_orders = q not in ("q1", "q6")
@@ -20,7 +21,8 @@ d = load_plan_dict(q)
 tabs = {}
 for t in d["tables"]:
     n = src[t["name"]][t["columns"][0]].shape[0]
-    tabs[t["name"]] = eng.upload_device(t["name"], TD.as_device_columns(src[t["name"]], t["columns"]), n, borrow=True)
+    cols = t["columns"] if mode == "borrow" else list(src[t["name"]].keys())     # owned: the whole table, schema order
+    tabs[t["name"]] = eng.upload_device(t["name"], TD.as_device_columns(src[t["name"]], cols), n, borrow=(mode == "borrow"))
 n = li["l_quantity"].numel()
 bpt = {"q1": 38, "q6": 28, "q3": 24}.get(q, 0)
 for i in range(reps):
