@@ -55,8 +55,54 @@ def _div_trunc(a, b):
 
 
 def _like(s, p):
-    rx = "".join(".*" if ch == "%" else "." if ch == "_" else re.escape(ch) for ch in p.decode("latin1"))
-    return 1 if re.fullmatch(rx, s.decode("latin1"), flags=re.S) else 0
+    """stringLikeCheck(string, like), restated statement by statement from src/qlib/scalar.h:57-120
+    (index form of its pointer walk). The reference matches the literal prefix and the literal
+    suffix independently - they may overlap ('aba' like 'ab%ba' is TRUE) - then scans the infix
+    pieces left to right; '_' matches any one character (cmpLike :50-54). Quirks that follow from
+    the code are kept: '%%' matches nothing, '%_' matches everything. Pinned against the reference
+    engine by tests/golden/like_matrix.json."""
+    s_end, p_end = len(s), len(p)
+    s = s + b"\0"
+    p = p + b"\0"
+
+    def cmp(c, l):
+        return c == l or l == 0x5F          # '_'
+
+    pct = 0x25                              # '%'
+    l_in_start, l_in_end, s_in_start, s_in_end = 0, p_end, 0, s_end
+    l_pos = s_pos = 0
+    if p[0] != pct:                         # prefix :72-81
+        while l_pos < p_end and s_pos < s_end and p[l_pos] != pct:
+            if not cmp(s[s_pos], p[l_pos]):
+                return 0
+            l_pos += 1
+            s_pos += 1
+        l_in_start, s_in_start = l_pos, s_pos
+    if l_in_start == p_end:                 # no-'%' likes :82-85
+        return 1 if s_in_start == s_end else 0
+    if p[p_end - 1] != pct:                 # suffix :88-97
+        s_pos, l_pos = s_end - 1, p_end - 1
+        while l_pos >= 0 and s_pos >= 0 and p[l_pos] != pct:
+            if not cmp(s[s_pos], p[l_pos]):
+                return 0
+            l_pos -= 1
+            s_pos -= 1
+        l_in_end, s_in_end = l_pos, s_pos + 1
+    if l_in_start < l_in_end:               # infixes :100-117
+        l_pos = l_in_start + 1
+        s_pos = s_in_start
+        while s_pos < s_in_end and l_pos < l_in_end:
+            l_trace, s_trace = l_pos, s_pos
+            while cmp(s[s_trace], p[l_trace]) and s_trace < s_in_end:
+                l_trace += 1
+                if p[l_trace] == pct:
+                    l_trace += 1
+                    l_pos = l_trace
+                    s_pos = s_trace
+                    break
+                s_trace += 1
+            s_pos += 1
+    return 1 if l_pos >= l_in_end else 0
 
 
 def _bcast(v, n):

@@ -102,20 +102,52 @@ __device__ __forceinline__ int64_t str_eq_varchar(const char* a, const char* b) 
     }
     return (*a == *b) ? 1 : 0;
 }
-// stringLikeCheck (qlib/scalar.h:57-120), restated: '%' matches any run, '_' any one char.
-// The reference anchors both ends and backtracks on the last '%'; a standard two-pointer
-// wildcard matcher yields the same accept set for patterns made of literal runs, '%' and '_'.
-__device__ __forceinline__ int64_t str_like(const char* s, const char* p) {
-    const char* star = nullptr;
-    const char* ss = nullptr;
-    while (*s != '\0') {
-        if (*p == '%') { star = p++; ss = s; }
-        else if (*p != '\0' && (*p == *s || *p == '_')) { p++; s++; }
-        else if (star) { p = star + 1; s = ++ss; }
-        else return 0;
+// stringLikeCheck(string, like) (qlib/scalar.h:57-120), restated statement by statement in index
+// form. The reference matches the literal prefix and the literal suffix of the pattern
+// independently (they may overlap: 'aba' like 'ab%ba' is true), then scans the infix pieces left
+// to right; '_' matches any one character (cmpLike :50-54). Behaviour that follows from its code is
+// kept ('%%' accepts nothing, '%_' accepts everything, '' like '%a' is true); pinned against the
+// reference engine by tests/golden/like_matrix.json.
+__device__ __forceinline__ bool like_cmp(char c, char l) { return c == l || l == '_'; }
+__device__ __noinline__ int64_t str_like(const char* s, const char* p) {
+    int s_end = 0, p_end = 0;
+    while (s[s_end] != '\0') s_end++;
+    while (p[p_end] != '\0') p_end++;
+    int l_in_start = 0, l_in_end = p_end, s_in_start = 0, s_in_end = s_end;
+    int l_pos = 0, s_pos = 0;
+    if (p[0] != '%') {                                  // prefix
+        for (; l_pos < p_end && s_pos < s_end && p[l_pos] != '%'; ++l_pos, ++s_pos)
+            if (!like_cmp(s[s_pos], p[l_pos])) return 0;
+        l_in_start = l_pos;
+        s_in_start = s_pos;
     }
-    while (*p == '%') p++;
-    return *p == '\0' ? 1 : 0;
+    if (l_in_start == p_end) return s_in_start == s_end ? 1 : 0;     // no-'%' likes
+    if (p[p_end - 1] != '%') {                          // suffix
+        s_pos = s_end - 1;
+        l_pos = p_end - 1;
+        for (; l_pos >= 0 && s_pos >= 0 && p[l_pos] != '%'; --l_pos, --s_pos)
+            if (!like_cmp(s[s_pos], p[l_pos])) return 0;
+        l_in_end = l_pos;
+        s_in_end = s_pos + 1;
+    }
+    if (l_in_start < l_in_end) {                        // infixes
+        l_pos = l_in_start + 1;
+        s_pos = s_in_start;
+        while (s_pos < s_in_end && l_pos < l_in_end) {
+            int l_trace = l_pos, s_trace = s_pos;
+            while (like_cmp(s[s_trace], p[l_trace]) && s_trace < s_in_end) {
+                ++l_trace;
+                if (p[l_trace] == '%') {
+                    l_pos = ++l_trace;
+                    s_pos = s_trace;
+                    break;
+                }
+                ++s_trace;
+            }
+            ++s_pos;
+        }
+    }
+    return l_pos >= l_in_end ? 1 : 0;
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t h) {

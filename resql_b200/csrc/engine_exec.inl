@@ -126,6 +126,9 @@ static void simplify_pipeline(const rq_pipeline& in, SimplePipe& sp) {
             nd.a = parts.back();
         } else if (nd.op == RQ_OP_SELECT) {
             nd.a = ref(i, nd.a); nd.b = ref(i, nd.b); nd.c = ref(i, nd.c);
+            // a constant condition picks its arm here (the device unit has a single immediate field,
+            // which the THEN arm may need)
+            if (tmp[nd.a].op == RQ_OP_CONST) { remap[i] = (tmp[nd.a].imm & 0xff) ? nd.b : nd.c; continue; }
         } else if (nd.op == RQ_OP_PROBE) {
             if (nd.b < 0 || nd.c < 0 || nd.b + nd.c > in.n_args) raise(RQ_ERR_INVALID, "node %d: probe args out of range", i);
             for (int k = 0; k < nd.c; k++) args[nd.b + k] = ref(i, in.args[nd.b + k]);
@@ -254,14 +257,24 @@ static void fuse_ranges(Lowerer& L) {
             j++;
         }
         HUnit& u = L.prog[i];
+        // value range of the compared column as the device sees it: 8-byte columns are int64, 4-byte
+        // columns compare as int32, 1-byte columns are zero-extended bytes. A bound outside it (from
+        // `col > INT32_MAX`, which became lo = 2^31) must not be truncated into the compare constant.
+        const int w = L.P.col_w[u.x.idx];
+        const __int128 tmin = w == 8 ? (__int128)INT64_MIN : w == 4 ? (__int128)INT32_MIN : 0;
+        const __int128 tmax = w == 8 ? (__int128)INT64_MAX : w == 4 ? (__int128)INT32_MAX : 255;
+        if ((lo != NEG && lo > tmax) || (hi != POS && hi < tmin)) {
+            // no value of the column can pass: x < (smallest compare constant) is always false
+            u.op = H_FCMP; u.gop = D_LT; u.imm = w == 8 ? INT64_MIN : INT32_MIN; u.imm2 = 0;
+            continue;
+        }
+        if (lo != NEG && lo <= tmin) lo = NEG;       // every value passes this side
+        if (hi != POS && hi >= tmax) hi = POS;
         if (lo != NEG && hi != POS) {
-            const int w = L.P.col_w[u.x.idx];
-            const bool fits = w == 8 || (lo >= INT32_MIN && hi <= INT32_MAX);
-            if (lo >= INT64_MIN && hi <= INT64_MAX && fits && (lo != hi || true)) {
-                u.op = H_FRANGE; u.gop = 0; u.imm = (int64_t)lo; u.imm2 = (int64_t)(uint64_t)(hi - lo);
-            }
+            u.op = H_FRANGE; u.gop = 0; u.imm = (int64_t)lo; u.imm2 = (int64_t)(uint64_t)(hi - lo);
         } else if (lo != NEG) { u.op = H_FCMP; u.gop = D_GE; u.imm = (int64_t)lo; }
         else if (hi != POS) { u.op = H_FCMP; u.gop = D_LE; u.imm = (int64_t)hi; }
+        else { u.op = H_FCMP; u.gop = D_GE; u.imm = w == 8 ? INT64_MIN : INT32_MIN; u.imm2 = 0; }   // always true
     }
 }
 
@@ -1075,6 +1088,20 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 raise(RQ_ERR_UNSUPPORTED, "pipeline %d does not fit in shared memory", pi);
         }
         encode_program(L, P);
+        if (impl == IMPL_REGAGG) {
+            for (int u = 0; u < kMaxAggs; u++) {
+                uint32_t form = AF_NONE;
+                if (u < P.na && P.agg_kind[u] != RQ_AGG_COUNT) {
+                    if (P.agg_kind[u] == RQ_AGG_MIN) form = AF_MIN;
+                    else if (P.agg_kind[u] == RQ_AGG_MAX) form = AF_MAX;
+                    else form = P.agg_mode[u] == AM_P1 ? AF_P1 : P.agg_mode[u] == AM_P2 ? AF_P2 : P.agg_mode[u] == AM_W64 ? AF_W64 : AF_FULL;
+                }
+                const VRef vr = P.agg_src[u];
+                uint32_t d = form;
+                if (form != AF_NONE && vr.kind == K_M64) d |= 8u | ((vr.slot & 1) ? 16u : 0u) | (((uint32_t)vr.off16 << 4) << 8);
+                P.agg_desc[u] = d;
+            }
+        }
         P.l2_prefetch = (P.n_cols > 0 && P.n_probes == 0 && impl != IMPL_BUILD && impl != IMPL_HASHAGG && !getenv("RQ_NO_PREFETCH")) ? 1 : 0;
         lower_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
@@ -1345,10 +1372,19 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
     for (int k = 0; k < pl.n_vals; k++)
         if (!(pl.sink_kind == RQ_SINK_AGG && pl.vals[k].kind == RQ_AGG_COUNT)) mark(pl.vals[k].node);
     for (int i = 0; i < p0; i++)
-        if (need[i] && (pl.nodes[i].op == RQ_OP_PAYLOAD || pl.nodes[i].op == RQ_OP_FILTER)) return false;
+        if (need[i] && pl.nodes[i].op == RQ_OP_FILTER) return false;
+    // A PAYLOAD of a probe in front of the cut is an ordinary live value (it sits in a value slot of
+    // pass A and is materialized like any other; string payloads are addresses into resident tables).
+    // PAYLOAD nodes that stand behind the cut but belong to a probe in front of it are evaluated by
+    // pass A as well: they are appended to its node list.
+    std::vector<int> late_payload;       // nodes i >= p0: PAYLOAD of a probe < p0
+    for (int i = p0; i < n; i++)
+        if (pl.nodes[i].op == RQ_OP_PAYLOAD && pl.nodes[i].a < p0) late_payload.push_back(i);
 
     // pass A
     sp.a_nodes.assign(pl.nodes, pl.nodes + p0);
+    std::vector<int> late_pos(n, -1);
+    for (int i : late_payload) { late_pos[i] = (int)sp.a_nodes.size(); sp.a_nodes.push_back(pl.nodes[i]); }
     rq_node semi = pr;
     semi.imm |= (mode == SPLIT_EXPAND ? 4 : 2);
     sp.a_nodes.push_back(semi);
@@ -1362,6 +1398,13 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
         newidx[i] = (int)sp.a_vals.size();
         sp.a_vals.push_back(v);
         sp.live_src_col.push_back(op == RQ_OP_COL ? pl.nodes[i].a : -1);
+    }
+    for (int i : late_payload) {
+        rq_value v;
+        v.node = late_pos[i]; v.kind = 0; v.sql_type = RQ_SQL_BIGINT; v.width = 0;
+        newidx[i] = (int)sp.a_vals.size();
+        sp.a_vals.push_back(v);
+        sp.live_src_col.push_back(-1);
     }
     if (mode == SPLIT_SEMI && sp.a_vals.empty()) return false;
     if ((int)sp.a_vals.size() + 1 > kMaxOut || (int)sp.a_vals.size() + 1 > kMaxStagedCols) {
@@ -1391,6 +1434,7 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
     }
     for (int i = p0; i < n; i++) {
         rq_node nd = pl.nodes[i];
+        if (late_pos[i] >= 0) continue;          // evaluated by pass A, a COL of pass B (newidx set above)
         if (is_binary(nd.op)) { nd.a = newidx[nd.a]; nd.b = newidx[nd.b]; }
         else if (nd.op == RQ_OP_FILTER) nd.a = newidx[nd.a];
         else if (nd.op == RQ_OP_SELECT) { nd.a = newidx[nd.a]; nd.b = newidx[nd.b]; nd.c = newidx[nd.c]; }

@@ -31,6 +31,8 @@ constexpr int kGroupTableCap = 2048;   // global table of the low-cardinality ag
 
 // register-path accumulation forms of a SUM aggregate (chosen on the host from the value bounds)
 enum AggMode : uint8_t { AM_FULL = 0, AM_P1 = 1, AM_P2 = 2, AM_W64 = 3 };
+// what the aggregate loop of the register path does for one aggregate (KParams::agg_desc bits 0-2)
+enum AggForm : uint32_t { AF_NONE = 0, AF_P1 = 1, AF_P2 = 2, AF_W64 = 3, AF_FULL = 4, AF_MIN = 5, AF_MAX = 6 };
 
 enum SinkImpl { IMPL_LOWAGG = 1, IMPL_HASHAGG = 2, IMPL_BUILD = 3, IMPL_EMIT = 4, IMPL_REGAGG = 5 };
 
@@ -195,6 +197,7 @@ struct KParams {
     uint8_t        agg_shift[kMaxAggs];  // AM_P2: bits of the low piece
     int32_t        flush_tiles;          // register path: flush the 32-bit piece sums every this many tiles (0 = never)
     int32_t        pad1_;
+    uint32_t       agg_desc[kMaxAggs];   // register path: AggForm | operand location, see the aggregate loop
     int32_t        G;                    // lane-private groups per warp (shared-memory path)
     // low-card global table (packed key)
     uint32_t*      g_state;              // [kGroupTableCap]

@@ -165,8 +165,9 @@ __device__ __forceinline__ void pack_keys32(const KParams& P, const WarpCtx& c, 
         if (vr.kind == K_M8) {
             uint32_t t[kR];
             ld_m8(base + c.lane * 2, t);
+            const uint32_t mul = 1u << sh;          // fields do not overlap: k32 + (t << sh) in one IMAD
 #pragma unroll
-            for (int r = 0; r < kR; r++) k32[r] |= t[r] << sh;
+            for (int r = 0; r < kR; r++) k32[r] = t[r] * mul + k32[r];
         } else if (vr.kind == K_M32) {
             int32_t t[kR];
             ld_m32(base + c.lane * 8, t);
@@ -370,6 +371,43 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         }
         reset_racc();
     };
+    // Mid-scan flush of the 32-bit accumulators only (piece sums and tuple counters), before any of
+    // them can wrap: 16-bit halves are summed over the warp with REDUX, so a flush costs a few
+    // hundred instructions per warp.
+    auto warp_sum_u32 = [&](uint32_t x) -> uint64_t {
+        const uint32_t lo = __reduce_add_sync(kFull, x & 0xffffu);
+        const uint32_t hi = __reduce_add_sync(kFull, x >> 16);
+        return (uint64_t)lo + ((uint64_t)hi << 16);
+    };
+    auto flush_small = [&]() {
+        int n = ngroups;
+        if (NK == 0) n = __any_sync(kFull, seen != 0) ? 1 : 0;
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            if (g >= n) continue;
+            int slot = -1;
+            if (lane == 0) {
+                slot = group_table_slot(P, NK == 0 ? 0ULL : dk[g]);
+                if (slot < 0) *P.overflow = 1;
+            }
+            slot = __shfl_sync(kFull, slot, 0);
+#pragma unroll
+            for (int a = 0; a < kNAR; a++) {
+                if (a >= NA) continue;
+                const int kind = P.agg_kind[a];
+                const int mode = P.agg_mode[a];
+                uint64_t part;
+                if (kind == 2) part = warp_sum_u32(rcnt[g]);
+                else if (kind == 1 && mode == AM_P1) { part = warp_sum_u32(racc[g][2 * a]); racc[g][2 * a] = 0; }
+                else if (kind == 1 && mode == AM_P2) {
+                    part = warp_sum_u32(racc[g][2 * a]) + (warp_sum_u32(racc[g][2 * a + 1]) << P.agg_shift[a]);
+                    racc[g][2 * a] = 0; racc[g][2 * a + 1] = 0;
+                } else continue;
+                if (lane == 0 && slot >= 0) group_table_add(P, slot, a, kind, (int64_t)part);
+            }
+            rcnt[g] = 0;
+        }
+    };
     int tiles_to_flush = P.flush_tiles;
     if (GR == 0 && sink == IMPL_LOWAGG) {
         for (int i = lane; i < P.G * NA * 32; i += 32) sts_b64(sacc + i * 8, agg_identity(P.agg_kind[(i >> 5) % NA]));
@@ -411,7 +449,20 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     const bool hash_sink = (GR == 0) && (sink == IMPL_BUILD || sink == IMPL_HASHAGG);
     for (int64_t tile = first; tile < n_tiles; tile += stride) {
         // a full hash table makes the host regrow it and rerun: stop early
-        if (hash_sink && *(volatile int32_t*)P.ht_full) break;
+        if (hash_sink && *(volatile int32_t*)P.ht_full) {
+            // the bulk copies already issued into this warp's stages must land before the CTA may
+            // exit (a pending cp.async.bulk into freed shared memory is undefined)
+            if (n_cols > 0) {
+                int ds = s;
+                uint32_t dphase = phase;
+                for (int k = 0; k < S; k++) {
+                    const int64_t t = tile + (int64_t)k * stride;
+                    if (t < n_tiles && t != guarded_tile) mbar_wait_s(bars + ds * 8, dphase);
+                    if (++ds == S) { ds = 0; dphase ^= 1u; }
+                }
+            }
+            break;
+        }
         WarpCtx c;
         c.stage = wbase + s * P.stage_bytes;
         c.wbase = wbase;
@@ -891,20 +942,22 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                 // (every P.flush_tiles tiles, see below).
 #pragma unroll
                 for (int a = 0; a < kNAR; a++) {
-                    if (a >= NA) continue;
-                    const int kind = P.agg_kind[a];
-                    if (kind == 2) continue;              // COUNT: rcnt
-                    const int mode = P.agg_mode[a];
-                    const VRef vr = P.agg_src[a];
+                    // one descriptor word per aggregate (host: choose_agg_modes): bits 0-2 form
+                    // (0 = nothing to do here: COUNT or unused), bit 3 = 64-bit operand in shared
+                    // memory at (bit 4 ? warp region : stage) + (desc >> 8)
+                    const uint32_t desc = P.agg_desc[a];
+                    const int form = (int)(desc & 7u);
+                    if (form == AF_NONE) continue;
                     int64_t v[kR];
-                    if (vr.kind == K_M64) ld_m64(((vr.slot & 1) ? c.wbase : c.stage) + ((uint32_t)vr.off16 << 4) + lane * 16, v);
-                    else fetch_vref(P, c, vr, v);
-                    if (mode == AM_P1) {
+                    if (desc & 8u) ld_m64(((desc & 16u) ? c.wbase : c.stage) + (desc >> 8) + lane * 16, v);
+                    else fetch_vref(P, c, P.agg_src[a], v);
+                    const int kind = form == AF_MIN ? 3 : 4;
+                    if (form == AF_P1) {
 #pragma unroll
                         for (int r = 0; r < kR; r++)
 #pragma unroll
                             for (int g = 0; g < NG; g++) racc[g][2 * a] += (uint32_t)v[r] * m[g][r];
-                    } else if (mode == AM_P2) {
+                    } else if (form == AF_P2) {
                         const int sh = P.agg_shift[a];
                         const uint32_t lomask = (1u << sh) - 1u;
 #pragma unroll
@@ -917,7 +970,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                                 racc[g][2 * a + 1] += hi * m[g][r];
                             }
                         }
-                    } else if (mode == AM_W64) {
+                    } else if (form == AF_W64) {
 #pragma unroll
                         for (int g = 0; g < NG; g++) {
                             uint64_t acc = (uint64_t)racc[g][2 * a] | ((uint64_t)racc[g][2 * a + 1] << 32);
@@ -925,7 +978,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                             for (int r = 0; r < kR; r++) acc += (uint64_t)(uint32_t)v[r] * (uint64_t)m[g][r];
                             racc[g][2 * a] = (uint32_t)acc; racc[g][2 * a + 1] = (uint32_t)(acc >> 32);
                         }
-                    } else if (kind == 1) {               // AM_FULL
+                    } else if (form == AF_FULL) {
 #pragma unroll
                         for (int g = 0; g < NG; g++) {
                             uint64_t acc = (uint64_t)racc[g][2 * a] | ((uint64_t)racc[g][2 * a + 1] << 32);
@@ -1153,7 +1206,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         }
         if (++s == S) { s = 0; phase ^= 1u; }
         if (GR > 0 && P.flush_tiles > 0 && --tiles_to_flush == 0) {
-            flush_regs();
+            flush_small();
             tiles_to_flush = P.flush_tiles;
         }
     }

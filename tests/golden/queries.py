@@ -65,6 +65,13 @@ QUERIES = {
     "join_dups_both": """select o_orderpriority, count(*) as c, max(c_acctbal) as m from customer, orders
         where c_nationkey = o_shippriority and c_acctbal > 9000.00 and o_orderkey < 3000
         group by o_orderpriority order by o_orderpriority""",
+    # three tables in one probe pipeline: customer probes nation (single match), then supplier (multi-match,
+    # four suppliers per nation on average), and an attribute of the FIRST build side is still read
+    # behind the multi-match probe (hashjoin.h:118-165 emits every match with all joined attributes)
+    "join_three_dups": """select n_name, s_name, c_custkey from nation, supplier, customer
+        where n_nationkey = c_nationkey and s_nationkey = c_nationkey and c_custkey < 40 order by c_custkey, s_name""",
+    "join_three_dups_agg": """select n_name, count(*) as c, sum(s_acctbal) as s, max(c_acctbal) as m from nation, supplier, customer
+        where n_nationkey = c_nationkey and s_nationkey = c_nationkey group by n_name order by n_name""",
     # the reference's README microbenchmark (README:69; BASELINE config 5): bigint join + avg + group by
     "micro_join_avg": "select c, avg(d * a) from foo, bar where a = d group by c order by c",
     "micro_join_few_groups": "select c * 0 as g, avg(d * a), count(*), max(a) from foo, bar where a = d group by c * 0",
