@@ -71,6 +71,11 @@ int rq_shutdown(void);
 const char* rq_last_error(void);
 /* cudaStream_t the engine launches on (so a harness can bracket it with its own events). */
 void* rq_stream(void);
+/* Engine knobs, the counterpart of the reference's control variables (`threads=4`, `emitmc=true`;
+ * processControl, execute.h:454-474). Keys: "split_min_rows", "split_frac" (two-pass probes),
+ * "prune_builds", "topk", "replay" (0/1), "stages", "warps" (scan-kernel layout, 0 = automatic),
+ * "trace" (0/1). Defaults are the production choices; the parity tests force rarely taken paths. */
+int rq_set_option(const char* key, double value);
 
 /* Multi-GPU (one process per GPU). rank 0 calls rq_dist_unique_id, the harness broadcasts the
  * 128 bytes (torch.distributed / MPI / file), every rank calls rq_dist_init. After that, plans
@@ -236,7 +241,7 @@ typedef struct {
     double  d2h_ms;          /* result read-back                                               */
     double  scan_kernel_ms;  /* time of the table-scan pipeline kernels only (roofline)        */
     int32_t kernel_launches;
-    int32_t reserved;
+    int32_t host_syncs;      /* stream synchronisations the host waited for during this call     */
     double  fact_scan_ms;    /* the last table-scan kernel of the plan: the probe/aggregate
                                 pipeline over the fact table (the roofline kernel)             */
 } rq_timings;

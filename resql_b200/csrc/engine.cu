@@ -102,8 +102,20 @@ struct rq_table {
     }
 };
 
+// knobs (rq_set_option): defaults are the production choices, tests force the rarely taken paths
+struct Options {
+    int stages = 0, warps = 0;            // override the shared-memory layout of the scan kernel (0 = automatic)
+    int64_t split_min_rows = -1;          // two-pass probes: minimal table size (-1 = default 4 Mi rows)
+    double split_frac = -1;               //                   maximal build/probe-domain ratio (-1 = default 0.3)
+    bool prune_builds = true;             // restrict build sides to the probe key's value range
+    bool topk = true;                     // ORDER BY ... LIMIT k through radix select
+    bool replay = true;                   // predicted host reads (engine_exec.inl "host reads of device values")
+    bool trace = false;                   // per-step wall-clock trace on stderr
+};
+
 struct Engine {
     bool init = false;
+    Options opt;
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -116,6 +128,7 @@ struct Engine {
     uint8_t* g_kinds = nullptr;
     int32_t* flags = nullptr;   // [0]=overflow [1]=ht_full [2]=err
     int32_t* h_flags = nullptr; // pinned
+    unsigned char* pinned = nullptr;   // pinned scratch: host reads (4 KB) + ring of small uploads
     Dist dist;
 };
 static Engine E;
@@ -125,6 +138,7 @@ static constexpr int kSmemMax = 227 * 1024;
 
 struct rq_table;
 static void compute_stats(rq_table& t);
+static void reset_plan_memos();
 
 // ------------------------------------------------------------------------------------------
 // lifecycle
@@ -159,6 +173,7 @@ extern "C" int rq_init(int device) {
         CK(dmalloc(&E.g_kinds, kMaxAggs));
         CK(dmalloc(&E.flags, 64));
         CK(cudaMallocHost(&E.h_flags, 64));
+        CK(cudaMallocHost(&E.pinned, 4096 + 256 * 64));
         CK(cudaFuncSetAttribute(rq_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         CK(cudaFuncSetAttribute(rq_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         CK(cudaFuncSetAttribute(rq_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
@@ -174,7 +189,8 @@ extern "C" int rq_shutdown(void) {
     cudaDeviceSynchronize();
     dist_shutdown(E.dist);
     dfree(E.g_state); dfree(E.g_keys); dfree(E.g_acc); dfree(E.g_kinds);
-    dfree(E.flags); cudaFreeHost(E.h_flags);
+    dfree(E.flags); cudaFreeHost(E.h_flags); cudaFreeHost(E.pinned);
+    reset_plan_memos();
     cudaStreamSynchronize(E.stream);
     for (auto& e : E.ev) cudaEventDestroy(e);
     cudaStreamDestroy(E.stream);
@@ -185,6 +201,22 @@ extern "C" int rq_shutdown(void) {
 }
 
 extern "C" const char* rq_last_error(void) { return g_err.c_str(); }
+
+extern "C" int rq_set_option(const char* key, double value) {
+    if (!key) return fail(RQ_ERR_INVALID, "rq_set_option: no key");
+    const std::string k = key;
+    Options& o = E.opt;
+    if (k == "stages") o.stages = (int)value;
+    else if (k == "warps") o.warps = (int)value;
+    else if (k == "split_min_rows") o.split_min_rows = (int64_t)value;
+    else if (k == "split_frac") o.split_frac = value;
+    else if (k == "prune_builds") o.prune_builds = value != 0;
+    else if (k == "topk") o.topk = value != 0;
+    else if (k == "replay") o.replay = value != 0;
+    else if (k == "trace") o.trace = value != 0;
+    else return fail(RQ_ERR_INVALID, "rq_set_option: unknown option '%s'", key);
+    return RQ_OK;
+}
 extern "C" void* rq_stream(void) { return (void*)E.stream; }
 
 extern "C" int rq_dist_unique_id(uint8_t out_id[128]) {

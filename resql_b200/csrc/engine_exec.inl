@@ -425,9 +425,9 @@ static bool layout_smem(KParams& P, int n_slots, int acc_bytes, int max_warps) {
     int bestW = fit(1), bestS = 1;
     if (bestW < 1) return false;
     if (fit(2) >= bestW) bestS = 2;
-    // tuning knobs for experiments (scripts/sweep.py): RQ_STAGES / RQ_WARPS override the choice
-    if (const char* e = getenv("RQ_STAGES")) { const int S = atoi(e); if (S >= 1 && S <= kMaxStages && fit(S) >= 1) { bestS = S; bestW = fit(S); } }
-    if (const char* e = getenv("RQ_WARPS")) { const int W = atoi(e); if (W >= 1 && W <= bestW) bestW = W; }
+    // rq_set_option("stages" / "warps") overrides the choice (scripts/sweep.sh)
+    if (E.opt.stages >= 1 && E.opt.stages <= kMaxStages && fit(E.opt.stages) >= 1) { bestS = E.opt.stages; bestW = fit(bestS); }
+    if (E.opt.warps >= 1 && E.opt.warps <= bestW) bestW = E.opt.warps;
     P.stages = bestS;
     P.warps = bestW;
     P.n_slots = n_slots;
@@ -671,10 +671,12 @@ static void set_types(rq_table& t, const rq_pipeline& pl) {
 static int max_warps_of(int gr) { return (gr == 4 ? ScanCfg<4>::kThreads : gr == 1 ? ScanCfg<1>::kThreads : ScanCfg<0>::kThreads) / 32; }
 
 static void launch_pipeline(const KParams& P, int gr, int64_t rows, rq_timings* tm, bool is_scan,
-                            size_t& ev_idx, std::vector<std::pair<size_t, bool>>& ev_used) {
+                            size_t& ev_idx, std::vector<std::pair<size_t, int>>& ev_used) {
     const int64_t tiles = std::max<int64_t>(1, (rows + kTile - 1) / kTile);
     const int W = P.warps;
     const int grid = (int)std::min<int64_t>((tiles + W - 1) / W, (int64_t)E.sm_count);
+    if (tiles + (int64_t)grid * W >= ((int64_t)1 << 32))
+        raise(RQ_ERR_UNSUPPORTED, "a pipeline over more than 2^40 rows (the kernel counts tiles in 32 bits)");
     EventPair& ep = event_pair(ev_idx);
     CK(cudaEventRecord(ep.a, E.stream));
     if (gr == 4) rq_scan_kernel<4><<<grid, 32 * W, P.smem_bytes, E.stream>>>(P);
@@ -682,7 +684,7 @@ static void launch_pipeline(const KParams& P, int gr, int64_t rows, rq_timings* 
     else rq_scan_kernel<0><<<grid, 32 * W, P.smem_bytes, E.stream>>>(P);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ep.b, E.stream));
-    ev_used.push_back({ev_idx, is_scan});
+    ev_used.push_back({ev_idx, is_scan ? 1 : 0});
     ev_idx++;
     if (tm) tm->kernel_launches++;
 }
@@ -715,10 +717,79 @@ static bool has_str_key(const rq_pipeline& pl) {
 // expanded two-pass form (split_at_probe, mode SPLIT_EXPAND)
 struct NeedExpand {};
 
-static void check_flags(const char* what, const void* d_extra = nullptr) {
-    CK(cudaMemcpyAsync(E.h_flags, E.flags, 32, cudaMemcpyDeviceToHost, E.stream));
-    if (d_extra) CK(cudaMemcpyAsync(E.h_flags + 8, d_extra, 8, cudaMemcpyDeviceToHost, E.stream));   // same round trip
+// ---- host reads of device values: recorded once, predicted afterwards ---------------------------
+// Executing a plan makes the host look at device values now and then: overflow / table-full /
+// error flags, the number of groups or materialized rows, the row counts of the other ranks. Every
+// such read goes through host_read(). The first clean execution of a plan on given tables RECORDS
+// the sequence of values it saw. Later executions REPLAY: host_read() returns the recorded value at
+// once (no stream synchronisation) and only enqueues a copy of the actual device value into a log;
+// the whole plan - all pipelines, NCCL exchanges, ORDER BY, result read-back - is enqueued without
+// a single host wait. At the end one small kernel compares the log with the recorded values and the
+// verdict comes back with the result (sharded plans: all-reduced, so every rank takes the same
+// decision). Any difference - other data under the same table name, a table that filled up, a
+// division by zero - discards the result and runs the plan again the careful way, which reports
+// errors exactly as before. Device code never trusts a predicted value: outputs and hash tables are
+// bounds-checked against their allocation, so a wrong prediction can only produce a discarded result.
+struct PlanMemo {
+    std::vector<std::vector<unsigned char>> reads;
+    bool valid = false;
+    int64_t n_out = 0;                 // result rows of the recorded run
+};
+static std::map<uint64_t, PlanMemo> g_plan_memo;
+struct ReplayState {
+    int mode = 0;                      // 0 careful, 1 careful + recording, 2 replaying
+    PlanMemo* memo = nullptr;
+    size_t idx = 0;
+    unsigned char* d_log = nullptr;    // replay: what the host would have read, in order
+    size_t log_bytes = 0, log_cap = 0;
+    int retries = 0;                   // recording: a retried pipeline makes the run unfit as a script
+    int syncs = 0;                     // host waits of this execution (reported through rq_timings)
+};
+static ReplayState RP;
+struct ReplayDiverged {};
+#define g_pinned (E.pinned)
+static constexpr size_t kPinnedRead = 4096, kSmallSlots = 256, kSmallBytes = 64;
+static size_t g_small_next = 0;
+
+static void stream_sync() {
     CK(cudaStreamSynchronize(E.stream));
+    RP.syncs++;
+}
+
+static void host_read(void* dst, const void* d_src, size_t bytes) {
+    if (bytes > kPinnedRead) raise(RQ_ERR_INVALID, "internal: host_read of %zu bytes", bytes);
+    if (RP.mode == 2) {
+        if (RP.idx >= RP.memo->reads.size() || RP.memo->reads[RP.idx].size() != bytes) throw ReplayDiverged{};
+        memcpy(dst, RP.memo->reads[RP.idx].data(), bytes);
+        const size_t padded = (bytes + 7) & ~(size_t)7;
+        if (RP.log_bytes + padded > RP.log_cap) throw ReplayDiverged{};
+        CK(cudaMemcpyAsync(RP.d_log + RP.log_bytes, d_src, bytes, cudaMemcpyDeviceToDevice, E.stream));
+        RP.log_bytes += padded;
+        RP.idx++;
+        return;
+    }
+    CK(cudaMemcpyAsync(g_pinned, d_src, bytes, cudaMemcpyDeviceToHost, E.stream));
+    stream_sync();
+    memcpy(dst, g_pinned, bytes);
+    if (RP.mode == 1) RP.memo->reads.emplace_back((const unsigned char*)dst, (const unsigned char*)dst + bytes);
+}
+
+// small host value -> device without a host wait: staged in a pinned ring
+static void upload_small(void* d_dst, const void* src, size_t bytes) {
+    if (bytes > kSmallBytes) raise(RQ_ERR_INVALID, "internal: upload_small of %zu bytes", bytes);
+    if (g_small_next == kSmallSlots) { stream_sync(); g_small_next = 0; }
+    unsigned char* slot = g_pinned + kPinnedRead + g_small_next++ * kSmallBytes;
+    memcpy(slot, src, bytes);
+    CK(cudaMemcpyAsync(d_dst, slot, bytes, cudaMemcpyHostToDevice, E.stream));
+}
+
+static void check_flags(const char* what, const void* d_extra = nullptr) {
+    if (d_extra) {        // one round trip for both: the extra word is parked behind the flags
+        CK(cudaMemcpyAsync(E.flags + 8, d_extra, 8, cudaMemcpyDeviceToDevice, E.stream));
+        host_read(E.h_flags, E.flags, 40);
+    } else {
+        host_read(E.h_flags, E.flags, 32);
+    }
     if (E.h_flags[2] == 2) raise(RQ_ERR_INVALID, "internal: %s was lowered for a kernel variant without probe support", what);
     if (E.h_flags[2]) raise(RQ_ERR_RUNTIME, "division by zero in %s (the reference raises SIGFPE here)", what);
     if (*(unsigned long long*)(E.h_flags + 4) != 0) throw NeedExpand{};
@@ -739,7 +810,7 @@ static std::map<uint64_t, int64_t> g_emit_rows;    // rows a materialize pipelin
 
 static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
                              const char* d_strpool, rq_timings* tm, size_t& ev_idx,
-                             std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
+                             std::vector<std::pair<size_t, int>>& ev_used, double& lower_ms,
                              bool is_fact_scan, const rq_table* src_override, PipeOut& result, bool allow_split);
 
 // ---- build-side pruning from probe-side statistics --------------------------------------------
@@ -807,7 +878,7 @@ static void layout_build_payload(const rq_plan& plan, int pi, const rq_pipeline&
     out.pl.vals = out.vals.data();
 }
 static bool prune_build_by_probe_stats(const rq_plan& plan, int pi, PrunedBuild& out) {
-    if (getenv("RQ_NO_PRUNE")) return false;
+    if (!E.opt.prune_builds) return false;
     const rq_pipeline& b = plan.pipelines[pi];
     const int nk = b.n_keys;
     if (nk < 1 || nk > kMaxKeys) return false;
@@ -881,7 +952,7 @@ static bool prune_build_by_probe_stats(const rq_plan& plan, int pi, PrunedBuild&
 
 static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs,
                          const char* d_strpool, rq_timings* tm, size_t& ev_idx,
-                         std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
+                         std::vector<std::pair<size_t, int>>& ev_used, double& lower_ms,
                          bool is_fact_scan = true) {
     PrunedBuild pb;
     BuildLayout bl;
@@ -902,18 +973,16 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
 
 static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
                               const char* d_strpool, rq_timings* tm, size_t& ev_idx,
-                              std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
+                              std::vector<std::pair<size_t, int>>& ev_used, double& lower_ms,
                               bool is_fact_scan, const rq_table* src_override, PipeOut& result, bool allow_split,
                               bool expand);
 
 // pipelines that met duplicate matches once are run in expanded form straight away afterwards
 static std::set<uint64_t> g_needs_expand;
-// join builds whose keys clustered under the order-preserving hash
-static std::set<uint64_t> g_no_monotone;
 
 static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
                              const char* d_strpool, rq_timings* tm, size_t& ev_idx,
-                             std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
+                             std::vector<std::pair<size_t, int>>& ev_used, double& lower_ms,
                              bool is_fact_scan, const rq_table* src_override, PipeOut& result, bool allow_split) {
     const uint64_t sig = pipeline_signature(pl_in, src_override ? -2 : -1) ^ 0x9e3779b97f4a7c15ULL;
     if (!g_needs_expand.count(sig)) {
@@ -923,6 +992,7 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
             return;
         } catch (NeedExpand&) {
             cudaStreamSynchronize(E.stream);
+            RP.retries++;
             result = PipeOut();
             g_needs_expand.insert(sig);
         }
@@ -933,7 +1003,7 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
 
 static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
                               const char* d_strpool, rq_timings* tm, size_t& ev_idx,
-                              std::vector<std::pair<size_t, bool>>& ev_used, double& lower_ms,
+                              std::vector<std::pair<size_t, int>>& ev_used, double& lower_ms,
                               bool is_fact_scan, const rq_table* src_override, PipeOut& result, bool allow_split,
                               bool expand) {
     SimplePipe sp;
@@ -956,9 +1026,8 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
         const rq_table& L = *outs[a].table;
         const rq_table& R = *outs[b].table;
         int64_t nl = L.n_rows, nr = R.n_rows;
-        if (nl < 0 || nr < 0) CK(cudaStreamSynchronize(E.stream));
-        if (nl < 0) CK(cudaMemcpy(&nl, L.d_n_rows, 8, cudaMemcpyDeviceToHost));
-        if (nr < 0) CK(cudaMemcpy(&nr, R.d_n_rows, 8, cudaMemcpyDeviceToHost));
+        if (nl < 0) host_read(&nl, L.d_n_rows, 8);
+        if (nr < 0) host_read(&nr, R.d_n_rows, 8);
         const int ncols = (int)(L.cols.size() + R.cols.size());
         if (ncols > kMaxStagedCols) raise(RQ_ERR_UNSUPPORTED, "nested-loops join over more than %d columns", kMaxStagedCols);
         if (nl > 0 && nr > ((int64_t)1 << 28) / nl)
@@ -977,8 +1046,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             if (tm) tm->kernel_launches++;
             CK(cudaGetLastError());
         }
-        CK(cudaMemcpyAsync(cross_holder->d_n_rows, &total, 8, cudaMemcpyHostToDevice, E.stream));
-        CK(cudaStreamSynchronize(E.stream));      // `total` is a stack variable
+        upload_small(cross_holder->d_n_rows, &total, 8);
         cross_holder->n_rows = total;
         src = cross_holder.get();
     } else if (pl.source_kind == RQ_SRC_PIPELINE) {
@@ -1050,7 +1118,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
         P.n_rows = src->n_rows;
         P.n_rows_ptr = src->n_rows < 0 ? src->d_n_rows : nullptr;
         P.borrowed = src->borrowed ? 1 : 0;
-        P.stream_hint = getenv("RQ_NO_HINT") ? 0 : 1;
+        P.stream_hint = 1;
         P.overflow = E.flags + 0;
         P.ht_full = E.flags + 1;
         P.err = E.flags + 2;
@@ -1102,7 +1170,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 P.agg_desc[u] = d;
             }
         }
-        P.l2_prefetch = (P.n_cols > 0 && P.n_probes == 0 && impl != IMPL_BUILD && impl != IMPL_HASHAGG && !getenv("RQ_NO_PREFETCH")) ? 1 : 0;
+        P.l2_prefetch = (P.n_cols > 0 && P.n_probes == 0 && impl != IMPL_BUILD && impl != IMPL_HASHAGG) ? 1 : 0;
         lower_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
         CK(cudaMemsetAsync(E.flags, 0, 32, E.stream));
@@ -1128,7 +1196,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             dfree(d_ptrs);
             check_flags("aggregation pipeline", dense->d_n_rows);
             const int64_t n_groups_host = *(const int64_t*)(E.h_flags + 8);
-            if (E.h_flags[0]) continue;   // more groups than this path tracks: next implementation
+            if (E.h_flags[0]) { RP.retries++; continue; }   // more groups than this path tracks: next implementation
             // expand duplicates by aliasing: copy the columns (tiny)
             for (int k = 0; k < pl.n_keys; k++)
                 CK(cudaMemcpyAsync(out->cols[k].d, dense->cols[k].d, (size_t)kGroupTableCap * 8, cudaMemcpyDeviceToDevice, E.stream));
@@ -1148,7 +1216,6 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             // scan; the dense second pass of a split pipeline inserts (nearly) every row it reads
             if (pl.size_hint > 0 && !src_override) want = std::min<int64_t>(rows_bound, std::max<int64_t>(pl.size_hint, 2048));
             uint64_t max_load_den = impl == IMPL_BUILD ? 3 : 2;   // joins: load factor <= 1/3
-            if (const char* e = getenv("RQ_LOAD_DEN")) max_load_den = (uint64_t)std::max(2, atoi(e));
             uint64_t cap = 4096;
             while (cap < (uint64_t)(max_load_den * want)) cap <<= 1;
             uint64_t cap_max = 4096;
@@ -1161,25 +1228,6 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             const int nk = pl.n_keys;
             if (nk > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
             const int nv = impl == IMPL_BUILD ? pl.n_vals : (int)ad.kind.size();
-            // Experimental (RQ_MONOTONE=1): a join build on one integer column whose value range is known
-            // (upload statistics) and dense relative to the table can use the order-preserving hash; if
-            // the keys turn out to cluster (long probe runs) the pipeline falls back to Fibonacci hashing.
-            // Same-box measurements at SF100 (orders build: 3.66 ms vs 3.14 ms with Fibonacci hashing) did
-            // not confirm a benefit - sorted keys make the lanes of a warp claim neighbouring slots and
-            // collide - so it is off by default.
-            bool monotone = false;
-            int64_t key_lo = 0, key_hi = 0;
-            const uint64_t mono_sig = sig ^ 0x6d6f6e6fULL;
-            if (impl == IMPL_BUILD && nk == 1 && getenv("RQ_MONOTONE") && !g_no_monotone.count(mono_sig)) {
-                const rq_node& kn = pl.nodes[pl.keys[0].node];
-                const int st = pl.keys[0].sql_type;
-                const bool int_key = !(st == RQ_SQL_VARCHAR || (st == RQ_SQL_CHAR && pl.keys[0].width > 1));
-                if (int_key && kn.op == RQ_OP_COL && kn.a >= 0 && kn.a < (int)src->cols.size() && src->cols[kn.a].has_stats) {
-                    key_lo = src->cols[kn.a].vmin; key_hi = src->cols[kn.a].vmax;
-                    const double range = (double)key_hi - (double)key_lo + 1.0;
-                    monotone = range >= 1.0 && range <= 64.0 * (double)rows_bound && range < 9.0e18;
-                }
-            }
             std::unique_ptr<HashTableDev> ht;
             unsigned long long n_used = 0;
             for (;;) {
@@ -1196,14 +1244,6 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 }
                 ht->d.nk = nk; ht->d.nv = nv;
                 ht->d.hmul = 0x9E3779B97F4A7C15ULL; ht->d.hsub = 0; ht->d.bloom_shift = 0;
-                if (monotone) {
-                    // order-preserving hash over the dense key domain [key_lo, key_hi]
-                    const unsigned __int128 range = (unsigned __int128)((__int128)key_hi - (__int128)key_lo) + 1;
-                    ht->d.hsub = key_lo;
-                    ht->d.hmul = (uint64_t)(((unsigned __int128)UINT64_MAX) / range);
-                    // (the Bloom filter keeps its mixed word index: an order-preserving one was measured to
-                    // pass more false positives into the dense pass than it saved in locality)
-                }
                 for (int k = 0; k < nk && k < kMaxKeys; k++) {
                     const int st = pl.keys[k].sql_type;
                     ht->d.key_kind[k] = st == RQ_SQL_VARCHAR ? 2 : (st == RQ_SQL_CHAR && pl.keys[k].width > 1) ? 1 : 0;
@@ -1226,16 +1266,10 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 check_flags(impl == IMPL_BUILD ? "join build pipeline" : "hash aggregation pipeline");
                 trace_point("hash sink kernel done", pi);
                 bool regrow = E.h_flags[1] != 0;
-                if (monotone && E.h_flags[3] != 0) {
-                    // a claim walked more than kLongRun slots: the keys cluster under the order-preserving
-                    // hash (or repeat thousands of times, which no hash helps) - use the mixing hash from now on
-                    monotone = false;
-                    g_no_monotone.insert(mono_sig);
-                    if (!regrow) continue;
-                }
                 n_used = *(unsigned long long*)(E.h_flags + 6);     // counted by the kernel itself
                 if (!regrow) regrow = n_used * max_load_den > cap && cap < cap_max;
                 if (!regrow) break;
+                RP.retries++;
                 if (cap >= cap_max) { raise(RQ_ERR_RUNTIME, "pipeline %d: hash table overflow at capacity %llu", pi, (unsigned long long)cap); }
                 uint64_t next = cap * 8;
                 if (!E.h_flags[1]) { next = cap; while (next < max_load_den * n_used) next <<= 1; }
@@ -1300,6 +1334,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 g_emit_rows[esig] = produced;
                 if (produced <= out->cap_rows) { out->n_rows = produced; break; }
                 if (round == 1) raise(RQ_ERR_RUNTIME, "materialize overflow");
+                RP.retries++;
                 cap = produced;
             }
             set_types(*out, pl);
@@ -1337,8 +1372,8 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
     } else {
         int64_t min_rows = 4 << 20;
         double max_frac = 0.3;
-        if (const char* e = getenv("RQ_SPLIT_MIN_ROWS")) min_rows = atoll(e);
-        if (const char* e = getenv("RQ_SPLIT_FRAC")) max_frac = atof(e);
+        if (E.opt.split_min_rows >= 0) min_rows = E.opt.split_min_rows;
+        if (E.opt.split_frac >= 0) max_frac = E.opt.split_frac;
         if (src.n_rows < min_rows) return false;
         for (int i = 0; i < n && p0 < 0; i++) if (pl.nodes[i].op == RQ_OP_PROBE) p0 = i;
         if (p0 < 0 || (pl.nodes[p0].imm & ~1LL) != 0) return false;
@@ -1478,12 +1513,17 @@ static bool is_str_type(int sql_type, int sql_width) {
     return sql_type == RQ_SQL_VARCHAR || (sql_type == RQ_SQL_CHAR && sql_width > 1);
 }
 
-static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timings* tm, std::vector<void*>& owned) {
+static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timings* tm, std::vector<void*>& owned,
+                                                 size_t& ev_idx, std::vector<std::pair<size_t, int>>& ev_used) {
     Dist& D = E.dist;
     const int W = D.world;
     const int ncols = (int)local.cols.size();
-    cudaEvent_t e0 = E.ev[3], e1 = E.ev[4];
-    CK(cudaEventRecord(e0, E.stream));
+    if (W > 64) raise(RQ_ERR_UNSUPPORTED, "sharded plans support up to 64 ranks");
+    if (ncols > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "sharded merge of more than %d columns", kMaxOut);
+    const EventPair ep = event_pair(ev_idx);
+    ev_used.push_back({ev_idx, 2});
+    ev_idx++;
+    CK(cudaEventRecord(ep.a, E.stream));
     // 1. row counts
     int64_t* d_counts = nullptr;
     CK(dmalloc(&d_counts, sizeof(int64_t) * W));
@@ -1491,7 +1531,7 @@ static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timin
     int64_t* d_tmp = nullptr;
     if (local.n_rows >= 0) {
         CK(dmalloc(&d_tmp, 8));
-        CK(cudaMemcpyAsync(d_tmp, &local.n_rows, 8, cudaMemcpyHostToDevice, E.stream));
+        upload_small(d_tmp, &local.n_rows, 8);
         d_n = d_tmp;
     }
     auto nccl_ck = [&](int rc, const char* what) {
@@ -1499,15 +1539,12 @@ static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timin
     };
     nccl_ck(D.all_gather(d_n, d_counts, 1, 4 /* ncclInt64 */, D.comm, E.stream), "ncclAllGather(counts)");
     std::vector<int64_t> counts(W);
-    CK(cudaMemcpyAsync(counts.data(), d_counts, sizeof(int64_t) * W, cudaMemcpyDeviceToHost, E.stream));
-    CK(cudaStreamSynchronize(E.stream));
+    host_read(counts.data(), d_counts, sizeof(int64_t) * W);
     int64_t maxn = 0, total = 0;
     for (int r = 0; r < W; r++) { maxn = std::max(maxn, counts[r]); total += counts[r]; }
     std::unique_ptr<rq_table> all = new_intermediate(ncols, total);
     all->sql_type = local.sql_type;
     all->sql_width = local.sql_width;
-    if (W > 64) raise(RQ_ERR_UNSUPPORTED, "sharded plans support up to 64 ranks");
-    if (ncols > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "sharded merge of more than %d columns", kMaxOut);
     if (maxn > 0 && ncols > 0) {
         // 2. [ncols][maxn] per rank -> [world][ncols][maxn], one pack and one unpack kernel
         int64_t *send = nullptr, *recv = nullptr;
@@ -1556,26 +1593,39 @@ static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timin
         dfree(rb);
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(all->d_n_rows, &total, 8, cudaMemcpyHostToDevice, E.stream));
-    CK(cudaEventRecord(e1, E.stream));
-    CK(cudaStreamSynchronize(E.stream));
+    upload_small(all->d_n_rows, &total, 8);
+    CK(cudaEventRecord(ep.b, E.stream));
     all->n_rows = total;
     dfree(d_counts);
     if (d_tmp) dfree(d_tmp);
-    if (tm) {
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, e0, e1));
-        tm->nccl_ms += ms;
-    }
     return all;
 }
 
+// Sharded plans: before the first exchange every rank learns whether some rank failed while running
+// its pipelines (division by zero on one shard, a table that cannot grow, out of memory ...), so that
+// all ranks leave the plan with an error instead of waiting in a collective the failed rank never joins.
+static void agree_on_status(int local_code, const std::string& local_msg) {
+    Dist& D = E.dist;
+    int32_t* d_st = nullptr;
+    CK(dmalloc(&d_st, sizeof(int32_t) * (D.world + 1)));
+    const int32_t mine = local_code;
+    upload_small(d_st + D.world, &mine, 4);
+    const int rc = D.all_gather(d_st + D.world, d_st, 1, 2 /* ncclInt32 */, D.comm, E.stream);
+    if (rc != 0) raise(RQ_ERR_NCCL, "ncclAllGather(status) failed: %s", D.get_error_string ? D.get_error_string(rc) : "?");
+    std::vector<int32_t> st(D.world);
+    host_read(st.data(), d_st, sizeof(int32_t) * D.world);
+    dfree(d_st);
+    if (local_code != 0) raise(local_code, "%s", local_msg.c_str());
+    for (int r = 0; r < D.world; r++)
+        if (st[r] != 0) raise(st[r], "rank %d failed while executing its shard of the plan (status %d); the plan was abandoned on all ranks", r, st[r]);
+}
+
 static void merge_sharded(const rq_plan& plan, int pi, std::vector<PipeOut>& outs, const char* d_strpool,
-                          rq_timings* tm, size_t& ev_idx, std::vector<std::pair<size_t, bool>>& ev_used,
+                          rq_timings* tm, size_t& ev_idx, std::vector<std::pair<size_t, int>>& ev_used,
                           double& lower_ms) {
     if (!outs[pi].table) raise(RQ_ERR_INVALID, "sharded merge: pipeline %d has no relation output", pi);
     const rq_pipeline& pl = plan.pipelines[pi];
-    std::unique_ptr<rq_table> all = gather_relation(*outs[pi].table, tm, outs[pi].owned);
+    std::unique_ptr<rq_table> all = gather_relation(*outs[pi].table, tm, outs[pi].owned, ev_idx, ev_used);
     trace_point("partials gathered", pi);
     if (pl.sink_kind != RQ_SINK_AGG) {       // no aggregation: the concatenation is the result
         outs[pi].table = std::move(all);
@@ -1638,38 +1688,80 @@ extern "C" int rq_result_free(rq_result* r) {
     return RQ_OK;
 }
 
-extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings* tm) {
-    if (!E.init) return fail(RQ_ERR_NOT_INIT, "rq_plan_execute before rq_init");
-    if (!plan || !out || plan->n_pipelines <= 0 || !plan->pipelines)
-        return fail(RQ_ERR_INVALID, "rq_plan_execute: bad arguments");
+// compares the logged device values of a replayed plan with the recorded ones
+__global__ void rq_validate_log(const uint64_t* log, const uint64_t* expect, int64_t n_words, int32_t* ok) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_words && log[i] != expect[i]) *ok = 0;
+}
+
+// One execution of the plan in the mode RP describes. `verdict` (may be null): careful runs report
+// whether the run was clean on every rank (fit to be replayed), replays whether every predicted
+// value was right on every rank.
+static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bool* verdict) {
     if (tm) memset(tm, 0, sizeof(*tm));
     char* d_strpool = nullptr;
     rq_result* res = nullptr;
     std::vector<void*> scratch;
+    const bool sharded = (plan->flags & RQ_PLAN_SHARDED) && E.dist.comm && E.dist.world > 1;
+    unsigned char* d_expect = nullptr;
+    int32_t* d_ok = nullptr;
+    g_small_next = 0;
     try {
+        if (RP.mode == 2) {
+            // the recorded values, flat (8-byte aligned), as the device-side reference of the validation
+            std::vector<unsigned char> flat;
+            for (auto& r : RP.memo->reads) {
+                flat.insert(flat.end(), r.begin(), r.end());
+                flat.resize((flat.size() + 7) & ~(size_t)7, 0);
+            }
+            RP.log_cap = flat.size();
+            CK(dmalloc(&d_expect, flat.size()));
+            CK(dmalloc(&RP.d_log, flat.size()));
+            scratch.push_back(d_expect);
+            scratch.push_back(RP.d_log);
+            if (!flat.empty()) {
+                CK(cudaMemcpyAsync(d_expect, flat.data(), flat.size(), cudaMemcpyHostToDevice, E.stream));   // pageable: staged before return
+                CK(cudaMemsetAsync(RP.d_log, 0, flat.size(), E.stream));
+            }
+        }
         if (plan->strpool_bytes > 0) {
             CK(dmalloc(&d_strpool, plan->strpool_bytes));
             CK(cudaMemcpyAsync(d_strpool, plan->strpool, plan->strpool_bytes, cudaMemcpyHostToDevice, E.stream));
         }
         std::vector<PipeOut> outs(plan->n_pipelines);
         size_t ev_idx = 0;
-        std::vector<std::pair<size_t, bool>> ev_used;
+        std::vector<std::pair<size_t, int>> ev_used;
         double lower_ms = 0;
-        g_trace = getenv("RQ_TRACE") != nullptr && E.dist.rank == 0;
+        g_trace = E.opt.trace && E.dist.rank == 0;
         g_trace_t0 = std::chrono::steady_clock::now();
         CK(cudaEventRecord(E.ev[0], E.stream));
         // sharded plans: merge after the last aggregation (or concatenate the final relation)
         int merge_after = -1;
-        if ((plan->flags & RQ_PLAN_SHARDED) && E.dist.comm && E.dist.world > 1) {
+        if (sharded) {
             for (int pi = 0; pi < plan->n_pipelines; pi++)
                 if (plan->pipelines[pi].sink_kind == RQ_SINK_AGG) merge_after = pi;
             if (merge_after < 0) merge_after = plan->n_pipelines - 1;
         }
+        int local_code = 0;
+        std::string local_msg;
         for (int pi = 0; pi < plan->n_pipelines; pi++) {
             trace_point("pipeline start", pi);
-            run_pipeline(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+            if (local_code == 0) {
+                if (pi <= merge_after) {
+                    // a failure on this rank's shard must not leave the other ranks waiting in the merge
+                    try {
+                        run_pipeline(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+                    } catch (RqError& e) {
+                        cudaStreamSynchronize(E.stream);
+                        local_code = e.code; local_msg = e.msg;
+                    }
+                } else {
+                    run_pipeline(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+                }
+            }
             trace_point("pipeline done", pi);
             if (pi == merge_after) {
+                agree_on_status(local_code, local_msg);
                 merge_sharded(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
                 trace_point("sharded merge done", pi);
             }
@@ -1678,7 +1770,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         rq_table* fin = outs[plan->n_pipelines - 1].table.get();
         if (!fin) raise(RQ_ERR_INVALID, "last pipeline must produce a relation");
         int64_t n = fin->n_rows;
-        if (n < 0) CK(cudaMemcpy(&n, fin->d_n_rows, 8, cudaMemcpyDeviceToHost));
+        if (n < 0) host_read(&n, fin->d_n_rows, 8);
         const int ncols = (int)fin->cols.size();
 
         trace_point("row count read");
@@ -1704,7 +1796,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
             CK(dmalloc(&perm, sizeof(uint32_t) * std::max<int64_t>(n, kBitonicMax)));
             scratch.push_back(perm);
             bool sorted_by_topk = false;
-            if (n > kBitonicMax && plan->limit >= 0 && plan->limit <= kBitonicMax / 2 && n <= 0xffffffffLL && !getenv("RQ_NO_TOPK")) {
+            if (n > kBitonicMax && plan->limit >= 0 && plan->limit <= kBitonicMax / 2 && n <= 0xffffffffLL && E.opt.topk) {
                 // ORDER BY ... LIMIT k: radix select of the k-th smallest first-key value (6 passes of
                 // 11 bits, all on the device), keep the rows up to it (ties included), sort those.
                 uint64_t* k1 = nullptr; uint32_t* hist = nullptr; unsigned long long* st = nullptr; uint32_t* cand = nullptr;
@@ -1716,7 +1808,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
                 rq_sort_iota<<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(perm, n);
                 rq_sort_make_keys<<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(K.col[0], perm, k1, n, K.is_str[0], 0, K.desc[0]);
                 const unsigned long long init[4] = {0ULL, (unsigned long long)std::max<int64_t>(plan->limit, 1), 0ULL, 0ULL};
-                CK(cudaMemcpyAsync(st, init, 32, cudaMemcpyHostToDevice, E.stream));
+                upload_small(st, init, 32);
                 CK(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * kSelBins, E.stream));
                 int shift = 64;
                 while (shift > 0) {
@@ -1729,8 +1821,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
                 rq_topk_compact<<<eb, 256, 0, E.stream>>>(k1, n, st, cand, kBitonicMax, st + 2);
                 if (tm) tm->kernel_launches += 3;
                 unsigned long long n_cand = 0;
-                CK(cudaMemcpyAsync(&n_cand, st + 2, 8, cudaMemcpyDeviceToHost, E.stream));
-                CK(cudaStreamSynchronize(E.stream));
+                host_read(&n_cand, st + 2, 8);
                 if (n_cand <= (unsigned long long)kBitonicMax) {
                     rq_sort_small<<<1, 1024, 0, E.stream>>>(K, (const int64_t*)(st + 2), perm, cand);
                     if (tm) tm->kernel_launches++;
@@ -1762,11 +1853,10 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
                     for (int w = words - 1; w >= 0; w--) {
                         rq_sort_make_keys<<<eb, 256, 0, E.stream>>>(K.col[k], perm, k1, n, K.is_str[k], w, K.desc[k]);
                         const unsigned long long init[2] = {0ULL, ~0ULL};
-                        CK(cudaMemcpyAsync(bits, init, 16, cudaMemcpyHostToDevice, E.stream));
+                        upload_small(bits, init, 16);
                         rq_sort_key_bits<<<std::min(eb, 1024u), 256, 0, E.stream>>>(k1, n, bits);
                         unsigned long long h_bits[2];
-                        CK(cudaMemcpyAsync(h_bits, bits, 16, cudaMemcpyDeviceToHost, E.stream));
-                        CK(cudaStreamSynchronize(E.stream));
+                        host_read(h_bits, bits, 16);
                         if (tm) tm->kernel_launches += 2;
                         const uint64_t varying = h_bits[0] ^ h_bits[1];
                         for (int shift = 0; shift < 64; shift += 4) {
@@ -1823,14 +1913,36 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         for (int c = 0; c < ncols; c++)
             if (n_out > 0)
                 CK(cudaMemcpyAsync(res->cols[c].data, d_out[c], (size_t)n_out * res->cols[c].width, cudaMemcpyDeviceToHost, E.stream));
+        // the verdict travels with the result: replay = all predictions right, careful = run was clean
+        // (sharded plans: the minimum over the ranks, so every rank draws the same conclusion)
+        int32_t h_ok_local = RP.retries == 0 ? 1 : 0;
+        if (RP.mode == 2 || sharded) {
+            CK(dmalloc(&d_ok, 8));
+            scratch.push_back(d_ok);
+            upload_small(d_ok, &h_ok_local, 4);
+            if (RP.mode == 2) {
+                if (RP.idx != RP.memo->reads.size()) throw ReplayDiverged{};
+                const int64_t words = (int64_t)(RP.log_cap / 8);
+                if (words > 0)
+                    rq_validate_log<<<(unsigned)((words + 255) / 256), 256, 0, E.stream>>>((const uint64_t*)RP.d_log, (const uint64_t*)d_expect, words, d_ok);
+            }
+            if (sharded) {
+                const int rc = E.dist.all_reduce(d_ok, d_ok, 1, 2 /* ncclInt32 */, 3 /* ncclMin */, E.dist.comm, E.stream);
+                if (rc != 0) raise(RQ_ERR_NCCL, "ncclAllReduce(verdict) failed");
+            }
+            CK(cudaMemcpyAsync(g_pinned, d_ok, 4, cudaMemcpyDeviceToHost, E.stream));
+        }
         CK(cudaEventRecord(E.ev[2], E.stream));
-        CK(cudaStreamSynchronize(E.stream));
+        stream_sync();
+        if (verdict) *verdict = (RP.mode == 2 || sharded) ? (*(const int32_t*)g_pinned != 0) : (h_ok_local != 0);
         if (tm) {
             float ms = 0;
             tm->lower_ms = lower_ms;
+            tm->host_syncs = RP.syncs;
             const bool trace = g_trace;
             for (auto& u : ev_used) {
                 CK(cudaEventElapsedTime(&ms, g_event_pool[u.first].a, g_event_pool[u.first].b));
+                if (u.second == 2) { tm->nccl_ms += ms; continue; }
                 tm->kernel_ms += ms;
                 if (u.second) { tm->scan_kernel_ms += ms; tm->fact_scan_ms = ms; }
                 if (trace) fprintf(stderr, "[rq] scan kernel launch %zu: %.3f ms%s\n", u.first, ms, u.second ? " (table scan)" : "");
@@ -1852,7 +1964,97 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         if (d_strpool) dfree(d_strpool);
         rq_result_free(res);
         return fail(e.code, "%s", e.msg.c_str());
+    } catch (ReplayDiverged&) {
+        // the recorded script does not fit this execution (only possible on a single rank: sharded
+        // replays take identical decisions on every rank): discard, the caller runs the careful way
+        cudaStreamSynchronize(E.stream);
+        for (void* p : scratch) dfree(p);
+        if (d_strpool) dfree(d_strpool);
+        rq_result_free(res);
+        if (verdict) *verdict = false;
+        *out = nullptr;
+        return RQ_OK;
     }
+}
+
+static uint64_t plan_signature(const rq_plan& plan) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    auto mixin = [&](const void* p, size_t n) {
+        const unsigned char* b = (const unsigned char*)p;
+        for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 0x100000001b3ULL; }
+    };
+    mixin(&plan.n_tables, sizeof plan.n_tables);
+    for (int t = 0; t < plan.n_tables; t++) {
+        const rq_table* tb = plan.tables[t];
+        if (!tb) continue;
+        mixin(tb->name.data(), tb->name.size());
+        mixin(&tb->n_rows, sizeof tb->n_rows);
+        mixin(&tb->borrowed, sizeof tb->borrowed);
+        for (auto& c : tb->cols) { mixin(&c.type, sizeof c.type); mixin(&c.width, sizeof c.width); mixin(&c.page_off, sizeof c.page_off); }
+    }
+    for (int pi = 0; pi < plan.n_pipelines; pi++) {
+        const rq_pipeline& pl = plan.pipelines[pi];
+        const uint64_t s = pipeline_signature(pl, pl.size_hint);
+        mixin(&s, sizeof s);
+        mixin(pl.args, sizeof(int32_t) * pl.n_args);
+        mixin(&pl.source_id2, sizeof pl.source_id2);
+    }
+    mixin(plan.order, sizeof(rq_order_key) * plan.n_order);
+    mixin(&plan.limit, sizeof plan.limit);
+    mixin(&plan.flags, sizeof plan.flags);
+    if (plan.strpool_bytes > 0) mixin(plan.strpool, (size_t)plan.strpool_bytes);
+    mixin(&E.dist.world, sizeof E.dist.world);
+    mixin(&E.opt.split_min_rows, sizeof E.opt.split_min_rows);
+    mixin(&E.opt.split_frac, sizeof E.opt.split_frac);
+    mixin(&E.opt.stages, sizeof E.opt.stages);
+    mixin(&E.opt.warps, sizeof E.opt.warps);
+    return h;
+}
+
+static void reset_plan_memos() {
+    g_plan_memo.clear();
+    g_ht_capacity.clear();
+    g_emit_rows.clear();
+    g_needs_expand.clear();
+    RP = ReplayState();
+}
+
+extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings* tm) {
+    if (!E.init) return fail(RQ_ERR_NOT_INIT, "rq_plan_execute before rq_init");
+    if (!plan || !out || plan->n_pipelines <= 0 || !plan->pipelines)
+        return fail(RQ_ERR_INVALID, "rq_plan_execute: bad arguments");
+    *out = nullptr;
+    if (!E.opt.replay) {
+        RP = ReplayState();
+        const int rc = execute_once(plan, out, tm, nullptr);
+        RP = ReplayState();
+        return rc;
+    }
+    PlanMemo& memo = g_plan_memo[plan_signature(*plan)];
+    if (memo.valid) {
+        RP = ReplayState();
+        RP.mode = 2;
+        RP.memo = &memo;
+        bool ok = false;
+        const int rc = execute_once(plan, out, tm, &ok);
+        RP = ReplayState();
+        if (rc != RQ_OK) { memo.valid = false; return rc; }
+        if (ok) return RQ_OK;
+        // some predicted value was wrong (other data under the same table name, a full table, a
+        // runtime error ...): drop the result and run the careful way, which also reports errors
+        if (*out) { rq_result_free(*out); *out = nullptr; }
+        memo.valid = false;
+    }
+    memo.reads.clear();
+    RP = ReplayState();
+    RP.mode = 1;
+    RP.memo = &memo;
+    bool clean = false;
+    const int rc = execute_once(plan, out, tm, &clean);
+    memo.valid = rc == RQ_OK && clean;
+    if (!memo.valid) memo.reads.clear();
+    RP = ReplayState();
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -300,9 +300,10 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     const uint32_t sacc = wbase + P.acc_rel;            // GR == 0 low-card path: [g][a][lane] int64
 
     const int64_t n_rows = P.n_rows_ptr ? *P.n_rows_ptr : P.n_rows;
-    const int64_t n_tiles = (n_rows + kTile - 1) / kTile;
-    const int64_t stride = (int64_t)gridDim.x * W;
-    const int64_t first = (int64_t)blockIdx.x * W + warp;
+    // tile indices are 32-bit (2^32 tiles = 10^12 rows): cheap to keep or recompute under register pressure
+    const uint32_t n_tiles = (uint32_t)((n_rows + kTile - 1) / kTile);
+    const uint32_t stride = gridDim.x * W;
+    const uint32_t first = blockIdx.x * W + warp;
     const int NA = P.na, NK = P.nk;
     const int sink = P.sink;
 
@@ -415,7 +416,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     __syncwarp();
 
     // a partial last tile of a borrowed (unpadded) source is staged with guarded plain loads
-    const int64_t guarded_tile = (P.borrowed && (n_rows % kTile) != 0) ? n_tiles - 1 : -1;
+    const uint32_t guarded_tile = (P.borrowed && ((uint32_t)n_rows & (kTile - 1)) != 0) ? n_tiles - 1 : 0xffffffffu;
     // One lane issues the bulk copies of all staged columns of a tile (uniform operands) after arming
     // the barrier with the stage's byte count. Scanned data is streamed once, so it is marked
     // evict-first in L2.
@@ -423,12 +424,12 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     const int n_cols = P.n_cols;
     const int n_runs = P.n_runs;
     const bool hint = P.stream_hint != 0;
-    auto issue = [&](int64_t tile, int s) {
+    auto issue = [&](uint32_t tile, int s) {
         if (tile == guarded_tile) return;
         if (elect_one()) {
             const uint32_t bar = bars + s * 8;
             const uint32_t dst0 = wbase + s * P.stage_bytes;
-            const uint32_t t32 = (uint32_t)tile;
+            const uint32_t t32 = tile;
             mbar_expect_tx_s(bar, P.stage_bytes);
             if (hint) {
                 for (int c = 0; c < n_runs; c++)
@@ -441,13 +442,14 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     };
     if (n_cols > 0) {
         for (int s = 0; s < S; s++)
-            if (first + s * stride < n_tiles) issue(first + s * stride, s);
+            if ((uint64_t)first + (uint64_t)s * stride < n_tiles) issue(first + s * stride, s);
     }
 
     int s = 0;
     uint32_t phase = 0;
     const bool hash_sink = (GR == 0) && (sink == IMPL_BUILD || sink == IMPL_HASHAGG);
-    for (int64_t tile = first; tile < n_tiles; tile += stride) {
+    // (the tile counter cannot wrap: first + k * stride < n_tiles + stride <= 2^32 is checked on the host)
+    for (uint32_t tile = first; tile < n_tiles; tile += stride) {
         // a full hash table makes the host regrow it and rerun: stop early
         if (hash_sink && *(volatile int32_t*)P.ht_full) {
             // the bulk copies already issued into this warp's stages must land before the CTA may
@@ -456,8 +458,8 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                 int ds = s;
                 uint32_t dphase = phase;
                 for (int k = 0; k < S; k++) {
-                    const int64_t t = tile + (int64_t)k * stride;
-                    if (t < n_tiles && t != guarded_tile) mbar_wait_s(bars + ds * 8, dphase);
+                    const uint64_t t = (uint64_t)tile + (uint64_t)k * stride;
+                    if (t < n_tiles && (uint32_t)t != guarded_tile) mbar_wait_s(bars + ds * 8, dphase);
                     if (++ds == S) { ds = 0; dphase ^= 1u; }
                 }
             }
@@ -466,7 +468,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         WarpCtx c;
         c.stage = wbase + s * P.stage_bytes;
         c.wbase = wbase;
-        c.row0 = tile * (int64_t)kTile;
+        c.row0 = (int64_t)tile * (int64_t)kTile;
         c.lane = lane;
 
         if (n_cols > 0) {
@@ -488,8 +490,8 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         // the bulk copy issued at the end of the tile is served from L2 (one stage per warp cannot
         // hide the DRAM latency otherwise)
         if (P.l2_prefetch && elect_one()) {
-            const int64_t nt = tile + (int64_t)S * stride;
-            if (nt < n_tiles && nt != guarded_tile)
+            const uint64_t nt = (uint64_t)tile + (uint64_t)S * stride;
+            if (nt < n_tiles && (uint32_t)nt != guarded_tile)
                 for (int c = 0; c < n_runs; c++)
                     tma_prefetch_l2(P.run_ptr[c] + (size_t)(uint32_t)nt * P.run_stride[c], P.run_bytes[c]);
         }
@@ -861,7 +863,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
 #pragma unroll
                         for (int r = 0; r < kR; r++) {
                             key[r] = k32[r];
-                            k32[r] = ((valid >> r) & 1) ? k32[r] : 0xffffffffu;
+                            k32[r] = (valid & (1u << r)) ? k32[r] : 0xffffffffu;
                         }
                     } else {
                         pack_keys(P, c, key);
@@ -905,7 +907,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                             uint32_t any = 0;
 #pragma unroll
                             for (int g = 0; g < NG; g++) any |= m[g][r];
-                            unk |= (((valid >> r) & 1u) & ~any) << r;
+                            if ((valid & (1u << r)) && any == 0) unk |= 1u << r;
                         }
                         const unsigned ball = __ballot_sync(kFull, unk != 0);
                         const int leader = __ffs(ball) - 1;
@@ -1201,8 +1203,8 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         // everyone is done with stage s (and the slots) before it is refilled
         __syncwarp();
         if (n_cols > 0) {
-            const int64_t nt = tile + (int64_t)S * stride;
-            if (nt < n_tiles) issue(nt, s);
+            const uint64_t nt = (uint64_t)tile + (uint64_t)S * stride;
+            if (nt < n_tiles) issue((uint32_t)nt, s);
         }
         if (++s == S) { s = 0; phase ^= 1u; }
         if (GR > 0 && P.flush_tiles > 0 && --tiles_to_flush == 0) {

@@ -7,7 +7,7 @@
 
 namespace rq {
 
-constexpr int kMaxSortKeys = 8;
+constexpr int kMaxSortKeys = 24;     // = kMaxOut: every output column may be an ORDER BY key
 constexpr int kBitonicMax = 4096;
 
 struct SortKeys {

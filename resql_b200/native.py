@@ -71,7 +71,7 @@ class rq_result(C.Structure):
 class rq_timings(C.Structure):
     _fields_ = [("lower_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double),
                 ("nccl_ms", C.c_double), ("d2h_ms", C.c_double), ("scan_kernel_ms", C.c_double),
-                ("kernel_launches", C.c_int32), ("reserved", C.c_int32), ("fact_scan_ms", C.c_double)]
+                ("kernel_launches", C.c_int32), ("host_syncs", C.c_int32), ("fact_scan_ms", C.c_double)]
 
 
 class Timings:
@@ -108,6 +108,7 @@ def load():
     lib.rq_last_error.restype = C.c_char_p
     lib.rq_stream.restype = C.c_void_p
     lib.rq_init.argtypes = [C.c_int]
+    lib.rq_set_option.argtypes = [C.c_char_p, C.c_double]
     lib.rq_table_upload.argtypes = [C.c_char_p, C.c_int32, C.POINTER(rq_column), C.c_int64,
                                     C.c_int32, C.POINTER(C.c_void_p)]
     lib.rq_table_upload_rows.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_int32),
@@ -151,7 +152,7 @@ def debug_lower(plan, pipeline, impl, col_types, col_widths, col_min=None, col_m
     return buf.value.decode()
 
 
-ABI_SYMBOLS = ["rq_init", "rq_shutdown", "rq_last_error", "rq_stream", "rq_dist_unique_id",
+ABI_SYMBOLS = ["rq_init", "rq_shutdown", "rq_last_error", "rq_stream", "rq_set_option", "rq_dist_unique_id",
                "rq_dist_init", "rq_table_upload", "rq_table_upload_rows", "rq_table_rows",
                "rq_table_free", "rq_plan_execute", "rq_result_free"]
 
@@ -205,6 +206,9 @@ class Engine:
 
     def stream(self):
         return self.lib.rq_stream()
+
+    def set_option(self, key, value):
+        self._check(self.lib.rq_set_option(key.encode(), float(value)))
 
     # -- multi-GPU --------------------------------------------------------------------------
     def dist_unique_id(self):

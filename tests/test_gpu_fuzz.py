@@ -56,11 +56,19 @@ def test_random_plan_matches_oracle(seed, sf001, engine, tables_on_gpu):
     assert_same_relation(got, want, d, f"random plan {seed}")
 
 
-def test_two_pass_forced_on_random_join_plans(sf001, engine, tables_on_gpu, monkeypatch):
+def test_two_pass_forced_on_random_join_plans(sf001, engine, tables_on_gpu):
     """the same random join plans with every probe forced through the Bloom semi-join + dense pass"""
+    engine.set_option("split_min_rows", 0)
+    engine.set_option("split_frac", 1e18)
+    try:
+        _two_pass_body(sf001, engine, tables_on_gpu)
+    finally:
+        engine.set_option("split_min_rows", -1)
+        engine.set_option("split_frac", -1)
+
+
+def _two_pass_body(sf001, engine, tables_on_gpu):
     from resql_b200 import EngineError
-    monkeypatch.setenv("RQ_SPLIT_MIN_ROWS", "0")
-    monkeypatch.setenv("RQ_SPLIT_FRAC", "1e18")
     ran = 0
     for seed in SEEDS:
         d = random_plan(seed)

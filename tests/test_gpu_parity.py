@@ -146,13 +146,17 @@ def _join_plans():
 
 
 @pytest.mark.parametrize("name", _join_plans())
-def test_two_pass_probe_matches_reference_engine(name, sf001, engine, monkeypatch):
+def test_two_pass_probe_matches_reference_engine(name, sf001, engine):
     """selective probes run as scan -> Bloom test -> materialize, then a dense probe pass
     (engine_exec.inl split_at_probe); forced here for every join fixture regardless of size"""
-    monkeypatch.setenv("RQ_SPLIT_MIN_ROWS", "0")
-    monkeypatch.setenv("RQ_SPLIT_FRAC", "1e18")
+    engine.set_option("split_min_rows", 0)
+    engine.set_option("split_frac", 1e18)
     d = load_plan_dict(name)
-    got, tm = _run(engine, d, plan_tables(d, sf001))
+    try:
+        got, tm = _run(engine, d, plan_tables(d, sf001))
+    finally:
+        engine.set_option("split_min_rows", -1)
+        engine.set_option("split_frac", -1)
     _, want = load_golden(name)
     assert_same_relation(got, want, d, name + " (two-pass)")
     n_scans = sum(1 for p in d["pipelines"] if p["source_kind"] == 1)
@@ -172,3 +176,58 @@ def test_order_by_limit_selects_top_k(name, limit, sf001, engine):
     want = serialize_columns(*run_plan(d, tabs))
     assert len(got) == limit
     assert got == want
+
+
+@pytest.mark.parametrize("name", ["q1", "q6", "q3", "q5", "q10", "sort_large", "agg_many_groups", "join_dups_rows", "nlj_cross_agg"])
+def test_replayed_execution_is_identical_and_sync_free(name, sf001, engine):
+    """The first clean execution records what the host read from the device; later executions of
+    the same plan on the same tables predict those values and wait for the device exactly once, at
+    the end (engine_exec.inl "host reads of device values"). Results must not change."""
+    d = load_plan_dict(name)
+    tabs = plan_tables(d, sf001)
+    handles = {n: engine.upload(n, c) for n, c in tabs.items()}
+    try:
+        runs = []
+        for _ in range(4):
+            res, tm = engine.execute(Plan(d), handles)
+            runs.append((serialize_columns(res.columns, res.sql_types, res.sql_widths), tm))
+    finally:
+        for h in handles.values():
+            h.free()
+    _, want = load_golden(name)
+    for got, _ in runs:
+        assert_same_relation(got, want, d, name + " (repeated)")
+    assert runs[0][1].host_syncs >= 1
+    assert runs[-1][1].host_syncs == 1, f"replay waited {runs[-1][1].host_syncs} times"
+
+
+def test_replay_notices_changed_data_and_errors(engine):
+    """Same table name, same row count, other contents: the predicted values are wrong, the replayed
+    result is discarded and the plan runs the careful way - including error reporting."""
+    from resql_b200 import EngineError
+    d = {"tables": [{"name": "t", "columns": ["a", "b"]}],
+         "pipelines": [{"source_kind": 1, "source_id": 0, "sink_kind": 1, "size_hint": 0,
+                        "nodes": [[1, 0, 0, 0, 0], [1, 1, 0, 0, 0], [7, 0, 1, 0, 0]], "args": [],
+                        "keys": [[1, 0, 4, 0]], "vals": [[2, 1, 4, 0], [0, 2, 4, 0]]}],
+         "order": [[0, 1]], "limit": -1, "strpool": ""}
+    n = 5000
+    a = np.arange(n, dtype=np.int64) * 7
+    variants = [np.full(n, 3, dtype=np.int64), (np.arange(n, dtype=np.int64) % 5) + 1, (np.arange(n, dtype=np.int64) % 900) + 1]
+    for b in variants:
+        t = engine.upload("t", {"a": a, "b": b})
+        try:
+            for _ in range(3):
+                res, _ = engine.execute(Plan(d), {"t": t})
+                got = serialize_columns(res.columns, res.sql_types, res.sql_widths)
+                want = serialize_columns(*run_plan(d, {"t": {"a": a, "b": b}}))
+                assert got == want
+        finally:
+            t.free()
+    bz = variants[0].copy()
+    bz[n // 2] = 0
+    t = engine.upload("t", {"a": a, "b": bz})
+    try:
+        with pytest.raises(EngineError):
+            engine.execute(Plan(d), {"t": t})
+    finally:
+        t.free()
