@@ -131,6 +131,124 @@ def run_reference(sample_sf, reps, threads):
     return {"kind": kind, "rows": n, "per_query_ms": per_q, "wall_s": wall, "threads": threads}
 
 
+# ---------------------------------------------------------------------------------------------
+# --workload micro: the reference's README microbenchmark (README:69, BASELINE config 5)
+#     select c, avg(d * a) from foo, bar where a = d group by c order by c
+# foo(a, c) and bar(d) have N rows each; a and d are permutations of 1..N (every foo row joins exactly
+# one bar row), c has G distinct values. With more than one GPU BOTH tables are row-range sharded and
+# the plan runs with RQ_PLAN_PARTITIONED: build and probe rows are shipped to the rank that owns
+# hash(key) (grouped ncclSend/ncclRecv), joined there, the partial groups are merged on the rank that
+# owns hash(c), the result is concatenated and ordered. Every result is compared with an independent
+# torch int64 evaluation (d * a = a * a because of the permutation property; wrap-around sums,
+# truncating AVG), all-reduced over the ranks. One JSON line per case.
+# ---------------------------------------------------------------------------------------------
+def main_micro(a):
+    import torch
+    import torch.distributed as dist
+    from resql_b200 import Engine, Plan
+    from resql_b200 import native as N
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("WARN", "VERSION"):
+        del os.environ["NCCL_DEBUG"]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(local_rank)
+    if world > 1:
+        uid = [eng.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.dist_init(rank, world, uid[0])
+    flags = N.RQ_PLAN_PARTITIONED if world > 1 else 0
+    stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
+    plan_d = load_plan("micro_join_avg")
+    plan = Plan(plan_d)
+    if a.micro_cases:
+        cases = [(int(float(x.split(":")[0])), int(float(x.split(":")[1]))) for x in a.micro_cases.split(",")]
+    else:
+        cases = [(10**8, 4), (10**8, 10**6), (10**8, 10**8)]
+        if world >= 4:
+            cases += [(10**9, 4), (10**9, 10**6), (10**9, 10**8)]
+    P_MUL, Q_MUL, Q_ADD = 2654435761, 1000003, 12345           # odd, not multiples of 5: coprime to N = 10^k
+    rc = 0
+    for n, g in cases:
+        if n % 2 == 0 and n % 5 == 0:
+            pass
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        idx = torch.arange(lo, hi, device=dev, dtype=torch.int64)
+        foo_a = (idx * P_MUL) % n + 1
+        foo_c = ((idx * 2654435769) & 0xFFFFFFFF) % g
+        bar_d = (idx * Q_MUL + Q_ADD) % n + 1
+        del idx
+        cols = {"foo": {"a": foo_a, "c": foo_c}, "bar": {"d": bar_d}}
+        tabs = {t["name"]: eng.upload_device(t["name"], {k: (cols[t["name"]][k].data_ptr(), 3, 8) for k in t["columns"]},
+                                             hi - lo, borrow=True) for t in plan_d["tables"]}
+
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        times, res, tm = [], None, None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 1 + max(a.warmup, 2) + max(1, min(a.steps, 5))
+        for i in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            ev0.record(stream)
+            res, tm = eng.execute(plan, tabs, flags)
+            ev1.record(stream)
+            barrier()
+            t = torch.tensor([ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(t.tolist())
+        timed = times[1 + max(a.warmup, 2):]
+        # ---- independent evaluation ------------------------------------------------------------
+        s = torch.zeros(g, dtype=torch.int64, device=dev).index_add_(0, foo_c, foo_a * foo_a)
+        k = torch.zeros(g, dtype=torch.int64, device=dev).index_add_(0, foo_c, torch.ones_like(foo_a))
+        if world > 1:
+            dist.all_reduce(s)
+            dist.all_reduce(k)
+        keep = k > 0
+        want_c = torch.nonzero(keep).flatten()
+        num = s[keep] * 100
+        want_avg = torch.div(num, k[keep], rounding_mode="trunc")
+        got_c = torch.from_numpy(res.columns[0]).to(dev)
+        got_avg = torch.from_numpy(res.columns[1]).to(dev)
+        ok = res.n_rows == want_c.numel() and bool((got_c == want_c).all()) and bool((got_avg == want_avg).all())
+        okt = torch.tensor([int(ok)], device=dev)
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        ok_all = bool(okt.item())
+        if not ok_all:
+            rc = 1
+        if rank == 0:
+            ms = statistics.median([x[0] for x in timed])
+            print(json.dumps({
+                "metric": "micro_join_groupby_probe_tuples_per_s", "value": n / (ms / 1e3), "unit": "tuples/s", "n_gpus": world,
+                "steps": len(timed), "warmup": max(a.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "dtype": "int64", "data": "synthetic",
+                "config": {"workload": f"README microbenchmark: foo {n} rows join bar {n} rows on a = d, group by c ({g} values), avg(d*a), order by c",
+                           "tables": "both row-range sharded, RQ_PLAN_PARTITIONED (hash-partitioned all-to-all)" if world > 1 else "one GPU",
+                           "timing": "CUDA events on the engine stream around rq_plan_execute, max over ranks, median of the timed runs"},
+                "result_rows": res.n_rows, "checks": {"identical_to_torch_int64_all_ranks": ok_all},
+                "first_execution_wall_ms": times[0][1], "wall_ms": statistics.median([x[1] for x in timed]),
+                "kernel_ms": tm.kernel_ms, "nccl_ms": tm.nccl_ms, "host_syncs": tm.host_syncs, "gpu_launches": tm.kernel_launches}), flush=True)
+        for t in tabs.values():
+            t.free()
+        del foo_a, foo_c, bar_d, s, k, keep, want_c, num, want_avg, got_c, got_avg, res
+        torch.cuda.empty_cache()
+    eng.shutdown()
+    if world > 1:
+        dist.destroy_process_group()
+    return rc
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -141,7 +259,11 @@ def main():
     ap.add_argument("--sample-sf", type=float, default=0.5, help="scale factor of the CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="tpch", choices=["tpch", "micro"])
+    ap.add_argument("--micro-cases", default="", help="N:G,N:G,... (default: 1e8 x {4,1e6,1e8}; with >= 4 GPUs also 1e9)")
     a = ap.parse_args()
+    if a.workload == "micro":
+        return main_micro(a)
     if a.warmup < 3:
         a.warmup = 3
     rank = int(os.environ.get("RANK", "0"))

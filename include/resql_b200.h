@@ -201,7 +201,14 @@ typedef struct {
     int32_t ascending;   /* 1 asc, 0 desc (qlib/sort.h:14)                                     */
 } rq_order_key;
 
-#define RQ_PLAN_SHARDED  1   /* tables hold this rank's row range; merge aggregates over NCCL  */
+#define RQ_PLAN_SHARDED      1   /* the scanned fact table holds this rank's row range, the other
+                                     tables are complete on every rank; partial aggregates are merged
+                                     over NCCL                                                        */
+#define RQ_PLAN_PARTITIONED  2   /* EVERY table holds this rank's row range (large join large): build
+                                     and probe rows are shipped to the rank that owns hash(join key)
+                                     (all-to-all: grouped ncclSend/ncclRecv), joined there, and the
+                                     groups of the last aggregation are merged on the rank that owns
+                                     hash(group key). The result is identical on every rank.          */
 
 typedef struct {
     int32_t             n_tables;

@@ -748,7 +748,7 @@ struct ReplayState {
 static ReplayState RP;
 struct ReplayDiverged {};
 #define g_pinned (E.pinned)
-static constexpr size_t kPinnedRead = 4096, kSmallSlots = 256, kSmallBytes = 64;
+static constexpr size_t kPinnedRead = 36864, kSmallSlots = 256, kSmallBytes = 64;
 static size_t g_small_next = 0;
 
 static void stream_sync() {
@@ -803,9 +803,9 @@ struct SplitPipes {
     std::vector<int> live_src_col;     // per materialized value: source column it copies, or -1
     rq_pipeline a, b;
 };
-enum SplitMode { SPLIT_SEMI = 0, SPLIT_EXPAND = 1 };
+enum SplitMode { SPLIT_SEMI = 0, SPLIT_EXPAND = 1, SPLIT_EXCHANGE = 2 };
 static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_table& src,
-                           const std::vector<PipeOut>& outs, SplitPipes& sp, SplitMode mode);
+                           const std::vector<PipeOut>& outs, SplitPipes& sp, SplitMode mode, int ordinal = 0);
 static std::map<uint64_t, int64_t> g_emit_rows;    // rows a materialize pipeline produced last time
 
 static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
@@ -950,6 +950,12 @@ static bool prune_build_by_probe_stats(const rq_plan& plan, int pi, PrunedBuild&
     return true;
 }
 
+static bool is_partitioned_plan(const rq_plan& plan);
+static void run_pipeline_partitioned(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
+                                     const char* d_strpool, rq_timings* tm, size_t& ev_idx,
+                                     std::vector<std::pair<size_t, int>>& ev_used, double& lower_ms,
+                                     const rq_table* src_override, bool first_probe_aligned, PipeOut& result);
+
 static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs,
                          const char* d_strpool, rq_timings* tm, size_t& ev_idx,
                          std::vector<std::pair<size_t, int>>& ev_used, double& lower_ms,
@@ -957,13 +963,18 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
     PrunedBuild pb;
     BuildLayout bl;
     const rq_pipeline* pl = &plan.pipelines[pi];
+    const bool part = is_partitioned_plan(plan);
     if (pl->sink_kind == RQ_SINK_BUILD) {
-        if (prune_build_by_probe_stats(plan, pi, pb)) pl = &pb.pl;
+        // (the probe-side statistics of ONE shard say nothing about the keys other ranks probe with)
+        if (!part && prune_build_by_probe_stats(plan, pi, pb)) pl = &pb.pl;
         layout_build_payload(plan, pi, *pl, bl);
         pl = &bl.pl;
     }
-    run_pipeline_one(plan, *pl, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, is_fact_scan,
-                     nullptr, outs[pi], true);
+    if (part)
+        run_pipeline_partitioned(plan, *pl, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, nullptr, false, outs[pi]);
+    else
+        run_pipeline_one(plan, *pl, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, is_fact_scan,
+                         nullptr, outs[pi], true);
     if (pl->sink_kind == RQ_SINK_BUILD) {
         outs[pi].pay_word = bl.pay_word;
         outs[pi].payload_sql_type = bl.sql_type;
@@ -979,6 +990,8 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
 
 // pipelines that met duplicate matches once are run in expanded form straight away afterwards
 static std::set<uint64_t> g_needs_expand;
+// aggregation pipelines: the implementation (register / shared-memory / hash) that did not overflow
+static std::map<uint64_t, int> g_agg_impl;
 
 static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
                              const char* d_strpool, rq_timings* tm, size_t& ev_idx,
@@ -1109,9 +1122,18 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
         raise(RQ_ERR_INVALID, "pipeline %d: bad sink kind %d", pi, pl.sink_kind);
     }
     const int64_t src_rows = src->n_rows >= 0 ? src->n_rows : src->cap_rows;
+    // the aggregation path that worked for this pipeline last time is tried first
+    const uint64_t impl_sig = pipeline_signature(pl_in, src_override ? -2 : -1) ^ 0x696d706cULL;
+    size_t first_attempt = 0;
+    {
+        auto known = g_agg_impl.find(impl_sig);
+        if (known != g_agg_impl.end())
+            for (size_t k = 0; k < impls.size(); k++) if (impls[k] == known->second) first_attempt = k;
+    }
 
-    for (size_t attempt = 0; attempt < impls.size(); attempt++) {
+    for (size_t attempt = first_attempt; attempt < impls.size(); attempt++) {
         const int impl = impls[attempt];
+        g_agg_impl[impl_sig] = impl;
         KParams P;
         memset(&P, 0, sizeof(P));
         P.expand_probe = -1;
@@ -1356,11 +1378,18 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
 // joined; results are identical. Pass A is a pure streaming kernel (no dependent table walks), pass
 // B runs the walks / atomics over dense tiles where every lane has work.
 static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_table& src,
-                           const std::vector<PipeOut>& outs, SplitPipes& sp, SplitMode mode) {
+                           const std::vector<PipeOut>& outs, SplitPipes& sp, SplitMode mode, int ordinal) {
     (void)plan;
     const int n = pl.n_nodes;
     int p0 = -1;
-    if (mode == SPLIT_EXPAND) {
+    if (mode == SPLIT_EXCHANGE) {
+        // partitioned plans: cut in front of the probe number `ordinal` (no probe node in pass A: the
+        // rows are shipped to the rank that owns their key before they probe)
+        int seen = 0;
+        for (int i = 0; i < n && p0 < 0; i++)
+            if (pl.nodes[i].op == RQ_OP_PROBE && seen++ == ordinal) p0 = i;
+        if (p0 < 0) return false;
+    } else if (mode == SPLIT_EXPAND) {
         // multi-match expansion (hashjoin.h:118-165): cut at the first probe that may match more than
         // one build tuple. Pass A emits one row per match together with the entry index, pass B
         // fetches the payload through that index.
@@ -1420,9 +1449,11 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
     sp.a_nodes.assign(pl.nodes, pl.nodes + p0);
     std::vector<int> late_pos(n, -1);
     for (int i : late_payload) { late_pos[i] = (int)sp.a_nodes.size(); sp.a_nodes.push_back(pl.nodes[i]); }
-    rq_node semi = pr;
-    semi.imm |= (mode == SPLIT_EXPAND ? 4 : 2);
-    sp.a_nodes.push_back(semi);
+    if (mode != SPLIT_EXCHANGE) {
+        rq_node semi = pr;
+        semi.imm |= (mode == SPLIT_EXPAND ? 4 : 2);
+        sp.a_nodes.push_back(semi);
+    }
     sp.a_args.assign(pl.args, pl.args + pl.n_args);
     std::vector<int> newidx(n, -1);
     for (int i = 0; i < p0; i++) {
@@ -1441,7 +1472,7 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
         sp.a_vals.push_back(v);
         sp.live_src_col.push_back(-1);
     }
-    if (mode == SPLIT_SEMI && sp.a_vals.empty()) return false;
+    if (mode != SPLIT_EXPAND && sp.a_vals.empty()) return false;
     if ((int)sp.a_vals.size() + 1 > kMaxOut || (int)sp.a_vals.size() + 1 > kMaxStagedCols) {
         if (mode == SPLIT_EXPAND) raise(RQ_ERR_UNSUPPORTED, "multi-match join carries more than %d live values", kMaxStagedCols - 1);
         return false;
@@ -1604,11 +1635,13 @@ static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timin
 // Sharded plans: before the first exchange every rank learns whether some rank failed while running
 // its pipelines (division by zero on one shard, a table that cannot grow, out of memory ...), so that
 // all ranks leave the plan with an error instead of waiting in a collective the failed rank never joins.
-static void agree_on_status(int local_code, const std::string& local_msg) {
+// The same exchange carries one more bit per rank (`big`: my partial result is large), so that all
+// ranks pick the same merge strategy. Returns whether any rank said so.
+static bool agree_on_status(int local_code, const std::string& local_msg, bool big) {
     Dist& D = E.dist;
     int32_t* d_st = nullptr;
     CK(dmalloc(&d_st, sizeof(int32_t) * (D.world + 1)));
-    const int32_t mine = local_code;
+    const int32_t mine = local_code != 0 ? local_code : (big ? -1 : 0);
     upload_small(d_st + D.world, &mine, 4);
     const int rc = D.all_gather(d_st + D.world, d_st, 1, 2 /* ncclInt32 */, D.comm, E.stream);
     if (rc != 0) raise(RQ_ERR_NCCL, "ncclAllGather(status) failed: %s", D.get_error_string ? D.get_error_string(rc) : "?");
@@ -1616,22 +1649,125 @@ static void agree_on_status(int local_code, const std::string& local_msg) {
     host_read(st.data(), d_st, sizeof(int32_t) * D.world);
     dfree(d_st);
     if (local_code != 0) raise(local_code, "%s", local_msg.c_str());
-    for (int r = 0; r < D.world; r++)
-        if (st[r] != 0) raise(st[r], "rank %d failed while executing its shard of the plan (status %d); the plan was abandoned on all ranks", r, st[r]);
+    bool any_big = false;
+    for (int r = 0; r < D.world; r++) {
+        if (st[r] > 0) raise(st[r], "rank %d failed while executing its shard of the plan (status %d); the plan was abandoned on all ranks", r, st[r]);
+        any_big |= st[r] < 0;
+    }
+    return any_big;
 }
 
-static void merge_sharded(const rq_plan& plan, int pi, std::vector<PipeOut>& outs, const char* d_strpool,
-                          rq_timings* tm, size_t& ev_idx, std::vector<std::pair<size_t, int>>& ev_used,
-                          double& lower_ms) {
-    if (!outs[pi].table) raise(RQ_ERR_INVALID, "sharded merge: pipeline %d has no relation output", pi);
-    const rq_pipeline& pl = plan.pipelines[pi];
-    std::unique_ptr<rq_table> all = gather_relation(*outs[pi].table, tm, outs[pi].owned, ev_idx, ev_used);
-    trace_point("partials gathered", pi);
-    if (pl.sink_kind != RQ_SINK_AGG) {       // no aggregation: the concatenation is the result
-        outs[pi].table = std::move(all);
-        return;
+// ---- hash-partitioned exchange (RQ_PLAN_PARTITIONED; kernels in exchange_kernels.cuh) -----------
+// Every row of `local` (may be null: this rank failed before it had anything to send) goes to rank
+// hash(key columns) mod world. The counts exchange doubles as the status agreement: a rank that failed
+// in the pipeline in front of the exchange reports its error code there and every rank raises.
+static std::unique_ptr<rq_table> exchange_relation(const rq_table* local, const std::vector<int>& key_cols,
+                                                   const std::vector<uint8_t>& key_kinds, int local_code,
+                                                   const std::string& local_msg, rq_timings* tm, size_t& ev_idx,
+                                                   std::vector<std::pair<size_t, int>>& ev_used) {
+    Dist& D = E.dist;
+    const int W = D.world;
+    if (W > kMaxRanks) raise(RQ_ERR_UNSUPPORTED, "partitioned plans support up to %d ranks", kMaxRanks);
+    const int ncols = local ? (int)local->cols.size() : 0;
+    if (ncols > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "exchange of more than %d columns", kMaxOut);
+    if (local)
+        for (int c = 0; c < ncols; c++)
+            if (c < (int)local->sql_type.size() && is_str_type(local->sql_type[c], local->sql_width[c]))
+                raise(RQ_ERR_UNSUPPORTED, "partitioned plans cannot ship string values between ranks yet (column %d)", c);
+    auto nccl_ck = [&](int rc, const char* what) {
+        if (rc != 0) raise(RQ_ERR_NCCL, "%s failed: %s", what, D.get_error_string ? D.get_error_string(rc) : "?");
+    };
+    const EventPair ep = event_pair(ev_idx);
+    ev_used.push_back({ev_idx, 2});
+    ev_idx++;
+    CK(cudaEventRecord(ep.a, E.stream));
+
+    const int64_t rows_bound = local ? std::max<int64_t>(local->n_rows >= 0 ? local->n_rows : local->cap_rows, 0) : 0;
+    // [cnt W][off W][cursor W][status 1] and the gathered matrix [W][W+1]
+    unsigned long long* d_meta = nullptr;
+    unsigned long long* d_matrix = nullptr;
+    CK(dmalloc(&d_meta, sizeof(unsigned long long) * (3 * W + 1)));
+    CK(dmalloc(&d_matrix, sizeof(unsigned long long) * W * (W + 1)));
+    CK(cudaMemsetAsync(d_meta, 0, sizeof(unsigned long long) * (3 * W + 1), E.stream));
+    unsigned long long *d_cnt = d_meta, *d_off = d_meta + W, *d_cur = d_meta + 2 * W;
+    uint8_t* d_dest = nullptr;
+    int64_t* d_send = nullptr;
+    ExCols X;
+    memset(&X, 0, sizeof(X));
+    X.ncols = ncols; X.world = W; X.nkeys = (int)key_cols.size();
+    if (X.nkeys > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, (rows_bound + kExBlockRows - 1) / kExBlockRows);
+    if (local && local_code == 0 && ncols > 0) {
+        for (int c = 0; c < ncols; c++) X.in[c] = (const int64_t*)local->cols[c].d;
+        for (int k = 0; k < X.nkeys; k++) { X.key_col[k] = key_cols[k]; X.key_kind[k] = key_kinds[k]; }
+        CK(dmalloc(&d_dest, (size_t)std::max<int64_t>(rows_bound, 1)));
+        CK(dmalloc(&d_send, (size_t)std::max<int64_t>(rows_bound, 1) * ncols * 8));
+        const int64_t* n_ptr = local->n_rows < 0 ? local->d_n_rows : nullptr;
+        rq_ex_count<<<blocks, kExThreads, 0, E.stream>>>(X, n_ptr, local->n_rows, d_dest, d_cnt);
+        rq_ex_offsets<<<1, 32, 0, E.stream>>>(d_cnt, d_off, d_cur, W);
+        rq_ex_scatter<<<blocks, kExThreads, 0, E.stream>>>(X, n_ptr, local->n_rows, d_dest, d_cnt, d_off, d_cur, d_send);
+        if (tm) tm->kernel_launches += 3;
+        CK(cudaGetLastError());
     }
-    // re-aggregate: column i of the gathered table is node i
+    // counts (+ status) of every rank
+    {
+        const unsigned long long st = (unsigned long long)(unsigned)local_code;
+        // row r of the matrix = [cnt of rank r for every destination][status of rank r]; the local row is
+        // assembled in place: cnt is followed by the status word
+        unsigned long long* d_row = nullptr;
+        CK(dmalloc(&d_row, sizeof(unsigned long long) * (W + 1)));
+        CK(cudaMemcpyAsync(d_row, d_cnt, sizeof(unsigned long long) * W, cudaMemcpyDeviceToDevice, E.stream));
+        upload_small(d_row + W, &st, 8);
+        nccl_ck(D.all_gather(d_row, d_matrix, (size_t)(W + 1), 5 /* ncclUint64 */, D.comm, E.stream), "ncclAllGather(exchange counts)");
+        dfree(d_row);
+    }
+    std::vector<unsigned long long> M((size_t)W * (W + 1));
+    host_read(M.data(), d_matrix, sizeof(unsigned long long) * M.size());
+    if (local_code != 0) raise(local_code, "%s", local_msg.c_str());
+    for (int r = 0; r < W; r++)
+        if (M[(size_t)r * (W + 1) + W] != 0)
+            raise((int)M[(size_t)r * (W + 1) + W], "rank %d failed in front of an exchange (status %d); the plan was abandoned on all ranks",
+                  r, (int)M[(size_t)r * (W + 1) + W]);
+    // every rank must ship the same columns (same plan): ncols is symmetric by construction
+    ExUnpack U;
+    memset(&U, 0, sizeof(U));
+    U.ncols = ncols; U.world = W;
+    int64_t total = 0;
+    for (int r = 0; r < W; r++) { U.count[r] = (int64_t)M[(size_t)r * (W + 1) + D.rank]; U.off[r] = total; total += U.count[r]; }
+    std::unique_ptr<rq_table> out = new_intermediate(ncols, total);
+    if (local) { out->sql_type = local->sql_type; out->sql_width = local->sql_width; }
+    int64_t* d_recv = nullptr;
+    CK(dmalloc(&d_recv, (size_t)std::max<int64_t>(total, 1) * std::max(ncols, 1) * 8));
+    if (ncols > 0) {
+        nccl_ck(D.group_start(), "ncclGroupStart");
+        int64_t soff = 0;
+        for (int r = 0; r < W; r++) {
+            const int64_t sc = (int64_t)M[(size_t)D.rank * (W + 1) + r];
+            if (sc > 0) nccl_ck(D.send(d_send + (size_t)soff * ncols, (size_t)sc * ncols, 4 /* ncclInt64 */, r, D.comm, E.stream), "ncclSend");
+            soff += sc;
+            if (U.count[r] > 0) nccl_ck(D.recv(d_recv + (size_t)U.off[r] * ncols, (size_t)U.count[r] * ncols, 4, r, D.comm, E.stream), "ncclRecv");
+        }
+        nccl_ck(D.group_end(), "ncclGroupEnd");
+        if (total > 0) {
+            for (int c = 0; c < ncols; c++) U.out[c] = (int64_t*)out->cols[c].d;
+            const unsigned ub = (unsigned)std::min<int64_t>((total * ncols + 255) / 256, 148 * 16);
+            rq_ex_unpack<<<ub, 256, 0, E.stream>>>(U, d_recv, total);
+            if (tm) tm->kernel_launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    upload_small(out->d_n_rows, &total, 8);
+    out->n_rows = total;
+    CK(cudaEventRecord(ep.b, E.stream));
+    dfree(d_meta); dfree(d_matrix); dfree(d_dest); dfree(d_send); dfree(d_recv);
+    return out;
+}
+
+// re-aggregation of exchanged partial groups: column i of `all` is key / partial aggregate i of
+// pipeline pl (SUM and COUNT partials add, MIN / MAX take min / max)
+static std::unique_ptr<rq_table> reaggregate(const rq_plan& plan, const rq_pipeline& pl, rq_table* all, const char* d_strpool,
+                                             rq_timings* tm, size_t& ev_idx, std::vector<std::pair<size_t, int>>& ev_used,
+                                             double& lower_ms) {
     const int nk = pl.n_keys, nv = pl.n_vals;
     std::vector<rq_node> nodes(nk + nv);
     std::vector<rq_value> keys(pl.keys, pl.keys + nk), vals(pl.vals, pl.vals + nv);
@@ -1649,7 +1785,7 @@ static void merge_sharded(const rq_plan& plan, int pi, std::vector<PipeOut>& out
     mp.n_keys = nk; mp.keys = keys.data();
     mp.n_vals = nv; mp.vals = vals.data();
     mp.size_hint = all->n_rows;
-    rq_table* tabs[1] = {all.get()};
+    rq_table* tabs[1] = {all};
     rq_plan mplan;
     memset(&mplan, 0, sizeof(mplan));
     mplan.n_tables = 1; mplan.tables = tabs;
@@ -1658,7 +1794,146 @@ static void merge_sharded(const rq_plan& plan, int pi, std::vector<PipeOut>& out
     mplan.strpool = plan.strpool; mplan.strpool_bytes = plan.strpool_bytes;
     std::vector<PipeOut> mouts(1);
     run_pipeline(mplan, 0, mouts, d_strpool, tm, ev_idx, ev_used, lower_ms, /*is_fact_scan=*/false);
-    outs[pi].table = std::move(mouts[0].table);
+    return std::move(mouts[0].table);
+}
+
+static void merge_sharded(const rq_plan& plan, int pi, std::vector<PipeOut>& outs, const char* d_strpool,
+                          rq_timings* tm, size_t& ev_idx, std::vector<std::pair<size_t, int>>& ev_used,
+                          double& lower_ms) {
+    if (!outs[pi].table) raise(RQ_ERR_INVALID, "sharded merge: pipeline %d has no relation output", pi);
+    const rq_pipeline& pl = plan.pipelines[pi];
+    std::unique_ptr<rq_table> all = gather_relation(*outs[pi].table, tm, outs[pi].owned, ev_idx, ev_used);
+    trace_point("partials gathered", pi);
+    if (pl.sink_kind != RQ_SINK_AGG) {       // no aggregation: the concatenation is the result
+        outs[pi].table = std::move(all);
+        return;
+    }
+    outs[pi].table = reaggregate(plan, pl, all.get(), d_strpool, tm, ev_idx, ev_used, lower_ms);
+}
+
+// Large partial results: every group goes to the rank that owns hash(group key) and is merged there
+// (each rank re-aggregates 1/world of the groups instead of all of them). The merged relation stays
+// partitioned; the final relation of the plan is concatenated before ORDER BY / LIMIT.
+static void merge_partitioned(const rq_plan& plan, int pi, std::vector<PipeOut>& outs, const char* d_strpool,
+                              rq_timings* tm, size_t& ev_idx, std::vector<std::pair<size_t, int>>& ev_used,
+                              double& lower_ms) {
+    if (!outs[pi].table) raise(RQ_ERR_INVALID, "partitioned merge: pipeline %d has no relation output", pi);
+    const rq_pipeline& pl = plan.pipelines[pi];
+    if (pl.sink_kind != RQ_SINK_AGG) return;      // plain relation: concatenated at the end of the plan
+    std::vector<int> key_cols;
+    std::vector<uint8_t> kinds;
+    for (int k = 0; k < pl.n_keys; k++) { key_cols.push_back(k); kinds.push_back(0); }
+    std::unique_ptr<rq_table> ex = exchange_relation(outs[pi].table.get(), key_cols, kinds, 0, "", tm, ev_idx, ev_used);
+    trace_point("partials exchanged", pi);
+    outs[pi].table = reaggregate(plan, pl, ex.get(), d_strpool, tm, ev_idx, ev_used, lower_ms);
+}
+
+// ---- RQ_PLAN_PARTITIONED: every table is a row range; joins meet by key hash -------------------
+static bool is_partitioned_plan(const rq_plan& plan) {
+    return (plan.flags & RQ_PLAN_PARTITIONED) && E.dist.comm && E.dist.world > 1;
+}
+
+static void run_pipeline_partitioned(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
+                                     const char* d_strpool, rq_timings* tm, size_t& ev_idx,
+                                     std::vector<std::pair<size_t, int>>& ev_used, double& lower_ms,
+                                     const rq_table* src_override, bool first_probe_aligned, PipeOut& result) {
+    SimplePipe sp;
+    simplify_pipeline(pl_in, sp);
+    const rq_pipeline& pl = sp.pl;
+    if (pl.source_kind == RQ_SRC_CROSS)
+        raise(RQ_ERR_UNSUPPORTED, "pipeline %d: nested-loops joins are not available in partitioned plans", pi);
+    const rq_table* src = src_override;
+    if (!src) {
+        if (pl.source_kind == RQ_SRC_TABLE) {
+            if (pl.source_id < 0 || pl.source_id >= plan.n_tables || !plan.tables[pl.source_id])
+                raise(RQ_ERR_INVALID, "pipeline %d: table %d out of range", pi, pl.source_id);
+            src = plan.tables[pl.source_id];
+        } else if (pl.source_kind == RQ_SRC_PIPELINE) {
+            if (pl.source_id < 0 || pl.source_id >= pi || !outs[pl.source_id].table)
+                raise(RQ_ERR_INVALID, "pipeline %d: source pipeline %d has no relation output", pi, pl.source_id);
+            src = outs[pl.source_id].table.get();
+        } else {
+            raise(RQ_ERR_INVALID, "pipeline %d: bad source kind %d", pi, pl.source_kind);
+        }
+    }
+    auto run_local = [&](const rq_pipeline& p, const rq_table* s, PipeOut& r) {
+        run_pipeline_one(plan, p, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, s == nullptr, s, r, false);
+    };
+    const rq_table* local_src = src_override;      // nullptr = the pipeline's own table
+
+    // 1. a probe whose input is not yet partitioned by its key: ship the rows first
+    SplitPipes sx;
+    if (split_at_probe(plan, pl, *src, outs, sx, SPLIT_EXCHANGE, first_probe_aligned ? 1 : 0)) {
+        int code = 0;
+        std::string msg;
+        PipeOut mid;
+        try {
+            run_local(sx.a, local_src, mid);
+        } catch (RqError& e) {
+            cudaStreamSynchronize(E.stream);
+            code = e.code; msg = e.msg;
+        }
+        // key columns of the probe in pass A's output: the probe is pass B's first PROBE node
+        std::vector<int> key_cols;
+        std::vector<uint8_t> kinds;
+        for (int i = 0; i < sx.b.n_nodes && key_cols.empty(); i++) {
+            const rq_node& nd = sx.b.nodes[i];
+            if (nd.op != RQ_OP_PROBE) continue;
+            if (nd.a < 0 || nd.a >= (int)outs.size() || !outs[nd.a].ht) raise(RQ_ERR_INVALID, "PROBE refers to pipeline %d which built no hash table", nd.a);
+            for (int k = 0; k < nd.c; k++) {
+                const rq_node& kn = sx.b.nodes[sx.b.args[nd.b + k]];
+                if (kn.op != RQ_OP_COL) raise(RQ_ERR_UNSUPPORTED, "pipeline %d: constant join key in a partitioned plan", pi);
+                key_cols.push_back(kn.a);
+                kinds.push_back(outs[nd.a].ht->d.key_kind[k]);
+            }
+        }
+        std::unique_ptr<rq_table> ex = exchange_relation(code == 0 ? mid.table.get() : nullptr, key_cols, kinds, code, msg, tm, ev_idx, ev_used);
+        run_pipeline_partitioned(plan, sx.b, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, ex.get(), true, result);
+        return;
+    }
+    // 2. a build: its rows go to the rank that owns their key, the table is built there
+    if (pl.sink_kind == RQ_SINK_BUILD) {
+        std::vector<rq_value> mvals;
+        for (int k = 0; k < pl.n_keys; k++) { rq_value v = pl.keys[k]; v.kind = 0; mvals.push_back(v); }
+        for (int k = 0; k < pl.n_vals; k++) { rq_value v = pl.vals[k]; v.kind = 0; mvals.push_back(v); }
+        rq_pipeline a = pl;
+        a.sink_kind = RQ_SINK_MATERIALIZE;
+        a.n_keys = 0; a.keys = nullptr;
+        a.n_vals = (int)mvals.size(); a.vals = mvals.data();
+        int code = 0;
+        std::string msg;
+        PipeOut mid;
+        try {
+            run_local(a, local_src, mid);
+        } catch (RqError& e) {
+            cudaStreamSynchronize(E.stream);
+            code = e.code; msg = e.msg;
+        }
+        std::vector<int> key_cols;
+        std::vector<uint8_t> kinds;
+        for (int k = 0; k < pl.n_keys; k++) {
+            key_cols.push_back(k);
+            const int st = pl.keys[k].sql_type;
+            kinds.push_back(st == RQ_SQL_VARCHAR ? 2 : (st == RQ_SQL_CHAR && pl.keys[k].width > 1) ? 1 : 0);
+        }
+        std::unique_ptr<rq_table> ex = exchange_relation(code == 0 ? mid.table.get() : nullptr, key_cols, kinds, code, msg, tm, ev_idx, ev_used);
+        const int nc = pl.n_keys + pl.n_vals;
+        std::vector<rq_node> bn(nc);
+        std::vector<rq_value> bk(pl.keys, pl.keys + pl.n_keys), bv(pl.vals, pl.vals + pl.n_vals);
+        for (int i = 0; i < nc; i++) bn[i] = rq_node{RQ_OP_COL, i, 0, 0, 0};
+        for (int k = 0; k < pl.n_keys; k++) bk[k].node = k;
+        for (int k = 0; k < pl.n_vals; k++) bv[k].node = pl.n_keys + k;
+        rq_pipeline b = pl;
+        b.source_kind = RQ_SRC_PIPELINE; b.source_id = 0;
+        b.n_nodes = nc; b.nodes = bn.data();
+        b.n_args = 0; b.args = nullptr;
+        b.keys = bk.data(); b.vals = bv.data();
+        b.size_hint = 0;
+        run_local(b, ex.get(), result);
+        return;
+    }
+    // 3. everything this rank needs is local now
+    run_local(pl, local_src, result);
 }
 
 }  // namespace
@@ -1702,7 +1977,8 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
     char* d_strpool = nullptr;
     rq_result* res = nullptr;
     std::vector<void*> scratch;
-    const bool sharded = (plan->flags & RQ_PLAN_SHARDED) && E.dist.comm && E.dist.world > 1;
+    const bool sharded = (plan->flags & (RQ_PLAN_SHARDED | RQ_PLAN_PARTITIONED)) && E.dist.comm && E.dist.world > 1;
+    const bool partitioned = is_partitioned_plan(*plan);
     unsigned char* d_expect = nullptr;
     int32_t* d_ok = nullptr;
     g_small_next = 0;
@@ -1736,6 +2012,8 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
         g_trace_t0 = std::chrono::steady_clock::now();
         CK(cudaEventRecord(E.ev[0], E.stream));
         // sharded plans: merge after the last aggregation (or concatenate the final relation)
+        bool final_gather = false;              // the last relation is partitioned over the ranks
+        std::vector<void*> gather_owned;        // string bytes a final gather received
         int merge_after = -1;
         if (sharded) {
             for (int pi = 0; pi < plan->n_pipelines; pi++)
@@ -1747,7 +2025,10 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
         for (int pi = 0; pi < plan->n_pipelines; pi++) {
             trace_point("pipeline start", pi);
             if (local_code == 0) {
-                if (pi <= merge_after) {
+                if (partitioned) {
+                    // (exchanges inside the pipeline carry the status of every rank themselves)
+                    run_pipeline(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+                } else if (pi <= merge_after) {
                     // a failure on this rank's shard must not leave the other ranks waiting in the merge
                     try {
                         run_pipeline(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
@@ -1761,8 +2042,21 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
             }
             trace_point("pipeline done", pi);
             if (pi == merge_after) {
-                agree_on_status(local_code, local_msg);
-                merge_sharded(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+                // small partial results (a few groups) are all-gathered and merged on every rank;
+                // large ones are hash-partitioned so that each rank merges its share
+                const rq_table* part_tab = outs[pi].table.get();
+                const bool big = partitioned || (local_code == 0 && part_tab && plan->pipelines[pi].sink_kind == RQ_SINK_AGG &&
+                                                 plan->pipelines[pi].n_keys > 0 && !has_str_key(plan->pipelines[pi]) &&
+                                                 (part_tab->n_rows < 0 || part_tab->n_rows > kGroupTableCap));
+                const bool any_big = agree_on_status(local_code, local_msg, big);
+                if (any_big && plan->pipelines[pi].sink_kind == RQ_SINK_AGG && !has_str_key(plan->pipelines[pi])) {
+                    merge_partitioned(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+                    final_gather = true;
+                } else if (partitioned && plan->pipelines[pi].sink_kind != RQ_SINK_AGG) {
+                    final_gather = true;      // no aggregation: the per-rank relations are concatenated at the end
+                } else {
+                    merge_sharded(*plan, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms);
+                }
                 trace_point("sharded merge done", pi);
             }
         }
@@ -1772,13 +2066,14 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
         int64_t n = fin->n_rows;
         if (n < 0) host_read(&n, fin->d_n_rows, 8);
         const int ncols = (int)fin->cols.size();
-
         trace_point("row count read");
-        // ORDER BY + LIMIT
-        std::vector<int64_t*> cols(ncols);
-        for (int c = 0; c < ncols; c++) cols[c] = (int64_t*)fin->cols[c].d;
-        int64_t n_out = n;
-        if (plan->limit >= 0 && plan->limit < n_out) n_out = plan->limit;
+        // ORDER BY + LIMIT over relation t (n rows): cols = the ordered columns, n_out = rows kept
+        auto order_limit = [&](rq_table* t, int64_t n, std::vector<int64_t*>& cols, int64_t& n_out) {
+            const int ncols = (int)t->cols.size();
+            cols.assign(ncols, nullptr);
+            for (int c = 0; c < ncols; c++) cols[c] = (int64_t*)t->cols[c].d;
+            n_out = n;
+            if (plan->limit >= 0 && plan->limit < n_out) n_out = plan->limit;
         if (plan->n_order > 0 && n > 1) {
             if (plan->n_order > kMaxSortKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d ORDER BY keys", kMaxSortKeys);
             SortKeys K;
@@ -1789,7 +2084,7 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
                 if (c < 0 || c >= ncols) raise(RQ_ERR_INVALID, "ORDER BY column %d out of range", c);
                 int w;
                 K.col[k] = cols[c];
-                K.is_str[k] = phys_type(fin->sql_type[c], fin->sql_width[c], &w) == RQ_STR;
+                K.is_str[k] = phys_type(t->sql_type[c], t->sql_width[c], &w) == RQ_STR;
                 K.desc[k] = plan->order[k].ascending ? 0 : 1;
             }
             uint32_t* perm = nullptr;
@@ -1831,7 +2126,7 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
             if (sorted_by_topk) {
                 // perm holds the first rows of the order; LIMIT cuts it below
             } else if (n <= kBitonicMax) {
-                rq_sort_small<<<1, 1024, 0, E.stream>>>(K, fin->d_n_rows, perm, nullptr);
+                rq_sort_small<<<1, 1024, 0, E.stream>>>(K, t->d_n_rows, perm, nullptr);
                 if (tm) tm->kernel_launches++;
             } else {
                 // LSD radix sort, least significant ORDER BY key first; every pass is stable
@@ -1849,7 +2144,7 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
                 if (tm) tm->kernel_launches++;
                 for (int k = plan->n_order - 1; k >= 0; k--) {
                     const int c = plan->order[k].column;
-                    const int words = K.is_str[k] ? (fin->sql_width[c] + 7) / 8 : 1;
+                    const int words = K.is_str[k] ? (t->sql_width[c] + 7) / 8 : 1;
                     for (int w = words - 1; w >= 0; w--) {
                         rq_sort_make_keys<<<eb, 256, 0, E.stream>>>(K.col[k], perm, k1, n, K.is_str[k], w, K.desc[k]);
                         const unsigned long long init[2] = {0ULL, ~0ULL};
@@ -1876,12 +2171,39 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
                 int64_t* sorted = nullptr;
                 CK(dmalloc(&sorted, sizeof(int64_t) * std::max<int64_t>(n_out, 1)));
                 scratch.push_back(sorted);
-                rq_apply_perm<<<(unsigned)((n_out + 255) / 256), 256, 0, E.stream>>>(cols[c], sorted, perm, fin->d_n_rows, plan->limit);
+                rq_apply_perm<<<(unsigned)((n_out + 255) / 256), 256, 0, E.stream>>>(cols[c], sorted, perm, t->d_n_rows, plan->limit);
                 if (tm) tm->kernel_launches++;
                 cols[c] = sorted;
             }
             CK(cudaGetLastError());
         }
+
+        };
+        std::vector<int64_t*> cols;
+        int64_t n_out = 0;
+        std::unique_ptr<rq_table> gathered;
+        if (final_gather) {
+            // The relation is hash-partitioned over the ranks (merge_partitioned): with ORDER BY ...
+            // LIMIT k every rank contributes only its first k rows, then the concatenation is ordered.
+            rq_table part;
+            std::vector<int64_t*> pc;
+            int64_t pn = n;
+            if (plan->n_order > 0 && plan->limit >= 0) order_limit(fin, n, pc, pn);
+            else { pc.resize(ncols); for (int c = 0; c < ncols; c++) pc[c] = (int64_t*)fin->cols[c].d; }
+            part.n_rows = pn;
+            part.cap_rows = pn;
+            for (int c = 0; c < ncols; c++) {
+                DevColumn dc;
+                dc.type = RQ_I64; dc.width = 8; dc.d = (unsigned char*)pc[c]; dc.owned = false; dc.tile_stride = (int64_t)kTile * 8;
+                part.cols.push_back(dc);
+            }
+            part.sql_type = fin->sql_type;
+            part.sql_width = fin->sql_width;
+            gathered = gather_relation(part, tm, gather_owned, ev_idx, ev_used);
+            fin = gathered.get();
+            n = fin->n_rows;
+        }
+        order_limit(fin, n, cols, n_out);
 
         trace_point("sorted");
         // narrow to the reference's physical widths on the device, then read back
@@ -1955,6 +2277,7 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
             }
         }
         for (void* p : scratch) dfree(p);
+        for (void* p : gather_owned) dfree(p);
         if (d_strpool) dfree(d_strpool);
         *out = res;
         return RQ_OK;
@@ -2016,6 +2339,7 @@ static void reset_plan_memos() {
     g_ht_capacity.clear();
     g_emit_rows.clear();
     g_needs_expand.clear();
+    g_agg_impl.clear();
     RP = ReplayState();
 }
 

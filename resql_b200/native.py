@@ -10,6 +10,7 @@ RQ_I8, RQ_I32, RQ_I64, RQ_STR = 1, 2, 3, 4
 RQ_HOST_PTR, RQ_DEVICE_PTR, RQ_BORROW = 0, 1, 2
 SQL_VARCHAR, SQL_CHAR, SQL_BOOL, SQL_INT, SQL_BIGINT, SQL_DECIMAL, SQL_FLOAT, SQL_DATE = range(8)
 RQ_PLAN_SHARDED = 1
+RQ_PLAN_PARTITIONED = 2
 
 
 def lib_path():

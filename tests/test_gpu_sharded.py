@@ -24,5 +24,10 @@ def test_sharded_plans_match_reference(world):
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(ROOT, "tests", "sharded_worker.py")],
                        capture_output=True, text=True, timeout=900)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"sharded_worker_n{world}.log"), "w") as f:
+        f.write(r.stdout + "\n--- stderr ---\n" + r.stderr[-4000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "sharded q3" in r.stdout
+    assert "partitioned micro_join_avg" in r.stdout
+    assert "sharded error agreement" in r.stdout
