@@ -167,6 +167,9 @@ typedef struct {
                                 follows as RQ_OP_FILTER). COL indices address the columns of
                                 source_id first, then those of source_id2.                       */
 
+#define RQ_SRC_ONE_ROW   4   /* a single tuple without attributes: leaf projection, "creates a
+                                single-line table from constants" (projection.h:49-58, `select 1+1`) */
+
 #define RQ_SINK_AGG          1   /* GROUP BY keys + aggregates (aggregation.h:240-295)          */
 #define RQ_SINK_BUILD        2   /* hash-join build: keys + payload (hashjoin.h:226-256)        */
 #define RQ_SINK_MATERIALIZE  3   /* append tuples to an output relation (materialize.h:78)     */

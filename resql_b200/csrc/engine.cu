@@ -84,8 +84,10 @@ struct DevColumn {
     bool has_stats = false;
     int64_t vmin = 0, vmax = 0;
 };
+static uint64_t g_next_table_uid = 1;
 struct rq_table {
     std::string name;
+    uint64_t uid = g_next_table_uid++;      // identity of this upload (plan memos are keyed by it)
     int64_t n_rows = 0;       // host-known row count (-1: only on device)
     int64_t cap_rows = 0;     // allocated rows (multiple of kTileRows for owned tables)
     int64_t* d_n_rows = nullptr;

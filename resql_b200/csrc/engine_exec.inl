@@ -507,8 +507,8 @@ static void encode_program(Lowerer& L, KParams& P) {
             u.code = U_PROBE;
         } else if (h.op == H_SEL) {
             u.code = U_GEN;
-            if (y.kind == K_IMM) u.imm = h.y.imm;
-            if (x.kind == K_IMM) u.imm = h.x.imm;
+            if (y.kind == K_IMM) u.imm = h.y.imm;                 // (a constant condition was folded: x is never K_IMM)
+            if (x.kind == K_IMM) raise(RQ_ERR_INVALID, "internal: SELECT with a constant condition reached the device program");
             if (z.kind == K_IMM) z.off = (uint32_t)L.imm_index(h.z.imm);
         } else {   // H_BIN
             const int bi = bin_index(h.gop);
@@ -527,10 +527,13 @@ static void encode_program(Lowerer& L, KParams& P) {
                 y = UOperand{K_NONE, 0, 0};
             } else {
                 u.code = U_GEN;
-                if (x.kind == K_IMM && y.kind == K_IMM && h.gop != D_LD)
-                    raise(RQ_ERR_INVALID, "internal: constant expression reached the device program");
                 if (y.kind == K_IMM) u.imm = h.y.imm;
-                if (x.kind == K_IMM) u.imm = h.x.imm;
+                if (x.kind == K_IMM) {
+                    // both operands constant (string predicates on two literals are not folded): the unit has
+                    // one immediate field, the second constant goes through the immediate table
+                    if (y.kind == K_IMM && h.gop != D_LD) { y.kind = K_IMM2; y.off = (uint32_t)L.imm_index(h.y.imm); }
+                    u.imm = h.x.imm;
+                }
             }
         }
         if (x.slot) u.flags |= UF_XSLOT;
@@ -1066,6 +1069,12 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
         if (pl.source_id < 0 || pl.source_id >= pi || !outs[pl.source_id].table)
             raise(RQ_ERR_INVALID, "pipeline %d: source pipeline %d has no relation output", pi, pl.source_id);
         src = outs[pl.source_id].table.get();
+    } else if (pl.source_kind == RQ_SRC_ONE_ROW) {
+        // leaf projection (projection.h:49-58): one tuple, no attributes
+        cross_holder.reset(new rq_table());
+        cross_holder->n_rows = 1;
+        cross_holder->cap_rows = kPadRows;
+        src = cross_holder.get();
     } else {
         raise(RQ_ERR_INVALID, "pipeline %d: bad source kind %d", pi, pl.source_kind);
     }
@@ -1139,6 +1148,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
         P.expand_probe = -1;
         P.n_rows = src->n_rows;
         P.n_rows_ptr = src->n_rows < 0 ? src->d_n_rows : nullptr;
+        P.n_rows_cap = src->cap_rows;
         P.borrowed = src->borrowed ? 1 : 0;
         P.stream_hint = 1;
         P.overflow = E.flags + 0;
@@ -1322,7 +1332,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             CK(dmalloc(&d_ptrs, sizeof(int64_t*) * ncols));
             CK(cudaMemcpyAsync(d_map, colmap.data(), sizeof(int) * ncols, cudaMemcpyHostToDevice, E.stream));
             CK(cudaMemcpyAsync(d_ptrs, h_cols.data(), sizeof(int64_t*) * ncols, cudaMemcpyHostToDevice, E.stream));
-            rq_ht_compact<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, d_map, ncols, d_ptrs, (unsigned long long*)out->d_n_rows);
+            rq_ht_compact<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, d_map, ncols, d_ptrs, (unsigned long long*)out->d_n_rows, (unsigned long long)out->cap_rows);
             if (tm) tm->kernel_launches++;
             CK(cudaGetLastError());
             dfree(d_map);                 // stream-ordered: freed after the compaction kernel ran
@@ -1703,9 +1713,9 @@ static std::unique_ptr<rq_table> exchange_relation(const rq_table* local, const 
         CK(dmalloc(&d_dest, (size_t)std::max<int64_t>(rows_bound, 1)));
         CK(dmalloc(&d_send, (size_t)std::max<int64_t>(rows_bound, 1) * ncols * 8));
         const int64_t* n_ptr = local->n_rows < 0 ? local->d_n_rows : nullptr;
-        rq_ex_count<<<blocks, kExThreads, 0, E.stream>>>(X, n_ptr, local->n_rows, d_dest, d_cnt);
+        rq_ex_count<<<blocks, kExThreads, 0, E.stream>>>(X, n_ptr, local->n_rows, rows_bound, d_dest, d_cnt);
         rq_ex_offsets<<<1, 32, 0, E.stream>>>(d_cnt, d_off, d_cur, W);
-        rq_ex_scatter<<<blocks, kExThreads, 0, E.stream>>>(X, n_ptr, local->n_rows, d_dest, d_cnt, d_off, d_cur, d_send);
+        rq_ex_scatter<<<blocks, kExThreads, 0, E.stream>>>(X, n_ptr, local->n_rows, rows_bound, d_dest, d_cnt, d_off, d_cur, d_send);
         if (tm) tm->kernel_launches += 3;
         CK(cudaGetLastError());
     }
@@ -2118,7 +2128,7 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
                 unsigned long long n_cand = 0;
                 host_read(&n_cand, st + 2, 8);
                 if (n_cand <= (unsigned long long)kBitonicMax) {
-                    rq_sort_small<<<1, 1024, 0, E.stream>>>(K, (const int64_t*)(st + 2), perm, cand);
+                    rq_sort_small<<<1, 1024, 0, E.stream>>>(K, (const int64_t*)(st + 2), (int64_t)kBitonicMax, perm, cand);
                     if (tm) tm->kernel_launches++;
                     sorted_by_topk = true;
                 }
@@ -2126,7 +2136,7 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
             if (sorted_by_topk) {
                 // perm holds the first rows of the order; LIMIT cuts it below
             } else if (n <= kBitonicMax) {
-                rq_sort_small<<<1, 1024, 0, E.stream>>>(K, t->d_n_rows, perm, nullptr);
+                rq_sort_small<<<1, 1024, 0, E.stream>>>(K, t->d_n_rows, n, perm, nullptr);
                 if (tm) tm->kernel_launches++;
             } else {
                 // LSD radix sort, least significant ORDER BY key first; every pass is stable
@@ -2171,7 +2181,7 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
                 int64_t* sorted = nullptr;
                 CK(dmalloc(&sorted, sizeof(int64_t) * std::max<int64_t>(n_out, 1)));
                 scratch.push_back(sorted);
-                rq_apply_perm<<<(unsigned)((n_out + 255) / 256), 256, 0, E.stream>>>(cols[c], sorted, perm, t->d_n_rows, plan->limit);
+                rq_apply_perm<<<(unsigned)((n_out + 255) / 256), 256, 0, E.stream>>>(cols[c], sorted, perm, t->d_n_rows, n, plan->limit);
                 if (tm) tm->kernel_launches++;
                 cols[c] = sorted;
             }
@@ -2310,7 +2320,10 @@ static uint64_t plan_signature(const rq_plan& plan) {
     for (int t = 0; t < plan.n_tables; t++) {
         const rq_table* tb = plan.tables[t];
         if (!tb) continue;
-        mixin(tb->name.data(), tb->name.size());
+        // table identity: the contents of a table never change after its upload (a new version is a
+        // new upload, like the reference's append-only relations), so predictions recorded for this
+        // handle stay exact; another table under the same name is another handle
+        mixin(&tb->uid, sizeof tb->uid);
         mixin(&tb->n_rows, sizeof tb->n_rows);
         mixin(&tb->borrowed, sizeof tb->borrowed);
         for (auto& c : tb->cols) { mixin(&c.type, sizeof c.type); mixin(&c.width, sizeof c.width); mixin(&c.page_off, sizeof c.page_off); }
@@ -2364,6 +2377,8 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         RP = ReplayState();
         if (rc != RQ_OK) { memo.valid = false; return rc; }
         if (ok) return RQ_OK;
+        if (E.opt.trace) fprintf(stderr, "[rq] rank %d: replayed plan discarded (%s); running the careful way\n", E.dist.rank,
+                                 *out ? "a predicted value was wrong on some rank" : "the recorded script did not fit");
         // some predicted value was wrong (other data under the same table name, a full table, a
         // runtime error ...): drop the result and run the careful way, which also reports errors
         if (*out) { rq_result_free(*out); *out = nullptr; }
@@ -2376,6 +2391,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
     bool clean = false;
     const int rc = execute_once(plan, out, tm, &clean);
     memo.valid = rc == RQ_OK && clean;
+    if (E.opt.trace) fprintf(stderr, "[rq] rank %d: careful run rc=%d clean=%d retries=%d reads=%zu\n", E.dist.rank, rc, (int)clean, RP.retries, memo.reads.size());
     if (!memo.valid) memo.reads.clear();
     RP = ReplayState();
     return rc;

@@ -39,9 +39,10 @@ __device__ __forceinline__ uint32_t ex_dest(const ExCols& X, int64_t row) {
 }
 
 __global__ void __launch_bounds__(kExThreads)
-rq_ex_count(ExCols X, const int64_t* n_ptr, int64_t n_host, uint8_t* dest, unsigned long long* cnt) {
+rq_ex_count(ExCols X, const int64_t* n_ptr, int64_t n_host, int64_t n_cap, uint8_t* dest, unsigned long long* cnt) {
     __shared__ unsigned int hist[kMaxRanks];
-    const int64_t n = n_ptr ? *n_ptr : n_host;
+    int64_t n = n_ptr ? *n_ptr : n_host;
+    if (n > n_cap) n = n_cap;
     if (threadIdx.x < kMaxRanks) hist[threadIdx.x] = 0;
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * kExBlockRows;
@@ -66,11 +67,12 @@ __global__ void rq_ex_offsets(const unsigned long long* cnt, unsigned long long*
 }
 
 __global__ void __launch_bounds__(kExThreads)
-rq_ex_scatter(ExCols X, const int64_t* n_ptr, int64_t n_host, const uint8_t* dest, const unsigned long long* cnt,
+rq_ex_scatter(ExCols X, const int64_t* n_ptr, int64_t n_host, int64_t n_cap, const uint8_t* dest, const unsigned long long* cnt,
               const unsigned long long* off, unsigned long long* cursor, int64_t* send) {
     __shared__ unsigned int hist[kMaxRanks];
     __shared__ unsigned long long base_of[kMaxRanks];
-    const int64_t n = n_ptr ? *n_ptr : n_host;
+    int64_t n = n_ptr ? *n_ptr : n_host;
+    if (n > n_cap) n = n_cap;
     if (threadIdx.x < kMaxRanks) hist[threadIdx.x] = 0;
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * kExBlockRows;

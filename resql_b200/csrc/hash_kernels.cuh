@@ -174,7 +174,7 @@ __global__ void rq_ht_init(DHashTable ht, const uint8_t* kinds, int init_vals) {
 // occupied slots -> dense int64 columns. colmap[c] < nk selects key word colmap[c], otherwise
 // accumulator colmap[c]-nk (duplicate aggregates share one accumulator).
 __global__ void rq_ht_compact(DHashTable ht, const int* colmap, int n_out, int64_t* const* out_cols,
-                              unsigned long long* count) {
+                              unsigned long long* count, unsigned long long out_cap) {
     const uint64_t cap = ht.cap_mask + 1;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool used = i < cap && *ht_entry(ht, i) != 0ULL;
@@ -187,7 +187,8 @@ __global__ void rq_ht_compact(DHashTable ht, const int* colmap, int n_out, int64
     if (used) {
         const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1));
         const uint64_t* e = ht_entry(ht, i);
-        for (int c = 0; c < n_out; c++) out_cols[c][pos] = (int64_t)e[1 + colmap[c]];
+        if (pos < out_cap)       // (sized from a count the host may only have predicted)
+            for (int c = 0; c < n_out; c++) out_cols[c][pos] = (int64_t)e[1 + colmap[c]];
     }
 }
 

@@ -54,7 +54,8 @@ enum DSrc : uint8_t { S_NONE = 0, S_COL = 1, S_SLOT = 2, S_IMM = 3, S_STR = 4 };
 // register shuffling. Opcode and operand form are fused into `code` on the host and operands are
 // precomputed byte offsets, so a unit does no address bookkeeping per tuple.
 enum UKind : uint8_t {             // operand kinds
-    K_NONE = 0, K_M64, K_M32, K_M8, K_IMM, K_STR
+    K_NONE = 0, K_M64, K_M32, K_M8, K_IMM, K_STR,
+    K_IMM2        // constant in KParams::imm[offset] (second constant of a unit)
 };
 
 #define RQ_BINOPS(X) X(ADD) X(SUB) X(RSUB) X(MUL) X(AND) X(OR) X(LT) X(LE) X(GT) X(GE) X(EQ) X(NE)
@@ -149,6 +150,7 @@ struct KParams {
     // source
     int64_t        n_rows;
     const int64_t* n_rows_ptr;          // if non-null the row count is read on the device
+    int64_t        n_rows_cap;          // ... and clamped to the rows the source has room for
     int32_t        borrowed;            // source buffers may end exactly at n_rows (no padding)
     int32_t        stream_hint;         // mark scanned data evict-first in L2
     int32_t        l2_prefetch;         // pull the next tile into L2 while the current one is processed

@@ -127,6 +127,12 @@ __device__ __forceinline__ void fetch(const KParams& P, const WarpCtx& c, int ki
             for (int r = 0; r < kR; r++)
                 v[r] = (int64_t)(P.str_ptr[off] + (size_t)(c.row0 + row_in_tile(r, c.lane)) * P.str_w[off]);
             break;
+        case K_IMM2: {
+            const int64_t k2 = P.imm[off];
+#pragma unroll
+            for (int r = 0; r < kR; r++) v[r] = k2;
+            break;
+        }
         default:
 #pragma unroll
             for (int r = 0; r < kR; r++) v[r] = imm;
@@ -299,7 +305,8 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     asm volatile("" : "+r"(lane));
     const uint32_t sacc = wbase + P.acc_rel;            // GR == 0 low-card path: [g][a][lane] int64
 
-    const int64_t n_rows = P.n_rows_ptr ? *P.n_rows_ptr : P.n_rows;
+    int64_t n_rows = P.n_rows;
+    if (P.n_rows_ptr) { n_rows = *P.n_rows_ptr; if (n_rows > P.n_rows_cap) n_rows = P.n_rows_cap; }
     // tile indices are 32-bit (2^32 tiles = 10^12 rows): cheap to keep or recompute under register pressure
     const uint32_t n_tiles = (uint32_t)((n_rows + kTile - 1) / kTile);
     const uint32_t stride = gridDim.x * W;

@@ -40,9 +40,14 @@ __device__ __forceinline__ bool row_less(const SortKeys& K, uint32_t i, uint32_t
 
 // single-CTA bitonic sort of row indices (n <= kBitonicMax), perm[] receives the order
 __global__ void __launch_bounds__(1024)
-rq_sort_small(const __grid_constant__ SortKeys K, const int64_t* n_ptr, uint32_t* perm, const uint32_t* cand) {
+rq_sort_small(const __grid_constant__ SortKeys K, const int64_t* n_ptr, int64_t n_cap, uint32_t* perm, const uint32_t* cand) {
     __shared__ uint32_t idx[kBitonicMax];
-    const int n = (int)*n_ptr;
+    // (the device-side count is clamped to what the host sized the buffers for: a replayed plan runs
+    // on predicted sizes, and a wrong prediction must stay inside its allocations)
+    int64_t n64 = *n_ptr;
+    if (n64 > n_cap) n64 = n_cap;
+    if (n64 > kBitonicMax) n64 = kBitonicMax;
+    const int n = (int)(n64 < 0 ? 0 : n64);
     int m = 1;
     while (m < n) m <<= 1;
     // rows to sort: all of 0..n-1, or the n candidate rows a top-k pre-selection left over
@@ -69,8 +74,9 @@ rq_sort_small(const __grid_constant__ SortKeys K, const int64_t* n_ptr, uint32_t
 
 // out[i] = in[perm[i]] for i < min(n, limit)
 __global__ void rq_apply_perm(const int64_t* in, int64_t* out, const uint32_t* perm,
-                              const int64_t* n_ptr, int64_t limit) {
+                              const int64_t* n_ptr, int64_t n_cap, int64_t limit) {
     int64_t n = *n_ptr;
+    if (n > n_cap) n = n_cap;
     if (limit >= 0 && limit < n) n = limit;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[perm[i]];

@@ -15,3 +15,11 @@ g++ -O2 -DNDEBUG -std=c++20 -pthread -fPIC -w -DASMJIT_STATIC \
     -L"$ROOT/resql_b200" -lresql_b200 -Wl,-rpath,'$ORIGIN/..' -Wl,--export-dynamic -lrt \
     -o "$HERE/resql-b200"
 ls -la "$HERE/resql-b200"
+# the reference's own test suites routed through the drop-in (ref_tests_gpu.cpp)
+g++ -O2 -DNDEBUG -std=c++20 -pthread -fPIC -w -DASMJIT_STATIC \
+    -I"$B/lib/cereal/include" -I"$B/lib/cxxopts" -I"$B/lib/asmjit/src" -I"$B/src" -I"$B" -I"$B/test" \
+    -I"$ROOT/include" -I"$HERE" \
+    "$HERE/ref_tests_gpu.cpp" "$B/lexer_hand.o" "$B/libasmjit.a" \
+    -L"$ROOT/resql_b200" -lresql_b200 -Wl,-rpath,'$ORIGIN/..' -Wl,--export-dynamic -lrt \
+    -o "$HERE/resql-reftests-gpu"
+ls -la "$HERE/resql-reftests-gpu"

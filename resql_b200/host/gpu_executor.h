@@ -334,7 +334,12 @@ public:
             return;
         }
         if ( auto* proj = dynamic_cast<ProjectionOp*> ( op ) ) {
-            if ( proj->_child == nullptr ) throw ResqlError ( "GPU engine: leaf projection (select without from) is not on the hot path" );
+            if ( proj->_child == nullptr ) {
+                /* leaf projection (projection.h:49-58): "creates a single-line table from constants" */
+                newPipeline ( RQ_SRC_ONE_ROW, 0 );
+                consume ( op, nullptr );
+                return;
+            }
             SymbolSet req = extractRequiredAttributes ( proj->_expr );
             produce ( proj->_child, req );
             return;

@@ -14,7 +14,7 @@ OPS = ["", "COL", "CONST", "CONST_STR", "ADD", "SUB", "MUL", "DIV", "AND", "OR",
        "FILTER", "PROBE", "PAYLOAD"]
 OP = {n: i for i, n in enumerate(OPS) if n}
 AGG = {"SUM": 1, "COUNT": 2, "MIN": 3, "MAX": 4}
-SRC_TABLE, SRC_PIPELINE, SRC_CROSS = 1, 2, 3
+SRC_TABLE, SRC_PIPELINE, SRC_CROSS, SRC_ONE_ROW = 1, 2, 3, 4
 SINK_AGG, SINK_BUILD, SINK_MATERIALIZE = 1, 2, 3
 
 

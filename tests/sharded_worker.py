@@ -35,6 +35,8 @@ def main():
     uid = [eng.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     eng.dist_init(rank, world, uid[0])
+    if os.environ.get("RQ_TEST_TRACE"):
+        eng.set_option("trace", 1)
     data = tpch.generate(0.01, seed=42)
     failures = []
     for name, fact in CASES:

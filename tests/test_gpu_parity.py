@@ -231,3 +231,17 @@ def test_replay_notices_changed_data_and_errors(engine):
             engine.execute(Plan(d), {"t": t})
     finally:
         t.free()
+
+
+def test_reference_suites_pass_through_the_gpu_shim():
+    """The reference's OWN test suites (test/test_datatypes.h, test_expressions.h, test_operators.h;
+    hand-built RelOperator trees checked by executeSelectAndCheckRelation, test_common.h:222) with
+    executeSelectPlan routed to executeSelectPlanGpu: resql_b200/host/ref_tests_gpu.cpp, prebuilt
+    in the container that has the reference checkout."""
+    exe = os.path.join(ROOT, "resql_b200/host/resql-reftests-gpu")
+    if not os.path.exists(exe):
+        pytest.skip("resql-reftests-gpu not built (needs the reference checkout at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ALL REFERENCE SUITES PASSED ON THE GPU PATH" in r.stdout
+    assert r.stdout.count(" OK") >= 40
