@@ -112,6 +112,7 @@ struct Options {
     double split_frac = -1;               //                   maximal build/probe-domain ratio (-1 = default 0.3)
     bool prune_builds = true;             // restrict build sides to the probe key's value range
     bool topk = true;                     // ORDER BY ... LIMIT k through radix select
+    bool direct_joins = true;             // direct-address join tables for dense unique integer keys
     bool replay = true;                   // predicted host reads (engine_exec.inl "host reads of device values")
     bool trace = false;                   // per-step wall-clock trace on stderr
 };
@@ -215,6 +216,7 @@ extern "C" int rq_set_option(const char* key, double value) {
     else if (k == "split_frac") o.split_frac = value;
     else if (k == "prune_builds") o.prune_builds = value != 0;
     else if (k == "topk") o.topk = value != 0;
+    else if (k == "direct_joins") o.direct_joins = value != 0;
     else if (k == "replay") o.replay = value != 0;
     else if (k == "trace") o.trace = value != 0;
     else return fail(RQ_ERR_INVALID, "rq_set_option: unknown option '%s'", key);
@@ -699,6 +701,27 @@ struct Lowerer {
         auto clampset = [&](int i, __int128 lo, __int128 hi) {
             if (lo < FMIN || hi > FMAX) { vlo[i] = FMIN; vhi[i] = FMAX; } else { vlo[i] = lo; vhi[i] = hi; }
         };
+        // A tuple reaches the sink only if it passes every selection, so `col CMP const` selections
+        // narrow the bounds of the column for everything the sink sees (values computed for tuples that
+        // are dropped anyway may fall outside; they are never used).
+        std::vector<__int128> clo(n, FMIN), chi(n, FMAX);
+        for (int f = 0; f < n; f++) {
+            if (pl.nodes[f].op != RQ_OP_FILTER) continue;
+            const rq_node& cm = pl.nodes[pl.nodes[f].a];
+            int op = cm.op, cn = -1, kn = -1;
+            if (op != RQ_OP_LT && op != RQ_OP_LE && op != RQ_OP_GT && op != RQ_OP_GE && op != RQ_OP_EQ) continue;
+            if (pl.nodes[cm.a].op == RQ_OP_COL && pl.nodes[cm.b].op == RQ_OP_CONST) { cn = cm.a; kn = cm.b; }
+            else if (pl.nodes[cm.a].op == RQ_OP_CONST && pl.nodes[cm.b].op == RQ_OP_COL) {
+                cn = cm.b; kn = cm.a;
+                op = op == RQ_OP_LT ? RQ_OP_GT : op == RQ_OP_LE ? RQ_OP_GE : op == RQ_OP_GT ? RQ_OP_LT : op == RQ_OP_GE ? RQ_OP_LE : op;
+            } else continue;
+            const __int128 k = pl.nodes[kn].imm;
+            if (op == RQ_OP_LT) chi[cn] = std::min(chi[cn], k - 1);
+            else if (op == RQ_OP_LE) chi[cn] = std::min(chi[cn], k);
+            else if (op == RQ_OP_GT) clo[cn] = std::max(clo[cn], k + 1);
+            else if (op == RQ_OP_GE) clo[cn] = std::max(clo[cn], k);
+            else { clo[cn] = std::max(clo[cn], k); chi[cn] = std::min(chi[cn], k); }
+        }
         for (int i = 0; i < n; i++) {
             const rq_node& nd = pl.nodes[i];
             switch (nd.op) {
@@ -708,6 +731,11 @@ struct Lowerer {
                     if (dc.has_stats) { vlo[i] = dc.vmin; vhi[i] = dc.vmax; }
                     else if (dc.type == RQ_I8) { vlo[i] = 0; vhi[i] = 255; }
                     else if (dc.type == RQ_I32) { vlo[i] = INT32_MIN; vhi[i] = INT32_MAX; }
+                    if (clo[i] > vlo[i]) vlo[i] = clo[i];
+                    if (chi[i] < vhi[i]) vhi[i] = chi[i];
+                    if (vlo[i] > vhi[i]) { vlo[i] = vhi[i] = clo[i] > FMIN ? clo[i] : chi[i]; }   // no tuple passes: any bounds do
+                    if (vlo[i] < FMIN) vlo[i] = FMIN;
+                    if (vhi[i] > FMAX) vhi[i] = FMAX;
                     break;
                 }
                 case RQ_OP_CONST: vlo[i] = vhi[i] = nd.imm; break;

@@ -362,7 +362,7 @@ static void emit_program(Lowerer& L, int impl, const AggDedup& ad) {
             for (int k = 0; k < nd.c; k++) L.hprobe_key[P.n_probes][k] = L.href_of(pl.args[nd.b + k]);
             pr.single = (int32_t)(nd.imm & 1);
             pr.bloom_only = (int32_t)(((nd.imm >> 1) | (nd.imm >> 2)) & 1);
-            if (pr.bloom_only && pr.ht.bloom == nullptr) raise(RQ_ERR_INVALID, "internal: semi-join pass without a Bloom filter");
+            if (pr.bloom_only && pr.ht.bloom == nullptr && !pr.ht.direct) raise(RQ_ERR_INVALID, "internal: semi-join pass without a filter");
             if ((nd.imm >> 2) & 1) {
                 if (impl != IMPL_EMIT || i != n - 1) raise(RQ_ERR_INVALID, "internal: expansion probe must end a materialize pipeline");
                 P.expand_probe = P.n_probes;
@@ -747,6 +747,7 @@ struct ReplayState {
     size_t log_bytes = 0, log_cap = 0;
     int retries = 0;                   // recording: a retried pipeline makes the run unfit as a script
     int syncs = 0;                     // host waits of this execution (reported through rq_timings)
+    const char* why = "";             // last retry reason (trace)
 };
 static ReplayState RP;
 struct ReplayDiverged {};
@@ -995,6 +996,8 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
 static std::set<uint64_t> g_needs_expand;
 // aggregation pipelines: the implementation (register / shared-memory / hash) that did not overflow
 static std::map<uint64_t, int> g_agg_impl;
+// join builds that met duplicate keys: hash form, not direct-address
+static std::set<uint64_t> g_no_direct;
 
 static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int pi, std::vector<PipeOut>& outs,
                              const char* d_strpool, rq_timings* tm, size_t& ev_idx,
@@ -1008,7 +1011,7 @@ static void run_pipeline_one(const rq_plan& plan, const rq_pipeline& pl_in, int 
             return;
         } catch (NeedExpand&) {
             cudaStreamSynchronize(E.stream);
-            RP.retries++;
+            RP.retries++; RP.why = "multi-match expansion";
             result = PipeOut();
             g_needs_expand.insert(sig);
         }
@@ -1228,7 +1231,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             dfree(d_ptrs);
             check_flags("aggregation pipeline", dense->d_n_rows);
             const int64_t n_groups_host = *(const int64_t*)(E.h_flags + 8);
-            if (E.h_flags[0]) { RP.retries++; continue; }   // more groups than this path tracks: next implementation
+            if (E.h_flags[0]) { RP.retries++; RP.why = "group overflow"; continue; }   // more groups than this path tracks: next implementation
             // expand duplicates by aliasing: copy the columns (tiny)
             for (int k = 0; k < pl.n_keys; k++)
                 CK(cudaMemcpyAsync(out->cols[k].d, dense->cols[k].d, (size_t)kGroupTableCap * 8, cudaMemcpyDeviceToDevice, E.stream));
@@ -1262,6 +1265,48 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             const int nv = impl == IMPL_BUILD ? pl.n_vals : (int)ad.kind.size();
             std::unique_ptr<HashTableDev> ht;
             unsigned long long n_used = 0;
+            // Direct-address form (rq_internal.h DHashTable): one integer key with a proven, dense
+            // enough value domain. The key bounds come from the upload statistics narrowed by the
+            // pipeline's own range selections (so a build pruned to the probe side's key range - or
+            // to one rank's share of it - gets a table of exactly that range).
+            if (impl == IMPL_BUILD && nk == 1 && E.opt.direct_joins && !g_no_direct.count(sig)) {
+                const HRef& hk = L.hkey[0];
+                const int st = pl.keys[0].sql_type;
+                const bool int_key = !(st == RQ_SQL_VARCHAR || (st == RQ_SQL_CHAR && pl.keys[0].width > 1));
+                if (int_key && hk.lo > INT64_MIN / 2 && hk.hi < INT64_MAX / 2 && hk.hi >= hk.lo) {
+                    const uint64_t dsize = (uint64_t)(hk.hi - hk.lo) + 1;
+                    const uint64_t bytes = dsize / 8 + dsize * (uint64_t)nv * 8;
+                    if (dsize <= (1ULL << 33) && bytes <= (24ULL << 30) &&
+                        dsize <= 64ULL * (uint64_t)std::max<int64_t>(rows_bound, 4096)) {
+                        ht.reset(new HashTableDev());
+                        ht->capacity = dsize;
+                        ht->d.direct = 1;
+                        ht->d.dlo = hk.lo;
+                        ht->d.dsize = dsize;
+                        ht->d.dnv = (uint32_t)nv;
+                        ht->d.nk = nk; ht->d.nv = nv;
+                        ht->d.cap_mask = 0; ht->d.shift = 63;
+                        ht->d.limit = ~0ULL;
+                        const size_t words = (size_t)(dsize + 31) / 32;
+                        CK(dmalloc(&ht->d.dbits, words * 4));
+                        CK(cudaMemsetAsync(ht->d.dbits, 0, words * 4, E.stream));
+                        if (nv > 0) CK(dmalloc(&ht->d.darr, (size_t)dsize * nv * 8));    // (not cleared: the bitmap says what is valid)
+                        P.ht = ht->d;
+                        CK(cudaMemsetAsync(E.flags, 0, 32, E.stream));
+                        launch_pipeline(P, 0, rows_bound, tm, is_scan, ev_idx, ev_used);
+                        check_flags("join build pipeline");
+                        if (E.h_flags[3] == 0) {
+                            ht->entries = *(unsigned long long*)(E.h_flags + 6);
+                            result.ht = std::move(ht);
+                            return;
+                        }
+                        // duplicate keys: this build needs the hash form (and will get it right away next time)
+                        g_no_direct.insert(sig);
+                        RP.retries++; RP.why = "direct-address build met duplicate keys";
+                        ht.reset();
+                    }
+                }
+            }
             for (;;) {
                 ht.reset(new HashTableDev());
                 ht->capacity = cap;
@@ -1301,7 +1346,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 n_used = *(unsigned long long*)(E.h_flags + 6);     // counted by the kernel itself
                 if (!regrow) regrow = n_used * max_load_den > cap && cap < cap_max;
                 if (!regrow) break;
-                RP.retries++;
+                RP.retries++; RP.why = "hash table regrown";
                 if (cap >= cap_max) { raise(RQ_ERR_RUNTIME, "pipeline %d: hash table overflow at capacity %llu", pi, (unsigned long long)cap); }
                 uint64_t next = cap * 8;
                 if (!E.h_flags[1]) { next = cap; while (next < max_load_den * n_used) next <<= 1; }
@@ -1366,7 +1411,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 g_emit_rows[esig] = produced;
                 if (produced <= out->cap_rows) { out->n_rows = produced; break; }
                 if (round == 1) raise(RQ_ERR_RUNTIME, "materialize overflow");
-                RP.retries++;
+                RP.retries++; RP.why = "materialize output regrown";
                 cap = produced;
             }
             set_types(*out, pl);
@@ -1417,7 +1462,7 @@ static bool split_at_probe(const rq_plan& plan, const rq_pipeline& pl, const rq_
         for (int i = 0; i < n && p0 < 0; i++) if (pl.nodes[i].op == RQ_OP_PROBE) p0 = i;
         if (p0 < 0 || (pl.nodes[p0].imm & ~1LL) != 0) return false;
         const rq_node& pr = pl.nodes[p0];
-        if (pr.a < 0 || pr.a >= (int)outs.size() || !outs[pr.a].ht || !outs[pr.a].ht->d.bloom) return false;
+        if (pr.a < 0 || pr.a >= (int)outs.size() || !outs[pr.a].ht || !(outs[pr.a].ht->d.bloom || outs[pr.a].ht->d.direct)) return false;
         // selectivity estimate: build entries / size of the probe key's value domain
         double frac = 1.0;
         if (pr.c == 1) {
@@ -2353,6 +2398,7 @@ static void reset_plan_memos() {
     g_emit_rows.clear();
     g_needs_expand.clear();
     g_agg_impl.clear();
+    g_no_direct.clear();
     RP = ReplayState();
 }
 
@@ -2391,7 +2437,7 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
     bool clean = false;
     const int rc = execute_once(plan, out, tm, &clean);
     memo.valid = rc == RQ_OK && clean;
-    if (E.opt.trace) fprintf(stderr, "[rq] rank %d: careful run rc=%d clean=%d retries=%d reads=%zu\n", E.dist.rank, rc, (int)clean, RP.retries, memo.reads.size());
+    if (E.opt.trace) fprintf(stderr, "[rq] rank %d: careful run rc=%d clean=%d retries=%d (%s) reads=%zu\n", E.dist.rank, rc, (int)clean, RP.retries, RP.why, memo.reads.size());
     if (!memo.valid) memo.reads.clear();
     RP = ReplayState();
     return rc;

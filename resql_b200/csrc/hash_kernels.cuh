@@ -15,7 +15,7 @@ struct HashTableDev {
     uint64_t capacity = 0;
     uint64_t entries = 0;       // occupied slots after the build
     ~HashTableDev() {
-        dfree(d.ent); dfree(d.bloom);
+        dfree(d.ent); dfree(d.bloom); dfree(d.dbits); dfree(d.darr);
     }
 };
 

@@ -131,6 +131,17 @@ struct DHashTable {
     uint32_t  pad_;
     int32_t   nk, nv;
     uint8_t   key_kind[kMaxKeys];   // 0 integer, 1 CHAR, 2 VARCHAR
+    // DIRECT-ADDRESS form (join builds on one integer key whose value domain [dlo, dlo + dsize) is
+    // known and dense enough, keys unique): no slots, no tags, no walks. A bitmap says which keys are
+    // present (exact semi-join filter, a few MB: L2 resident), payload word q of key k lives at
+    // darr[(k - dlo) * dnv + q]. A build is a plain store per tuple, a probe one bit test and at
+    // most one payload fetch. Duplicate keys raise a flag and the host rebuilds the hash form.
+    uint32_t  direct;
+    uint32_t  dnv;                  // payload words per key
+    int64_t   dlo;
+    uint64_t  dsize;
+    uint32_t* dbits;
+    uint64_t* darr;
 };
 
 struct DProbe {

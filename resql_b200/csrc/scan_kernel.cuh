@@ -731,6 +731,43 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         __syncwarp();
                         break;
                     }
+                    if (pr.ht.direct) {
+                        // direct-address build side: one bit test per tuple (all 8 words of a lane are
+                        // fetched together), the payload of a hit is one more load; no walk, no compare
+                        int64_t dk8[kR];
+                        fetch_vref(P, c, pr.key[0], dk8);
+                        uint32_t w[kR];
+#pragma unroll
+                        for (int r = 0; r < kR; r++) {
+                            const uint64_t idx = (uint64_t)dk8[r] - (uint64_t)pr.ht.dlo;
+                            w[r] = (((valid >> r) & 1) && idx < pr.ht.dsize) ? pr.ht.dbits[idx >> 5] : 0u;
+                        }
+#pragma unroll
+                        for (int r = 0; r < kR; r++) {
+                            const uint64_t idx = (uint64_t)dk8[r] - (uint64_t)pr.ht.dlo;
+                            if (!((w[r] >> (idx & 31)) & 1u)) valid &= ~(1u << r);
+                        }
+                        if (!pr.bloom_only) {
+#pragma unroll 1
+                            for (int q = 0; q < pr.n_out; q++) {
+                                if (pr.out_slot[q] == 0xff) continue;
+                                const int word = (int)pr.pay_word[q] - 2;      // < 0: the payload repeats the join key
+                                const uint32_t dst = wbase + P.slots_rel + pr.out_slot[q] * (kTile * 8);
+                                int64_t pv[kR];
+#pragma unroll
+                                for (int r = 0; r < kR; r++) {
+                                    const uint64_t idx = (uint64_t)dk8[r] - (uint64_t)pr.ht.dlo;
+                                    pv[r] = word < 0 ? dk8[r]
+                                                     : (((valid >> r) & 1) ? (int64_t)pr.ht.darr[idx * pr.ht.dnv + word] : 0);
+                                }
+#pragma unroll
+                                for (int r = 0; r < kR; r++) sts_b64(dst + row_in_tile(r, lane) * 8, pv[r]);
+                            }
+                            __syncwarp();
+                        }
+                        if (!__any_sync(kFull, valid != 0)) pc = n_insn;
+                        break;
+                    }
                     const uint64_t cap = pr.ht.cap_mask + 1;
                     const int pnk = pr.ht.nk;
                     const bool k1 = pnk == 1 && pr.ht.key_kind[0] == 0;   // one integer key: the usual join
@@ -1075,7 +1112,22 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
             } else if (sink == IMPL_BUILD) {
                 // hash-join build (hashjoin.h:226-256): every tuple claims its own entry.
                 const int bnk = P.ht.nk;
-                if (bnk == 1 && P.ht.key_kind[0] == 0) {
+                if (P.ht.direct) {
+                    // direct-address build: set the key's bit, store its payload words (plain stores)
+                    int64_t bk[kR];
+                    fetch_vref(P, c, P.key[0], bk);
+#pragma unroll 1
+                    for (int r = 0; r < kR; r++) {
+                        if (!((valid >> r) & 1)) continue;
+                        const uint64_t idx = (uint64_t)bk[r] - (uint64_t)P.ht.dlo;
+                        if (idx >= P.ht.dsize) { *const_cast<int32_t*>(P.ht_full + 2) = 1; continue; }   // outside the proven domain
+                        const uint32_t bit = 1u << (idx & 31);
+                        const uint32_t old = atomicOr(&P.ht.dbits[idx >> 5], bit);
+                        if (old & bit) *const_cast<int32_t*>(P.ht_full + 2) = 1;       // duplicate key: the host falls back to the hash form
+                        for (int q = 0; q < P.n_out; q++) P.ht.darr[idx * P.ht.dnv + q] = (uint64_t)ld_row(P, c, P.out[q], r);
+                        n_inserted++;
+                    }
+                } else if (bnk == 1 && P.ht.key_kind[0] == 0) {
                     // One integer key. The claims (atomicCAS on the home slot) of a lane's tuples
                     // are issued together: a dense tile costs one atomic round trip per lane; a
                     // tuple whose home slot is taken walks on alone.

@@ -274,7 +274,15 @@ class Engine:
     # -- execution --------------------------------------------------------------------------
     def execute(self, plan, tables, flags=0):
         """plan: resql_b200.plan.Plan; tables: dict name -> Table. Returns (Result, Timings)."""
-        cplan, keep = plan.to_c(tables, flags)
+        # the flat C plan is built once per (plan, table handles, flags): a repeated query costs no
+        # Python-side marshalling (the reference likewise re-runs a prepared plan)
+        key = (flags,) + tuple((t["name"], tables[t["name"]].handle.value) for t in plan.tables)
+        cache = plan.__dict__.setdefault("_c_cache", {})
+        if key not in cache:
+            if len(cache) > 16:
+                cache.clear()
+            cache[key] = plan.to_c(tables, flags)
+        cplan, keep = cache[key]
         res = C.POINTER(rq_result)()
         tm = rq_timings()
         self._check(self.lib.rq_plan_execute(C.byref(cplan), C.byref(res), C.byref(tm)))
@@ -296,5 +304,4 @@ class Engine:
                 sw.append(rc.sql_width)
         finally:
             self.lib.rq_result_free(res)
-        del keep
         return Result(cols, st, sw, plan.result_names), Timings(tm)

@@ -121,15 +121,18 @@ def run_pipeline_vm(plan, pi, src_cols, pool_strings, agg_impl=IMPL_LOWAGG, with
             xs = x.astype(object)
             valid = valid & np.array([imm <= v <= imm + (imm2 & 0xFFFFFFFFFFFFFFFF) for v in xs], dtype=bool)
             continue
-        def narrow_ok(*vs):     # the 32-bit forms are only legal for values proven to be in [0, 2^32)
-            return all(len(v) == 0 or (int(v.min()) >= 0 and int(v.max()) < 2 ** 32) for v in vs)
+        def mul32(u, v):
+            # the 32-bit multiply forms compute (uint32)u * (uint32)v exactly as the device does
+            # (IMAD.WIDE.U32). They are only chosen when interval analysis proves both factors lie in
+            # [0, 2^32) for every tuple that REACHES THE SINK (selections narrow the column bounds), so a
+            # wrong choice shows up as a wrong result, not as an assertion here.
+            lo = (u.astype(np.uint64) & np.uint64(0xFFFFFFFF)) * (v.astype(np.uint64) & np.uint64(0xFFFFFFFF))
+            return lo.astype(np.int64)
         if op == H_BIN:
-            t = _binop(gop, x, y, valid)
-            assert not n32 or narrow_ok(x, y), "narrow multiply on wide operands"
+            t = mul32(x, y) if (n32 and gop == D_MUL) else _binop(gop, x, y, valid)
         elif op == H_MULI:
             inner = _binop(gop, x, np.full(n, imm, dtype=np.int64), valid)
-            assert not n32 or narrow_ok(inner, y), "narrow multiply on wide operands"
-            t = inner * y
+            t = mul32(inner, y) if n32 else inner * y
         elif op == H_SEL: t = np.where((x & 0xFF) != 0, y, z)
         else: raise NotImplementedError(op)
         if dst >= 0:
