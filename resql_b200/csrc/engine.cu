@@ -177,7 +177,7 @@ extern "C" int rq_init(int device) {
         CK(dmalloc(&E.g_kinds, kMaxAggs));
         CK(dmalloc(&E.flags, 64));
         CK(cudaMallocHost(&E.h_flags, 64));
-        CK(cudaMallocHost(&E.pinned, 36864 + 256 * 64));
+        CK(cudaMallocHost(&E.pinned, 36864));
         CK(cudaFuncSetAttribute(rq_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         CK(cudaFuncSetAttribute(rq_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         CK(cudaFuncSetAttribute(rq_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));

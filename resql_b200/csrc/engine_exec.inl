@@ -671,6 +671,7 @@ static void set_types(rq_table& t, const rq_pipeline& pl) {
     for (int k = 0; k < pl.n_vals; k++) { t.sql_type.push_back(pl.vals[k].sql_type); t.sql_width.push_back(pl.vals[k].width); }
 }
 
+static void record_event(cudaEvent_t ev);
 static int max_warps_of(int gr) { return (gr == 4 ? ScanCfg<4>::kThreads : gr == 1 ? ScanCfg<1>::kThreads : ScanCfg<0>::kThreads) / 32; }
 
 static void launch_pipeline(const KParams& P, int gr, int64_t rows, rq_timings* tm, bool is_scan,
@@ -681,12 +682,12 @@ static void launch_pipeline(const KParams& P, int gr, int64_t rows, rq_timings* 
     if (tiles + (int64_t)grid * W >= ((int64_t)1 << 32))
         raise(RQ_ERR_UNSUPPORTED, "a pipeline over more than 2^40 rows (the kernel counts tiles in 32 bits)");
     EventPair& ep = event_pair(ev_idx);
-    CK(cudaEventRecord(ep.a, E.stream));
+    record_event(ep.a);
     if (gr == 4) rq_scan_kernel<4><<<grid, 32 * W, P.smem_bytes, E.stream>>>(P);
     else if (gr == 1) rq_scan_kernel<1><<<grid, 32 * W, P.smem_bytes, E.stream>>>(P);
     else rq_scan_kernel<0><<<grid, 32 * W, P.smem_bytes, E.stream>>>(P);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ep.b, E.stream));
+    record_event(ep.b);
     ev_used.push_back({ev_idx, is_scan ? 1 : 0});
     ev_idx++;
     if (tm) tm->kernel_launches++;
@@ -748,12 +749,18 @@ struct ReplayState {
     int retries = 0;                   // recording: a retried pipeline makes the run unfit as a script
     int syncs = 0;                     // host waits of this execution (reported through rq_timings)
     const char* why = "";             // last retry reason (trace)
+    bool capturing = false;            // the stream is being captured into a CUDA graph
 };
 static ReplayState RP;
 struct ReplayDiverged {};
+// (event records inside a stream capture must be external nodes to stay usable for timing)
+static void record_event(cudaEvent_t ev);
 #define g_pinned (E.pinned)
-static constexpr size_t kPinnedRead = 36864, kSmallSlots = 256, kSmallBytes = 64;
-static size_t g_small_next = 0;
+static constexpr size_t kPinnedRead = 36864;
+
+static void record_event(cudaEvent_t ev) {
+    CK(cudaEventRecordWithFlags(ev, E.stream, RP.capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+}
 
 static void stream_sync() {
     CK(cudaStreamSynchronize(E.stream));
@@ -778,13 +785,15 @@ static void host_read(void* dst, const void* d_src, size_t bytes) {
     if (RP.mode == 1) RP.memo->reads.emplace_back((const unsigned char*)dst, (const unsigned char*)dst + bytes);
 }
 
-// small host value -> device without a host wait: staged in a pinned ring
+// small host value -> device without a host wait and without a host buffer: the bytes travel as
+// kernel arguments
 static void upload_small(void* d_dst, const void* src, size_t bytes) {
-    if (bytes > kSmallBytes) raise(RQ_ERR_INVALID, "internal: upload_small of %zu bytes", bytes);
-    if (g_small_next == kSmallSlots) { stream_sync(); g_small_next = 0; }
-    unsigned char* slot = g_pinned + kPinnedRead + g_small_next++ * kSmallBytes;
-    memcpy(slot, src, bytes);
-    CK(cudaMemcpyAsync(d_dst, slot, bytes, cudaMemcpyHostToDevice, E.stream));
+    if (bytes > sizeof(SmallBytes)) raise(RQ_ERR_INVALID, "internal: upload_small of %zu bytes", bytes);
+    SmallBytes v;
+    memset(&v, 0, sizeof(v));
+    memcpy(v.b, src, bytes);
+    rq_store_bytes<<<1, 64, 0, E.stream>>>((unsigned char*)d_dst, v, (int)bytes);
+    CK(cudaGetLastError());
 }
 
 static void check_flags(const char* what, const void* d_extra = nullptr) {
@@ -1180,7 +1189,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                 bool fits = false;
                 for (int G = (pl.n_keys == 0 ? 1 : kLowCardMaxGroups); G >= 1 && !fits; G >>= 1) {
                     P.G = G;
-                    fits = layout_smem(P, L.n_slots, G * P.na * 32 * 8, max_warps_of(0)) && (P.stages > 1 || G == 1);
+                    fits = layout_smem(P, L.n_slots, G * P.na * 32 * 8, max_warps_of(0)) && P.warps >= 8;
                     if (pl.n_keys == 0) break;
                 }
                 if (!fits) continue;
@@ -1210,8 +1219,9 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
 
         CK(cudaMemsetAsync(E.flags, 0, 32, E.stream));
         if (impl == IMPL_REGAGG || impl == IMPL_LOWAGG) {
-            CK(cudaMemcpyAsync(E.g_kinds, P.agg_kind, kMaxAggs, cudaMemcpyHostToDevice, E.stream));
-            rq_group_table_init<<<(kGroupTableCap + 255) / 256, 256, 0, E.stream>>>(E.g_state, E.g_acc, E.g_kinds, P.na);
+            AggKinds gk;
+            memcpy(gk.kind, P.agg_kind, kMaxAggs);
+            rq_group_table_init<<<(kGroupTableCap + 255) / 256, 256, 0, E.stream>>>(E.g_state, E.g_acc, gk, P.na);
             if (tm) tm->kernel_launches++;
             launch_pipeline(P, gr, src_rows, tm, is_scan, ev_idx, ev_used);
             // dense output: keys, then every requested aggregate (duplicates expanded)
@@ -1221,14 +1231,14 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             std::unique_ptr<rq_table> dense = new_intermediate(pl.n_keys + nuniq, kGroupTableCap);
             std::vector<int64_t*> h_dense(pl.n_keys + nuniq);
             for (int c = 0; c < pl.n_keys + nuniq; c++) h_dense[c] = (int64_t*)dense->cols[c].d;
-            int64_t** d_ptrs = nullptr;
-            CK(dmalloc(&d_ptrs, sizeof(int64_t*) * h_dense.size()));
-            CK(cudaMemcpyAsync(d_ptrs, h_dense.data(), sizeof(int64_t*) * h_dense.size(), cudaMemcpyHostToDevice, E.stream));
+            if ((int)h_dense.size() > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d output columns", kMaxOut);
+            ColPtrs cp;
+            memset(&cp, 0, sizeof(cp));
+            for (size_t c = 0; c < h_dense.size(); c++) cp.p[c] = h_dense[c];
             rq_group_table_compact<<<(kGroupTableCap + 255) / 256, 256, 0, E.stream>>>(
-                E.g_state, E.g_keys, E.g_acc, ku, nuniq, d_ptrs, dense->d_n_rows);
+                E.g_state, E.g_keys, E.g_acc, ku, nuniq, cp, dense->d_n_rows);
             if (tm) tm->kernel_launches++;
             CK(cudaGetLastError());
-            dfree(d_ptrs);
             check_flags("aggregation pipeline", dense->d_n_rows);
             const int64_t n_groups_host = *(const int64_t*)(E.h_flags + 8);
             if (E.h_flags[0]) { RP.retries++; RP.why = "group overflow"; continue; }   // more groups than this path tracks: next implementation
@@ -1263,6 +1273,13 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             const int nk = pl.n_keys;
             if (nk > kMaxKeys) raise(RQ_ERR_UNSUPPORTED, "more than %d key columns", kMaxKeys);
             const int nv = impl == IMPL_BUILD ? pl.n_vals : (int)ad.kind.size();
+            // hash aggregation on keys that pack into < 64 bits: the entry's first word is the key
+            bool packed = false;
+            if (impl == IMPL_HASHAGG && nk >= 1 && pl.n_keys + pl.n_vals <= kMaxOut && !has_str_key(pl) && pack_group_key(L, P, ku)) {
+                int total = 0;
+                for (int k = 0; k < ku.nk; k++) total += ku.bits[k];
+                packed = total <= 63;
+            }
             std::unique_ptr<HashTableDev> ht;
             unsigned long long n_used = 0;
             // Direct-address form (rq_internal.h DHashTable): one integer key with a proven, dense
@@ -1325,11 +1342,11 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                     const int st = pl.keys[k].sql_type;
                     ht->d.key_kind[k] = st == RQ_SQL_VARCHAR ? 2 : (st == RQ_SQL_CHAR && pl.keys[k].width > 1) ? 1 : 0;
                 }
-                ht->d.stride = (uint32_t)((1 + nk + nv + 3) / 4 * 4);
+                ht->d.packed = packed ? 1 : 0;
+                ht->d.stride = (uint32_t)((1 + (packed ? 0 : nk) + nv + 3) / 4 * 4);
                 CK(dmalloc(&ht->d.ent, cap * ht->d.stride * 8));
-                if (impl == IMPL_HASHAGG) CK(cudaMemcpyAsync(E.g_kinds, P.agg_kind, kMaxAggs, cudaMemcpyHostToDevice, E.stream));
                 if (impl == IMPL_HASHAGG) {
-                    rq_ht_init<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, E.g_kinds, 1);
+                    { HtKinds hk; memcpy(hk.kind, P.agg_kind, kMaxAggs); rq_ht_init<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, hk, 1); }
                     if (tm) tm->kernel_launches++;
                 } else {
                     // whole sectors are cleared (a tag-only clear is a partial write per sector)
@@ -1371,17 +1388,27 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             for (int k = 0; k < pl.n_keys; k++) colmap[k] = k;
             for (int k = 0; k < pl.n_vals; k++) colmap[pl.n_keys + k] = pl.n_keys + ad.uniq_of[k];
             for (int c = 0; c < ncols; c++) h_cols[c] = (int64_t*)out->cols[c].d;
-            int* d_map = nullptr;
-            int64_t** d_ptrs = nullptr;
-            CK(dmalloc(&d_map, sizeof(int) * ncols));
-            CK(dmalloc(&d_ptrs, sizeof(int64_t*) * ncols));
-            CK(cudaMemcpyAsync(d_map, colmap.data(), sizeof(int) * ncols, cudaMemcpyHostToDevice, E.stream));
-            CK(cudaMemcpyAsync(d_ptrs, h_cols.data(), sizeof(int64_t*) * ncols, cudaMemcpyHostToDevice, E.stream));
-            rq_ht_compact<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, d_map, ncols, d_ptrs, (unsigned long long*)out->d_n_rows, (unsigned long long)out->cap_rows);
+            if (packed) {
+                PackedCompact pc;
+                memset(&pc, 0, sizeof(pc));
+                pc.nk = nk; pc.n_out = ncols;
+                for (int k = 0; k < nk; k++) { pc.shift[k] = ku.shift[k]; pc.bits[k] = ku.bits[k]; pc.sign[k] = ku.sign[k]; }
+                for (int c = 0; c < ncols; c++) { pc.colmap[c] = colmap[c]; pc.out[c] = h_cols[c]; }
+                rq_ht_compact_packed<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, pc, (unsigned long long*)out->d_n_rows, (unsigned long long)out->cap_rows);
+                if (tm) tm->kernel_launches++;
+                CK(cudaGetLastError());
+                out->n_rows = (int64_t)n_groups;
+                set_types(*out, pl);
+                result.table = std::move(out);
+                return;
+            }
+            if (ncols > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d output columns", kMaxOut);
+            HtCompact hc;
+            memset(&hc, 0, sizeof(hc));
+            for (int c = 0; c < ncols; c++) { hc.colmap[c] = colmap[c]; hc.out[c] = h_cols[c]; }
+            rq_ht_compact<<<(unsigned)((cap + 255) / 256), 256, 0, E.stream>>>(ht->d, hc, ncols, (unsigned long long*)out->d_n_rows, (unsigned long long)out->cap_rows);
             if (tm) tm->kernel_launches++;
             CK(cudaGetLastError());
-            dfree(d_map);                 // stream-ordered: freed after the compaction kernel ran
-            dfree(d_ptrs);
             out->n_rows = (int64_t)n_groups;
             set_types(*out, pl);
             result.table = std::move(out);
@@ -1609,7 +1636,7 @@ static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timin
     const EventPair ep = event_pair(ev_idx);
     ev_used.push_back({ev_idx, 2});
     ev_idx++;
-    CK(cudaEventRecord(ep.a, E.stream));
+    record_event(ep.a);
     // 1. row counts
     int64_t* d_counts = nullptr;
     CK(dmalloc(&d_counts, sizeof(int64_t) * W));
@@ -1680,7 +1707,7 @@ static std::unique_ptr<rq_table> gather_relation(const rq_table& local, rq_timin
     }
     CK(cudaGetLastError());
     upload_small(all->d_n_rows, &total, 8);
-    CK(cudaEventRecord(ep.b, E.stream));
+    record_event(ep.b);
     all->n_rows = total;
     dfree(d_counts);
     if (d_tmp) dfree(d_tmp);
@@ -1735,7 +1762,7 @@ static std::unique_ptr<rq_table> exchange_relation(const rq_table* local, const 
     const EventPair ep = event_pair(ev_idx);
     ev_used.push_back({ev_idx, 2});
     ev_idx++;
-    CK(cudaEventRecord(ep.a, E.stream));
+    record_event(ep.a);
 
     const int64_t rows_bound = local ? std::max<int64_t>(local->n_rows >= 0 ? local->n_rows : local->cap_rows, 0) : 0;
     // [cnt W][off W][cursor W][status 1] and the gathered matrix [W][W+1]
@@ -1813,7 +1840,7 @@ static std::unique_ptr<rq_table> exchange_relation(const rq_table* local, const 
     }
     upload_small(out->d_n_rows, &total, 8);
     out->n_rows = total;
-    CK(cudaEventRecord(ep.b, E.stream));
+    record_event(ep.b);
     dfree(d_meta); dfree(d_matrix); dfree(d_dest); dfree(d_send); dfree(d_recv);
     return out;
 }
@@ -2036,7 +2063,6 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
     const bool partitioned = is_partitioned_plan(*plan);
     unsigned char* d_expect = nullptr;
     int32_t* d_ok = nullptr;
-    g_small_next = 0;
     try {
         if (RP.mode == 2) {
             // the recorded values, flat (8-byte aligned), as the device-side reference of the validation
@@ -2065,7 +2091,7 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
         double lower_ms = 0;
         g_trace = E.opt.trace && E.dist.rank == 0;
         g_trace_t0 = std::chrono::steady_clock::now();
-        CK(cudaEventRecord(E.ev[0], E.stream));
+        record_event(E.ev[0]);
         // sharded plans: merge after the last aggregation (or concatenate the final relation)
         bool final_gather = false;              // the last relation is partitioned over the ranks
         std::vector<void*> gather_owned;        // string bytes a final gather received
@@ -2286,7 +2312,7 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
             if (tm) tm->kernel_launches++;
         }
         CK(cudaGetLastError());
-        CK(cudaEventRecord(E.ev[1], E.stream));
+        record_event(E.ev[1]);
         for (int c = 0; c < ncols; c++)
             if (n_out > 0)
                 CK(cudaMemcpyAsync(res->cols[c].data, d_out[c], (size_t)n_out * res->cols[c].width, cudaMemcpyDeviceToHost, E.stream));
@@ -2309,7 +2335,7 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
             }
             CK(cudaMemcpyAsync(g_pinned, d_ok, 4, cudaMemcpyDeviceToHost, E.stream));
         }
-        CK(cudaEventRecord(E.ev[2], E.stream));
+        record_event(E.ev[2]);
         stream_sync();
         if (verdict) *verdict = (RP.mode == 2 || sharded) ? (*(const int32_t*)g_pinned != 0) : (h_ok_local != 0);
         if (tm) {

@@ -160,20 +160,23 @@ __device__ __forceinline__ bool ht_find_or_insert(const DHashTable& ht, const in
 
 // ---- helper kernels ------------------------------------------------------------------------
 // clear the tags and set the accumulators of a hash-aggregation table to their identities
-__global__ void rq_ht_init(DHashTable ht, const uint8_t* kinds, int init_vals) {
+struct HtKinds { uint8_t kind[kMaxAggs]; };
+__global__ void rq_ht_init(DHashTable ht, HtKinds kinds, int init_vals) {
     const uint64_t cap = ht.cap_mask + 1;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cap) {
         uint64_t* e = ht_entry(ht, i);
         e[0] = 0;
+        const int first = ht.packed ? 1 : 1 + ht.nk;
         if (init_vals)
-            for (int a = 0; a < ht.nv; a++) e[1 + ht.nk + a] = (uint64_t)agg_identity(kinds[a]);
+            for (int a = 0; a < ht.nv; a++) e[first + a] = (uint64_t)agg_identity(kinds.kind[a]);
     }
 }
 
 // occupied slots -> dense int64 columns. colmap[c] < nk selects key word colmap[c], otherwise
 // accumulator colmap[c]-nk (duplicate aggregates share one accumulator).
-__global__ void rq_ht_compact(DHashTable ht, const int* colmap, int n_out, int64_t* const* out_cols,
+struct HtCompact { int32_t colmap[kMaxOut]; int64_t* out[kMaxOut]; };
+__global__ void rq_ht_compact(DHashTable ht, HtCompact hc, int n_out,
                               unsigned long long* count, unsigned long long out_cap) {
     const uint64_t cap = ht.cap_mask + 1;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,7 +191,44 @@ __global__ void rq_ht_compact(DHashTable ht, const int* colmap, int n_out, int64
         const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1));
         const uint64_t* e = ht_entry(ht, i);
         if (pos < out_cap)       // (sized from a count the host may only have predicted)
-            for (int c = 0; c < n_out; c++) out_cols[c][pos] = (int64_t)e[1 + colmap[c]];
+            for (int c = 0; c < n_out; c++) hc.out[c][pos] = (int64_t)e[1 + hc.colmap[c]];
+    }
+}
+
+// the same for tables whose entries carry the packed group key in their first word
+struct PackedCompact {
+    int32_t nk;                     // logical key columns
+    uint8_t shift[kMaxKeys], bits[kMaxKeys], sign[kMaxKeys];
+    int32_t n_out;
+    int32_t colmap[kMaxOut];        // < nk: key column, else accumulator colmap - nk
+    int64_t* out[kMaxOut];
+};
+__global__ void rq_ht_compact_packed(DHashTable ht, PackedCompact pc, unsigned long long* count, unsigned long long out_cap) {
+    const uint64_t cap = ht.cap_mask + 1;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool used = i < cap && *ht_entry(ht, i) != 0ULL;
+    const unsigned bal = __ballot_sync(0xffffffffu, used);
+    if (!bal) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (used) {
+        const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1));
+        if (pos >= out_cap) return;
+        const uint64_t* e = ht_entry(ht, i);
+        const uint64_t k = e[0] - 1;
+        for (int c = 0; c < pc.n_out; c++) {
+            const int m = pc.colmap[c];
+            if (m < pc.nk) {
+                const int b = pc.bits[m];
+                uint64_t f = (b >= 64) ? k : ((k >> pc.shift[m]) & ((1ULL << b) - 1));
+                if (pc.sign[m] && b < 64 && ((f >> (b - 1)) & 1)) f |= ~((1ULL << b) - 1);
+                pc.out[c][pos] = (int64_t)f;
+            } else {
+                pc.out[c][pos] = (int64_t)e[1 + (m - pc.nk)];
+            }
+        }
     }
 }
 

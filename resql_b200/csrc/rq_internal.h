@@ -136,6 +136,8 @@ struct DHashTable {
     // present (exact semi-join filter, a few MB: L2 resident), payload word q of key k lives at
     // darr[(k - dlo) * dnv + q]. A build is a plain store per tuple, a probe one bit test and at
     // most one payload fetch. Duplicate keys raise a flag and the host rebuilds the hash form.
+    uint32_t  packed;               // hash aggregation: entry = [packed group key + 1][accumulators] (no tag, no key words)
+    uint32_t  pad3_;
     uint32_t  direct;
     uint32_t  dnv;                  // payload words per key
     int64_t   dlo;

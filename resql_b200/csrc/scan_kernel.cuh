@@ -1116,14 +1116,19 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                     // direct-address build: set the key's bit, store its payload words (plain stores)
                     int64_t bk[kR];
                     fetch_vref(P, c, P.key[0], bk);
+                    uint32_t was[kR];          // the 8 bit-set atomics of a lane are in flight together
+#pragma unroll
+                    for (int r = 0; r < kR; r++) {
+                        const uint64_t idx = (uint64_t)bk[r] - (uint64_t)P.ht.dlo;
+                        was[r] = 0;
+                        if (((valid >> r) & 1) && idx < P.ht.dsize) was[r] = atomicOr(&P.ht.dbits[idx >> 5], 1u << (idx & 31));
+                    }
 #pragma unroll 1
                     for (int r = 0; r < kR; r++) {
                         if (!((valid >> r) & 1)) continue;
                         const uint64_t idx = (uint64_t)bk[r] - (uint64_t)P.ht.dlo;
                         if (idx >= P.ht.dsize) { *const_cast<int32_t*>(P.ht_full + 2) = 1; continue; }   // outside the proven domain
-                        const uint32_t bit = 1u << (idx & 31);
-                        const uint32_t old = atomicOr(&P.ht.dbits[idx >> 5], bit);
-                        if (old & bit) *const_cast<int32_t*>(P.ht_full + 2) = 1;       // duplicate key: the host falls back to the hash form
+                        if (was[r] & (1u << (idx & 31))) *const_cast<int32_t*>(P.ht_full + 2) = 1;     // duplicate key: the host falls back to the hash form
                         for (int q = 0; q < P.n_out; q++) P.ht.darr[idx * P.ht.dnv + q] = (uint64_t)ld_row(P, c, P.out[q], r);
                         n_inserted++;
                     }
@@ -1170,6 +1175,47 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                         for (int q = 0; q < P.n_out; q++) e[1 + bnk + q] = (uint64_t)ld_row(P, c, P.out[q], r);
                         if (P.ht.bloom != nullptr) atomicOr(&P.ht.bloom[bloom_word(P.ht, hh)], bloom_bits(P.ht, hh));
                         n_inserted++;
+                    }
+                }
+            } else if (sink == IMPL_HASHAGG && P.ht.packed) {
+                // GROUP BY whose keys pack into one word (bit fields from the value bounds, < 64 bits):
+                // the entry's first word IS the key (+1, 0 = empty), so claiming a slot and publishing its
+                // key are one atomicCAS - no lock state, no fence, nobody ever waits. The home-slot claims
+                // of a lane's 8 tuples are issued together; aggregates are fire-and-forget atomics.
+                uint64_t key[kR];
+                pack_keys(P, c, key);
+                unsigned long long old[kR];
+#pragma unroll
+                for (int r = 0; r < kR; r++) {
+                    old[r] = 0;
+                    if ((valid >> r) & 1) {
+                        const uint64_t hh = mix64(key[r] + 0x9E3779B97F4A7C15ULL);
+                        old[r] = atomicCAS((unsigned long long*)ht_entry(P.ht, hh >> P.ht.shift), 0ULL, (unsigned long long)(key[r] + 1));
+                    }
+                }
+#pragma unroll 1
+                for (int r = 0; r < kR; r++) {
+                    if (!((valid >> r) & 1)) continue;
+                    const unsigned long long want = (unsigned long long)(key[r] + 1);
+                    const uint64_t hh = mix64(key[r] + 0x9E3779B97F4A7C15ULL);
+                    uint64_t slot = hh >> P.ht.shift;
+                    unsigned long long cur = old[r];
+                    bool ok = true;
+                    for (uint64_t tries = 1; cur != 0ULL && cur != want; tries++) {
+                        slot = (slot + 1) & P.ht.cap_mask;
+                        cur = atomicCAS((unsigned long long*)ht_entry(P.ht, slot), 0ULL, want);
+                        if ((tries & (kFullCheckEvery - 1)) == 0 && (*(volatile int32_t*)P.ht_full || tries > P.ht.cap_mask)) { ok = false; break; }
+                    }
+                    if (!ok) { *P.ht_full = 1; continue; }
+                    if (cur == 0ULL) n_inserted++;
+                    uint64_t* acc = ht_entry(P.ht, slot) + 1;
+                    for (int a = 0; a < NA; a++) {
+                        const int kind = P.agg_kind[a];
+                        if (kind == 2) { atomicAdd((unsigned long long*)&acc[a], 1ULL); continue; }
+                        const int64_t v = ld_row(P, c, P.agg_src[a], r);
+                        if (kind == 1) atomicAdd((unsigned long long*)&acc[a], (unsigned long long)v);
+                        else if (kind == 3) atomicMin((long long*)&acc[a], (long long)v);
+                        else atomicMax((long long*)&acc[a], (long long)v);
                     }
                 }
             } else if (sink == IMPL_HASHAGG) {
@@ -1305,12 +1351,12 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
 // small helper kernels
 // ------------------------------------------------------------------------------------------
 // reset the global group table: state 0, accumulators to their identities
-__global__ void rq_group_table_init(uint32_t* state, int64_t* acc, const uint8_t* kinds_dev,
-                                    int na) {
+struct AggKinds { uint8_t kind[kMaxAggs]; };
+__global__ void rq_group_table_init(uint32_t* state, int64_t* acc, AggKinds kinds, int na) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < kGroupTableCap) {
         state[i] = 0;
-        for (int a = 0; a < na; a++) acc[(size_t)i * kMaxAggs + a] = agg_identity(kinds_dev[a]);
+        for (int a = 0; a < na; a++) acc[(size_t)i * kMaxAggs + a] = agg_identity(kinds.kind[a]);
     }
 }
 
@@ -1323,9 +1369,10 @@ struct KeyUnpack {
 
 // group table -> dense int64 columns (keys unpacked first, then aggregates); order is
 // unspecified, as in the reference where it is hash-slot order (aggregation.h:298-343)
+struct ColPtrs { int64_t* p[kMaxOut]; };
 __global__ void rq_group_table_compact(const uint32_t* state, const int64_t* keys,
                                        const int64_t* acc, KeyUnpack ku, int na,
-                                       int64_t* const* out_cols, int64_t* out_count) {
+                                       ColPtrs out_cols, int64_t* out_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < kGroupTableCap && state[i] == 2u) {
         const long long pos = atomicAdd((unsigned long long*)out_count, 1ULL);
@@ -1334,9 +1381,9 @@ __global__ void rq_group_table_compact(const uint32_t* state, const int64_t* key
             const int b = ku.bits[j];
             uint64_t f = (b >= 64) ? k : ((k >> ku.shift[j]) & ((1ULL << b) - 1));
             if (ku.sign[j] && b < 64 && ((f >> (b - 1)) & 1)) f |= ~((1ULL << b) - 1);
-            out_cols[j][pos] = (int64_t)f;
+            out_cols.p[j][pos] = (int64_t)f;
         }
-        for (int a = 0; a < na; a++) out_cols[ku.nk + a][pos] = acc[(size_t)i * kMaxAggs + a];
+        for (int a = 0; a < na; a++) out_cols.p[ku.nk + a][pos] = acc[(size_t)i * kMaxAggs + a];
     }
 }
 
@@ -1344,6 +1391,13 @@ __global__ void rq_group_table_compact(const uint32_t* state, const int64_t* key
 // the page size
 __device__ __forceinline__ const unsigned char* col_row(const unsigned char* col, int width, int64_t tile_stride, int64_t i) {
     return col + (i / kTile) * tile_stride + (i % kTile) * width;
+}
+
+// a few host bytes -> device memory as kernel ARGUMENTS (no host buffer is read when the launch
+// executes, so the launch can be recorded into a CUDA graph and replayed)
+struct SmallBytes { unsigned char b[64]; };
+__global__ void rq_store_bytes(unsigned char* dst, SmallBytes v, int n) {
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = v.b[threadIdx.x];
 }
 
 // min / max of an integer column (upload-time statistics): out[0] = min, out[1] = max

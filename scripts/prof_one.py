@@ -1,6 +1,6 @@
 """Runs one TPC-H plan fixture a few times on synthetic data generated in HBM (for ncu captures
 and quick timings):  python scripts/prof_one.py q1 10 3"""
-import os, sys
+import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
@@ -24,11 +24,14 @@ for t in d["tables"]:
     cols = t["columns"] if mode == "borrow" else list(src[t["name"]].keys())     # owned: the whole table, schema order
     tabs[t["name"]] = eng.upload_device(t["name"], TD.as_device_columns(src[t["name"]], cols), n, borrow=(mode == "borrow"))
 n = li["l_quantity"].numel()
+plan = Plan(d)
 bpt = {"q1": 38, "q6": 28, "q3": 24}.get(q, 0)
 for i in range(reps):
     if i == reps - 1:
         torch.cuda.cudart().cudaProfilerStart()     # ncu --profile-from-start off: only the last (warm) run
-    res, tm = eng.execute(Plan(d), tabs)
-    print(q, "rows", n, "scan_ms", round(tm.scan_kernel_ms, 3), "Gtuples/s", round(n / tm.scan_kernel_ms / 1e6, 2),
+    torch.cuda.synchronize(); _t0 = time.perf_counter()
+    res, tm = eng.execute(plan, tabs)
+    _wall = 1e3 * (time.perf_counter() - _t0)
+    print(q, "wall_ms", round(_wall, 3), "syncs", tm.host_syncs, "rows", n, "scan_ms", round(tm.scan_kernel_ms, 3), "Gtuples/s", round(n / tm.scan_kernel_ms / 1e6, 2),
           "GB/s", round(n * bpt / tm.scan_kernel_ms / 1e6, 1), "launches", tm.kernel_launches, "kernel_ms", round(tm.kernel_ms, 3))
 print([c.tolist()[:4] for c in res.columns][:4])
