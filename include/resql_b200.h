@@ -73,7 +73,7 @@ const char* rq_last_error(void);
 void* rq_stream(void);
 /* Engine knobs, the counterpart of the reference's control variables (`threads=4`, `emitmc=true`;
  * processControl, execute.h:454-474). Keys: "split_min_rows", "split_frac" (two-pass probes),
- * "prune_builds", "topk", "replay", "direct_joins" (0/1), "stages", "warps" (scan-kernel layout, 0 = automatic),
+ * "prune_builds", "topk", "replay", "graphs", "direct_joins" (0/1), "stages", "warps" (scan-kernel layout, 0 = automatic),
  * "trace" (0/1). Defaults are the production choices; the parity tests force rarely taken paths. */
 int rq_set_option(const char* key, double value);
 

@@ -114,6 +114,7 @@ struct Options {
     bool topk = true;                     // ORDER BY ... LIMIT k through radix select
     bool direct_joins = true;             // direct-address join tables for dense unique integer keys
     bool replay = true;                   // predicted host reads (engine_exec.inl "host reads of device values")
+    bool graphs = true;                   // replayed plans are captured into CUDA graphs
     bool trace = false;                   // per-step wall-clock trace on stderr
 };
 
@@ -218,6 +219,7 @@ extern "C" int rq_set_option(const char* key, double value) {
     else if (k == "topk") o.topk = value != 0;
     else if (k == "direct_joins") o.direct_joins = value != 0;
     else if (k == "replay") o.replay = value != 0;
+    else if (k == "graphs") o.graphs = value != 0;
     else if (k == "trace") o.trace = value != 0;
     else return fail(RQ_ERR_INVALID, "rq_set_option: unknown option '%s'", key);
     return RQ_OK;

@@ -734,10 +734,39 @@ struct NeedExpand {};
 // division by zero - discards the result and runs the plan again the careful way, which reports
 // errors exactly as before. Device code never trusts a predicted value: outputs and hash tables are
 // bounds-checked against their allocation, so a wrong prediction can only produce a discarded result.
+// A replayed plan is a fixed sequence of launches with fixed arguments (table identities are part
+// of the memo key), so the second replay is recorded into a CUDA graph: later executions are ONE
+// graph launch and one wait - no per-launch host cost, which is what bounds short plans and the
+// 8-GPU runs, where the kernels of a shard take fractions of a millisecond.
 struct PlanMemo {
     std::vector<std::vector<unsigned char>> reads;
     bool valid = false;
-    int64_t n_out = 0;                 // result rows of the recorded run
+    int replays = 0;                   // plain replays that succeeded
+    bool no_graph = false;             // capture failed once: stay with plain replays
+    // buffers that live as long as the memo (so that a captured graph may refer to them)
+    char* d_strpool = nullptr;
+    unsigned char* d_expect = nullptr;
+    unsigned char* d_log = nullptr;
+    int32_t* d_ok = nullptr;
+    size_t log_cap = 0;
+    // the graph and what is needed to hand out its result
+    cudaGraphExec_t gexec = nullptr;
+    struct Col { int type = 0, width = 0, sql_type = 0, sql_width = 0; unsigned char* h = nullptr; };
+    std::vector<Col> cols;             // pinned landing buffers of the result columns
+    int64_t res_rows = 0;
+    std::vector<std::pair<size_t, int>> ev_used;
+    rq_timings tm_static{};            // launches / lowering time of the captured run
+    void release() {
+        if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+        for (auto& c : cols) if (c.h) cudaFreeHost(c.h);
+        cols.clear();
+        if (d_strpool) cudaFree(d_strpool);
+        if (d_expect) cudaFree(d_expect);
+        if (d_log) cudaFree(d_log);
+        if (d_ok) cudaFree(d_ok);
+        d_strpool = nullptr; d_expect = nullptr; d_log = nullptr; d_ok = nullptr;
+        log_cap = 0; replays = 0; valid = false; reads.clear();
+    }
 };
 static std::map<uint64_t, PlanMemo> g_plan_memo;
 struct ReplayState {
@@ -2051,6 +2080,20 @@ __global__ void rq_validate_log(const uint64_t* log, const uint64_t* expect, int
     if (i < n_words && log[i] != expect[i]) *ok = 0;
 }
 
+static void read_timings(const std::vector<std::pair<size_t, int>>& ev_used, rq_timings* tm) {
+    float ms = 0;
+    for (auto& u : ev_used) {
+        if (cudaEventElapsedTime(&ms, g_event_pool[u.first].a, g_event_pool[u.first].b) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (u.second == 2) { tm->nccl_ms += ms; continue; }
+        tm->kernel_ms += ms;
+        if (u.second) { tm->scan_kernel_ms += ms; tm->fact_scan_ms = ms; }
+        if (g_trace) fprintf(stderr, "[rq] scan kernel launch %zu: %.3f ms%s\n", u.first, ms, u.second ? " (table scan)" : "");
+    }
+    if (cudaEventElapsedTime(&ms, E.ev[1], E.ev[2]) == cudaSuccess) tm->d2h_ms = ms; else cudaGetLastError();
+    if (g_trace && cudaEventElapsedTime(&ms, E.ev[0], E.ev[2]) == cudaSuccess)
+        fprintf(stderr, "[rq] plan: %.3f ms on the stream from first launch to result read-back, %.3f ms in pipeline kernels\n", ms, tm->kernel_ms);
+}
+
 // One execution of the plan in the mode RP describes. `verdict` (may be null): careful runs report
 // whether the run was clean on every rank (fit to be replayed), replays whether every predicted
 // value was right on every rank.
@@ -2063,25 +2106,18 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
     const bool partitioned = is_partitioned_plan(*plan);
     unsigned char* d_expect = nullptr;
     int32_t* d_ok = nullptr;
+    bool capture_open = RP.capturing;
     try {
         if (RP.mode == 2) {
-            // the recorded values, flat (8-byte aligned), as the device-side reference of the validation
-            std::vector<unsigned char> flat;
-            for (auto& r : RP.memo->reads) {
-                flat.insert(flat.end(), r.begin(), r.end());
-                flat.resize((flat.size() + 7) & ~(size_t)7, 0);
-            }
-            RP.log_cap = flat.size();
-            CK(dmalloc(&d_expect, flat.size()));
-            CK(dmalloc(&RP.d_log, flat.size()));
-            scratch.push_back(d_expect);
-            scratch.push_back(RP.d_log);
-            if (!flat.empty()) {
-                CK(cudaMemcpyAsync(d_expect, flat.data(), flat.size(), cudaMemcpyHostToDevice, E.stream));   // pageable: staged before return
-                CK(cudaMemsetAsync(RP.d_log, 0, flat.size(), E.stream));
-            }
-        }
-        if (plan->strpool_bytes > 0) {
+            // recorded values and log live in the memo (memo_prepare); string constants too
+            RP.log_cap = RP.memo->log_cap;
+            RP.d_log = RP.memo->d_log;
+            d_expect = RP.memo->d_expect;
+            d_ok = RP.memo->d_ok;
+            d_strpool = RP.memo->d_strpool;
+            if (RP.capturing) CK(cudaStreamBeginCapture(E.stream, cudaStreamCaptureModeRelaxed));
+            if (RP.log_cap) CK(cudaMemsetAsync(RP.d_log, 0, RP.log_cap, E.stream));
+        } else if (plan->strpool_bytes > 0) {
             CK(dmalloc(&d_strpool, plan->strpool_bytes));
             CK(cudaMemcpyAsync(d_strpool, plan->strpool, plan->strpool_bytes, cudaMemcpyHostToDevice, E.stream));
         }
@@ -2293,12 +2329,18 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
         res->n_cols = ncols;
         res->cols = (rq_result_col*)calloc(ncols, sizeof(rq_result_col));
         std::vector<void*> d_out(ncols, nullptr);
+        if (RP.capturing) { RP.memo->cols.assign(ncols, PlanMemo::Col()); RP.memo->res_rows = n_out; }
         for (int c = 0; c < ncols; c++) {
             int w = 8;
             const int pt = phys_type(fin->sql_type[c], fin->sql_width[c], &w);
             rq_result_col& rc = res->cols[c];
             rc.type = pt; rc.width = w; rc.sql_type = fin->sql_type[c]; rc.sql_width = fin->sql_width[c];
             rc.data = malloc((size_t)std::max<int64_t>(n_out, 1) * w);
+            if (RP.capturing) {
+                PlanMemo::Col& mc = RP.memo->cols[c];
+                mc.type = pt; mc.width = w; mc.sql_type = rc.sql_type; mc.sql_width = rc.sql_width;
+                CK(cudaMallocHost(&mc.h, (size_t)std::max<int64_t>(n_out, 1) * w));
+            }
             if (n_out == 0) continue;
             const unsigned blocks = (unsigned)((n_out + 255) / 256);
             if (pt == RQ_I64) { d_out[c] = cols[c]; continue; }
@@ -2315,13 +2357,16 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
         record_event(E.ev[1]);
         for (int c = 0; c < ncols; c++)
             if (n_out > 0)
-                CK(cudaMemcpyAsync(res->cols[c].data, d_out[c], (size_t)n_out * res->cols[c].width, cudaMemcpyDeviceToHost, E.stream));
+                CK(cudaMemcpyAsync(RP.capturing ? (void*)RP.memo->cols[c].h : res->cols[c].data, d_out[c],
+                                   (size_t)n_out * res->cols[c].width, cudaMemcpyDeviceToHost, E.stream));
         // the verdict travels with the result: replay = all predictions right, careful = run was clean
         // (sharded plans: the minimum over the ranks, so every rank draws the same conclusion)
         int32_t h_ok_local = RP.retries == 0 ? 1 : 0;
         if (RP.mode == 2 || sharded) {
-            CK(dmalloc(&d_ok, 8));
-            scratch.push_back(d_ok);
+            if (!d_ok) {
+                CK(dmalloc(&d_ok, 8));
+                scratch.push_back(d_ok);
+            }
             upload_small(d_ok, &h_ok_local, 4);
             if (RP.mode == 2) {
                 if (RP.idx != RP.memo->reads.size()) throw ReplayDiverged{};
@@ -2336,44 +2381,50 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
             CK(cudaMemcpyAsync(g_pinned, d_ok, 4, cudaMemcpyDeviceToHost, E.stream));
         }
         record_event(E.ev[2]);
+        // everything that lives on the device is released here, in stream order (inside a capture the
+        // frees must be part of the graph)
+        outs.clear();
+        gathered.reset();
+        for (void* p : scratch) dfree(p);
+        scratch.clear();
+        for (void* p : gather_owned) dfree(p);
+        gather_owned.clear();
+        if (d_strpool && RP.mode != 2) { dfree(d_strpool); d_strpool = nullptr; }
+        if (RP.capturing) {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamEndCapture(E.stream, &graph));
+            capture_open = false;
+            cudaError_t ge = cudaGraphInstantiate(&RP.memo->gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ge != cudaSuccess) { RP.memo->gexec = nullptr; raise(RQ_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ge)); }
+            CK(cudaGraphLaunch(RP.memo->gexec, E.stream));
+        }
         stream_sync();
+        if (RP.capturing)
+            for (int c = 0; c < ncols; c++)
+                if (n_out > 0) memcpy(res->cols[c].data, RP.memo->cols[c].h, (size_t)n_out * res->cols[c].width);
         if (verdict) *verdict = (RP.mode == 2 || sharded) ? (*(const int32_t*)g_pinned != 0) : (h_ok_local != 0);
         if (tm) {
-            float ms = 0;
             tm->lower_ms = lower_ms;
             tm->host_syncs = RP.syncs;
-            const bool trace = g_trace;
-            for (auto& u : ev_used) {
-                CK(cudaEventElapsedTime(&ms, g_event_pool[u.first].a, g_event_pool[u.first].b));
-                if (u.second == 2) { tm->nccl_ms += ms; continue; }
-                tm->kernel_ms += ms;
-                if (u.second) { tm->scan_kernel_ms += ms; tm->fact_scan_ms = ms; }
-                if (trace) fprintf(stderr, "[rq] scan kernel launch %zu: %.3f ms%s\n", u.first, ms, u.second ? " (table scan)" : "");
-            }
-            CK(cudaEventElapsedTime(&ms, E.ev[1], E.ev[2]));
-            tm->d2h_ms = ms;
-            if (trace) {
-                CK(cudaEventElapsedTime(&ms, E.ev[0], E.ev[2]));
-                fprintf(stderr, "[rq] plan: %.3f ms on the stream from first launch to result read-back, %.3f ms in pipeline kernels\n", ms, tm->kernel_ms);
-            }
+            read_timings(ev_used, tm);
         }
-        for (void* p : scratch) dfree(p);
-        for (void* p : gather_owned) dfree(p);
-        if (d_strpool) dfree(d_strpool);
+        if (RP.capturing) { RP.memo->ev_used = ev_used; if (tm) RP.memo->tm_static = *tm; }
         *out = res;
         return RQ_OK;
     } catch (RqError& e) {
+        if (capture_open) { cudaGraph_t g = nullptr; cudaStreamEndCapture(E.stream, &g); if (g) cudaGraphDestroy(g); }
         cudaStreamSynchronize(E.stream);
         for (void* p : scratch) dfree(p);
-        if (d_strpool) dfree(d_strpool);
+        if (d_strpool && RP.mode != 2) dfree(d_strpool);
         rq_result_free(res);
         return fail(e.code, "%s", e.msg.c_str());
     } catch (ReplayDiverged&) {
         // the recorded script does not fit this execution (only possible on a single rank: sharded
         // replays take identical decisions on every rank): discard, the caller runs the careful way
+        if (capture_open) { cudaGraph_t g = nullptr; cudaStreamEndCapture(E.stream, &g); if (g) cudaGraphDestroy(g); }
         cudaStreamSynchronize(E.stream);
         for (void* p : scratch) dfree(p);
-        if (d_strpool) dfree(d_strpool);
         rq_result_free(res);
         if (verdict) *verdict = false;
         *out = nullptr;
@@ -2418,7 +2469,30 @@ static uint64_t plan_signature(const rq_plan& plan) {
     return h;
 }
 
+// device-side copies of what a replay needs: the recorded values (flat, 8-byte aligned), the log, the
+// verdict word and the plan's string constants
+static bool memo_prepare(PlanMemo& memo, const rq_plan& plan) {
+    std::vector<unsigned char> flat;
+    for (auto& r : memo.reads) {
+        flat.insert(flat.end(), r.begin(), r.end());
+        flat.resize((flat.size() + 7) & ~(size_t)7, 0);
+    }
+    memo.log_cap = flat.size();
+    bool ok = true;
+    ok &= cudaMalloc(&memo.d_expect, std::max<size_t>(flat.size(), 8)) == cudaSuccess;
+    ok &= cudaMalloc(&memo.d_log, std::max<size_t>(flat.size(), 8)) == cudaSuccess;
+    ok &= cudaMalloc(&memo.d_ok, 8) == cudaSuccess;
+    if (ok && !flat.empty()) ok &= cudaMemcpy(memo.d_expect, flat.data(), flat.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && plan.strpool_bytes > 0) {
+        ok &= cudaMalloc(&memo.d_strpool, (size_t)plan.strpool_bytes) == cudaSuccess;
+        if (ok) ok &= cudaMemcpy(memo.d_strpool, plan.strpool, (size_t)plan.strpool_bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) { cudaGetLastError(); memo.release(); }
+    return ok;
+}
+
 static void reset_plan_memos() {
+    for (auto& m : g_plan_memo) m.second.release();
     g_plan_memo.clear();
     g_ht_capacity.clear();
     g_emit_rows.clear();
@@ -2440,21 +2514,65 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         return rc;
     }
     PlanMemo& memo = g_plan_memo[plan_signature(*plan)];
+    if (memo.valid && memo.gexec) {
+        // the whole plan is one graph launch
+        if (tm) memset(tm, 0, sizeof(*tm));
+        cudaError_t ge = cudaGraphLaunch(memo.gexec, E.stream);
+        if (ge == cudaSuccess) ge = cudaStreamSynchronize(E.stream);
+        if (ge != cudaSuccess) return fail(RQ_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(ge));
+        if (*(const int32_t*)g_pinned != 0) {
+            rq_result* res = (rq_result*)calloc(1, sizeof(rq_result));
+            res->n_rows = memo.res_rows;
+            res->n_cols = (int)memo.cols.size();
+            res->cols = (rq_result_col*)calloc(memo.cols.size(), sizeof(rq_result_col));
+            for (size_t c = 0; c < memo.cols.size(); c++) {
+                const PlanMemo::Col& mc = memo.cols[c];
+                rq_result_col& rc = res->cols[c];
+                rc.type = mc.type; rc.width = mc.width; rc.sql_type = mc.sql_type; rc.sql_width = mc.sql_width;
+                const size_t bytes = (size_t)std::max<int64_t>(memo.res_rows, 1) * mc.width;
+                rc.data = malloc(bytes);
+                if (memo.res_rows > 0) memcpy(rc.data, mc.h, (size_t)memo.res_rows * mc.width);
+            }
+            if (tm) {
+                tm->lower_ms = 0;
+                tm->kernel_launches = memo.tm_static.kernel_launches;
+                tm->host_syncs = 1;
+                g_trace = false;
+                read_timings(memo.ev_used, tm);
+            }
+            *out = res;
+            return RQ_OK;
+        }
+        if (E.opt.trace) fprintf(stderr, "[rq] rank %d: graph result discarded (a predicted value was wrong on some rank)\n", E.dist.rank);
+        memo.release();
+    }
     if (memo.valid) {
         RP = ReplayState();
         RP.mode = 2;
         RP.memo = &memo;
+        // the second replay is captured into a graph (the first proved the script right)
+        RP.capturing = E.opt.graphs && !memo.no_graph && memo.replays >= 1;
         bool ok = false;
         const int rc = execute_once(plan, out, tm, &ok);
+        const bool captured = RP.capturing;
         RP = ReplayState();
-        if (rc != RQ_OK) { memo.valid = false; return rc; }
-        if (ok) return RQ_OK;
+        if (rc != RQ_OK) {
+            if (captured) {            // capture problems are not plan problems: fall back to plain replays
+                cudaGetLastError();
+                if (memo.gexec) { cudaGraphExecDestroy(memo.gexec); memo.gexec = nullptr; }
+                memo.no_graph = true;
+                return rq_plan_execute(plan, out, tm);
+            }
+            memo.release();
+            return rc;
+        }
+        if (ok) { memo.replays++; return RQ_OK; }
         if (E.opt.trace) fprintf(stderr, "[rq] rank %d: replayed plan discarded (%s); running the careful way\n", E.dist.rank,
                                  *out ? "a predicted value was wrong on some rank" : "the recorded script did not fit");
-        // some predicted value was wrong (other data under the same table name, a full table, a
-        // runtime error ...): drop the result and run the careful way, which also reports errors
+        // some predicted value was wrong (a full table, a runtime error ...): drop the result and run
+        // the careful way, which also reports errors
         if (*out) { rq_result_free(*out); *out = nullptr; }
-        memo.valid = false;
+        memo.release();
     }
     memo.reads.clear();
     RP = ReplayState();
@@ -2463,8 +2581,9 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
     bool clean = false;
     const int rc = execute_once(plan, out, tm, &clean);
     memo.valid = rc == RQ_OK && clean;
+    if (memo.valid && !memo_prepare(memo, *plan)) memo.valid = false;
     if (E.opt.trace) fprintf(stderr, "[rq] rank %d: careful run rc=%d clean=%d retries=%d (%s) reads=%zu\n", E.dist.rank, rc, (int)clean, RP.retries, RP.why, memo.reads.size());
-    if (!memo.valid) memo.reads.clear();
+    if (!memo.valid) memo.release();
     RP = ReplayState();
     return rc;
 }

@@ -29,6 +29,11 @@ bpt = {"q1": 38, "q6": 28, "q3": 24}.get(q, 0)
 for i in range(reps):
     if i == reps - 1:
         torch.cuda.cudart().cudaProfilerStart()     # ncu --profile-from-start off: only the last (warm) run
+    if os.environ.get("RQ_PROF_TRACE") and i == reps - 1:
+        eng.set_option("graphs", 0); eng.set_option("replay", 0); eng.set_option("trace", 1)   # per-launch times on stderr
+    for k in ("stages", "warps"):
+        if os.environ.get("RQ_OPT_" + k.upper()):
+            eng.set_option(k, float(os.environ["RQ_OPT_" + k.upper()]))
     torch.cuda.synchronize(); _t0 = time.perf_counter()
     res, tm = eng.execute(plan, tabs)
     _wall = 1e3 * (time.perf_counter() - _t0)

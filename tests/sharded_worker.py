@@ -48,7 +48,7 @@ def main():
         handles = {n: eng.upload(n, c) for n, c in tabs.items()}
         try:
             # three executions: careful, careful (warm memos), replayed without host waits
-            for rep in range(3):
+            for rep in range(6):
                 res, tm = eng.execute(Plan(d), handles, N.RQ_PLAN_SHARDED)
                 got = serialize_columns(res.columns, res.sql_types, res.sql_widths)
                 _, want = load_golden(name)
@@ -68,7 +68,7 @@ def main():
         tabs = {n: shard_columns(c, rank, world) for n, c in plan_tables(d, data).items()}
         handles = {n: eng.upload(n, c) for n, c in tabs.items()}
         try:
-            for rep in range(3):
+            for rep in range(6):
                 res, tm = eng.execute(Plan(d), handles, N.RQ_PLAN_PARTITIONED)
                 got = serialize_columns(res.columns, res.sql_types, res.sql_widths)
                 _, want = load_golden(name)

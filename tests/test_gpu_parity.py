@@ -188,8 +188,9 @@ def test_replayed_execution_is_identical_and_sync_free(name, sf001, engine):
     handles = {n: engine.upload(n, c) for n, c in tabs.items()}
     try:
         runs = []
-        for _ in range(4):
-            res, tm = engine.execute(Plan(d), handles)
+        p = Plan(d)
+        for _ in range(6):           # careful, careful, replay, replay + capture, graph, graph
+            res, tm = engine.execute(p, handles)
             runs.append((serialize_columns(res.columns, res.sql_types, res.sql_widths), tm))
     finally:
         for h in handles.values():
@@ -199,6 +200,7 @@ def test_replayed_execution_is_identical_and_sync_free(name, sf001, engine):
         assert_same_relation(got, want, d, name + " (repeated)")
     assert runs[0][1].host_syncs >= 1
     assert runs[-1][1].host_syncs == 1, f"replay waited {runs[-1][1].host_syncs} times"
+    assert runs[-1][1].kernel_launches > 0 and runs[-1][1].kernel_ms > 0      # graph launches still report device times
 
 
 def test_replay_notices_changed_data_and_errors(engine):
