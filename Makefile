@@ -8,7 +8,7 @@ LIB = resql_b200/libresql_b200.so
 all: $(LIB)
 
 $(LIB): $(CSRC)/engine.cu $(CSRC)/engine_exec.inl $(CSRC)/scan_kernel.cuh $(CSRC)/device_util.cuh $(CSRC)/hash_kernels.cuh \
-        $(CSRC)/sort_kernels.cuh $(CSRC)/rq_internal.h $(CSRC)/dist.h include/resql_b200.h
+        $(CSRC)/sort_kernels.cuh $(CSRC)/exchange_kernels.cuh $(CSRC)/host_narrow.h $(CSRC)/rq_internal.h $(CSRC)/dist.h include/resql_b200.h
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/engine.cu -ldl
 
 ptxas-info:

@@ -26,6 +26,10 @@
 #include "hash_kernels.cuh"
 #include "exchange_kernels.cuh"
 #include "dist.h"
+#include "host_narrow.h"
+#include <thread>
+#include <atomic>
+#include <mutex>
 
 using namespace rq;
 
@@ -115,6 +119,9 @@ struct Options {
     bool direct_joins = true;             // direct-address join tables for dense unique integer keys
     bool replay = true;                   // predicted host reads (engine_exec.inl "host reads of device values")
     bool graphs = true;                   // replayed plans are captured into CUDA graphs
+    bool narrow = true;                   // host-buffer uploads send 8-byte columns over PCIe in the narrowest exact width
+    int up_threads = 0;                   // host-buffer uploads: converting threads (0 = all cores of this rank's share)
+    int up_chunk_krows = 512;             //                      rows per conversion / DMA chunk, in 1024 rows
     bool trace = false;                   // per-step wall-clock trace on stderr
 };
 
@@ -135,6 +142,11 @@ struct Engine {
     int32_t* h_flags = nullptr; // pinned
     unsigned char* pinned = nullptr;   // pinned scratch: host reads (4 KB) + ring of small uploads
     Dist dist;
+    // host-buffer uploads: one converting thread per worker, each with its own stream and a
+    // double-buffered pair of (pinned host, device) staging chunks (host_narrow.h)
+    struct UpWorker { size_t cap = 0; double conv_ms = 0, wait_ms = 0; cudaStream_t s = nullptr; cudaEvent_t ev[2] = {nullptr, nullptr}; unsigned char* h[2] = {nullptr, nullptr}; unsigned char* d[2] = {nullptr, nullptr}; };
+    std::vector<UpWorker> up;
+    cudaEvent_t up_ready = nullptr;
 };
 static Engine E;
 
@@ -192,9 +204,19 @@ extern "C" int rq_init(int device) {
 extern "C" int rq_shutdown(void) {
     if (!E.init) return RQ_OK;
     cudaDeviceSynchronize();
+    // captured plans hold NCCL kernel nodes: ncclCommDestroy waits until every graph that refers to
+    // the communicator is gone (measured: the 2-GPU test worker never left rq_shutdown), so the
+    // memos - and with them the graph executables - go first
+    reset_plan_memos();
+    cudaDeviceSynchronize();
     dist_shutdown(E.dist);
     dfree(E.g_state); dfree(E.g_keys); dfree(E.g_acc); dfree(E.g_kinds);
     dfree(E.flags); cudaFreeHost(E.h_flags); cudaFreeHost(E.pinned);
+    for (auto& w : E.up) {
+        for (int b = 0; b < 2; b++) { if (w.h[b]) cudaFreeHost(w.h[b]); if (w.d[b]) cudaFree(w.d[b]); if (w.ev[b]) cudaEventDestroy(w.ev[b]); }
+        if (w.s) cudaStreamDestroy(w.s);
+    }
+    if (E.up_ready) cudaEventDestroy(E.up_ready);
     reset_plan_memos();
     cudaStreamSynchronize(E.stream);
     for (auto& e : E.ev) cudaEventDestroy(e);
@@ -220,6 +242,9 @@ extern "C" int rq_set_option(const char* key, double value) {
     else if (k == "direct_joins") o.direct_joins = value != 0;
     else if (k == "replay") o.replay = value != 0;
     else if (k == "graphs") o.graphs = value != 0;
+    else if (k == "narrow") o.narrow = value != 0;
+    else if (k == "up_threads") o.up_threads = (int)value;
+    else if (k == "up_chunk_krows") o.up_chunk_krows = std::max(1, std::min((int)value, 8192));
     else if (k == "trace") o.trace = value != 0;
     else return fail(RQ_ERR_INVALID, "rq_set_option: unknown option '%s'", key);
     return RQ_OK;
@@ -283,6 +308,182 @@ static void alloc_tile_major(rq_table& t, int n_cols, FT type_of, FW width_of) {
     }
 }
 
+// ---- upload from host buffers with host-side narrowing (host_narrow.h) ------------------------------
+
+static std::map<std::string, std::vector<int>> g_width_hint; // physical widths that held for a table name last time
+
+// rows [row0, row0 + n) of a column, as they are, into their place in the table (row0 is a multiple of kTile)
+static void copy_column_rows(rq_table& t, int c, const void* data, int64_t row0, int64_t n, cudaMemcpyKind kind, cudaStream_t st) {
+    DevColumn& dc = t.cols[c];
+    const unsigned char* src = (const unsigned char*)data + (size_t)row0 * dc.width;
+    if (dc.type == RQ_STR) {
+        if (n) CK(cudaMemcpyAsync(dc.d + (size_t)row0 * dc.width, src, (size_t)n * dc.width, kind, st));
+        return;
+    }
+    // full pages with one pitched copy, the partial last page with a plain one
+    unsigned char* dst = dc.d + (size_t)(row0 / kTile) * t.page_bytes;
+    const size_t chunk = (size_t)kTile * dc.width;
+    const int64_t full = n / kTile;
+    if (full > 0) CK(cudaMemcpy2DAsync(dst, t.page_bytes, src, chunk, chunk, (size_t)full, kind, st));
+    const size_t rest = (size_t)n * dc.width - (size_t)full * chunk;
+    if (rest) CK(cudaMemcpyAsync(dst + (size_t)full * t.page_bytes, src + (size_t)full * chunk, rest, kind, st));
+}
+static void copy_column_plain(rq_table& t, int c, const void* data, int64_t n_rows, cudaMemcpyKind kind) {
+    copy_column_rows(t, c, data, 0, n_rows, kind, E.stream);
+}
+
+// Returns the finished table, or null when no column can be narrowed (the caller takes the plain
+// path). The table in HBM keeps the reference's widths (the scan kernel's operand forms and the
+// roofline's algorithmic bytes are defined on them; with the present kernels Q1/Q6/Q3 are bound by
+// instruction issue, not by HBM bytes, so narrower resident columns measured no gain - DESIGN.md):
+// a chunk is widened again by rq_repack_col when it lands. The transfer width of every 8-byte column is guessed from a sample (or from the widths that
+// held for the same table name before), the columns are converted chunk by chunk on all host cores
+// while the exact value range is taken; a value that does not fit its guess widens the guess and the
+// upload starts over (at most twice; data whose sample lies about its range is rare).
+static std::unique_ptr<rq_table> upload_host_narrow(const char* name, int n_cols, const rq_column* cols, int64_t n_rows) {
+    const int64_t kUpChunkRows = (int64_t)E.opt.up_chunk_krows * 1024;      // (a multiple of kTile)
+    if (!E.opt.narrow || n_rows < 4 * kUpChunkRows) return nullptr;
+    const std::string hint_key = std::string(name ? name : "") + "/" + std::to_string(n_cols);
+    std::vector<int> gw(n_cols);
+    {
+        auto h = g_width_hint.find(hint_key);
+        for (int c = 0; c < n_cols; c++) {
+            gw[c] = cols[c].width;
+            if (cols[c].type != RQ_I64) continue;
+            if (h != g_width_hint.end()) { gw[c] = h->second[c]; continue; }
+            const int64_t* p = (const int64_t*)cols[c].data;
+            const int64_t step = std::max<int64_t>(1, n_rows / 4096);
+            int64_t lo = p[n_rows - 1], hi = lo;
+            for (int64_t i = 0; i < n_rows; i += step) { lo = std::min(lo, p[i]); hi = std::max(hi, p[i]); }
+            gw[c] = (lo >= 0 && hi <= 255) ? 1 : (lo >= INT32_MIN && hi <= INT32_MAX) ? 4 : 8;
+        }
+    }
+    const auto t_begin = std::chrono::steady_clock::now();
+    for (int attempt = 0; attempt < 3; attempt++) {
+        std::vector<int> ncols;
+        for (int c = 0; c < n_cols; c++) if (cols[c].type == RQ_I64 && gw[c] != 8) ncols.push_back(c);
+        if (ncols.empty()) { g_width_hint[hint_key] = gw; return nullptr; }
+        std::unique_ptr<rq_table> t(new rq_table());
+        t->name = name ? name : "";
+        t->n_rows = n_rows;
+        t->cap_rows = round_up(std::max<int64_t>(n_rows, 1), kPadRows);
+        alloc_tile_major(*t, n_cols, [&](int c) { return cols[c].type; }, [&](int c) { return cols[c].width; });
+        if (!E.up_ready) CK(cudaEventCreateWithFlags(&E.up_ready, cudaEventDisableTiming));
+        CK(cudaEventRecord(E.up_ready, E.stream));            // storage allocated and cleared
+        // columns that travel as they are: queued first, the link is busy while the host converts
+        // Work items are (row chunk, column) pairs in chunk-major order: a narrowed column is converted
+        // into a staging buffer and copied from there, any other column is copied as it is - from the
+        // same queue, so that the copy engine always has both kinds of chunks to move while the host
+        // converts (one huge copy per direct column in front would keep the engine to itself: measured,
+        // the converted chunks then wait and nothing overlaps).
+        std::vector<int> icols;
+        for (int c = 0; c < n_cols; c++) icols.push_back(c);
+        const int64_t chunks = (n_rows + kUpChunkRows - 1) / kUpChunkRows;
+        const int64_t n_items = chunks * (int64_t)icols.size();
+        int T = (int)std::thread::hardware_concurrency();
+        T = std::max(2, std::min(T / std::max(1, E.dist.world), 32));
+        if (E.opt.up_threads > 0) T = std::min(E.opt.up_threads, 64);
+        T = (int)std::min<int64_t>(T, n_items);
+        for (auto& w : E.up)                        // chunk size raised since the buffers were made
+            if (w.cap < (size_t)kUpChunkRows * 4) {
+                for (int b = 0; b < 2; b++) {
+                    CK(cudaFreeHost(w.h[b])); CK(cudaFree(w.d[b]));
+                    CK(cudaMallocHost(&w.h[b], (size_t)kUpChunkRows * 4));
+                    CK(cudaMalloc(&w.d[b], (size_t)kUpChunkRows * 4));
+                }
+                w.cap = (size_t)kUpChunkRows * 4;
+            }
+        while ((int)E.up.size() < T) {
+            Engine::UpWorker w;
+            CK(cudaStreamCreateWithFlags(&w.s, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; b++) {
+                CK(cudaEventCreateWithFlags(&w.ev[b], cudaEventDisableTiming));
+                CK(cudaMallocHost(&w.h[b], (size_t)kUpChunkRows * 4));
+                CK(cudaMalloc(&w.d[b], (size_t)kUpChunkRows * 4));
+                w.cap = (size_t)kUpChunkRows * 4;
+            }
+            E.up.push_back(w);
+        }
+        std::atomic<int64_t> next{0};
+        std::atomic<int> bad_col{-1};
+        std::atomic<int> cuda_err{0};
+        std::mutex mu;
+        std::vector<int64_t> lo(n_cols, INT64_MAX), hi(n_cols, INT64_MIN);
+        auto work = [&](int tid) {
+            Engine::UpWorker& w = E.up[tid];
+            if (cudaSetDevice(E.device) != cudaSuccess || cudaStreamWaitEvent(w.s, E.up_ready, 0) != cudaSuccess) { cuda_err = 1; return; }
+            std::vector<int64_t> tlo(n_cols, INT64_MAX), thi(n_cols, INT64_MIN);
+            int b = 0;
+            bool used[2] = {false, false};
+            for (;;) {
+                const int64_t it = next.fetch_add(1);
+                if (it >= n_items || bad_col.load() >= 0 || cuda_err.load()) break;
+                // chunk-major order: the chunks of all narrowed columns of a row range are converted together
+                const int c = icols[(size_t)(it % (int64_t)icols.size())];
+                const int64_t row0 = (it / (int64_t)icols.size()) * kUpChunkRows;
+                const int64_t n = std::min<int64_t>(kUpChunkRows, n_rows - row0);
+                const int w8 = gw[c];
+                if (!(cols[c].type == RQ_I64 && w8 != 8)) {
+                    try { copy_column_rows(*t, c, cols[c].data, row0, n, cudaMemcpyHostToDevice, w.s); }
+                    catch (RqError&) { cuda_err = 1; break; }
+                    continue;
+                }
+                const auto t0 = std::chrono::steady_clock::now();
+                if (used[b] && cudaEventSynchronize(w.ev[b]) != cudaSuccess) { cuda_err = 1; break; }
+                const auto t1 = std::chrono::steady_clock::now();
+                if (!hostnarrow::convert_chunk((const int64_t*)cols[c].data + row0, w.h[b], (size_t)n, w8, &tlo[c], &thi[c])) {
+                    bad_col = c;
+                    break;
+                }
+                w.wait_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+                w.conv_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+                const DevColumn& dc = t->cols[c];
+                const int grid = (int)std::min<int64_t>((n + 255) / 256, 1024);
+                bool ok = cudaMemcpyAsync(w.d[b], w.h[b], (size_t)n * w8, cudaMemcpyHostToDevice, w.s) == cudaSuccess;
+                rq_repack_col<<<grid, 256, 0, w.s>>>(w.d[b], w8, dc.d + (size_t)(row0 / kTile) * dc.tile_stride, dc.width, dc.tile_stride, n);
+                ok = ok && cudaGetLastError() == cudaSuccess && cudaEventRecord(w.ev[b], w.s) == cudaSuccess;
+                if (!ok) { cuda_err = 1; break; }
+                used[b] = true;
+                b ^= 1;
+            }
+            if (cudaStreamSynchronize(w.s) != cudaSuccess) cuda_err = 1;
+            std::lock_guard<std::mutex> g(mu);
+            for (int c = 0; c < n_cols; c++) { lo[c] = std::min(lo[c], tlo[c]); hi[c] = std::max(hi[c], thi[c]); }
+        };
+        for (auto& w : E.up) { w.conv_ms = 0; w.wait_ms = 0; }
+        std::vector<std::thread> th;
+        for (int i = 1; i < T; i++) th.emplace_back(work, i);
+        work(0);
+        for (auto& x : th) x.join();
+        if (cuda_err.load()) raise(RQ_ERR_CUDA, "rq_table_upload: a staging copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (bad_col.load() >= 0) {
+            // the sample lied: widen that column's guess and start over
+            const int c = bad_col.load();
+            gw[c] = gw[c] == 1 ? 4 : 8;
+            CK(cudaStreamSynchronize(E.stream));
+            continue;
+        }
+        for (int c : ncols) { t->cols[c].has_stats = true; t->cols[c].vmin = lo[c]; t->cols[c].vmax = hi[c]; }
+        g_width_hint[hint_key] = gw;
+        if (E.opt.trace) {
+            const double conv_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+            CK(cudaStreamSynchronize(E.stream));
+            const double all_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+            size_t wire = 0, logical = 0;
+            for (int c = 0; c < n_cols; c++) { wire += (size_t)n_rows * gw[c]; logical += (size_t)n_rows * cols[c].width; }
+            double cv = 0, wt = 0;
+            for (int i = 0; i < T; i++) { cv += E.up[i].conv_ms; wt += E.up[i].wait_ms; }
+            fprintf(stderr, "[rq] upload %s: %lld rows, %d of %d columns narrowed on %d host threads (attempt %d): %.1f MB on the wire for %.1f MB, "
+                            "conversion done after %.1f ms (per thread: %.1f ms converting, %.1f ms waiting for its staging buffers), "
+                            "all copies after %.1f ms (%.1f GB/s of table bytes)\n",
+                    t->name.c_str(), (long long)n_rows, (int)ncols.size(), n_cols, T, attempt, wire / 1e6, logical / 1e6, conv_ms, cv / T, wt / T,
+                    all_ms, logical / 1e6 / all_ms);
+        }
+        return t;
+    }
+    return nullptr;
+}
+
 extern "C" int rq_table_upload(const char* name, int32_t n_cols, const rq_column* cols,
                                int64_t n_rows, int32_t flags, rq_table** out) {
     if (!E.init) return fail(RQ_ERR_NOT_INIT, "rq_table_upload before rq_init");
@@ -298,6 +499,15 @@ extern "C" int rq_table_upload(const char* name, int32_t n_cols, const rq_column
         for (int c = 0; c < n_cols; c++)
             if (!valid_col(cols[c].type, cols[c].width))
                 raise(RQ_ERR_INVALID, "rq_table_upload: column %d has bad type/width %d/%d", c, cols[c].type, cols[c].width);
+        if (!dev) {
+            std::unique_ptr<rq_table> nt = upload_host_narrow(name, n_cols, cols, n_rows);
+            if (nt) {
+                compute_stats(*nt);
+                CK(cudaStreamSynchronize(E.stream));
+                *out = nt.release();
+                return RQ_OK;
+            }
+        }
         if (!borrow) alloc_tile_major(*t, n_cols, [&](int c) { return cols[c].type; }, [&](int c) { return cols[c].width; });
         const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
         for (int c = 0; c < n_cols; c++) {
@@ -313,21 +523,7 @@ extern "C" int rq_table_upload(const char* name, int32_t n_cols, const rq_column
                 t->cols.push_back(dc);
                 continue;
             }
-            DevColumn& dc = t->cols[c];
-            const size_t used = (size_t)n_rows * dc.width;
-            if (dc.type == RQ_STR) {
-                if (used) CK(cudaMemcpyAsync(dc.d, cols[c].data, used, kind, E.stream));
-                continue;
-            }
-            // full pages with one pitched copy, the partial last page with a plain one
-            const size_t chunk = (size_t)kTile * dc.width;
-            const int64_t full = n_rows / kTile;
-            if (full > 0)
-                CK(cudaMemcpy2DAsync(dc.d, t->page_bytes, cols[c].data, chunk, chunk, (size_t)full, kind, E.stream));
-            const size_t rest = used - (size_t)full * chunk;
-            if (rest)
-                CK(cudaMemcpyAsync(dc.d + (size_t)full * t->page_bytes, (const unsigned char*)cols[c].data + (size_t)full * chunk,
-                                   rest, kind, E.stream));
+            copy_column_plain(*t, c, cols[c].data, n_rows, kind);
         }
         compute_stats(*t);
         CK(cudaStreamSynchronize(E.stream));
@@ -404,7 +600,7 @@ static void compute_stats(rq_table& t) {
     if (t.n_rows <= 0) return;
     std::vector<int> idx;
     for (size_t c = 0; c < t.cols.size(); c++)
-        if (t.cols[c].type != RQ_STR) idx.push_back((int)c);
+        if (t.cols[c].type != RQ_STR && !t.cols[c].has_stats) idx.push_back((int)c);     // (host-converted columns bring their range)
     if (idx.empty()) return;
     int64_t* d = nullptr;
     CK(dmalloc(&d, idx.size() * 16));

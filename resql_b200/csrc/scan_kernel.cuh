@@ -1420,6 +1420,23 @@ __global__ void rq_col_minmax(const unsigned char* col, int width, int64_t tile_
     }
 }
 
+// re-encodes a chunk of an integer column (plain array, `sw` bytes per value) into its place in a
+// tile-major table (`dw` bytes per value): the device side of an upload whose 8-byte columns crossed
+// PCIe in a narrower exact encoding (host_narrow.h)
+__global__ void rq_repack_col(const unsigned char* src, int sw, unsigned char* dst, int dw, int64_t dstride, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned char* p = src + i * sw;
+        int64_t v;
+        if (sw == 8) v = *reinterpret_cast<const int64_t*>(p);
+        else if (sw == 4) v = *reinterpret_cast<const int32_t*>(p);
+        else v = *p;
+        unsigned char* q = dst + (i / kTile) * dstride + (i % kTile) * dw;
+        if (dw == 8) *reinterpret_cast<int64_t*>(q) = v;
+        else if (dw == 4) *reinterpret_cast<int32_t*>(q) = (int32_t)v;
+        else *q = (unsigned char)v;
+    }
+}
+
 // result columns: int64 values -> physical width, strings by value
 __global__ void rq_narrow_i32(const int64_t* in, int32_t* out, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -46,6 +46,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <unistd.h>
 #include "resql_b200.h"
 
 namespace rqshim {
@@ -614,14 +615,24 @@ public:
 
 /* ---- device mirror of the row store (dbdata.h) ----------------------------------------------- */
 struct MirrorKey {
-    Relation* rel; size_t tuples; std::string cols;
+    Relation* rel; size_t tuples; std::string cols; bool shard;
     bool operator< ( const MirrorKey& o ) const {
         if ( rel != o.rel ) return rel < o.rel;
         if ( tuples != o.tuples ) return tuples < o.tuples;
+        if ( shard != o.shard ) return shard < o.shard;
         return cols < o.cols;
     }
 };
 static std::map<MirrorKey, rq_table*>& mirrors() { static std::map<MirrorKey, rq_table*> m; return m; }
+/* Multi-GPU (`gpus=N`, the counterpart of the reference's `threads=N` control variable,
+ * execute.h:454-474): one process per GPU, every process runs the same statements on the same row
+ * store. For a select the table scanned by the last aggregation's pipeline (the fact table) is
+ * mirrored as THIS rank's row range, all other tables completely, and the plan runs with
+ * RQ_PLAN_SHARDED: partial results are merged over NCCL inside the library and every rank holds
+ * the full result. rank / world / the file that carries the NCCL id are set by the host program
+ * (resql_b200_driver.cpp) before the first select. */
+struct Group { int rank = 0, world = 1; std::string idFile; bool joined = false; };
+static Group& group() { static Group g; return g; }
 static bool& engineUp() { static bool up = false; return up; }
 static double& lastLoadMs() { static double ms = 0; return ms; }
 
@@ -629,10 +640,10 @@ static void check ( int rc ) {
     if ( rc != RQ_OK ) throw ResqlError ( std::string ( "GPU engine: " ) + rq_last_error() );
 }
 
-static rq_table* mirrorTable ( TableDesc& t ) {
+static rq_table* mirrorTable ( TableDesc& t, bool shard = false ) {
     std::string cols;
     for ( auto& a : t.attrs ) cols += a.name + ",";
-    MirrorKey key { t.rel, t.rel->tupleNum(), cols };
+    MirrorKey key { t.rel, t.rel->tupleNum(), cols, shard };
     auto it = mirrors().find ( key );
     if ( it != mirrors().end() ) return it->second;
     Schema& s = t.rel->_schema;
@@ -654,7 +665,19 @@ static rq_table* mirrorTable ( TableDesc& t ) {
     }
     std::vector<const uint8_t*> blocks;
     std::vector<size_t> sizes;
-    for ( auto& b : t.rel->_dataBlocks ) { blocks.push_back ( b->begin() ); sizes.push_back ( b->_contentSize ); }
+    /* this rank's row range [lo, hi) of the relation (whole relation unless sharded); blocks hold
+     * whole tuples, so a range is a list of (pointer, bytes) pieces of the blocks */
+    const size_t tup = s._tupSize;
+    const size_t total = t.rel->tupleNum();
+    size_t lo = 0, hi = total;
+    if ( shard ) { lo = total * (size_t) group().rank / (size_t) group().world; hi = total * (size_t) ( group().rank + 1 ) / (size_t) group().world; }
+    size_t first = 0;
+    for ( auto& b : t.rel->_dataBlocks ) {
+        const size_t n = b->_contentSize / tup;
+        const size_t a = std::max ( lo, first ), z = std::min ( hi, first + n );
+        if ( a < z ) { blocks.push_back ( b->begin() + ( a - first ) * tup ); sizes.push_back ( ( z - a ) * tup ); }
+        first += n;
+    }
     rq_table* h = nullptr;
     Timer tm;
     check ( rq_table_upload_rows ( t.name.c_str(), (int) t.attrs.size(), types.data(), widths.data(), offsets.data(),
@@ -730,13 +753,45 @@ std::unique_ptr < SelectResult > executeSelectPlanGpu ( RelOperator*  root,
         if ( dump != nullptr ) { std::ofstream f ( dump ); f << low.toJson(); }
 
         if ( getenv ( "RESQL_B200_DRY" ) == nullptr ) {
+            rqshim::Group& grp = rqshim::group();
             if ( !rqshim::engineUp() ) {
                 const char* dev = getenv ( "RESQL_B200_DEVICE" );
-                rqshim::check ( rq_init ( dev ? atoi ( dev ) : 0 ) );
+                rqshim::check ( rq_init ( dev ? atoi ( dev ) : grp.rank ) );
                 rqshim::engineUp() = true;
             }
+            if ( grp.world > 1 && !grp.joined ) {
+                /* rank 0 creates the NCCL id and publishes it through a file, the others wait for it */
+                uint8_t id[128];
+                if ( grp.rank == 0 ) {
+                    rqshim::check ( rq_dist_unique_id ( id ) );
+                    std::ofstream f ( grp.idFile + ".tmp", std::ios::binary );
+                    f.write ( (const char*) id, 128 );
+                    f.close();
+                    rename ( ( grp.idFile + ".tmp" ).c_str(), grp.idFile.c_str() );
+                } else {
+                    for ( int tries = 0; ; tries++ ) {
+                        std::ifstream f ( grp.idFile, std::ios::binary );
+                        if ( f.is_open() && f.read ( (char*) id, 128 ) && f.gcount() == 128 ) break;
+                        if ( tries > 60000 ) throw ResqlError ( "GPU engine: rank 0 never published the NCCL id" );
+                        usleep ( 1000 );
+                    }
+                }
+                rqshim::check ( rq_dist_init ( grp.rank, grp.world, id ) );
+                grp.joined = true;
+            }
+            /* the fact table of a sharded execution: the table scanned by the pipeline the library
+             * merges after (the last aggregation, else the final relation) */
+            int shardTable = -1;
+            if ( grp.world > 1 ) {
+                int mergePipe = (int) low.pipelines.size() - 1;
+                for ( size_t i = 0; i < low.pipelines.size(); i++ ) if ( low.pipelines[i].sink_kind == RQ_SINK_AGG ) mergePipe = (int) i;
+                if ( low.pipelines[mergePipe].source_kind == RQ_SRC_TABLE ) shardTable = low.pipelines[mergePipe].source_id;
+                /* a table that is also scanned by another pipeline must stay complete there */
+                for ( size_t i = 0; i < low.pipelines.size(); i++ )
+                    if ( (int) i != mergePipe && low.pipelines[i].source_kind == RQ_SRC_TABLE && low.pipelines[i].source_id == shardTable ) shardTable = -1;
+            }
             std::vector<rq_table*> handles;
-            for ( auto& t : low.tables ) handles.push_back ( rqshim::mirrorTable ( t ) );
+            for ( size_t t = 0; t < low.tables.size(); t++ ) handles.push_back ( rqshim::mirrorTable ( low.tables[t], (int) t == shardTable ) );
 
             std::vector<rq_pipeline> pls ( low.pipelines.size() );
             for ( size_t i = 0; i < pls.size(); i++ ) {
@@ -756,7 +811,7 @@ std::unique_ptr < SelectResult > executeSelectPlanGpu ( RelOperator*  root,
             rp.n_order = (int) low.order.size(); rp.order = low.order.data();
             rp.limit = low.limit;
             rp.strpool = low.strpool.data(); rp.strpool_bytes = (int64_t) low.strpool.size();
-            rp.flags = 0;
+            rp.flags = shardTable >= 0 ? RQ_PLAN_SHARDED : 0;
             rq_timings tm;
             rqshim::check ( rq_plan_execute ( &rp, &res, &tm ) );
             report.compilationTime += tm.lower_ms;

@@ -7,7 +7,13 @@
  * (execute.h:509-543). `engine=cpu` switches back to the reference's own JIT for A/B runs.
  *
  * Usage: resql-b200 [--quiet] STATEMENT...   (same driver statements as the oracle driver:
- *        "out <file>", "repeat <n>", "binload <table> <file>", plus "engine=gpu|cpu")
+ *        "out <file>", "repeat <n>", "binload <table> <file>", plus "engine=gpu|cpu" and "gpus=N")
+ *
+ * gpus=N (must be the first statement; the counterpart of the reference's `threads=N`): the
+ * program re-executes itself N-1 times, one process per GPU. Every process runs the same
+ * statements on its own copy of the row store; selects run with the fact table row-range sharded
+ * (gpu_executor.h) and are merged over NCCL, so every rank computes the full result. Rank 0 prints
+ * and writes the output files, the other ranks are silent.
  */
 #include <cstdio>
 #include <cstring>
@@ -15,6 +21,8 @@
 #include <vector>
 #include <fstream>
 #include <iostream>
+#include <unistd.h>
+#include <sys/wait.h>
 
 #include "operators/JitOperators.h"
 #include "execute.h"
@@ -68,10 +76,39 @@ static QueryResult executeStatementGpu(std::string statement, Database& db, DBCo
     return ResqlError("unwanted fallthrough");
 }
 
+/* gpus=N: become rank 0 and start ranks 1..N-1 as copies of this process */
+static std::vector<pid_t> startRanks ( int world, int argc, char** argv ) {
+    std::vector<pid_t> kids;
+    char idFile[] = "/tmp/resql_b200_nccl_id_XXXXXX";
+    int fd = mkstemp ( idFile );
+    if ( fd >= 0 ) { close ( fd ); unlink ( idFile ); }
+    setenv ( "RESQL_B200_WORLD", std::to_string ( world ).c_str(), 1 );
+    setenv ( "RESQL_B200_IDFILE", idFile, 1 );
+    for ( int r = 1; r < world; r++ ) {
+        pid_t pid = fork();             /* before any CUDA call of this process */
+        if ( pid == 0 ) {
+            setenv ( "RESQL_B200_RANK", std::to_string ( r ).c_str(), 1 );
+            execv ( "/proc/self/exe", argv );
+            _exit ( 127 );
+        }
+        kids.push_back ( pid );
+    }
+    setenv ( "RESQL_B200_RANK", "0", 1 );
+    (void) argc;
+    return kids;
+}
+
 int main(int argc, char** argv) {
     Database db;
     DBConfig config;
     bool quiet = false, gpu = true;
+    std::vector<pid_t> kids;
+    if ( getenv ( "RESQL_B200_RANK" ) != nullptr ) {        /* one of the ranks a gpus=N parent started */
+        rqshim::group().rank = atoi ( getenv ( "RESQL_B200_RANK" ) );
+        rqshim::group().world = atoi ( getenv ( "RESQL_B200_WORLD" ) );
+        rqshim::group().idFile = getenv ( "RESQL_B200_IDFILE" );
+    }
+    const bool silent = rqshim::group().rank != 0;
     std::string outFile;
     int outCount = 0, repeat = 1;
     for (int i = 1; i < argc; i++) {
@@ -87,6 +124,17 @@ int main(int argc, char** argv) {
         for (auto& s : statements) {
             std::string st = s;
             rtrim(st); ltrim(st);
+            if (startsWith(st, "gpus=")) {
+                const int n = std::stoi(st.substr(5));
+                if (getenv("RESQL_B200_RANK") == nullptr && n > 1) {
+                    if (rqshim::engineUp()) { std::cout << "Query error: gpus=N must come before the first select" << std::endl; continue; }
+                    kids = startRanks(n, argc, argv);
+                    rqshim::group().rank = 0;
+                    rqshim::group().world = n;
+                    rqshim::group().idFile = getenv("RESQL_B200_IDFILE");
+                }
+                continue;
+            }
             if (st == "engine=gpu") { gpu = true; continue; }
             if (st == "engine=cpu") { gpu = false; continue; }
             if (startsWith(st, "out ")) { outFile = st.substr(4); outCount = 0; continue; }
@@ -96,7 +144,7 @@ int main(int argc, char** argv) {
                 auto sp = rest.find(' ');
                 try {
                     size_t n = binload(db, rest.substr(0, sp), rest.substr(sp + 1));
-                    std::cout << "Inserted " << n << " tuples" << std::endl;
+                    if (!silent) std::cout << "Inserted " << n << " tuples" << std::endl;
                 } catch (ResqlError& e) {
                     std::cout << "Query error: " << e.message() << std::endl;
                 }
@@ -107,6 +155,7 @@ int main(int argc, char** argv) {
                 QueryResult res = executeStatementGpu(st, db, config, gpu);
                 if (!res.error && res.tag == Query::SELECT) {
                     reps = repeat;
+                    if (silent) continue;
                     SelectResult* sel = res.selectResult();
                     std::cout << "#select rows=" << sel->relation->tupleNum()
                               << " compile_ms=" << sel->jitReport.compilationTime
@@ -123,10 +172,17 @@ int main(int argc, char** argv) {
                         serializeRelation(*sel->relation, f);
                     }
                 }
-                if (!quiet || res.error) printQueryResult(res);
+                if (!silent && (!quiet || res.error)) printQueryResult(res);
             }
         }
     }
     rq_shutdown();
-    return 0;
+    int rc = 0;
+    for (pid_t k : kids) {
+        int status = 0;
+        waitpid(k, &status, 0);
+        if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) rc = 1;
+    }
+    if (!kids.empty() && getenv("RESQL_B200_IDFILE")) unlink(getenv("RESQL_B200_IDFILE"));
+    return rc;
 }

@@ -14,6 +14,9 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 mode = sys.argv[4] if len(sys.argv) > 4 else "owned"     # owned: engine storage (tile-major); borrow: plain torch columns
 dev = torch.device("cuda:0")
 eng = Engine(0)
+for k in ("stages", "warps", "narrow"):
+    if os.environ.get("RQ_OPT_" + k.upper()):
+        eng.set_option(k, float(os.environ["RQ_OPT_" + k.upper()]))
 need_orders = q not in ("q1", "q6")
 orders, li, cust = TD.gen_orders_lineitem(sf, 42, dev, want_orders=need_orders)
 src = {"lineitem": li, "orders": orders, "customer": cust}
@@ -31,9 +34,6 @@ for i in range(reps):
         torch.cuda.cudart().cudaProfilerStart()     # ncu --profile-from-start off: only the last (warm) run
     if os.environ.get("RQ_PROF_TRACE") and i == reps - 1:
         eng.set_option("graphs", 0); eng.set_option("replay", 0); eng.set_option("trace", 1)   # per-launch times on stderr
-    for k in ("stages", "warps"):
-        if os.environ.get("RQ_OPT_" + k.upper()):
-            eng.set_option(k, float(os.environ["RQ_OPT_" + k.upper()]))
     torch.cuda.synchronize(); _t0 = time.perf_counter()
     res, tm = eng.execute(plan, tabs)
     _wall = 1e3 * (time.perf_counter() - _t0)

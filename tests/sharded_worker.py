@@ -37,6 +37,11 @@ def main():
     eng.dist_init(rank, world, uid[0])
     if os.environ.get("RQ_TEST_TRACE"):
         eng.set_option("trace", 1)
+    progress = bool(os.environ.get("RQ_TEST_PROGRESS"))
+
+    def note(*a):
+        if progress:
+            print(f"[rank {rank}]", *a, file=sys.stderr, flush=True)
     data = tpch.generate(0.01, seed=42)
     failures = []
     for name, fact in CASES:
@@ -49,6 +54,7 @@ def main():
         try:
             # three executions: careful, careful (warm memos), replayed without host waits
             for rep in range(6):
+                note("sharded", name, "run", rep)
                 res, tm = eng.execute(Plan(d), handles, N.RQ_PLAN_SHARDED)
                 got = serialize_columns(res.columns, res.sql_types, res.sql_widths)
                 _, want = load_golden(name)
@@ -69,6 +75,7 @@ def main():
         handles = {n: eng.upload(n, c) for n, c in tabs.items()}
         try:
             for rep in range(6):
+                note("partitioned", name, "run", rep)
                 res, tm = eng.execute(Plan(d), handles, N.RQ_PLAN_PARTITIONED)
                 got = serialize_columns(res.columns, res.sql_types, res.sql_widths)
                 _, want = load_golden(name)
@@ -96,6 +103,7 @@ def main():
         tabs[fact] = shard_columns(tabs[fact], rank, world)
         handles = {n: eng.upload(n, c) for n, c in tabs.items()}
         try:
+            note("random plan", seed)
             res, tm = eng.execute(Plan(d), handles, N.RQ_PLAN_SHARDED)
             assert_same_relation(serialize_columns(res.columns, res.sql_types, res.sql_widths), want, d,
                                  f"random plan {seed} on {world} GPUs (rank {rank})")
@@ -123,6 +131,7 @@ def main():
         b[100] = 0
     t = eng.upload("t", {"a": np.arange(4096, dtype=np.int64), "b": b})
     try:
+        note("error agreement")
         eng.execute(Plan(dz), {"t": t}, N.RQ_PLAN_SHARDED)
         failures.append("division by zero on one shard was not reported on rank %d" % rank)
     except N.EngineError as e:

@@ -17,12 +17,27 @@ QUERIES = ["q1", "q6", "q3", "q5", "q10", "q12", "q14", "q19", "micro_join_avg",
 
 
 def test_all_tpch_queries_match_the_reference_engine_at_sf05(tmp_path):
+    _program_vs_program(tmp_path, 0.5, 1)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_gpus_n_drop_in_matches_the_reference_engine(tmp_path, world):
+    """`gpus=N` (the counterpart of the reference's `threads=N`, execute.h:454-474): resql-b200 starts one
+    process per GPU, shards the fact table of every select by row range and merges over NCCL; rank 0's
+    output files must equal the reference engine's."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _program_vs_program(tmp_path, 0.2, world)
+
+
+def _program_vs_program(tmp_path, sf, world):
     ref = os.path.join(ROOT, "oracle/_ref/resql-oracle")
     gpu = os.path.join(ROOT, "resql_b200/host/resql-b200")
     if not (os.path.exists(ref) and os.path.exists(gpu)):
         pytest.skip("needs the prebuilt reference and drop-in binaries (built where /root/reference exists)")
     from golden.queries import QUERIES as SQL
-    data = tpch.generate(0.5, seed=20260101)
+    data = tpch.generate(sf, seed=20260101)
     stm = []
     for name, schema in tpch.SCHEMAS.items():
         if name not in data:
@@ -42,7 +57,7 @@ def test_all_tpch_queries_match_the_reference_engine_at_sf05(tmp_path):
     del data
     outs = {}
     for tag, exe in (("ref", ref), ("gpu", gpu)):
-        args = [exe, "--quiet"] + loads
+        args = [exe, "--quiet"] + ([f"gpus={world}"] if tag == "gpu" and world > 1 else []) + loads
         if tag == "ref":
             args.append(f"threads={os.cpu_count() or 1}")
         for q in QUERIES:
@@ -59,4 +74,4 @@ def test_all_tpch_queries_match_the_reference_engine_at_sf05(tmp_path):
             assert keys(outs["gpu"][q]) == keys(outs["ref"][q]), q
             assert len(outs["gpu"][q]) == len(outs["ref"][q]), q
         else:
-            assert_same_relation(outs["gpu"][q], outs["ref"][q], d, f"{q} at SF0.5, resql-b200 vs the reference engine")
+            assert_same_relation(outs["gpu"][q], outs["ref"][q], d, f"{q} at SF{sf}, resql-b200 (gpus={world}) vs the reference engine")

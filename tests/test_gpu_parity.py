@@ -66,6 +66,34 @@ def test_sf1_q1_q6_match_oracle(engine):
         assert_same_relation(got, want, d, name + "@sf1")
 
 
+@pytest.mark.parametrize("case", ["fits", "outliers", "narrow_off"])
+def test_transfer_narrowing_is_exact(case, engine):
+    """Uploads from host buffers send 8-byte columns over PCIe in 1 or 4 bytes when every value fits and
+    widen them again on the device (host_narrow.h); the width is GUESSED from a sample. Values the sample
+    cannot see (a single wide or negative value at an unsampled row) must widen the transfer, not be
+    truncated: results stay identical to the oracle, and to the engine with narrowing switched off."""
+    data = tpch.generate(0.4, seed=4321, tables=("lineitem",))
+    li = data["lineitem"]
+    n = len(li["l_quantity"])
+    assert n >= 4 * 512 * 1024
+    if case == "outliers":
+        li["l_quantity"] = li["l_quantity"].copy(); li["l_quantity"][n // 2 + 1] = 300            # no longer one byte
+        li["l_discount"] = li["l_discount"].copy(); li["l_discount"][7] = -3                      # negative: not a byte
+        li["l_extendedprice"] = li["l_extendedprice"].copy(); li["l_extendedprice"][n - 5] = 1 << 33   # not int32
+        li["l_tax"] = li["l_tax"].copy(); li["l_tax"][n // 3 + 2] = -(1 << 40)
+    if case == "narrow_off":
+        engine.set_option("narrow", 0)
+    try:
+        for name in ("q1", "q6", "agg_nogroup_minmax", "agg_wrap"):
+            d = load_plan_dict(name)
+            tabs = plan_tables(d, data)
+            got, _ = _run(engine, d, tabs)
+            want = serialize_columns(*run_plan(d, tabs))
+            assert_same_relation(got, want, d, f"{name} ({case})")
+    finally:
+        engine.set_option("narrow", 1)
+
+
 def test_row_store_upload_matches_columns(sf001, engine):
     """rq_table_upload_rows (the bulk-insert hook) transposes reference DataBlocks on the GPU"""
     d = load_plan_dict("q1")
