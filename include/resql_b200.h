@@ -112,6 +112,17 @@ int rq_table_upload_rows(const char* name, int32_t n_cols, const int32_t* types,
                          const int32_t* widths, const int32_t* offsets, int32_t tuple_size,
                          int32_t n_blocks, const uint8_t* const* blocks,
                          const size_t* block_bytes, rq_table** out);
+/* Replicated tables on several GPUs (the build sides of a sharded plan: "small build sides are
+ * NCCL-broadcast over NVLink", north_star). One rank uploads the table from its host (rq_table_upload /
+ * rq_table_upload_rows); every other rank creates an empty table of the same schema and row count with
+ * rq_table_alloc; then ALL ranks call rq_table_broadcast (collective, after rq_dist_init): the
+ * contents of `root`'s table replace the others' over NVLink (ncclBroadcast of the column storage),
+ * and every rank takes the column statistics of its copy. N ranks cost one host upload instead of N.
+ * The reference has no counterpart (one process, one row store: dbdata.h:105-461). */
+int rq_table_alloc(const char* name, int32_t n_cols, const int32_t* types, const int32_t* widths,
+                   int64_t n_rows, rq_table** out);
+int rq_table_broadcast(rq_table* t, int32_t root);
+
 int64_t rq_table_rows(const rq_table* t);
 int rq_table_free(rq_table* t);
 

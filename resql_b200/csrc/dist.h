@@ -15,6 +15,7 @@ typedef int (*nccl_comm_init_rank_t)(void**, int, NcclId, int);
 typedef int (*nccl_comm_destroy_t)(void*);
 typedef int (*nccl_all_gather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*nccl_all_reduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_broadcast_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*nccl_send_t)(const void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*nccl_recv_t)(void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*nccl_group_t)(void);
@@ -29,6 +30,7 @@ struct Dist {
     nccl_comm_destroy_t comm_destroy = nullptr;
     nccl_all_gather_t all_gather = nullptr;
     nccl_all_reduce_t all_reduce = nullptr;
+    nccl_broadcast_t broadcast = nullptr;
     nccl_send_t send = nullptr;
     nccl_recv_t recv = nullptr;
     nccl_group_t group_start = nullptr, group_end = nullptr;
@@ -48,12 +50,13 @@ inline bool dist_load(Dist& d, std::string& err) {
     d.comm_destroy = (nccl_comm_destroy_t)dlsym(d.lib, "ncclCommDestroy");
     d.all_gather = (nccl_all_gather_t)dlsym(d.lib, "ncclAllGather");
     d.all_reduce = (nccl_all_reduce_t)dlsym(d.lib, "ncclAllReduce");
+    d.broadcast = (nccl_broadcast_t)dlsym(d.lib, "ncclBroadcast");
     d.send = (nccl_send_t)dlsym(d.lib, "ncclSend");
     d.recv = (nccl_recv_t)dlsym(d.lib, "ncclRecv");
     d.group_start = (nccl_group_t)dlsym(d.lib, "ncclGroupStart");
     d.group_end = (nccl_group_t)dlsym(d.lib, "ncclGroupEnd");
     d.get_error_string = (nccl_get_error_string_t)dlsym(d.lib, "ncclGetErrorString");
-    if (!d.get_unique_id || !d.comm_init_rank || !d.all_gather || !d.all_reduce || !d.send || !d.recv || !d.group_start || !d.group_end) {
+    if (!d.get_unique_id || !d.comm_init_rank || !d.all_gather || !d.all_reduce || !d.broadcast || !d.send || !d.recv || !d.group_start || !d.group_end) {
         err = "libnccl lacks required symbols";
         return false;
     }

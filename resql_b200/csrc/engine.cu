@@ -87,6 +87,8 @@ struct DevColumn {
     // lowering prove that a value fits in 32 bits and pick the narrow instruction forms.
     bool has_stats = false;
     int64_t vmin = 0, vmax = 0;
+    bool sorted = false;            // values are non-decreasing over the rows (taken with the statistics): range
+                                    // selections on this column restrict the scan to a row range
 };
 static uint64_t g_next_table_uid = 1;
 struct rq_table {
@@ -119,6 +121,9 @@ struct Options {
     bool direct_joins = true;             // direct-address join tables for dense unique integer keys
     bool replay = true;                   // predicted host reads (engine_exec.inl "host reads of device values")
     bool graphs = true;                   // replayed plans are captured into CUDA graphs
+    bool zone_skip = true;                // selections on sorted columns restrict the scan to a tile range
+    bool share_builds = true;             // sharded plans: replicated pure-scan builds are split over the ranks and all-reduced
+    int64_t share_min_rows = 1 << 20;
     bool narrow = true;                   // host-buffer uploads send 8-byte columns over PCIe in the narrowest exact width
     int up_threads = 0;                   // host-buffer uploads: converting threads (0 = all cores of this rank's share)
     int up_chunk_krows = 512;             //                      rows per conversion / DMA chunk, in 1024 rows
@@ -243,6 +248,9 @@ extern "C" int rq_set_option(const char* key, double value) {
     else if (k == "replay") o.replay = value != 0;
     else if (k == "graphs") o.graphs = value != 0;
     else if (k == "narrow") o.narrow = value != 0;
+    else if (k == "zone_skip") o.zone_skip = value != 0;
+    else if (k == "share_builds") o.share_builds = value != 0;
+    else if (k == "share_min_rows") o.share_min_rows = (int64_t)value;
     else if (k == "up_threads") o.up_threads = (int)value;
     else if (k == "up_chunk_krows") o.up_chunk_krows = std::max(1, std::min((int)value, 8192));
     else if (k == "trace") o.trace = value != 0;
@@ -595,22 +603,89 @@ extern "C" int rq_table_upload_rows(const char* name, int32_t n_cols, const int3
     return RQ_OK;
 }
 
-// min / max of every integer column (one pass over the resident data, on the engine stream)
+extern "C" int rq_table_alloc(const char* name, int32_t n_cols, const int32_t* types, const int32_t* widths,
+                              int64_t n_rows, rq_table** out) {
+    if (!E.init) return fail(RQ_ERR_NOT_INIT, "rq_table_alloc before rq_init");
+    if (!out || n_cols <= 0 || !types || !widths || n_rows < 0) return fail(RQ_ERR_INVALID, "rq_table_alloc: bad arguments");
+    std::unique_ptr<rq_table> t(new rq_table());
+    try {
+        t->name = name ? name : "";
+        t->n_rows = n_rows;
+        t->cap_rows = round_up(std::max<int64_t>(n_rows, 1), kPadRows);
+        for (int c = 0; c < n_cols; c++)
+            if (!valid_col(types[c], widths[c])) raise(RQ_ERR_INVALID, "rq_table_alloc: column %d has bad type/width %d/%d", c, types[c], widths[c]);
+        alloc_tile_major(*t, n_cols, [&](int c) { return types[c]; }, [&](int c) { return widths[c]; });
+        CK(cudaStreamSynchronize(E.stream));
+    } catch (RqError& e) {
+        return fail(e.code, "%s", e.msg.c_str());
+    }
+    *out = t.release();
+    return RQ_OK;
+}
+
+extern "C" int rq_table_broadcast(rq_table* t, int32_t root) {
+    if (!E.init) return fail(RQ_ERR_NOT_INIT, "rq_table_broadcast before rq_init");
+    if (!t || t->borrowed) return fail(RQ_ERR_INVALID, "rq_table_broadcast: needs a table the engine owns");
+    Dist& D = E.dist;
+    if (!D.comm || D.world <= 1) return RQ_OK;
+    if (root < 0 || root >= D.world) return fail(RQ_ERR_INVALID, "rq_table_broadcast: root %d of %d ranks", root, D.world);
+    try {
+        // the layout is a function of the schema and the row count, which all ranks passed alike: a
+        // rank that disagrees would make the collective hang or scribble, so the shapes are compared first
+        int64_t shape[4] = {t->n_rows, (int64_t)t->cols.size(), (int64_t)t->page_bytes, t->cap_rows};
+        for (auto& c : t->cols) shape[2] = shape[2] * 131 + c.width * 7 + c.type;
+        int64_t* d_shape = nullptr;
+        CK(dmalloc(&d_shape, sizeof(shape) * (size_t)(D.world + 1)));
+        CK(cudaMemcpyAsync(d_shape + 4 * D.world, shape, sizeof(shape), cudaMemcpyHostToDevice, E.stream));
+        int rc = D.all_gather(d_shape + 4 * D.world, d_shape, 4, 4 /* ncclInt64 */, D.comm, E.stream);
+        if (rc != 0) raise(RQ_ERR_NCCL, "ncclAllGather(table shape) failed: %s", D.get_error_string ? D.get_error_string(rc) : "?");
+        std::vector<int64_t> all(4 * (size_t)D.world);
+        CK(cudaMemcpyAsync(all.data(), d_shape, all.size() * 8, cudaMemcpyDeviceToHost, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+        dfree(d_shape);
+        for (int r = 0; r < D.world; r++)
+            if (memcmp(&all[4 * (size_t)r], shape, sizeof(shape)) != 0)
+                raise(RQ_ERR_INVALID, "rq_table_broadcast: rank %d holds a table of another shape (%lld rows) than rank %d (%lld rows)",
+                      r, (long long)all[4 * (size_t)r], D.rank, (long long)t->n_rows);
+        if (t->pax_base) {
+            const size_t bytes = (size_t)(t->cap_rows / kTile) * t->page_bytes;
+            rc = D.broadcast(t->pax_base, t->pax_base, bytes, 0 /* ncclInt8 */, root, D.comm, E.stream);
+            if (rc != 0) raise(RQ_ERR_NCCL, "ncclBroadcast(table pages) failed: %s", D.get_error_string ? D.get_error_string(rc) : "?");
+        }
+        for (auto& c : t->cols) {
+            if (c.type != RQ_STR) continue;
+            rc = D.broadcast(c.d, c.d, (size_t)t->cap_rows * c.width, 0, root, D.comm, E.stream);
+            if (rc != 0) raise(RQ_ERR_NCCL, "ncclBroadcast(string column) failed: %s", D.get_error_string ? D.get_error_string(rc) : "?");
+        }
+        for (auto& c : t->cols) c.has_stats = false;
+        compute_stats(*t);
+        CK(cudaStreamSynchronize(E.stream));
+        t->uid = g_next_table_uid++;          // new contents: plans recorded against the old ones do not apply
+    } catch (RqError& e) {
+        return fail(e.code, "%s", e.msg.c_str());
+    }
+    return RQ_OK;
+}
+
+// min / max and sortedness of every integer column (passes over the resident data, on the engine stream)
 static void compute_stats(rq_table& t) {
     if (t.n_rows <= 0) return;
     std::vector<int> idx;
     for (size_t c = 0; c < t.cols.size(); c++)
-        if (t.cols[c].type != RQ_STR && !t.cols[c].has_stats) idx.push_back((int)c);     // (host-converted columns bring their range)
+        if (t.cols[c].type != RQ_STR) idx.push_back((int)c);
     if (idx.empty()) return;
+    // per column: [min][max][sorted flag (int32) + pad]
     int64_t* d = nullptr;
-    CK(dmalloc(&d, idx.size() * 16));
-    std::vector<int64_t> h(idx.size() * 2);
-    for (size_t k = 0; k < idx.size(); k++) { h[2 * k] = INT64_MAX; h[2 * k + 1] = INT64_MIN; }
+    CK(dmalloc(&d, idx.size() * 24));
+    std::vector<int64_t> h(idx.size() * 3);
+    for (size_t k = 0; k < idx.size(); k++) { h[3 * k] = INT64_MAX; h[3 * k + 1] = INT64_MIN; h[3 * k + 2] = 1; }
     CK(cudaMemcpyAsync(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice, E.stream));
     for (size_t k = 0; k < idx.size(); k++) {
         const DevColumn& dc = t.cols[idx[k]];
         const int grid = (int)std::min<int64_t>((t.n_rows + 256 * 16 - 1) / (256 * 16), (int64_t)E.sm_count * 8);
-        rq_col_minmax<<<std::max(grid, 1), 256, 0, E.stream>>>(dc.d, dc.width, dc.tile_stride, t.n_rows, d + 2 * k);
+        if (!dc.has_stats)            // (host-converted columns bring their range)
+            rq_col_minmax<<<std::max(grid, 1), 256, 0, E.stream>>>(dc.d, dc.width, dc.tile_stride, t.n_rows, d + 3 * k);
+        rq_col_sorted<<<std::max(grid, 1), 256, 0, E.stream>>>(dc.d, dc.width, dc.tile_stride, t.n_rows, (int32_t*)(d + 3 * k + 2));
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, E.stream));
@@ -618,7 +693,8 @@ static void compute_stats(rq_table& t) {
     dfree(d);
     for (size_t k = 0; k < idx.size(); k++) {
         DevColumn& dc = t.cols[idx[k]];
-        dc.has_stats = true; dc.vmin = h[2 * k]; dc.vmax = h[2 * k + 1];
+        if (!dc.has_stats) { dc.has_stats = true; dc.vmin = h[3 * k]; dc.vmax = h[3 * k + 1]; }
+        dc.sorted = (int32_t)(h[3 * k + 2] & 0xffffffff) != 0;
     }
 }
 

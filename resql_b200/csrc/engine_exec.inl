@@ -837,6 +837,70 @@ static void check_flags(const char* what, const void* d_extra = nullptr) {
     if (*(unsigned long long*)(E.h_flags + 4) != 0) throw NeedExpand{};
 }
 
+// ---- tile ranges (KParams::tile_range) ----------------------------------------------------------
+// (1) Zone skipping. A selection `col CMP const` / `lo <= col <= hi` on a source column whose values
+// are non-decreasing over the rows (DevColumn::sorted, taken with the upload statistics: o_orderkey,
+// l_orderkey, any surrogate key of a table loaded in key order) can only pass inside one row range.
+// Two binary searches on the device (rq_sorted_tile_range) turn it into the tile range the scan
+// visits; the selection itself stays in the program, so the result is exact. This is what makes a
+// pruned build (prune_build_by_probe_stats) cheap on a sharded plan: a rank whose lineitem shard
+// covers 1/8 of the order keys reads 1/8 of orders instead of filtering all of it.
+// (2) Shared builds. A join build over a table that is complete on every rank and whose program is
+// the same on every rank is split: rank r scans tiles [T*r/W, T*(r+1)/W) and the direct-address
+// tables (bitmap; disjoint bits because the keys are unique) are summed with one ncclAllReduce.
+struct SharedBuild { bool active = false; };
+static SharedBuild g_shared_build;       // set by run_pipeline for the pipeline it is about to run
+struct TileRangeBuf {
+    uint32_t* d = nullptr;
+    ~TileRangeBuf() { if (d) dfree(d); }     // (stream-ordered: after the launches that read it)
+};
+static constexpr int64_t kZoneSkipMinRows = 1 << 18;
+
+static void restrict_tiles(const Lowerer& L, KParams& P, const rq_table& src, TileRangeBuf& buf, bool share, rq_timings* tm) {
+    if (src.n_rows < 0 || src.n_rows < kZoneSkipMinRows) { if (!share) return; }
+    if (src.n_rows < 0) return;
+    const uint32_t n_tiles = (uint32_t)((src.n_rows + kTile - 1) / kTile);
+    uint32_t init[2] = {0u, n_tiles};
+    if (share) {
+        const uint64_t W = (uint64_t)E.dist.world, r = (uint64_t)E.dist.rank;
+        init[0] = (uint32_t)((uint64_t)n_tiles * r / W);
+        init[1] = (uint32_t)((uint64_t)n_tiles * (r + 1) / W);
+    }
+    struct Zone { int col; int64_t lo, hi; };
+    std::vector<Zone> zones;
+    std::vector<int> src_of(P.n_cols, -1);
+    for (size_t k = 0; k < L.staged_of_col.size(); k++)
+        if (src.cols[k].type != RQ_STR && L.staged_of_col[k] >= 0) src_of[L.staged_of_col[k]] = (int)k;
+    for (const HUnit& u : L.prog) {
+        if ((u.op != H_FCMP && u.op != H_FRANGE) || u.x.kind != S_COL || u.x.idx >= (uint16_t)P.n_cols) continue;
+        const int sc = src_of[u.x.idx];
+        if (sc < 0 || !src.cols[sc].sorted) continue;
+        int64_t lo = INT64_MIN, hi = INT64_MAX;
+        if (u.op == H_FRANGE) {
+            lo = u.imm;
+            const __int128 h = (__int128)u.imm + (__int128)(uint64_t)u.imm2;
+            hi = h > (__int128)INT64_MAX ? INT64_MAX : (int64_t)h;
+        } else if (u.gop == D_GE) lo = u.imm;
+        else if (u.gop == D_GT) { if (u.imm == INT64_MAX) continue; lo = u.imm + 1; }
+        else if (u.gop == D_LE) hi = u.imm;
+        else if (u.gop == D_LT) { if (u.imm == INT64_MIN) continue; hi = u.imm - 1; }
+        else if (u.gop == D_EQ) { lo = u.imm; hi = u.imm; }
+        else continue;
+        zones.push_back({sc, lo, hi});
+    }
+    if (zones.empty() && !share) return;
+    CK(dmalloc(&buf.d, 8));
+    upload_small(buf.d, init, 8);
+    for (const Zone& z : zones) {
+        const DevColumn& dc = src.cols[z.col];
+        rq_sorted_tile_range<<<1, 32, 0, E.stream>>>(dc.d, dc.width, dc.tile_stride ? dc.tile_stride : (int64_t)kTile * dc.width,
+                                                      src.n_rows, z.lo, z.hi, buf.d);
+        if (tm) tm->kernel_launches++;
+    }
+    CK(cudaGetLastError());
+    P.tile_range = buf.d;
+}
+
 // ---- one pipeline -------------------------------------------------------------------------
 struct SplitPipes {
     std::vector<rq_node> a_nodes, b_nodes;
@@ -998,6 +1062,37 @@ static void run_pipeline_partitioned(const rq_plan& plan, const rq_pipeline& pl_
                                      std::vector<std::pair<size_t, int>>& ev_used, double& lower_ms,
                                      const rq_table* src_override, bool first_probe_aligned, PipeOut& result);
 
+// May build pipeline `pi` of a sharded plan be split over the ranks ("shared builds" above)? Every rank
+// must take the same decisions and meet the same errors up to and including this pipeline, so all of
+// pipelines 0..pi must be rank-invariant: scans of tables that are complete on every rank (not the
+// fact table, which is the one the merged pipeline scans), probing only rank-invariant builds, and
+// pruned (prune_build_by_probe_stats) only by statistics of complete tables. The pipeline itself must
+// be a plain scan of a table large enough to be worth a collective.
+static bool build_is_shareable(const rq_plan& plan, int pi) {
+    if (!E.opt.share_builds || !(plan.flags & RQ_PLAN_SHARDED) || (plan.flags & RQ_PLAN_PARTITIONED)) return false;
+    if (!E.dist.comm || E.dist.world <= 1) return false;
+    int merge = plan.n_pipelines - 1;
+    for (int q = 0; q < plan.n_pipelines; q++) if (plan.pipelines[q].sink_kind == RQ_SINK_AGG) merge = q;
+    const rq_pipeline& mp = plan.pipelines[merge];
+    const int fact = mp.source_kind == RQ_SRC_TABLE ? mp.source_id : -1;
+    if (fact < 0) return false;         // the sharded table is not scanned directly: nothing is known
+    for (int q = 0; q <= pi; q++) {
+        const rq_pipeline& p = plan.pipelines[q];
+        if (p.source_kind != RQ_SRC_TABLE || p.source_id == fact || p.source_id < 0 || p.source_id >= plan.n_tables) return false;
+        if (p.sink_kind != RQ_SINK_BUILD) return false;
+        for (int i = 0; i < p.n_nodes; i++)
+            if (p.nodes[i].op == RQ_OP_PROBE && (q == pi || p.nodes[i].a < 0 || p.nodes[i].a >= q)) return false;
+        for (int r = q + 1; r < plan.n_pipelines; r++) {
+            const rq_pipeline& pr = plan.pipelines[r];
+            bool probes_q = false;
+            for (int i = 0; i < pr.n_nodes; i++) probes_q |= pr.nodes[i].op == RQ_OP_PROBE && pr.nodes[i].a == q;
+            if (probes_q && pr.source_kind == RQ_SRC_TABLE && pr.source_id == fact) return false;
+        }
+    }
+    const rq_table* t = plan.tables[plan.pipelines[pi].source_id];
+    return t && t->n_rows >= E.opt.share_min_rows;
+}
+
 static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs,
                          const char* d_strpool, rq_timings* tm, size_t& ev_idx,
                          std::vector<std::pair<size_t, int>>& ev_used, double& lower_ms,
@@ -1012,6 +1107,8 @@ static void run_pipeline(const rq_plan& plan, int pi, std::vector<PipeOut>& outs
         layout_build_payload(plan, pi, *pl, bl);
         pl = &bl.pl;
     }
+    g_shared_build.active = !part && pl->sink_kind == RQ_SINK_BUILD && build_is_shareable(plan, pi);
+    struct Reset { ~Reset() { g_shared_build.active = false; } } reset_share;
     if (part)
         run_pipeline_partitioned(plan, *pl, pi, outs, d_strpool, tm, ev_idx, ev_used, lower_ms, nullptr, false, outs[pi]);
     else
@@ -1245,6 +1342,9 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
         }
         P.l2_prefetch = (P.n_cols > 0 && P.n_probes == 0 && impl != IMPL_BUILD && impl != IMPL_HASHAGG) ? 1 : 0;
         lower_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        // zone skipping on sorted source columns (table scans only; a shared build adds its rank share below)
+        TileRangeBuf tile_buf;
+        if (pl.source_kind == RQ_SRC_TABLE && !src_override && E.opt.zone_skip) restrict_tiles(L, P, *src, tile_buf, false, tm);
 
         CK(cudaMemsetAsync(E.flags, 0, 32, E.stream));
         if (impl == IMPL_REGAGG || impl == IMPL_LOWAGG) {
@@ -1339,7 +1439,35 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
                         if (nv > 0) CK(dmalloc(&ht->d.darr, (size_t)dsize * nv * 8));    // (not cleared: the bitmap says what is valid)
                         P.ht = ht->d;
                         CK(cudaMemsetAsync(E.flags, 0, 32, E.stream));
+                        const bool shared = g_shared_build.active && nv == 0 && pl.source_kind == RQ_SRC_TABLE && !src_override;
+                        TileRangeBuf share_buf;
+                        const uint32_t* zone_range = P.tile_range;
+                        if (shared) {
+                            // this rank's share of the tiles (intersected with the zone range, if any)
+                            P.tile_range = nullptr;
+                            restrict_tiles(L, P, *src, share_buf, true, tm);
+                        }
                         launch_pipeline(P, 0, rows_bound, tm, is_scan, ev_idx, ev_used);
+                        if (shared) {
+                            // bitmaps are summed (unique keys: disjoint bits), and so are the flag words, so that
+                            // every rank sees the same entry count, error and duplicate flags and decides alike;
+                            // a key present on two ranks shows as population count != entry count
+                            Dist& D = E.dist;
+                            const EventPair ep = event_pair(ev_idx);
+                            ev_used.push_back({ev_idx, 2});
+                            ev_idx++;
+                            record_event(ep.a);
+                            int rc = D.all_reduce(ht->d.dbits, ht->d.dbits, words, 3 /* ncclUint32 */, 0 /* ncclSum */, D.comm, E.stream);
+                            if (rc == 0) rc = D.all_reduce(E.flags, E.flags, 4, 5 /* ncclUint64 */, 0, D.comm, E.stream);
+                            if (rc != 0) raise(RQ_ERR_NCCL, "ncclAllReduce(shared build) failed: %s", D.get_error_string ? D.get_error_string(rc) : "?");
+                            CK(cudaMemsetAsync(E.flags + 12, 0, 8, E.stream));
+                            rq_popcount_words<<<(unsigned)std::min<size_t>((words + 255) / 256, 1184), 256, 0, E.stream>>>(ht->d.dbits, words, (unsigned long long*)(E.flags + 12));
+                            rq_shared_build_check<<<1, 32, 0, E.stream>>>(E.flags);
+                            if (tm) tm->kernel_launches += 2;
+                            CK(cudaGetLastError());
+                            record_event(ep.b);
+                        }
+                        P.tile_range = zone_range;      // (a fallback to the hash form below builds the whole table locally)
                         check_flags("join build pipeline");
                         if (E.h_flags[3] == 0) {
                             ht->entries = *(unsigned long long*)(E.h_flags + 6);
@@ -2464,6 +2592,9 @@ static uint64_t plan_signature(const rq_plan& plan) {
     mixin(&E.dist.world, sizeof E.dist.world);
     mixin(&E.opt.split_min_rows, sizeof E.opt.split_min_rows);
     mixin(&E.opt.split_frac, sizeof E.opt.split_frac);
+    mixin(&E.opt.zone_skip, sizeof E.opt.zone_skip);
+    mixin(&E.opt.share_builds, sizeof E.opt.share_builds);
+    mixin(&E.opt.share_min_rows, sizeof E.opt.share_min_rows);
     mixin(&E.opt.stages, sizeof E.opt.stages);
     mixin(&E.opt.warps, sizeof E.opt.warps);
     return h;

@@ -169,6 +169,7 @@ struct KParams {
     int32_t        l2_prefetch;         // pull the next tile into L2 while the current one is processed
                                         // (pure scans only: pipelines with hash structures want L2 for those)
     int32_t        pad0_;
+    const uint32_t* tile_range;         // if non-null: only tiles [tile_range[0], tile_range[1]) are scanned
     int32_t        n_cols;              // staged (TMA) columns
     // A tile is staged by one bulk copy per RUN: a contiguous byte range of the source that holds
     // the tile's chunk of one column (plain column arrays) or of several adjacent columns (tables

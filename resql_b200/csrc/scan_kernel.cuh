@@ -309,8 +309,16 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     if (P.n_rows_ptr) { n_rows = *P.n_rows_ptr; if (n_rows > P.n_rows_cap) n_rows = P.n_rows_cap; }
     // tile indices are 32-bit (2^32 tiles = 10^12 rows): cheap to keep or recompute under register pressure
     const uint32_t n_tiles = (uint32_t)((n_rows + kTile - 1) / kTile);
+    // a launch may be restricted to the tiles [tile_range[0], tile_range[1]) of the source: the row
+    // range a selection on a sorted column can match at all (zone skipping), or one rank's share of a
+    // replicated build table (engine_exec.inl "tile ranges")
+    uint32_t t_end = n_tiles, t_begin = 0;
+    if (P.tile_range) {
+        t_begin = min(P.tile_range[0], n_tiles);
+        t_end = max(min(P.tile_range[1], n_tiles), t_begin);
+    }
     const uint32_t stride = gridDim.x * W;
-    const uint32_t first = blockIdx.x * W + warp;
+    const uint32_t first = t_begin + blockIdx.x * W + warp;
     const int NA = P.na, NK = P.nk;
     const int sink = P.sink;
 
@@ -449,14 +457,14 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     };
     if (n_cols > 0) {
         for (int s = 0; s < S; s++)
-            if ((uint64_t)first + (uint64_t)s * stride < n_tiles) issue(first + s * stride, s);
+            if ((uint64_t)first + (uint64_t)s * stride < t_end) issue(first + s * stride, s);
     }
 
     int s = 0;
     uint32_t phase = 0;
     const bool hash_sink = (GR == 0) && (sink == IMPL_BUILD || sink == IMPL_HASHAGG);
     // (the tile counter cannot wrap: first + k * stride < n_tiles + stride <= 2^32 is checked on the host)
-    for (uint32_t tile = first; tile < n_tiles; tile += stride) {
+    for (uint32_t tile = first; tile < t_end; tile += stride) {
         // a full hash table makes the host regrow it and rerun: stop early
         if (hash_sink && *(volatile int32_t*)P.ht_full) {
             // the bulk copies already issued into this warp's stages must land before the CTA may
@@ -466,7 +474,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
                 uint32_t dphase = phase;
                 for (int k = 0; k < S; k++) {
                     const uint64_t t = (uint64_t)tile + (uint64_t)k * stride;
-                    if (t < n_tiles && (uint32_t)t != guarded_tile) mbar_wait_s(bars + ds * 8, dphase);
+                    if (t < t_end && (uint32_t)t != guarded_tile) mbar_wait_s(bars + ds * 8, dphase);
                     if (++ds == S) { ds = 0; dphase ^= 1u; }
                 }
             }
@@ -498,7 +506,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         // hide the DRAM latency otherwise)
         if (P.l2_prefetch && elect_one()) {
             const uint64_t nt = (uint64_t)tile + (uint64_t)S * stride;
-            if (nt < n_tiles && (uint32_t)nt != guarded_tile)
+            if (nt < t_end && (uint32_t)nt != guarded_tile)
                 for (int c = 0; c < n_runs; c++)
                     tma_prefetch_l2(P.run_ptr[c] + (size_t)(uint32_t)nt * P.run_stride[c], P.run_bytes[c]);
         }
@@ -1309,7 +1317,7 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
         __syncwarp();
         if (n_cols > 0) {
             const uint64_t nt = (uint64_t)tile + (uint64_t)S * stride;
-            if (nt < n_tiles) issue((uint32_t)nt, s);
+            if (nt < t_end) issue((uint32_t)nt, s);
         }
         if (++s == S) { s = 0; phase ^= 1u; }
         if (GR > 0 && P.flush_tiles > 0 && --tiles_to_flush == 0) {
@@ -1398,6 +1406,80 @@ __device__ __forceinline__ const unsigned char* col_row(const unsigned char* col
 struct SmallBytes { unsigned char b[64]; };
 __global__ void rq_store_bytes(unsigned char* dst, SmallBytes v, int n) {
     if ((int)threadIdx.x < n) dst[threadIdx.x] = v.b[threadIdx.x];
+}
+
+// is an integer column non-decreasing over the rows? *flag is cleared when a descent is found
+__global__ void rq_col_sorted(const unsigned char* col, int width, int64_t tile_stride, int64_t n, int32_t* flag) {
+    int seen = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned char* p = col_row(col, width, tile_stride, i);
+        const unsigned char* q = col_row(col, width, tile_stride, i + 1);
+        int64_t a, b;
+        if (width == 8) { a = *reinterpret_cast<const int64_t*>(p); b = *reinterpret_cast<const int64_t*>(q); }
+        else if (width == 4) { a = *reinterpret_cast<const int32_t*>(p); b = *reinterpret_cast<const int32_t*>(q); }
+        else { a = *p; b = *q; }
+        // one writer is enough, and nobody needs to look further once the answer is known (an unsorted
+        // column would otherwise make every thread hammer the same word)
+        if (a > b) { *flag = 0; return; }
+        if ((++seen & 15) == 0 && *(volatile int32_t*)flag == 0) return;
+    }
+}
+
+// tiles of a non-decreasing column that can hold a value in [lo, hi]: out = [first tile, last tile + 1),
+// intersected with the range already there (several selections on sorted columns). One warp, 33-ary
+// search: every step costs one round of 32 independent loads instead of a chain of dependent ones.
+__global__ void rq_sorted_tile_range(const unsigned char* col, int width, int64_t tile_stride, int64_t n,
+                                     int64_t lo, int64_t hi, uint32_t* out) {
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    auto val = [&](int64_t i) -> int64_t {
+        const unsigned char* p = col_row(col, width, tile_stride, i);
+        if (width == 8) return *reinterpret_cast<const int64_t*>(p);
+        if (width == 4) return *reinterpret_cast<const int32_t*>(p);
+        return *p;
+    };
+    // first row whose value is >= key (upper = false) or > key (upper = true)
+    auto bound = [&](int64_t key, bool upper, int64_t a, int64_t b) -> int64_t {
+        while (a < b) {
+            const int64_t step = (b - a + 32) / 33;
+            const int64_t p = a + (int64_t)(lane + 1) * step - 1;
+            bool left = false;
+            if (p < b) { const int64_t v = val(p); left = upper ? (v <= key) : (v < key); }
+            const unsigned m = __ballot_sync(kFull, left);
+            const int c = __popc(m);               // positions are increasing and `left` is monotone: lanes 0..c-1
+            const int64_t na = c > 0 ? a + (int64_t)c * step : a;
+            const int64_t pc = a + (int64_t)(c + 1) * step - 1;
+            const int64_t nb = (c < 32 && pc < b) ? pc : b;
+            a = na; b = nb;
+        }
+        return a;
+    };
+    const int64_t r0 = bound(lo, false, 0, n);
+    const int64_t r1 = bound(hi, true, r0, n);
+    if (lane == 0) {
+        const uint32_t t0 = (uint32_t)(r0 / kTile), t1 = (uint32_t)((r1 + kTile - 1) / kTile);
+        if (t0 > out[0]) out[0] = t0;
+        if (t1 < out[1]) out[1] = t1;
+        if (out[1] < out[0]) out[1] = out[0];
+    }
+}
+
+// shared builds (engine_exec.inl "tile ranges"): population count of the summed bitmap ...
+__global__ void rq_popcount_words(const uint32_t* w, size_t n, unsigned long long* out) {
+    unsigned long long c = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c += __popc(w[i]);
+    c = (unsigned long long)warp_reduce((int64_t)c, 1);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+// ... must equal the summed entry count (flags words 6-7), else two ranks inserted the same key: raise
+// the duplicate flag (word 3) so that every rank falls back to the hash form
+__global__ void rq_shared_build_check(int32_t* flags) {
+    if (threadIdx.x != 0) return;
+    const unsigned long long entries = *reinterpret_cast<unsigned long long*>(flags + 6);
+    const unsigned long long bits = *reinterpret_cast<unsigned long long*>(flags + 12);
+    if (entries != bits) flags[3] = 1;
+    if (flags[2] > 1) flags[2] = 1;         // (error flags were summed over the ranks)
+    if (flags[3] > 1) flags[3] = 1;
 }
 
 // min / max of an integer column (upload-time statistics): out[0] = min, out[1] = max

@@ -680,8 +680,15 @@ static rq_table* mirrorTable ( TableDesc& t, bool shard = false ) {
     }
     rq_table* h = nullptr;
     Timer tm;
+    /* gpus=N: a table that is complete on every rank crosses PCIe once, on rank 0, and reaches the other
+     * GPUs over NVLink (rq_table_broadcast); all ranks mirror the same tables in the same order */
+    const bool replicate = !shard && group().world > 1;
+    if ( replicate && group().rank != 0 ) {
+        check ( rq_table_alloc ( t.name.c_str(), (int) t.attrs.size(), types.data(), widths.data(), (int64_t) total, &h ) );
+    } else
     check ( rq_table_upload_rows ( t.name.c_str(), (int) t.attrs.size(), types.data(), widths.data(), offsets.data(),
                                    (int) s._tupSize, (int) blocks.size(), blocks.data(), sizes.data(), &h ) );
+    if ( replicate ) check ( rq_table_broadcast ( h, 0 ) );
     lastLoadMs() += tm.get();
     mirrors() [ key ] = h;
     return h;
@@ -758,6 +765,19 @@ std::unique_ptr < SelectResult > executeSelectPlanGpu ( RelOperator*  root,
                 const char* dev = getenv ( "RESQL_B200_DEVICE" );
                 rqshim::check ( rq_init ( dev ? atoi ( dev ) : grp.rank ) );
                 rqshim::engineUp() = true;
+                /* engine knobs (rq_set_option) for tests and experiments: RESQL_B200_OPTIONS="key=value,key=value" */
+                if ( const char* opts = getenv ( "RESQL_B200_OPTIONS" ) ) {
+                    std::string o ( opts );
+                    size_t pos = 0;
+                    while ( pos < o.size() ) {
+                        size_t end = o.find ( ',', pos );
+                        if ( end == std::string::npos ) end = o.size();
+                        const std::string kv = o.substr ( pos, end - pos );
+                        const size_t eq = kv.find ( '=' );
+                        if ( eq != std::string::npos ) rqshim::check ( rq_set_option ( kv.substr ( 0, eq ).c_str(), atof ( kv.substr ( eq + 1 ).c_str() ) ) );
+                        pos = end + 1;
+                    }
+                }
             }
             if ( grp.world > 1 && !grp.joined ) {
                 /* rank 0 creates the NCCL id and publishes it through a file, the others wait for it */

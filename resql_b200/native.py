@@ -116,6 +116,9 @@ def load():
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32,
                                          C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                          C.POINTER(C.c_void_p)]
+    lib.rq_table_alloc.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64,
+                                   C.POINTER(C.c_void_p)]
+    lib.rq_table_broadcast.argtypes = [C.c_void_p, C.c_int32]
     lib.rq_table_rows.argtypes = [C.c_void_p]
     lib.rq_table_rows.restype = C.c_int64
     lib.rq_table_free.argtypes = [C.c_void_p]
@@ -154,7 +157,7 @@ def debug_lower(plan, pipeline, impl, col_types, col_widths, col_min=None, col_m
 
 
 ABI_SYMBOLS = ["rq_init", "rq_shutdown", "rq_last_error", "rq_stream", "rq_set_option", "rq_dist_unique_id",
-               "rq_dist_init", "rq_table_upload", "rq_table_upload_rows", "rq_table_rows",
+               "rq_dist_init", "rq_table_upload", "rq_table_upload_rows", "rq_table_alloc", "rq_table_broadcast", "rq_table_rows",
                "rq_table_free", "rq_plan_execute", "rq_result_free"]
 
 _NP_OF = {RQ_I8: np.uint8, RQ_I32: np.int32, RQ_I64: np.int64}
@@ -256,6 +259,29 @@ class Engine:
         flags = RQ_DEVICE_PTR | (RQ_BORROW if borrow else 0)
         self._check(self.lib.rq_table_upload(name.encode(), len(names), cols, n_rows, flags, C.byref(h)))
         return Table(h, names, keepalive=columns)
+
+    def alloc(self, name, schema, n_rows):
+        """empty table: schema = ordered dict name -> (rq_type, width); filled by broadcast()"""
+        names = list(schema.keys())
+        ty = (C.c_int32 * len(names))(*[schema[n][0] for n in names])
+        wi = (C.c_int32 * len(names))(*[schema[n][1] for n in names])
+        h = C.c_void_p()
+        self._check(self.lib.rq_table_alloc(name.encode(), len(names), ty, wi, n_rows, C.byref(h)))
+        return Table(h, names)
+
+    def broadcast(self, table, root=0):
+        """collective: every rank's `table` gets the contents of rank `root`'s (NVLink, ncclBroadcast)"""
+        self._check(self.lib.rq_table_broadcast(table.handle, root))
+        return table
+
+    def upload_replicated(self, name, columns, root=0, rank=0):
+        """columns (host numpy, as for upload) are read on `root` only; other ranks only use dtype / shape"""
+        if rank == root:
+            t = self.upload(name, columns)
+        else:
+            schema = {n: _phys(np.asarray(a)) for n, a in columns.items()}
+            t = self.alloc(name, schema, len(next(iter(columns.values()))))
+        return self.broadcast(t, root)
 
     def upload_rows(self, name, names, types, widths, offsets, tuple_size, blocks):
         """Row-store upload (reference DataBlocks): blocks = list of bytes-like objects."""

@@ -67,6 +67,58 @@ def main():
         finally:
             for h in handles.values():
                 h.free()
+    # replicated tables uploaded once (rank 0) and broadcast over NVLink: the other ranks never see the data
+    for name, fact in [("q3", "lineitem"), ("q10", "lineitem"), ("join_dups_agg", "orders")]:
+        d = load_plan_dict(name)
+        tabs = plan_tables(d, data)
+        if fact not in tabs:
+            continue
+        handles = {}
+        for n, c in tabs.items():
+            if n == fact:
+                handles[n] = eng.upload(n, shard_columns(c, rank, world))
+            else:
+                import numpy as np
+                blind = c if rank == 0 else {k: np.zeros_like(v) for k, v in c.items()}
+                handles[n] = eng.upload_replicated(n, blind, 0, rank)
+        try:
+            res, tm = eng.execute(Plan(d), handles, N.RQ_PLAN_SHARDED)
+            got = serialize_columns(res.columns, res.sql_types, res.sql_widths)
+            _, want = load_golden(name)
+            assert_same_relation(got, want, d, f"{name} with broadcast build tables on {world} GPUs (rank {rank})")
+            if rank == 0:
+                print(f"broadcast {name}: {res.n_rows} rows identical on {world} GPUs", flush=True)
+        except Exception as e:  # noqa: BLE001
+            failures.append(f"broadcast {name}: {e}")
+        finally:
+            for h in handles.values():
+                h.free()
+    # shared builds (replicated pure-scan build sides split over the ranks, bitmaps all-reduced), forced
+    # on these small tables; q3's customer build qualifies
+    eng.set_option("share_min_rows", 0)
+    for name, fact in [("q3", "lineitem"), ("join_orders_lineitem", "lineitem"), ("join_dups_agg", "orders"), ("join_cust_orders", "orders")]:
+        d = load_plan_dict(name)
+        tabs = plan_tables(d, data)
+        if fact not in tabs:
+            continue
+        tabs[fact] = shard_columns(tabs[fact], rank, world)
+        handles = {n: eng.upload(n, c) for n, c in tabs.items()}
+        try:
+            for rep in range(5):
+                note("shared-build", name, "run", rep)
+                res, tm = eng.execute(Plan(d), handles, N.RQ_PLAN_SHARDED)
+                got = serialize_columns(res.columns, res.sql_types, res.sql_widths)
+                _, want = load_golden(name)
+                assert_same_relation(got, want, d, f"{name} with shared builds on {world} GPUs (rank {rank}, run {rep})")
+            if rank == 0:
+                print(f"shared-build {name}: {res.n_rows} rows identical on {world} GPUs, nccl_ms={tm.nccl_ms:.3f} "
+                      f"host_syncs={tm.host_syncs}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            failures.append(f"shared-build {name}: {e}")
+        finally:
+            for h in handles.values():
+                h.free()
+    eng.set_option("share_min_rows", 1 << 20)
     # RQ_PLAN_PARTITIONED: EVERY table is a row range; build and probe rows meet on the rank that owns
     # hash(join key) (all-to-all), groups are merged on the rank that owns hash(group key)
     for name in PART_CASES:

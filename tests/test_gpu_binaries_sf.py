@@ -31,7 +31,20 @@ def test_gpus_n_drop_in_matches_the_reference_engine(tmp_path, world):
     _program_vs_program(tmp_path, 0.2, world)
 
 
-def _program_vs_program(tmp_path, sf, world):
+def test_gpus_2_with_shared_builds_forced(tmp_path):
+    """the same with every eligible build split over the ranks and all-reduced (tables far below the
+    size at which the engine does that by itself)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    # (SF0.2, not smaller: at SF0.1 the REFERENCE loses matches of Q5 - its ht_get continues a probe behind
+    # the last slot of the table without wrapping, qlib/hash.h:438-441, so a chain of hash-equal entries
+    # that crosses the end of the table is cut short; an independent pandas evaluation agrees with the
+    # GPU result there. DESIGN.md section 4 "reference defects")
+    _program_vs_program(tmp_path, 0.2, 2, options="share_min_rows=0")
+
+
+def _program_vs_program(tmp_path, sf, world, options=None):
     ref = os.path.join(ROOT, "oracle/_ref/resql-oracle")
     gpu = os.path.join(ROOT, "resql_b200/host/resql-b200")
     if not (os.path.exists(ref) and os.path.exists(gpu)):
@@ -62,7 +75,10 @@ def _program_vs_program(tmp_path, sf, world):
             args.append(f"threads={os.cpu_count() or 1}")
         for q in QUERIES:
             args += [f"out {tmp_path / (tag + '_' + q + '.out')}", " ".join(SQL[q].split())]
-        r = subprocess.run(args, capture_output=True, text=True, timeout=900)
+        env = dict(os.environ)
+        if options and tag == "gpu":
+            env["RESQL_B200_OPTIONS"] = options
+        r = subprocess.run(args, capture_output=True, text=True, timeout=900, env=env)
         assert r.stdout.count("#select") == len(QUERIES), f"{tag}: {r.stdout[-1500:]}{r.stderr[-1500:]}"
         outs[tag] = {q: [l for l in (tmp_path / f"{tag}_{q}.out").read_text().split("\n")[1:] if l] for q in QUERIES}
     for q in QUERIES:

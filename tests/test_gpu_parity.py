@@ -94,6 +94,53 @@ def test_transfer_narrowing_is_exact(case, engine):
         engine.set_option("narrow", 1)
 
 
+def _range_plan(filters):
+    """select count(*), sum(v), min(k), max(k) from t where <filters on k>; filters = [(op, const)]"""
+    nodes = [[1, 0, 0, 0, 0], [1, 1, 0, 0, 0]]
+    for op, c in filters:
+        nodes.append([2, 0, 0, 0, int(c)])
+        nodes.append([op, 0, len(nodes) - 1, 0, 0])
+        nodes.append([22, len(nodes) - 1, 0, 0, 0])
+    return {"tables": [{"name": "t", "columns": ["k", "v"]}],
+            "pipelines": [{"source_kind": 1, "source_id": 0, "source_id2": 0, "sink_kind": 1, "size_hint": 0, "nodes": nodes, "args": [],
+                           "keys": [], "vals": [[0, 2, 4, 0], [1, 1, 4, 0], [0, 3, 4, 0], [0, 4, 4, 0]]},
+                          {"source_kind": 2, "source_id": 0, "source_id2": 0, "sink_kind": 3, "size_hint": 0,
+                           "nodes": [[1, 0, 0, 0, 0], [1, 1, 0, 0, 0], [1, 2, 0, 0, 0], [1, 3, 0, 0, 0]], "args": [], "keys": [],
+                           "vals": [[0, 0, 4, 0], [1, 0, 4, 0], [2, 0, 4, 0], [3, 0, 4, 0]]}],
+            "order": [], "limit": -1, "strpool": "", "result_names": ["n", "s", "lo", "hi"], "result_types": ["BIGINT"] * 4}
+
+
+@pytest.mark.parametrize("dtype", ["int64", "int32"])
+def test_zone_skipping_on_sorted_columns_is_exact(dtype, engine):
+    """A selection on a column whose values are non-decreasing over the rows restricts the scan to a
+    tile range (engine_exec.inl "tile ranges"); the result must be the one of the full scan. Keys with
+    duplicates and gaps, ranges that start / end inside tiles, empty and out-of-domain ranges."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    n = 1_500_003
+    k = np.cumsum(rng.integers(0, 3, n)).astype(dtype) + 1000            # sorted, duplicates, gaps
+    v = rng.integers(-10**9, 10**9, n).astype(np.int64)
+    t = {"t": {"k": k, "v": v}}
+    LT, LE, GT, GE, EQ = 10, 11, 12, 13, 14
+    lo, hi, mid = int(k[0]), int(k[-1]), int(k[n // 2])
+    cases = [[(GE, mid), (LE, mid + 5000)], [(GT, mid), (LT, mid + 3)], [(EQ, int(k[777_777]))], [(EQ, mid), (EQ, mid + 1)],
+             [(GE, lo), (LE, hi)], [(GT, hi)], [(LT, lo)], [(LE, lo)], [(GE, hi)], [(GE, hi + 10)], [(LE, lo - 10)],
+             [(GE, int(k[255])), (LE, int(k[256]))], [(GE, int(k[n - 300]))], [(LE, int(k[300]))], [(GT, -2**31), (LT, 2**31 - 1)]]
+    for zs in (1, 0):
+        engine.set_option("zone_skip", zs)
+        try:
+            h = engine.upload("t", t["t"])
+            for f in cases:
+                d = _range_plan(f)
+                res, _ = engine.execute(Plan(d), {"t": h})
+                got = serialize_columns(res.columns, res.sql_types, res.sql_widths)
+                want = serialize_columns(*run_plan(d, t))
+                assert got == want, f"filters {f} zone_skip={zs}: {got} != {want}"
+            h.free()
+        finally:
+            engine.set_option("zone_skip", 1)
+
+
 def test_row_store_upload_matches_columns(sf001, engine):
     """rq_table_upload_rows (the bulk-insert hook) transposes reference DataBlocks on the GPU"""
     d = load_plan_dict("q1")

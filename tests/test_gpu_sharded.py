@@ -31,3 +31,4 @@ def test_sharded_plans_match_reference(world):
     assert "sharded q3" in r.stdout
     assert "partitioned micro_join_avg" in r.stdout
     assert "sharded error agreement" in r.stdout
+    assert "broadcast q3" in r.stdout and "shared-build q3" in r.stdout
