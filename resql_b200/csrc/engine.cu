@@ -351,6 +351,13 @@ static void copy_column_plain(rq_table& t, int c, const void* data, int64_t n_ro
 static std::unique_ptr<rq_table> upload_host_narrow(const char* name, int n_cols, const rq_column* cols, int64_t n_rows) {
     const int64_t kUpChunkRows = (int64_t)E.opt.up_chunk_krows * 1024;      // (a multiple of kTile)
     if (!E.opt.narrow || n_rows < 4 * kUpChunkRows) return nullptr;
+    {   // Converting pays only while the host cores outrun the link: measured, one core converts about
+        // 8 GB/s of 8-byte values and the link moves 52 GB/s, so with fewer than 7 cores for this rank
+        // (several ranks share the host) the columns travel as they are - every rank has its own link.
+        int hw = (int)std::thread::hardware_concurrency();
+        const int share = E.opt.up_threads > 0 ? E.opt.up_threads : hw / std::max(1, E.dist.world);
+        if (share < 7) return nullptr;
+    }
     const std::string hint_key = std::string(name ? name : "") + "/" + std::to_string(n_cols);
     std::vector<int> gw(n_cols);
     {
