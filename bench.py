@@ -519,17 +519,27 @@ def main():
                 d[c] = arr
             return d
 
+        phases = {}
+
         def step_e2e():
             d2h = 0
             # N > 1: the replicated build sides cross PCIe once (rank 0) and reach the other GPUs over
             # NVLink (rq_table_broadcast); every rank uploads its own lineitem shard
-            up = {name: (host_table(name, union[name]) if world == 1 or name == "lineitem"
-                         else eng.upload_replicated(name, host_arrays(name, union[name]), 0, rank)) for name in union}
+            up = {}
+            for name in union:
+                t0 = time.perf_counter()
+                up[name] = (host_table(name, union[name]) if world == 1 or name == "lineitem"
+                            else eng.upload_replicated(name, host_arrays(name, union[name]), 0, rank))
+                phases["upload_" + name] = 1e3 * (time.perf_counter() - t0)
             for q in QUERIES:
+                t0 = time.perf_counter()
                 res, _ = eng.execute(cplans[q], up, flags)
                 d2h += sum(c.nbytes for c in res.columns)
+                phases["execute_" + q] = 1e3 * (time.perf_counter() - t0)
+            t0 = time.perf_counter()
             for h in up.values():
                 h.free()
+            phases["free"] = 1e3 * (time.perf_counter() - t0)
             return d2h
 
         for _ in range(2):
@@ -550,6 +560,7 @@ def main():
             h2d_step = int(tb.item())
         e2e = {"value": 3.0 * n_total * e_steps / et, "unit": "tuples/s", "h2d_bytes_per_step": int(h2d_step),
                "d2h_bytes_per_step": int(d2h), "steps": e_steps, "ms_per_step": 1e3 * et / e_steps,
+               "phases_ms_last_step_rank0": {k: round(v, 2) for k, v in phases.items()},
                "path": "pinned host columns -> rq_table_upload (8-byte columns narrowed on the host cores, H2D, widened on arrival; "
                        "N > 1: replicated tables uploaded by rank 0 and broadcast over NVLink) -> rq_plan_execute -> host result, per step",
                "h2d_bytes_note": "bytes of the host columns in the reference's widths, all ranks; fewer cross PCIe (narrowing)"}

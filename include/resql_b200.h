@@ -112,6 +112,15 @@ int rq_table_upload_rows(const char* name, int32_t n_cols, const int32_t* types,
                          const int32_t* widths, const int32_t* offsets, int32_t tuple_size,
                          int32_t n_blocks, const uint8_t* const* blocks,
                          const size_t* block_bytes, rq_table** out);
+/* Parallel text loader: parses a `.tbl` file (one row per line, every field followed by `terminator`)
+ * straight into a device-resident table; replaces the row-store fill of executeBulkInsert
+ * (execute.h:332-388; field semantics of parse*Constant, expressions.h:369-455, incl. DECIMAL = the
+ * literal's digits with the point removed and DATE yyyy-mm-dd / yyyy/mm/dd). The text crosses PCIe in
+ * segments cut at line ends; the GPU finds the line starts and parses one row per thread.
+ * sql_types[] = RQ_SQL_*, sql_widths[] = n of CHAR(n) / VARCHAR(n) (ignored for other types). */
+int rq_table_load_tbl(const char* name, const char* path, char terminator, int32_t n_cols,
+                      const int32_t* sql_types, const int32_t* sql_widths, rq_table** out);
+
 /* Replicated tables on several GPUs (the build sides of a sharded plan: "small build sides are
  * NCCL-broadcast over NVLink", north_star). One rank uploads the table from its host (rq_table_upload /
  * rq_table_upload_rows); every other rank creates an empty table of the same schema and row count with

@@ -1092,3 +1092,4 @@ struct Lowerer {
 }  // namespace
 
 #include "engine_exec.inl"
+#include "tbl_loader.inl"

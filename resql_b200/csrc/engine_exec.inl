@@ -1344,7 +1344,7 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
         lower_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         // zone skipping on sorted source columns (table scans only; a shared build adds its rank share below)
         TileRangeBuf tile_buf;
-        if (pl.source_kind == RQ_SRC_TABLE && !src_override && E.opt.zone_skip) restrict_tiles(L, P, *src, tile_buf, false, tm);
+        if (pl.source_kind == RQ_SRC_TABLE && !src_override && E.opt.zone_skip && gr != 4) restrict_tiles(L, P, *src, tile_buf, false, tm);
 
         CK(cudaMemsetAsync(E.flags, 0, 32, E.stream));
         if (impl == IMPL_REGAGG || impl == IMPL_LOWAGG) {

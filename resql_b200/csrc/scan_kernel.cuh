@@ -312,10 +312,16 @@ rq_scan_kernel(const __grid_constant__ KParams P) {
     // a launch may be restricted to the tiles [tile_range[0], tile_range[1]) of the source: the row
     // range a selection on a sorted column can match at all (zone skipping), or one rank's share of a
     // replicated build table (engine_exec.inl "tile ranges")
+    // (not in the 4-group register kernel: it has no register to spare - measured, the extra live value
+    // cost Q1 2 % - and the host never hands it a range)
     uint32_t t_end = n_tiles, t_begin = 0;
-    if (P.tile_range) {
+    if (GR != 4 && P.tile_range) {
         t_begin = min(P.tile_range[0], n_tiles);
         t_end = max(min(P.tile_range[1], n_tiles), t_begin);
+        // (read through a lane-0 shuffle so that the compiler keeps the loop bounds in uniform registers,
+        // like the parameter-derived tile count they replace)
+        t_begin = __shfl_sync(kFull, t_begin, 0);
+        t_end = __shfl_sync(kFull, t_end, 0);
     }
     const uint32_t stride = gridDim.x * W;
     const uint32_t first = t_begin + blockIdx.x * W + warp;

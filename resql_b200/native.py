@@ -119,6 +119,8 @@ def load():
     lib.rq_table_alloc.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64,
                                    C.POINTER(C.c_void_p)]
     lib.rq_table_broadcast.argtypes = [C.c_void_p, C.c_int32]
+    lib.rq_table_load_tbl.argtypes = [C.c_char_p, C.c_char_p, C.c_char, C.c_int32, C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
     lib.rq_table_rows.argtypes = [C.c_void_p]
     lib.rq_table_rows.restype = C.c_int64
     lib.rq_table_free.argtypes = [C.c_void_p]
@@ -157,7 +159,7 @@ def debug_lower(plan, pipeline, impl, col_types, col_widths, col_min=None, col_m
 
 
 ABI_SYMBOLS = ["rq_init", "rq_shutdown", "rq_last_error", "rq_stream", "rq_set_option", "rq_dist_unique_id",
-               "rq_dist_init", "rq_table_upload", "rq_table_upload_rows", "rq_table_alloc", "rq_table_broadcast", "rq_table_rows",
+               "rq_dist_init", "rq_table_upload", "rq_table_upload_rows", "rq_table_alloc", "rq_table_broadcast", "rq_table_load_tbl", "rq_table_rows",
                "rq_table_free", "rq_plan_execute", "rq_result_free"]
 
 _NP_OF = {RQ_I8: np.uint8, RQ_I32: np.int32, RQ_I64: np.int64}
@@ -282,6 +284,15 @@ class Engine:
             schema = {n: _phys(np.asarray(a)) for n, a in columns.items()}
             t = self.alloc(name, schema, len(next(iter(columns.values()))))
         return self.broadcast(t, root)
+
+    def load_tbl(self, name, path, schema, terminator="|"):
+        """parallel text loader; schema = ordered [(column, RQ_SQL_* type, n of CHAR(n)/VARCHAR(n) or 0)]"""
+        n = len(schema)
+        ty = (C.c_int32 * n)(*[s[1] for s in schema])
+        wi = (C.c_int32 * n)(*[s[2] for s in schema])
+        h = C.c_void_p()
+        self._check(self.lib.rq_table_load_tbl(name.encode(), str(path).encode(), terminator.encode(), n, ty, wi, C.byref(h)))
+        return Table(h, [s[0] for s in schema])
 
     def upload_rows(self, name, names, types, widths, offsets, tuple_size, blocks):
         """Row-store upload (reference DataBlocks): blocks = list of bytes-like objects."""
