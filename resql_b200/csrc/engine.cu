@@ -268,6 +268,30 @@ extern "C" int rq_dist_init(int rank, int world, const uint8_t id[128]) {
     if (!E.init) return fail(RQ_ERR_NOT_INIT, "rq_dist_init before rq_init");
     std::string err;
     if (!dist_init(E.dist, rank, world, id, err)) return fail(RQ_ERR_NCCL, "%s", err.c_str());
+    // NCCL sets up its rings and peer-to-peer channels at the first use of every kind of operation
+    // (seconds on 8 ranks: measured 7 s inside the first Q3). That belongs to joining the group, not to
+    // the first query: one tiny collective of every kind the engine uses, and a send/receive with every
+    // peer, are run here.
+    if (world > 1) {
+        Dist& D = E.dist;
+        unsigned long long* buf = nullptr;
+        if (cudaMalloc(&buf, sizeof(unsigned long long) * (size_t)(2 * world + 2)) == cudaSuccess) {
+            cudaMemsetAsync(buf, 0, sizeof(unsigned long long) * (size_t)(2 * world + 2), E.stream);
+            int rc = D.all_reduce(buf, buf, 1, 5, 0, D.comm, E.stream);
+            if (rc == 0) rc = D.all_gather(buf + 2 * world, buf, 1, 5, D.comm, E.stream);
+            if (rc == 0) rc = D.broadcast(buf, buf, 1, 5, 0, D.comm, E.stream);
+            if (rc == 0) rc = D.group_start();
+            for (int r = 0; r < world && rc == 0; r++) {
+                if (r == rank) continue;
+                rc = D.send(buf + world + r, 1, 5, r, D.comm, E.stream);
+                if (rc == 0) rc = D.recv(buf + r, 1, 5, r, D.comm, E.stream);
+            }
+            if (rc == 0) rc = D.group_end();
+            const cudaError_t ce = cudaStreamSynchronize(E.stream);
+            cudaFree(buf);
+            if (rc != 0 || ce != cudaSuccess) return fail(RQ_ERR_NCCL, "rq_dist_init: warm-up collectives failed");
+        }
+    }
     return RQ_OK;
 }
 

@@ -1,15 +1,17 @@
 #!/usr/bin/env bash
-# 8-GPU visit (charged 8x): sharded/partitioned parity worker, micro bench at 1e9, TPC-H bench at N=8 (and 4).
-TAG=${1:-n8}
-CASES=${2:-"1e9:1e6"}
-EXTRA=${3:-""}
-O=gpurun_out/$TAG
+# 8-GPU visit (expensive: 8x box time): multi-GPU parity worker + bench with e2e
+O=gpurun_out/${1:-n8}
+G=${2:-8}
 mkdir -p $O
-nvidia-smi --query-gpu=name,clocks.max.sm --format=csv > $O/gpu.txt 2>&1; nproc >> $O/gpu.txt; free -g >> $O/gpu.txt
-echo "== sharded worker N=8"; RQ_TEST_TRACE=${RQ_TEST_TRACE:-} timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 \
-    tests/sharded_worker.py > $O/sharded_worker_n8.log 2> $O/sharded_worker_n8.err; tail -n 30 $O/sharded_worker_n8.log; grep -v "^\s*$\|OMP_NUM\|\*\*\*" $O/sharded_worker_n8.err | tail -n 15
-echo "== bench N=8"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
-    bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu $EXTRA > $O/bench_n8.json 2> $O/bench_n8.err; tail -c 300 $O/bench_n8.json; tail -n 3 $O/bench_n8.err
-echo "== micro N=8"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 \
-    bench.py --workload micro --gpus 8 --micro-cases $CASES --steps 3 --warmup 2 > $O/micro_n8.jsonl 2> $O/micro_n8.err; cut -c1-400 $O/micro_n8.jsonl; grep -v "^\s*$\|OMP_NUM\|\*\*\*" $O/micro_n8.err | tail -n 8
-ls -la $O
+nvidia-smi --query-gpu=name --format=csv,noheader | sort | uniq -c > $O/gpu.txt; nproc >> $O/gpu.txt
+echo "== sharded parity N=$G"; timeout 400 python -m pytest tests/test_gpu_sharded.py -m gpu -q -x -k "$G" 2>&1 | tail -n 4
+cp gpurun_out/sharded_worker_n$G.log $O/ 2>/dev/null; grep -c "identical" $O/sharded_worker_n$G.log
+echo "== bench N=$G (with e2e)"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $G --steps 20 --warmup 4 --no-cpu > $O/bench_n$G.json 2> $O/bench_n$G.err; python - <<PY
+import json
+d=json.load(open("$O/bench_n$G.json"))
+print("value %.1f G/s" % (d["value"]/1e9), "ms/step", round(d["ms_per_step"],3), d["checks"])
+for q,v in d["queries"].items(): print("  ",q,"kernel",round(v["kernel_ms"],3),"scan",round(v["lineitem_scan_kernel_ms"],3),"nccl",round(v["nccl_ms"],3),"syncs",v["host_syncs_per_execution"],"cold",round(v["cold"]["first_execution_wall_ms"],1))
+e=d.get("e2e",{}); print("e2e", e.get("value"), e.get("ms_per_step"), e.get("phases_ms_last_step_rank0"))
+PY
+grep -v "^\s*$\|OMP_NUM\|\*\*\*" $O/bench_n$G.err | tail -n 5

@@ -10,7 +10,7 @@ from resql_b200 import Plan
 
 pytestmark = pytest.mark.gpu
 
-SEEDS = list(range(120))
+SEEDS = list(range(250))
 
 
 @pytest.fixture(scope="module")
