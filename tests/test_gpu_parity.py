@@ -141,6 +141,38 @@ def test_zone_skipping_on_sorted_columns_is_exact(dtype, engine):
             engine.set_option("zone_skip", 1)
 
 
+def test_char_equality_has_comparechar_semantics(engine):
+    """compareChar (qlib/scalar.h:27-46) on a CHAR column against constants: equality ignores trailing blanks
+    on either side, prefixes are not equal, differences behind the first 8 bytes count, '' matches blanks"""
+    import numpy as np
+    vals = [b"BUILDING", b"BUILDING  ", b"BUILDIN", b"BUILDINGS", b"BUILDING X", b"", b" ", b"B", b"AUTOMOBILE", b"AUTOMOBILF",
+            b"ABCDEFGHIJKL", b"ABCDEFGHIJKM", b"ABCDEFGH", b"ABCDEFGH    ", b"abcdefgh", b"MACHINERY", b"HOUSEHOLD", b"FURNITURE"]
+    rng = np.random.default_rng(5)
+    n = 70_001
+    col = np.array([vals[i] for i in rng.integers(0, len(vals), n)], dtype="S13")
+    ids = np.arange(n, dtype=np.int64)
+    t = {"t": {"s": col, "i": ids}}
+    h = engine.upload("t", t["t"])
+    try:
+        for const in (b"BUILDING", b"BUILDING ", b"ABCDEFGHIJKL", b"ABCDEFGH", b"", b"B", b"AUTOMOBILE", b"NOPE", b"ABCDEFGHIJKLMNOP"):
+            for op in (16, 18):          # EQ_CHAR, NEQ_CHAR
+                pool = const + b"\0"
+                d = {"tables": [{"name": "t", "columns": ["s", "i"]}],
+                     "pipelines": [{"source_kind": 1, "source_id": 0, "source_id2": 0, "sink_kind": 1, "size_hint": 0,
+                                    "nodes": [[1, 0, 0, 0, 0], [1, 1, 0, 0, 0], [3, 0, 0, 0, 0], [op, 0, 2, 0, 0], [22, 3, 0, 0, 0]],
+                                    "args": [], "keys": [], "vals": [[1, 2, 4, 0], [1, 1, 4, 0]]},
+                                   {"source_kind": 2, "source_id": 0, "source_id2": 0, "sink_kind": 3, "size_hint": 0,
+                                    "nodes": [[1, 0, 0, 0, 0], [1, 1, 0, 0, 0]], "args": [], "keys": [],
+                                    "vals": [[0, 0, 4, 0], [1, 0, 4, 0]]}],
+                     "order": [], "limit": -1, "strpool": pool.decode("latin1"), "result_names": ["n", "s"], "result_types": ["BIGINT"] * 2}
+                res, _ = engine.execute(Plan(d), {"t": h})
+                got = serialize_columns(res.columns, res.sql_types, res.sql_widths)
+                want = serialize_columns(*run_plan(d, t))
+                assert got == want, f"{const!r} op {op}: {got} != {want}"
+    finally:
+        h.free()
+
+
 def test_row_store_upload_matches_columns(sf001, engine):
     """rq_table_upload_rows (the bulk-insert hook) transposes reference DataBlocks on the GPU"""
     d = load_plan_dict("q1")
