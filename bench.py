@@ -628,7 +628,7 @@ def main():
     }
     if e2e is not None:
         out["e2e"] = e2e
-    if not a.no_cpu:
+    if not a.no_cpu and world == 1:          # (the CPU baseline is reported at N = 1 only)
         try:
             ref = run_reference_with_fallback(a, 3, cores)
             if ref is not None:

@@ -16,7 +16,8 @@ BPT = {"q1": 38, "q6": 28, "q3": 24}
 ROWS_SF10 = 59998861
 
 for f in ("bench_ours.json", "bench_reference.json", "gpu.txt"):
-    shutil.copy(os.path.join(src, f), os.path.join(out, f"{tag}_{f.replace('bench_ours', 'bench_ours_sf100')}"))
+    if os.path.exists(os.path.join(src, f)):
+        shutil.copy(os.path.join(src, f), os.path.join(out, f"{tag}_{f.replace('bench_ours', 'bench_ours_sf100')}"))
 shutil.copy(os.path.join(src, "launches.csv"), os.path.join(out, f"{tag}_launches_bench_sf100.csv"))
 
 # ---- launch shares ---------------------------------------------------------------------------
@@ -30,7 +31,7 @@ for r in rows[hdr + 1:]:
         agg.setdefault(r[ik][:64], []).append(float(r[iv].replace(",", "")))
 tot = sum(sum(v) for v in agg.values())
 with open(os.path.join(out, f"{tag}_launch_share.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:rq_ -c 400 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e  (SF100, 1 GPU)\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:rq_ -c 600 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e  (SF100, 1 GPU)\n")
     f.write("# per-launch times are cold-cache and serialised; compare SHARES, not absolutes. 5 steps (3 warm-up + 2 timed) + table statistics at upload\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"{k:64s} n={len(v):4d} total={sum(v)/1e6:9.3f} ms  share={100*sum(v)/tot:5.1f}%  avg={sum(v)/len(v)/1e3:9.1f} us\n")
