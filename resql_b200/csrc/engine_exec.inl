@@ -425,7 +425,7 @@ static bool layout_smem(KParams& P, int n_slots, int acc_bytes, int max_warps) {
     int bestW = fit(1), bestS = 1;
     if (bestW < 1) return false;
     if (fit(2) >= bestW) bestS = 2;
-    // rq_set_option("stages" / "warps") overrides the choice (scripts/sweep.sh)
+    // rq_set_option("stages" / "warps") overrides the choice (profiles/r01_q1_sweep.txt was made that way)
     if (E.opt.stages >= 1 && E.opt.stages <= kMaxStages && fit(E.opt.stages) >= 1) { bestS = E.opt.stages; bestW = fit(bestS); }
     if (E.opt.warps >= 1 && E.opt.warps <= bestW) bestW = E.opt.warps;
     P.stages = bestS;

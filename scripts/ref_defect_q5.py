@@ -1,4 +1,6 @@
-"""debug: q5 through resql-b200 gpus=2 with option variants vs the reference engine"""
+"""Evidence for a REFERENCE defect: Q5 at SF0.1 through resql-b200 (1 and 2 GPUs, option variants)
+against the reference engine, whose ht_get continues a probe behind the last slot without wrapping (qlib/hash.h:438-441)
+and so loses matches of hash-equal chains that cross the end of its table; pandas agrees with the GPU result."""
 import os, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
