@@ -48,7 +48,7 @@ QUERIES = {
         group by l_returnflag order by l_returnflag""",
     "sel_strings": """select c_custkey, c_name, c_mktsegment, c_acctbal from customer
         where c_mktsegment = 'BUILDING  ' and c_acctbal > 9000.00 order by c_custkey""",
-    "sel_star_limit": "select * from customer where c_custkey < 4 order by c_custkey",
+    "sel_star_ordered": "select * from customer where c_custkey < 4 order by c_custkey",
     # joins
     "join_orders_lineitem": """select o_orderpriority, count(*) as c, sum(l_extendedprice) as s from orders, lineitem
         where o_orderkey = l_orderkey and l_shipdate > date '1998-06-01' group by o_orderpriority order by o_orderpriority""",

@@ -173,6 +173,25 @@ def test_char_equality_has_comparechar_semantics(engine):
         h.free()
 
 
+@pytest.mark.parametrize("limit", [0, 1, 7, 100000])
+def test_limit_without_order_by_keeps_that_many_rows_of_the_result(limit, sf001, engine):
+    """LIMIT without ORDER BY (materialize.h:135-140; Relation::applyLimit dbdata.h:407-425): WHICH rows
+    survive is up to the scan order (per thread in the reference), but there are exactly min(limit, n) of
+    them and each belongs to the unlimited result"""
+    d = dict(load_plan_dict("sel_or"), order=[])          # the fixture's plan without its ORDER BY
+    tabs = plan_tables(d, sf001)
+    full, _ = _run(engine, d, tabs)
+    d2 = dict(d, limit=limit)
+    got, _ = _run(engine, d2, tabs)
+    assert len(got) == min(limit, len(full))
+    pool = {}
+    for line in full:
+        pool[line] = pool.get(line, 0) + 1
+    for line in got:
+        assert pool.get(line, 0) > 0, line
+        pool[line] -= 1
+
+
 def test_row_store_upload_matches_columns(sf001, engine):
     """rq_table_upload_rows (the bulk-insert hook) transposes reference DataBlocks on the GPU"""
     d = load_plan_dict("q1")
