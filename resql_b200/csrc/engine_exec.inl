@@ -738,6 +738,12 @@ struct NeedExpand {};
 // of the memo key), so the second replay is recorded into a CUDA graph: later executions are ONE
 // graph launch and one wait - no per-launch host cost, which is what bounds short plans and the
 // 8-GPU runs, where the kernels of a shard take fractions of a millisecond.
+// a result and the one host block its columns live in (rq_result_col::data point into it)
+struct ResultBox {
+    rq_result r;
+    unsigned char* block;
+};
+
 struct PlanMemo {
     std::vector<std::vector<unsigned char>> reads;
     bool valid = false;
@@ -751,14 +757,17 @@ struct PlanMemo {
     size_t log_cap = 0;
     // the graph and what is needed to hand out its result
     cudaGraphExec_t gexec = nullptr;
-    struct Col { int type = 0, width = 0, sql_type = 0, sql_width = 0; unsigned char* h = nullptr; };
-    std::vector<Col> cols;             // pinned landing buffers of the result columns
+    struct Col { int type = 0, width = 0, sql_type = 0, sql_width = 0; size_t off = 0; };
+    std::vector<Col> cols;             // result columns inside the packed result
+    unsigned char* h_pack = nullptr;   // pinned landing buffer of the packed result
+    size_t pack_bytes = 0;
     int64_t res_rows = 0;
     std::vector<std::pair<size_t, int>> ev_used;
     rq_timings tm_static{};            // launches / lowering time of the captured run
     void release() {
         if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
-        for (auto& c : cols) if (c.h) cudaFreeHost(c.h);
+        if (h_pack) cudaFreeHost(h_pack);
+        h_pack = nullptr; pack_bytes = 0;
         cols.clear();
         if (d_strpool) cudaFree(d_strpool);
         if (d_expect) cudaFree(d_expect);
@@ -1372,12 +1381,22 @@ static void run_pipeline_impl(const rq_plan& plan, const rq_pipeline& pl_in, int
             const int64_t n_groups_host = *(const int64_t*)(E.h_flags + 8);
             if (E.h_flags[0]) { RP.retries++; RP.why = "group overflow"; continue; }   // more groups than this path tracks: next implementation
             // expand duplicates by aliasing: copy the columns (tiny)
-            for (int k = 0; k < pl.n_keys; k++)
-                CK(cudaMemcpyAsync(out->cols[k].d, dense->cols[k].d, (size_t)kGroupTableCap * 8, cudaMemcpyDeviceToDevice, E.stream));
-            for (int k = 0; k < pl.n_vals; k++)
-                CK(cudaMemcpyAsync(out->cols[pl.n_keys + k].d, dense->cols[pl.n_keys + ad.uniq_of[k]].d,
-                                   (size_t)kGroupTableCap * 8, cudaMemcpyDeviceToDevice, E.stream));
-            CK(cudaMemcpyAsync(out->d_n_rows, dense->d_n_rows, 8, cudaMemcpyDeviceToDevice, E.stream));
+            {
+                if (ncols > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d output columns", kMaxOut);
+                CopyCols cc;
+                memset(&cc, 0, sizeof(cc));
+                for (int k = 0; k < pl.n_keys; k++) { cc.in[k] = (const int64_t*)dense->cols[k].d; cc.out[k] = (int64_t*)out->cols[k].d; cc.len[k] = kGroupTableCap; }
+                for (int k = 0; k < pl.n_vals; k++) {
+                    cc.in[pl.n_keys + k] = (const int64_t*)dense->cols[pl.n_keys + ad.uniq_of[k]].d;
+                    cc.out[pl.n_keys + k] = (int64_t*)out->cols[pl.n_keys + k].d;
+                    cc.len[pl.n_keys + k] = kGroupTableCap;
+                }
+                cc.in[ncols] = dense->d_n_rows; cc.out[ncols] = out->d_n_rows; cc.len[ncols] = 1;
+                cc.ncols = ncols + 1;
+                rq_copy_cols<<<dim3(2, (unsigned)cc.ncols), 256, 0, E.stream>>>(cc);
+                if (tm) tm->kernel_launches++;
+                CK(cudaGetLastError());
+            }
             out->n_rows = n_groups_host;      // (the copies above are stream-ordered; no host wait needed)
             set_types(*out, pl);
             result.table = std::move(out);
@@ -2194,11 +2213,10 @@ static int phys_type(int sql_type, int sql_width, int* width) {
 
 extern "C" int rq_result_free(rq_result* r) {
     if (!r) return RQ_OK;
-    if (r->cols) {
-        for (int c = 0; c < r->n_cols; c++) free(r->cols[c].data);
-        free(r->cols);
-    }
-    free(r);
+    ResultBox* box = reinterpret_cast<ResultBox*>(r);      // every result is allocated as a ResultBox
+    free(box->block);
+    free(r->cols);
+    free(box);
     return RQ_OK;
 }
 
@@ -2313,6 +2331,9 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
         const int ncols = (int)fin->cols.size();
         trace_point("row count read");
         // ORDER BY + LIMIT over relation t (n rows): cols = the ordered columns, n_out = rows kept
+        // (defer_perm: the columns stay as they are and the permutation is handed to the result kernel)
+        bool defer_perm = false;
+        const uint32_t* final_perm = nullptr;
         auto order_limit = [&](rq_table* t, int64_t n, std::vector<int64_t*>& cols, int64_t& n_out) {
             const int ncols = (int)t->cols.size();
             cols.assign(ncols, nullptr);
@@ -2412,15 +2433,19 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
                 }
                 CK(cudaGetLastError());
             }
-            for (int c = 0; c < ncols; c++) {
-                int64_t* sorted = nullptr;
-                CK(dmalloc(&sorted, sizeof(int64_t) * std::max<int64_t>(n_out, 1)));
-                scratch.push_back(sorted);
-                rq_apply_perm<<<(unsigned)((n_out + 255) / 256), 256, 0, E.stream>>>(cols[c], sorted, perm, t->d_n_rows, n, plan->limit);
-                if (tm) tm->kernel_launches++;
-                cols[c] = sorted;
+            if (defer_perm) {
+                final_perm = perm;           // applied by rq_finish_result together with narrowing
+            } else {
+                for (int c = 0; c < ncols; c++) {
+                    int64_t* sorted = nullptr;
+                    CK(dmalloc(&sorted, sizeof(int64_t) * std::max<int64_t>(n_out, 1)));
+                    scratch.push_back(sorted);
+                    rq_apply_perm<<<(unsigned)((n_out + 255) / 256), 256, 0, E.stream>>>(cols[c], sorted, perm, t->d_n_rows, n, plan->limit);
+                    if (tm) tm->kernel_launches++;
+                    cols[c] = sorted;
+                }
+                CK(cudaGetLastError());
             }
-            CK(cudaGetLastError());
         }
 
         };
@@ -2448,45 +2473,57 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
             fin = gathered.get();
             n = fin->n_rows;
         }
+        defer_perm = true;
         order_limit(fin, n, cols, n_out);
 
         trace_point("sorted");
-        // narrow to the reference's physical widths on the device, then read back
-        res = (rq_result*)calloc(1, sizeof(rq_result));
+        // one kernel permutes, cuts, narrows to the reference's physical widths and copies strings by
+        // value for all columns into one packed buffer; one copy brings it to the host
+        ResultBox* box = (ResultBox*)calloc(1, sizeof(ResultBox));
+        res = &box->r;
         res->n_rows = n_out;
         res->n_cols = ncols;
         res->cols = (rq_result_col*)calloc(ncols, sizeof(rq_result_col));
-        std::vector<void*> d_out(ncols, nullptr);
+        if (ncols > kMaxOut) raise(RQ_ERR_UNSUPPORTED, "more than %d result columns", kMaxOut);
+        FinishCols F;
+        memset(&F, 0, sizeof(F));
+        F.ncols = ncols;
+        size_t total = 0;
         if (RP.capturing) { RP.memo->cols.assign(ncols, PlanMemo::Col()); RP.memo->res_rows = n_out; }
         for (int c = 0; c < ncols; c++) {
             int w = 8;
             const int pt = phys_type(fin->sql_type[c], fin->sql_width[c], &w);
             rq_result_col& rc = res->cols[c];
             rc.type = pt; rc.width = w; rc.sql_type = fin->sql_type[c]; rc.sql_width = fin->sql_width[c];
-            rc.data = malloc((size_t)std::max<int64_t>(n_out, 1) * w);
+            if (w > 0xffff) raise(RQ_ERR_UNSUPPORTED, "result column %d is %d bytes wide", c, w);
+            F.in[c] = cols[c];
+            F.off[c] = (uint64_t)total;
+            F.width[c] = (uint16_t)w;
+            F.kind[c] = pt == RQ_I64 ? 0 : pt == RQ_I32 ? 1 : pt == RQ_I8 ? 2 : 3;
             if (RP.capturing) {
                 PlanMemo::Col& mc = RP.memo->cols[c];
-                mc.type = pt; mc.width = w; mc.sql_type = rc.sql_type; mc.sql_width = rc.sql_width;
-                CK(cudaMallocHost(&mc.h, (size_t)std::max<int64_t>(n_out, 1) * w));
+                mc.type = pt; mc.width = w; mc.sql_type = rc.sql_type; mc.sql_width = rc.sql_width; mc.off = total;
             }
-            if (n_out == 0) continue;
-            const unsigned blocks = (unsigned)((n_out + 255) / 256);
-            if (pt == RQ_I64) { d_out[c] = cols[c]; continue; }
-            void* d = nullptr;
-            CK(dmalloc(&d, (size_t)n_out * w));
-            scratch.push_back(d);
-            d_out[c] = d;
-            if (pt == RQ_I32) rq_narrow_i32<<<blocks, 256, 0, E.stream>>>(cols[c], (int32_t*)d, n_out);
-            else if (pt == RQ_I8) rq_narrow_i8<<<blocks, 256, 0, E.stream>>>(cols[c], (uint8_t*)d, n_out);
-            else rq_gather_str<<<blocks, 256, 0, E.stream>>>(cols[c], (unsigned char*)d, w, n_out);
+            total = (total + (size_t)std::max<int64_t>(n_out, 1) * w + 15) & ~(size_t)15;
+        }
+        box->block = (unsigned char*)malloc(std::max<size_t>(total, 16));
+        for (int c = 0; c < ncols; c++) res->cols[c].data = box->block + F.off[c];
+        unsigned char* d_pack = nullptr;
+        if (n_out > 0) {
+            CK(dmalloc(&d_pack, total));
+            scratch.push_back(d_pack);
+            const unsigned blocks = (unsigned)std::min<int64_t>((n_out + 255) / 256, 148 * 16);
+            rq_finish_result<<<blocks, 256, 0, E.stream>>>(F, final_perm, fin->d_n_rows, n, plan->limit, d_pack);
             if (tm) tm->kernel_launches++;
         }
         CK(cudaGetLastError());
         record_event(E.ev[1]);
-        for (int c = 0; c < ncols; c++)
-            if (n_out > 0)
-                CK(cudaMemcpyAsync(RP.capturing ? (void*)RP.memo->cols[c].h : res->cols[c].data, d_out[c],
-                                   (size_t)n_out * res->cols[c].width, cudaMemcpyDeviceToHost, E.stream));
+        if (RP.capturing) {
+            RP.memo->pack_bytes = total;
+            CK(cudaMallocHost(&RP.memo->h_pack, std::max<size_t>(total, 16)));
+        }
+        if (n_out > 0)
+            CK(cudaMemcpyAsync(RP.capturing ? (void*)RP.memo->h_pack : (void*)box->block, d_pack, total, cudaMemcpyDeviceToHost, E.stream));
         // the verdict travels with the result: replay = all predictions right, careful = run was clean
         // (sharded plans: the minimum over the ranks, so every rank draws the same conclusion)
         int32_t h_ok_local = RP.retries == 0 ? 1 : 0;
@@ -2528,9 +2565,7 @@ static int execute_once(const rq_plan* plan, rq_result** out, rq_timings* tm, bo
             CK(cudaGraphLaunch(RP.memo->gexec, E.stream));
         }
         stream_sync();
-        if (RP.capturing)
-            for (int c = 0; c < ncols; c++)
-                if (n_out > 0) memcpy(res->cols[c].data, RP.memo->cols[c].h, (size_t)n_out * res->cols[c].width);
+        if (RP.capturing && n_out > 0) memcpy(box->block, RP.memo->h_pack, RP.memo->pack_bytes);
         if (verdict) *verdict = (RP.mode == 2 || sharded) ? (*(const int32_t*)g_pinned != 0) : (h_ok_local != 0);
         if (tm) {
             tm->lower_ms = lower_ms;
@@ -2652,17 +2687,18 @@ extern "C" int rq_plan_execute(const rq_plan* plan, rq_result** out, rq_timings*
         if (ge == cudaSuccess) ge = cudaStreamSynchronize(E.stream);
         if (ge != cudaSuccess) return fail(RQ_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(ge));
         if (*(const int32_t*)g_pinned != 0) {
-            rq_result* res = (rq_result*)calloc(1, sizeof(rq_result));
+            ResultBox* box = (ResultBox*)calloc(1, sizeof(ResultBox));
+            rq_result* res = &box->r;
             res->n_rows = memo.res_rows;
             res->n_cols = (int)memo.cols.size();
             res->cols = (rq_result_col*)calloc(memo.cols.size(), sizeof(rq_result_col));
+            box->block = (unsigned char*)malloc(std::max<size_t>(memo.pack_bytes, 16));
+            if (memo.res_rows > 0) memcpy(box->block, memo.h_pack, memo.pack_bytes);
             for (size_t c = 0; c < memo.cols.size(); c++) {
                 const PlanMemo::Col& mc = memo.cols[c];
                 rq_result_col& rc = res->cols[c];
                 rc.type = mc.type; rc.width = mc.width; rc.sql_type = mc.sql_type; rc.sql_width = mc.sql_width;
-                const size_t bytes = (size_t)std::max<int64_t>(memo.res_rows, 1) * mc.width;
-                rc.data = malloc(bytes);
-                if (memo.res_rows > 0) memcpy(rc.data, mc.h, (size_t)memo.res_rows * mc.width);
+                rc.data = box->block + mc.off;
             }
             if (tm) {
                 tm->lower_ms = 0;

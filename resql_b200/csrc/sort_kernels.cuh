@@ -82,6 +82,50 @@ __global__ void rq_apply_perm(const int64_t* in, int64_t* out, const uint32_t* p
     if (i < n) out[i] = in[perm[i]];
 }
 
+// ---- result path: ORDER BY permutation, LIMIT, narrowing to the reference's physical widths and
+// strings by value for ALL output columns in one launch, into one packed buffer (one D2H copy per
+// query instead of a permutation, a narrowing kernel and a copy per column: a result of 10 columns
+// cost 30 graph nodes of a few microseconds each, which is what a 0.4 ms shard of Q6 notices)
+struct FinishCols {
+    int32_t ncols;
+    int32_t pad_;
+    const int64_t* in[kMaxOut];
+    uint64_t off[kMaxOut];          // byte offset of the column in the packed buffer (16-byte aligned)
+    uint16_t width[kMaxOut];        // bytes per row in the result
+    uint8_t kind[kMaxOut];          // 0 int64, 1 int32, 2 byte, 3 string (value = address of NUL-terminated bytes)
+};
+__global__ void rq_finish_result(FinishCols F, const uint32_t* perm, const int64_t* n_ptr, int64_t n_cap, int64_t limit,
+                                 unsigned char* out) {
+    int64_t n = n_ptr ? *n_ptr : n_cap;
+    if (n > n_cap) n = n_cap;
+    if (limit >= 0 && limit < n) n = limit;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = perm ? (int64_t)perm[i] : i;
+        for (int c = 0; c < F.ncols; c++) {
+            const int64_t v = F.in[c][j];
+            unsigned char* d = out + F.off[c] + (size_t)i * F.width[c];
+            switch (F.kind[c]) {
+                case 0: *reinterpret_cast<int64_t*>(d) = v; break;
+                case 1: *reinterpret_cast<int32_t*>(d) = (int32_t)v; break;
+                case 2: *d = (unsigned char)v; break;
+                default: {
+                    const unsigned char* sp = reinterpret_cast<const unsigned char*>(v);
+                    const int w = F.width[c];
+                    int k = 0;
+                    for (; k < w - 1 && sp[k] != 0; k++) d[k] = sp[k];
+                    for (; k < w; k++) d[k] = 0;
+                }
+            }
+        }
+    }
+}
+// column-wise copy of a few small relations' worth of int64 columns in one launch
+struct CopyCols { int32_t ncols; int32_t rows; const int64_t* in[kMaxOut + 1]; int64_t* out[kMaxOut + 1]; int32_t len[kMaxOut + 1]; };
+__global__ void rq_copy_cols(CopyCols C) {
+    for (int c = blockIdx.y; c < C.ncols; c += gridDim.y)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C.len[c]; i += gridDim.x * blockDim.x) C.out[c][i] = C.in[c][i];
+}
+
 // ---- ORDER BY ... LIMIT k over many rows: radix select on the first key, then a small sort ------
 // state[0] = key prefix decided so far, state[1] = rank still to find inside that prefix.
 constexpr int kSelBits = 11;
