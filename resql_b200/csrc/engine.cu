@@ -523,6 +523,14 @@ static std::unique_ptr<rq_table> upload_host_narrow(const char* name, int n_cols
     return nullptr;
 }
 
+// debug aid (no GPU needed, not part of the public ABI): the host-side conversion of one chunk, so that the
+// CPU-only tests can check fit detection and value ranges (tests/test_host_narrow.py)
+extern "C" int rq_debug_convert_chunk(const int64_t* in, int64_t n, int32_t width, uint8_t* out, int64_t* lo, int64_t* hi) {
+    if (!in || !out || !lo || !hi || n < 0 || (width != 1 && width != 4)) return -1;
+    *lo = INT64_MAX; *hi = INT64_MIN;
+    return hostnarrow::convert_chunk(in, out, (size_t)n, width, lo, hi) ? 1 : 0;
+}
+
 extern "C" int rq_table_upload(const char* name, int32_t n_cols, const rq_column* cols,
                                int64_t n_rows, int32_t flags, rq_table** out) {
     if (!E.init) return fail(RQ_ERR_NOT_INIT, "rq_table_upload before rq_init");
