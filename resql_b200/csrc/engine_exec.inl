@@ -2811,7 +2811,11 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
                 if (fake.cols[k].type != RQ_STR && L.staged_of_col[k] == c) srccol = (int)k;
             snprintf(line, sizeof line, "col %d src %d w %d\n", c, srccol, (int)P.col_w[c]);
             s += line;
+            snprintf(line, sizeof line, "coloff %d %u\n", c, P.col_off[c]);
+            s += line;
         }
+        snprintf(line, sizeof line, "layout %u %u\n", P.stage_bytes, P.slots_rel);
+        s += line;
         for (int c = 0; c < P.n_strcols; c++) {
             int srccol = -1;
             for (size_t k = 0; k < L.staged_of_col.size(); k++)
@@ -2833,6 +2837,10 @@ extern "C" int rq_debug_lower(const rq_plan* plan, int pi, int impl, const int32
                      u.xkind, u.ykind, u.zkind, u.xrel, u.yrel, u.zrel, (long long)u.imm);
             s += line;
         }
+        // the device-side value references of the sinks (to_vref): kind, slot / u32 bits, offset >> 4
+        for (int k = 0; k < P.nk; k++) { snprintf(line, sizeof line, "vkey %d %d %u\n", P.key[k].kind, P.key[k].slot, P.key[k].off16); s += line; }
+        for (int k = 0; k < P.n_out; k++) { snprintf(line, sizeof line, "vout %d %d %u\n", P.out[k].kind, P.out[k].slot, P.out[k].off16); s += line; }
+        for (size_t u = 0; u < ad.kind.size(); u++) { snprintf(line, sizeof line, "vagg %d %d %u\n", P.agg_src[u].kind, P.agg_src[u].slot, P.agg_src[u].off16); s += line; }
         for (size_t k = 0; k < L.hkey.size(); k++) { snprintf(line, sizeof line, "key %d %d\n", L.hkey[k].kind, L.hkey[k].idx); s += line; }
         for (size_t k = 0; k < L.hout.size(); k++) { snprintf(line, sizeof line, "out %d %d\n", L.hout[k].kind, L.hout[k].idx); s += line; }
         for (int k = 0; k < kMaxImm; k++) { snprintf(line, sizeof line, "imm %d %lld\n", k, (long long)P.imm[k]); s += line; }

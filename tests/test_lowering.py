@@ -19,10 +19,13 @@ def _has_string_key(plan):
     return any(PO._is_str(k[2], k[3]) for p in plan["pipelines"] if p["sink_kind"] == 1 for k in p["keys"])
 
 
+# level "host": the host-level units (HUnit); level "device": the encoded program (UInsn) and the device value
+# references of the sinks, i.e. encode_program / to_vref as well
+@pytest.mark.parametrize("level", ["host", "device"])
 @pytest.mark.parametrize("with_stats", [True, False])
 @pytest.mark.parametrize("agg_impl", [vm_model.IMPL_REGAGG, vm_model.IMPL_LOWAGG])
 @pytest.mark.parametrize("name", plan_names())
-def test_lowered_program_matches_oracle(name, agg_impl, with_stats, sf001):
+def test_lowered_program_matches_oracle(name, agg_impl, with_stats, level, sf001):
     d = load_plan_dict(name)
     if _has_join(d) or _has_string_key(d):
         pytest.skip("hash paths are lowered on the device side (covered by the gpu tests)")
@@ -41,7 +44,8 @@ def test_lowered_program_matches_oracle(name, agg_impl, with_stats, sf001):
         for nd in p["nodes"]:
             if nd[0] == 3:
                 pool_strings[nd[4]] = pool[nd[4]:].split(b"\0")[0]
-        outs.append(vm_model.run_pipeline_vm(plan, pi, src, pool_strings, agg_impl, with_stats))
+        run = vm_model.run_pipeline_vm if level == "host" else vm_model.run_pipeline_device
+        outs.append(run(plan, pi, src, pool_strings, agg_impl, with_stats))
     last = d["pipelines"][-1]
     st = [k[2] for k in last["keys"]] + [v[2] for v in last["vals"]]
     sw = [k[3] for k in last["keys"]] + [v[3] for v in last["vals"]]

@@ -25,9 +25,10 @@ def test_enough_random_plans_are_eligible():
     assert len(SEEDS) >= 50
 
 
+@pytest.mark.parametrize("level", ["host", "device"])
 @pytest.mark.parametrize("agg_impl", [vm_model.IMPL_REGAGG, vm_model.IMPL_LOWAGG])
 @pytest.mark.parametrize("seed", SEEDS)
-def test_lowered_random_plan_matches_oracle(seed, agg_impl, sf001):
+def test_lowered_random_plan_matches_oracle(seed, agg_impl, level, sf001):
     d = random_plan(seed)
     tables = plan_tables(d, sf001)
     try:
@@ -44,7 +45,8 @@ def test_lowered_random_plan_matches_oracle(seed, agg_impl, sf001):
         else:
             src = outs[p["source_id"]]
         pool_strings = {nd[4]: pool[nd[4]:].split(b"\0")[0] for nd in p["nodes"] if nd[0] == 3}
-        outs.append(vm_model.run_pipeline_vm(plan, pi, src, pool_strings, agg_impl, True))
+        run = vm_model.run_pipeline_vm if level == "host" else vm_model.run_pipeline_device
+        outs.append(run(plan, pi, src, pool_strings, agg_impl, True))
     last = d["pipelines"][-1]
     st = [k[2] for k in last["keys"]] + [v[2] for v in last["vals"]]
     sw = [k[3] for k in last["keys"]] + [v[3] for v in last["vals"]]
