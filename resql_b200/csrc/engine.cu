@@ -388,10 +388,17 @@ static std::unique_ptr<rq_table> upload_host_narrow(const char* name, int n_cols
         auto h = g_width_hint.find(hint_key);
         for (int c = 0; c < n_cols; c++) {
             gw[c] = cols[c].width;
-            if (cols[c].type != RQ_I64) continue;
+            if (cols[c].type != RQ_I64 && cols[c].type != RQ_I32) continue;
             if (h != g_width_hint.end()) { gw[c] = h->second[c]; continue; }
-            const int64_t* p = (const int64_t*)cols[c].data;
             const int64_t step = std::max<int64_t>(1, n_rows / 4096);
+            if (cols[c].type == RQ_I32) {           // 4-byte columns: one byte or as they are
+                const int32_t* p = (const int32_t*)cols[c].data;
+                int32_t lo = p[n_rows - 1], hi = lo;
+                for (int64_t i = 0; i < n_rows; i += step) { lo = std::min(lo, p[i]); hi = std::max(hi, p[i]); }
+                gw[c] = (lo >= 0 && hi <= 255) ? 1 : 4;
+                continue;
+            }
+            const int64_t* p = (const int64_t*)cols[c].data;
             int64_t lo = p[n_rows - 1], hi = lo;
             for (int64_t i = 0; i < n_rows; i += step) { lo = std::min(lo, p[i]); hi = std::max(hi, p[i]); }
             gw[c] = (lo >= 0 && hi <= 255) ? 1 : (lo >= INT32_MIN && hi <= INT32_MAX) ? 4 : 8;
@@ -400,7 +407,8 @@ static std::unique_ptr<rq_table> upload_host_narrow(const char* name, int n_cols
     const auto t_begin = std::chrono::steady_clock::now();
     for (int attempt = 0; attempt < 3; attempt++) {
         std::vector<int> ncols;
-        for (int c = 0; c < n_cols; c++) if (cols[c].type == RQ_I64 && gw[c] != 8) ncols.push_back(c);
+        auto narrowed = [&](int c) { return (cols[c].type == RQ_I64 || cols[c].type == RQ_I32) && gw[c] != cols[c].width; };
+        for (int c = 0; c < n_cols; c++) if (narrowed(c)) ncols.push_back(c);
         if (ncols.empty()) { g_width_hint[hint_key] = gw; return nullptr; }
         std::unique_ptr<rq_table> t(new rq_table());
         t->name = name ? name : "";
@@ -462,7 +470,7 @@ static std::unique_ptr<rq_table> upload_host_narrow(const char* name, int n_cols
                 const int64_t row0 = (it / (int64_t)icols.size()) * kUpChunkRows;
                 const int64_t n = std::min<int64_t>(kUpChunkRows, n_rows - row0);
                 const int w8 = gw[c];
-                if (!(cols[c].type == RQ_I64 && w8 != 8)) {
+                if (!narrowed(c)) {
                     try { copy_column_rows(*t, c, cols[c].data, row0, n, cudaMemcpyHostToDevice, w.s); }
                     catch (RqError&) { cuda_err = 1; break; }
                     continue;
@@ -470,7 +478,10 @@ static std::unique_ptr<rq_table> upload_host_narrow(const char* name, int n_cols
                 const auto t0 = std::chrono::steady_clock::now();
                 if (used[b] && cudaEventSynchronize(w.ev[b]) != cudaSuccess) { cuda_err = 1; break; }
                 const auto t1 = std::chrono::steady_clock::now();
-                if (!hostnarrow::convert_chunk((const int64_t*)cols[c].data + row0, w.h[b], (size_t)n, w8, &tlo[c], &thi[c])) {
+                const bool fits = cols[c].type == RQ_I32
+                                      ? hostnarrow::convert_chunk32((const int32_t*)cols[c].data + row0, w.h[b], (size_t)n, &tlo[c], &thi[c])
+                                      : hostnarrow::convert_chunk((const int64_t*)cols[c].data + row0, w.h[b], (size_t)n, w8, &tlo[c], &thi[c]);
+                if (!fits) {
                     bad_col = c;
                     break;
                 }
@@ -498,7 +509,7 @@ static std::unique_ptr<rq_table> upload_host_narrow(const char* name, int n_cols
         if (bad_col.load() >= 0) {
             // the sample lied: widen that column's guess and start over
             const int c = bad_col.load();
-            gw[c] = gw[c] == 1 ? 4 : 8;
+            gw[c] = cols[c].type == RQ_I32 ? 4 : (gw[c] == 1 ? 4 : 8);
             CK(cudaStreamSynchronize(E.stream));
             continue;
         }
@@ -526,8 +537,9 @@ static std::unique_ptr<rq_table> upload_host_narrow(const char* name, int n_cols
 // debug aid (no GPU needed, not part of the public ABI): the host-side conversion of one chunk, so that the
 // CPU-only tests can check fit detection and value ranges (tests/test_host_narrow.py)
 extern "C" int rq_debug_convert_chunk(const int64_t* in, int64_t n, int32_t width, uint8_t* out, int64_t* lo, int64_t* hi) {
-    if (!in || !out || !lo || !hi || n < 0 || (width != 1 && width != 4)) return -1;
+    if (!in || !out || !lo || !hi || n < 0 || (width != 1 && width != 4 && width != -1)) return -1;
     *lo = INT64_MAX; *hi = INT64_MIN;
+    if (width == -1) return hostnarrow::convert_chunk32((const int32_t*)in, out, (size_t)n, lo, hi) ? 1 : 0;    // int32 source -> bytes
     return hostnarrow::convert_chunk(in, out, (size_t)n, width, lo, hi) ? 1 : 0;
 }
 

@@ -47,6 +47,15 @@ static void mm32_plain(const int32_t* p, size_t n, int64_t* lo, int64_t* hi) { R
 #undef RQ_HN_MM8
 #undef RQ_HN_MM32
 
+// the same from 4-byte values (INT columns whose values fit one byte: flags, small enumerations)
+#define RQ_HN_BODY8_32                                                            \
+    uint32_t a = 0;                                                               \
+    for (size_t i = 0; i < n; i++) { const int32_t v = in[i]; a |= (uint32_t)v; out[i] = (uint8_t)v; } \
+    *acc |= a;
+__attribute__((target("avx2"))) static void conv8_from32_avx2(const int32_t* in, uint8_t* out, size_t n, uint64_t* acc) { RQ_HN_BODY8_32 }
+static void conv8_from32_plain(const int32_t* in, uint8_t* out, size_t n, uint64_t* acc) { RQ_HN_BODY8_32 }
+#undef RQ_HN_BODY8_32
+
 static bool has_avx2() {
     static const bool v = __builtin_cpu_supports("avx2");
     return v;
@@ -66,6 +75,16 @@ static bool convert_chunk(const int64_t* in, void* out, size_t n, int w, int64_t
         if (acc >= (1ULL << 32)) return false;
         if (vx) mm32_avx2((const int32_t*)out, n, lo, hi); else mm32_plain((const int32_t*)out, n, lo, hi);
     }
+    return true;
+}
+
+// one chunk of an int32 column -> bytes; false when a value does not fit [0, 255]
+static bool convert_chunk32(const int32_t* in, void* out, size_t n, int64_t* lo, int64_t* hi) {
+    uint64_t acc = 0;
+    const bool vx = has_avx2();
+    if (vx) conv8_from32_avx2(in, (uint8_t*)out, n, &acc); else conv8_from32_plain(in, (uint8_t*)out, n, &acc);
+    if (acc >= 256) return false;
+    if (vx) mm8_avx2((const uint8_t*)out, n, lo, hi); else mm8_plain((const uint8_t*)out, n, lo, hi);
     return true;
 }
 

@@ -81,12 +81,15 @@ def test_transfer_narrowing_is_exact(case, engine):
         li["l_discount"] = li["l_discount"].copy(); li["l_discount"][7] = -3                      # negative: not a byte
         li["l_extendedprice"] = li["l_extendedprice"].copy(); li["l_extendedprice"][n - 5] = 1 << 33   # not int32
         li["l_tax"] = li["l_tax"].copy(); li["l_tax"][n // 3 + 2] = -(1 << 40)
+        li["l_linenumber"] = li["l_linenumber"].copy(); li["l_linenumber"][n // 5 + 3] = 300     # INT column: no longer one byte
     if case == "narrow_off":
         engine.set_option("narrow", 0)
     try:
-        for name in ("q1", "q6", "agg_nogroup_minmax", "agg_wrap"):
+        for name in ("q1", "q6", "agg_nogroup_minmax", "agg_wrap", "agg_linenumber"):
             d = load_plan_dict(name)
             tabs = plan_tables(d, data)
+            if name == "agg_linenumber":          # (an INT column whose values fit one byte: 1..7, or 300 in the outlier case)
+                assert "l_linenumber" in tabs["lineitem"]
             got, _ = _run(engine, d, tabs)
             want = serialize_columns(*run_plan(d, tabs))
             assert_same_relation(got, want, d, f"{name} ({case})")

@@ -41,3 +41,28 @@ def test_one_value_that_does_not_fit_is_noticed_wherever_it_sits(pos, bad, width
 def test_boundary_values_fit():
     assert convert([0, 255], 1)[0] == 1
     assert convert([-2**31, 2**31 - 1], 4)[0] == 1
+
+
+def convert32(values):
+    lib = N.load()
+    a = np.ascontiguousarray(values, dtype=np.int32)
+    out = np.zeros(max(len(a), 1), dtype=np.uint8)
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    rc = lib.rq_debug_convert_chunk(a.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(len(a)), C.c_int32(-1),
+                                    out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(lo), C.byref(hi))
+    return rc, out[: len(a)], lo.value, hi.value
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 1000, 65537])
+def test_int_columns_that_fit_a_byte(n):
+    v = np.random.default_rng(n).integers(0, 256, n)
+    rc, out, lo, hi = convert32(v)
+    assert rc == 1 and np.array_equal(out, v.astype(np.uint8)) and (lo, hi) == (int(v.min()), int(v.max()))
+
+
+@pytest.mark.parametrize("pos", [0, 501, 999])
+@pytest.mark.parametrize("bad", [256, -1, 2**31 - 1, -2**31])
+def test_int_value_that_does_not_fit_a_byte_is_noticed(pos, bad):
+    v = np.full(1000, 3, dtype=np.int32)
+    v[pos] = bad
+    assert convert32(v)[0] == 0
